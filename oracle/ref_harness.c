@@ -85,6 +85,11 @@ int refh_init(const char *deck) {
   STATUS = Generate_One_Phase_Analysis__InOutFun__(&MPM_Mesh, SimulationFile, FEM_Mesh, Params);
   if (STATUS == EXIT_FAILURE) return 2;
   GramsOutputs(SimulationFile);
+  /* GramsBox malloc()s ActiveNode and never clears it (Read_GramsBox.c:118), while
+   * initialize__LME__ only ever sets entries to true (LME.c:122-141): the reference's
+   * first neighbour lists depend on uninitialised heap.  The harness pins the
+   * deterministic reading (all false before the first activation pass). */
+  memset(FEM_Mesh.ActiveNode, 0, sizeof(bool) * FEM_Mesh.NumNodesMesh);
   initialise_shapefun__MeshTools__(MPM_Mesh, FEM_Mesh);
   size_t nb = (size_t)FEM_Mesh.NumNodesMesh * NumberDimensions * sizeof(double);
   g_mass = (double *)calloc(1, nb);

@@ -1,0 +1,148 @@
+"""Generate the golden fixtures that pin the oracle (and through it the CUDA engine) to the
+reference's OWN compiled 2D code.
+
+Run here (the container that has /root/reference), after `make -C oracle ref`:
+
+    python tests/golden/make_golden.py
+
+Each case is produced in a fresh subprocess (the reference keeps its state in process globals):
+a deck is written with tests/deckgen.py, parsed by the reference's parser, initialised by the
+reference's initialize__LME__, and stepped by oracle/ref_harness.c::refh_step (reference stage
+functions driven by the restated NPC-FS loop, 1 OpenMP thread for determinism).  The point-wise
+files drive one material point through Stress_integration__Constitutive__ along strain paths that
+include the reference's own stand-alone test path (tests/Constitutive/
+Drucker-Prager-Backward-Euler.c:377-472: E=1e4, nu=0.2, kappa0=40, phi=39, psi=6, H=0.1, m=1,
+DF=diag(1,0.999,1)) and sheared paths that rotate the principal axes (so that the transposed
+eigenvector indexing of the plastic branches, SURVEY F10-i, is exercised).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, os.path.join(HERE, "..", "..", "nl-partsol_b200"))
+
+import deckgen  # noqa: E402
+
+MATERIALS = {
+    "nh": ("Neo-Hookean-Wriggers", dict(rho=1000.0, E=1.0e6, nu=0.3), None),
+    "dp": ("Drucker-Prager", {"rho": 2000.0, "E": 1e6, "nu": 0.3, "m": 1.0, "Hardening-modulus": 1.0,
+                              "Reference-plastic-strain": 1e-2, "kappa-0": 20.0, "Friction-angle": 30.0,
+                              "Dilatancy-angle": 0.0}, (1e7 / 2000) ** 0.5),
+    "mn": ("Matsuoka-Nakai", {"rho": 2000.0, "E": 1e7, "nu": 0.3, "alpha": 0.5, "a1": 20000.0,
+                              "a2": 0.005, "a3": 35.0, "Friction-angle": 30.0, "Cohesion": 1e3,
+                              "kappa-0": 8.0 / 3.0}, 1.2 * (1e7 / 2000) ** 0.5),
+}
+POINT_MATERIALS = {
+    "dp": ("Drucker-Prager", {"rho": 2000.0, "E": 1e4, "nu": 0.2, "m": 1.0, "Hardening-modulus": 0.1,
+                              "kappa-0": 40.0, "Friction-angle": 39.0, "Dilatancy-angle": 6.0}),
+    "mn": ("Matsuoka-Nakai", {"rho": 2000.0, "E": 1e7, "nu": 0.3, "alpha": 0.5, "a1": 20000.0,
+                              "a2": 0.005, "a3": 35.0, "Friction-angle": 30.0, "Cohesion": 1e3,
+                              "kappa-0": 8.0 / 3.0}),
+}
+CHECKPOINTS = {"nh": (1, 2, 5, 20, 60), "dp": (1, 2, 5, 20, 60, 120), "mn": (1, 2, 5, 20, 60)}
+TRACE_FIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "DF", "Stress", "rho", "J_n", "W", "b_e_n",
+                "EPS_n", "Kappa_n", "lambda", "Beta", "C_ep")
+
+
+def spec_for(case):
+    model, params, cel = MATERIALS[case]
+    spec = deckgen.DeckSpec()
+    spec.material = deckgen.Material(model, params)
+    if cel:
+        spec.cel = cel
+    spec.nsteps = max(CHECKPOINTS[case])
+    return spec
+
+
+def gen_sim(case):
+    import refexport
+    import refharness
+    tmp = tempfile.mkdtemp(prefix="nlps_golden_")
+    h = refharness.RefHarness(deckgen.write_deck(spec_for(case), tmp), threads=1)
+    P = refexport.problem_from_ref(h)
+    np.savez_compressed(os.path.join(HERE, f"{case}_problem.npz"), **P.to_npz_dict())
+    cap = int((P.r2p[1:] - P.r2p[:-1]).max())
+    trace = {}
+    for k in range(max(CHECKPOINTS[case])):
+        assert h.step(k) == 0, (case, k)
+        if k + 1 in CHECKPOINTS[case]:
+            t = f"s{k + 1}_"
+            for f in TRACE_FIELDS:
+                trace[t + f] = h.field(f)
+            for w, nm in enumerate(("M", "dU", "F", "A", "R")):
+                trace[t + "g" + nm] = h.nodal(w)
+            lp, li = h.table(4)
+            trace[t + "lists"] = refexport.lists_dense(lp, li, cap)
+            trace[t + "I0"] = h.ints("I0")
+            trace[t + "NumberNodes"] = h.ints("NumberNodes")
+            trace[t + "active"] = h.active()
+            n2m = np.zeros(P.nn, np.int32)
+            d2m = np.zeros(P.nn * P.ndim, np.int32)
+            import ctypes
+            ip = ctypes.POINTER(ctypes.c_int)
+            na = h.lib.refh_masks(k, n2m.ctypes.data_as(ip), d2m.ctypes.data_as(ip))
+            trace[t + "nodes2mask"] = n2m
+            trace[t + "dofs2mask"] = d2m[:na * P.ndim]
+    trace["checkpoints"] = np.array(CHECKPOINTS[case])
+    np.savez_compressed(os.path.join(HERE, f"{case}_trace.npz"), **trace)
+    print(case, "ok: np", P.np_, "nn", P.nn, "max EPS", float(h.field("EPS_n").max()))
+
+
+def gen_points(case):
+    import refexport
+    import refharness
+    model, params = POINT_MATERIALS[case]
+    spec = deckgen.DeckSpec(nx=6, ny=6, pnx=2, pny=2, porigin=(0.125, 0.125))
+    spec.material = deckgen.Material(model, params)
+    tmp = tempfile.mkdtemp(prefix="nlps_golden_")
+    h = refharness.RefHarness(deckgen.write_deck(spec, tmp), threads=1)
+    P = refexport.problem_from_ref(h)
+    rng = np.random.default_rng(20261018)
+    rows_in, rows_out = [], []
+    for path in range(24):
+        be = np.array([1, 0, 0, 1, 1.0])
+        eps, kap = float(P.fields["EPS_n"][0]), float(P.fields["Kappa_n"][0])
+        F = np.array([1, 0, 0, 1, 1.0])
+        amp = 10.0 ** rng.uniform(-4, -2)
+        drift = rng.standard_normal(4)
+        for step in range(50):
+            D = np.eye(2) + amp * (drift.reshape(2, 2) + 0.3 * rng.standard_normal((2, 2)))
+            if path == 0:
+                D = np.diag([1.0, 0.999])  # the reference's own stand-alone test path
+            elif path % 4 == 0:
+                D = np.diag([1.0, 1 - amp])
+            DF = np.array([D[0, 0], D[0, 1], D[1, 0], D[1, 1], 1.0])
+            Fm = D @ F[:4].reshape(2, 2)
+            F = np.array([Fm[0, 0], Fm[0, 1], Fm[1, 0], Fm[1, 1], 1.0])
+            J = float(np.linalg.det(Fm))
+            a = h.stress_point(0, DF, F, J, be, eps, kap)
+            if a["status"] != 0 or not np.all(np.isfinite(a["stress"])):
+                break
+            rows_in.append(np.concatenate([DF, F, [J], be, [eps, kap]]))
+            rows_out.append(np.concatenate([a["stress"], a["b_e_n1"], [a["eps_n1"], a["kappa_n1"], a["W"]],
+                                            a["C_ep"]]))
+            be, eps, kap = a["b_e_n1"], a["eps_n1"], a["kappa_n1"]
+    mt, mp = P.materials[0]
+    np.savez_compressed(os.path.join(HERE, f"{case}_points.npz"), inputs=np.array(rows_in),
+                        outputs=np.array(rows_out), mat_type=np.array(mt), mat_params=mp,
+                        tol_radial=P.solver["tol_radial"], maxiter_radial=P.solver["maxiter_radial"])
+    nplastic = int((np.array(rows_out)[:, 10] != np.array(rows_in)[:, 16]).sum())
+    print(case, "points:", len(rows_in), "plastic:", nplastic)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) == 3:
+        {"sim": gen_sim, "points": gen_points}[sys.argv[1]](sys.argv[2])
+    else:
+        for c in ("nh", "dp", "mn"):
+            subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
+                           if os.environ.get("QUIET") else None)
+        for c in ("dp", "mn"):
+            subprocess.run([sys.executable, __file__, "points", c], check=True)

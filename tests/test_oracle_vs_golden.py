@@ -1,0 +1,78 @@
+"""The oracle port (oracle/nlps_oracle.c) against fixtures produced by the reference's own
+compiled 2D code (tests/golden/make_golden.py).  CPU only.  This is what "pins" the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+from util import NODAL, TRACE_FIELDS, assert_close, field_scales, load_points, load_problem, load_trace
+
+CASES = ("nh", "dp", "mn")
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_locality_bit_exact(case):
+    P = load_problem(case)
+    r1p, r1i, r2p, r2i, h_avg, dx = oracle.build_locality(P.ndim, P.coords, P.conn)
+    assert np.array_equal(r1p, P.r1p) and np.array_equal(r1i, P.r1i)
+    assert np.array_equal(r2p, P.r2p) and np.array_equal(r2i, P.r2i)
+    assert np.array_equal(h_avg, P.h_avg)
+    assert dx == P.dx
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_initialize_lme(case):
+    P = load_problem(case)
+    P0 = P.copy()
+    P0.fields["Beta"][:] = 0.0
+    P0.fields["lambda"][:] = 0.0
+    o = oracle.Oracle(P0)
+    assert o.init_lme() == 0
+    assert np.array_equal(o.field("Beta"), P.fields["Beta"])
+    assert_close(o.field("lambda"), P.fields["lambda"], "lambda after initialize__LME__")
+    # partition of unity / first-order consistency of the converged weights
+    for p in (0, P.np_ // 2, P.np_ - 1):
+        N, dN = o.shape(p)
+        assert abs(N.sum() - 1.0) < 1e-14
+        assert np.abs(dN.sum(0)).max() < 1e-6
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_steps_match_reference(case):
+    P = load_problem(case)
+    tr = load_trace(case)
+    o = oracle.Oracle(P)
+    scales = field_scales(P)
+    cps = [int(c) for c in tr["checkpoints"]]
+    for k in range(max(cps)):
+        assert o.step(k) == 0, (k, o.error())
+        if k + 1 not in cps:
+            continue
+        t = f"s{k + 1}_"
+        assert np.array_equal(o.ints("I0"), tr[t + "I0"]), f"I0 step {k + 1}"
+        assert np.array_equal(o.ints("NumberNodes"), tr[t + "NumberNodes"])
+        assert np.array_equal(o.lists()[:, :tr[t + "lists"].shape[1]], tr[t + "lists"]), f"lists step {k + 1}"
+        assert np.array_equal(o.active(), tr[t + "active"])
+        for f in TRACE_FIELDS + ("C_ep",):
+            assert_close(o.field(f), tr[t + f], f"{case} step {k + 1} {f}", scale=scales.get(f))
+        for w, nm in enumerate(NODAL):
+            assert_close(o.nodal(w), tr[t + "g" + nm], f"{case} step {k + 1} nodal {nm}")
+
+
+@pytest.mark.parametrize("case", ("dp", "mn"))
+def test_material_points(case):
+    z = load_points(case)
+    P = load_problem(case)
+    P.materials = [(str(z["mat_type"]), z["mat_params"])]
+    P.solver["tol_radial"] = float(z["tol_radial"])
+    P.solver["maxiter_radial"] = int(z["maxiter_radial"])
+    o = oracle.Oracle(P)
+    X, Y = z["inputs"], z["outputs"]
+    worst = 0.0
+    for x, y in zip(X, Y):
+        r = o.stress_point(0, x[0:5], x[5:10], x[10], x[11:16], x[16], x[17])
+        assert r["status"] == 0
+        got = np.concatenate([r["stress"], r["b_e_n1"], [r["eps_n1"], r["kappa_n1"], r["W"]], r["C_ep"]])
+        for sl in (slice(0, 5), slice(5, 10), slice(10, 11), slice(11, 12), slice(12, 13), slice(13, 17)):
+            s = max(np.abs(y[sl]).max(), 1e-12)
+            worst = max(worst, np.abs(got[sl] - y[sl]).max() / s)
+    assert worst <= 1e-12, worst

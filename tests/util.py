@@ -1,0 +1,56 @@
+"""Shared helpers for the parity tests."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from nlps_b200.problem import Problem
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# SURVEY 8(d) parity protocol / north_star: <= 1e-10 relative in fp64, with an absolute floor of
+# 1e-14 x the field's scale (a field that is ~0 everywhere compares against that floor).
+RTOL = 1e-10
+FLOOR = 1e-14
+
+TRACE_FIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "DF", "Stress", "rho", "J_n", "W",
+                "b_e_n", "EPS_n", "Kappa_n", "lambda", "Beta")
+NODAL = ("M", "dU", "F", "A", "R")
+
+
+def load_problem(case) -> Problem:
+    return Problem.from_npz(np.load(os.path.join(GOLDEN, f"{case}_problem.npz")))
+
+
+def load_trace(case):
+    return np.load(os.path.join(GOLDEN, f"{case}_trace.npz"))
+
+
+def load_points(case):
+    return np.load(os.path.join(GOLDEN, f"{case}_points.npz"))
+
+
+def rel_err(a, b, scale=None):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    fin = np.isfinite(b)
+    a, b = a[fin], b[fin]
+    s = max(float(np.abs(b).max()) if b.size else 0.0, scale or 0.0, 1e-300)
+    return float(np.abs(a - b).max()) / s if a.size else 0.0
+
+
+def assert_close(a, b, what, rtol=RTOL, scale=None):
+    e = rel_err(a, b, scale)
+    # the reference itself yields inf/nan in places (e.g. the apex tangent with psi = 0 divides by
+    # alpha_Q = 0, Drucker-Prager.c:1225): the non-finite pattern must agree, finite entries compare.
+    assert np.array_equal(np.isfinite(np.asarray(a, float)), np.isfinite(np.asarray(b, float))), \
+        f"{what}: non-finite pattern differs"
+    assert e <= rtol, f"{what}: rel err {e:.3e} > {rtol:.1e}"
+
+
+def field_scales(prob):
+    """Natural scale of each field (for the absolute floor of near-zero fields)."""
+    E = max(m[1][1] for m in prob.materials)
+    h = prob.dx
+    dt = prob.dt()
+    return dict(Stress=E * 1e-6, W=E * 1e-9, vel=h / dt * 1e-6, acc=9.81e-3, dis=h * 1e-6,
+                D_dis=h * 1e-6, x_GC=h, **{"lambda": 1.0 / h * 1e-3})
