@@ -1,0 +1,212 @@
+/*
+ * nlps_b200.h -- C ABI of the B200-native NL-PartSol explicit (NPC-FS) hot path.
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference
+ * interface it replaces (paths relative to nl-partsol/src of migmolper/NL-PartSol).
+ * The library is libnlps_b200.so (nl-partsol_b200/csrc).  Host code of the reference
+ * stays C: the scheme shim nl-partsol_b200/host/U-Verlet-b200.c flattens the
+ * reference's `Mesh` / `Particle` / `Time_Int_Params` structs into these PODs and is
+ * linked in place of Formulations/Displacements/U-Verlet.c.
+ *
+ * Conventions
+ *   - all reals are IEEE fp64, all indices 32-bit int (as in the reference).
+ *   - host particle arrays are the reference's own `Matrix.nV` buffers:
+ *     row-major Np x cols (cols = d for vectors, T = 5 (2D) / 9 (3D) for tensors,
+ *     d*d for C_ep), or bare double[Np]; see Types.h:184-283, U-Analisys.c:5-170.
+ *   - adjacency is the reference's linked lists flattened to CSR in CHAIN
+ *     (traversal) order: NodalLocality_0 -> ring1, NodalLocality -> ring2
+ *     (Types.h:631-760, Read_GramsBox.c:334-456).
+ *   - return value 0 = EXIT_SUCCESS, 1 = EXIT_FAILURE (the reference's error
+ *     convention, U-Verlet.c:101-135); details via nlps_b200_last_error().
+ *   - there is NO CPU fallback: every call fails loudly without a CUDA device.
+ */
+#ifndef NLPS_B200_H
+#define NLPS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLPS_MAT_NEO_HOOKEAN_WRIGGERS 0 /* Constitutive/Hyperelastic/Neo-Hookean.c:38 */
+#define NLPS_MAT_DRUCKER_PRAGER 1       /* Constitutive/Plasticity/Drucker-Prager.c:319 */
+#define NLPS_MAT_MATSUOKA_NAKAI 2       /* Constitutive/Plasticity/Matsuoka-Nakai.c:300 */
+
+/* error codes latched on the device (first offender wins) */
+#define NLPS_ERR_NONE 0
+#define NLPS_ERR_NEGATIVE_JACOBIAN 2   /* U-Verlet.c:608-613 */
+#define NLPS_ERR_FEW_NEIGHBOURS 3      /* LME.c:1087-1092 */
+#define NLPS_ERR_SINGULAR_HESSIAN 4    /* LME.c:308-313 */
+#define NLPS_ERR_NEWTON_LME 5          /* LME.c:343-350 */
+#define NLPS_ERR_RETURN_MAP_DP 6       /* Drucker-Prager.c:469-482 and __eps/__kappa */
+#define NLPS_ERR_RETURN_MAP_MN 7       /* Matsuoka-Nakai.c:__solver / tangent */
+#define NLPS_ERR_SINGULAR_DF 8         /* TensorLib.c:829-905 (compute_adjunt) */
+#define NLPS_ERR_CUDA 100
+
+/* Background mesh: the parts of `Mesh` (Types.h:631-760) the stepped path reads. */
+typedef struct nlps_mesh {
+  int ndim;               /* NumberDimensions (Macros.h:33-37) */
+  int n_nodes;            /* Mesh.NumNodesMesh */
+  const double *coords;   /* Mesh.Coordinates.nV, n_nodes x ndim */
+  const int *ring1_ptr;   /* NodalLocality_0 (1 ring), CSR chain order, n_nodes+1 */
+  const int *ring1_idx;
+  const int *ring2_ptr;   /* NodalLocality (2 rings), CSR chain order */
+  const int *ring2_idx;
+  const double *h_avg;    /* Mesh.h_avg */
+  double delta_x;         /* Mesh.DeltaX */
+} nlps_mesh;
+
+/* One `Load` (Types.h:296-332): Dirichlet set (ids = nodes), Neumann set
+ * (ids = particles).  dir/val are dim x num_steps, value k at step s is
+ * Value[k].Fx[s], active iff Dir[k*NumTimeStep+s] == 1. */
+typedef struct nlps_load {
+  int n_ids;
+  int dim;
+  const int *ids;
+  const int *dir;
+  const double *val;
+} nlps_load;
+
+/* The slice of `Material` (Types.h:359-458) the three in-scope laws read. */
+typedef struct nlps_material {
+  int type;
+  double rho, E, nu;
+  double reference_pressure;          /* ReferencePressure */
+  double kappa_0, hardening_modulus;  /* kappa_0, Hardening_modulus */
+  double plastic_strain_0;            /* Plastic_Strain_0 */
+  double phi_frictional, psi_frictional; /* degrees */
+  double exponent_hardening_ortiz;    /* m */
+  double cohesion;
+  double alpha_hardening_borja;
+  double a_hardening_borja[3];
+} nlps_material;
+
+/* `Time_Int_Params` (Types.h:804-865) + the process globals the scheme reads
+ * (Globals.h:16-109): gamma_LME, TOL_zero_LME, TOL_wrapper_LME, max_iter_LME,
+ * TOL_Radial_Returning, Max_Iterations_Radial_Returning, Thickness_Plain_Stress. */
+typedef struct nlps_solver {
+  double cfl, cel;
+  int initial_step, num_steps;
+  double gamma_lme, tol_zero_lme, tol_wrapper_lme;
+  int max_iter_lme;
+  double tol_radial_returning;
+  int max_iter_radial_returning;
+  double thickness;
+  int quirk_transposed_eigvec; /* -1 = default (1 in 2D, 0 in 3D); SURVEY F10-i */
+  int compute_c_ep;            /* write Phi.C_ep (needed by the implicit tangent only) */
+} nlps_solver;
+
+/* Host views of `Particle` / `Fields` (Types.h:548-623,184-283).  Any pointer may
+ * be NULL in download()/upload() calls (then that field is skipped); create()
+ * needs x_GC, mass, Vol_0, rho, F_n, I0, MatIdx and treats NULL as "zero /
+ * identity as allocate_U_vars__Fields__ leaves it". */
+typedef struct nlps_particles {
+  int n; /* Particle.NumGP */
+  double *x_GC, *dis, *D_dis, *vel, *acc;                 /* n x d */
+  double *F_n, *F_n1, *DF, *b_e_n, *b_e_n1, *Stress;     /* n x T */
+  double *C_ep;                                           /* n x d*d */
+  double *J_n, *J_n1, *mass, *rho, *Vol_0, *W;            /* n */
+  double *EPS_n, *EPS_n1, *Kappa_n, *Kappa_n1;            /* n */
+  double *lambda; /* n x d  (Particle.lambda) */
+  double *Beta;   /* n      (Particle.Beta)   */
+  int *I0, *NumberNodes, *MatIdx;                         /* n */
+} nlps_particles;
+
+typedef struct nlps_engine nlps_engine;
+
+/* stages of one explicit step, in order */
+enum nlps_stage {
+  NLPS_STAGE_SEARCH = 0,        /* local_search__MeshTools__  Shape-Functions.c:31 -> LME.c:895 */
+  NLPS_STAGE_P2G_MASS_DISP = 1, /* __mass_NODES, __predictor_PARTICLES, __d_displacement_NODES U-Verlet.c:166-367 */
+  NLPS_STAGE_GRID_DISP = 2,     /* /M and impose_Dirichlet_Boundary_Conditions U-Verlet.c:359-363,458-526 (fused into stage 1 on the device; no-op) */
+  NLPS_STAGE_KIN_STRESS = 3,    /* __update_Local_State U-Verlet.c:530-676 + Constitutive.c:18 */
+  NLPS_STAGE_FORCE = 4,         /* __nodal_internal_forces U-Newmark-beta.c:1257-1374 + tractions U-Verlet.c:805-902 */
+  NLPS_STAGE_GRID_ACC = 5,      /* solve_Nodal_Equilibrium nodal part U-Verlet.c:947-958 (fused into stage 4; no-op) */
+  NLPS_STAGE_G2P = 6            /* G2P + compute_Explicit_Newmark_Corrector U-Verlet.c:963-1084 */
+};
+
+/* Replaces the setup the scheme functions do implicitly by receiving the
+ * reference structs by value (U-Verlet.c:64-87): copies mesh, loads, materials
+ * and the particle state to the device (AoS -> SoA, chains -> CSR).  gravity is
+ * ndim x num_steps (gravity_field.Value[k].Fx, U-Newmark-beta.c:1539-1543) or NULL.
+ * Returns NULL on failure and writes a message into err. */
+nlps_engine *nlps_b200_create(const nlps_mesh *mesh, const nlps_solver *solver,
+                              int n_bounds, const nlps_load *bounds,
+                              int n_neumann, const nlps_load *neumann,
+                              const double *gravity, int n_materials,
+                              const nlps_material *materials,
+                              const nlps_particles *state, int device,
+                              char *err, int err_len);
+void nlps_b200_destroy(nlps_engine *e);
+
+/* initialize__LME__ (LME.c:45-173) phases 2-3, given I0: activate nodes,
+ * first neighbour lists (Beta = 0 => infinite radius), Beta, Newton for lambda. */
+int nlps_b200_initialize_lme(nlps_engine *e);
+
+/* One iteration of the U_Verlet time loop (U-Verlet.c:89-159, intended form). */
+int nlps_b200_step(nlps_engine *e, int time_step);
+/* `count` consecutive steps; the error flag is polled once at the end. */
+int nlps_b200_run(nlps_engine *e, int first_step, int count);
+/* One stage (stage-by-stage parity tests). */
+int nlps_b200_stage(nlps_engine *e, int stage, int time_step);
+
+/* D2H of particle fields into the caller's (reference-owned) buffers before
+ * particle_results_vtk__InOutFun__ (U-Verlet.c:1088-1227); never reallocates. */
+int nlps_b200_download(nlps_engine *e, nlps_particles *out);
+int nlps_b200_upload(nlps_engine *e, const nlps_particles *in);
+
+/* Nodal arrays of the last step in full-grid indexing, n_nodes x ndim, zero on
+ * inactive nodes.  which: 0 lumped mass (per DOF, d identical copies as
+ * U-Verlet.c:216), 1 D_Displacement, 2 Forces, 3 Acceleration, 4 Reactions. */
+int nlps_b200_get_nodal(nlps_engine *e, int which, double *out);
+int nlps_b200_get_active(nlps_engine *e, unsigned char *out); /* Mesh.ActiveNode */
+/* Particle.ListNodes expanded in chain order: lists is n x cap (-1 padded). */
+int nlps_b200_list_capacity(nlps_engine *e);
+int nlps_b200_get_lists(nlps_engine *e, int *counts, int *lists, int cap);
+
+int nlps_b200_last_error(nlps_engine *e, int *code, int *particle);
+double nlps_b200_dt(nlps_engine *e); /* U_DeltaT__SolversLib__ Courant.c:6 */
+
+/* Per-kernel device times (CUDA events on the engine's stream), accumulated
+ * since the last reset.  names/ms/launches have room for `cap` entries;
+ * returns the number of kernels. */
+int nlps_b200_profile(nlps_engine *e, int enable);
+int nlps_b200_kernel_times(nlps_engine *e, int cap, const char **names, double *ms, int *launches);
+void nlps_b200_reset_kernel_times(nlps_engine *e);
+long long nlps_b200_launch_count(nlps_engine *e);
+
+/* The whole scheme call with HOST buffers (what U_Verlet does for the driver):
+ * create + initialize (optional) + steps [initial_step, num_steps) + download
+ * every `results_every` steps (callback may be NULL) + destroy. */
+typedef void (*nlps_results_cb)(int time_step, void *user);
+int nlps_b200_u_verlet(const nlps_mesh *mesh, const nlps_solver *solver,
+                       int n_bounds, const nlps_load *bounds, int n_neumann,
+                       const nlps_load *neumann, const double *gravity,
+                       int n_materials, const nlps_material *materials,
+                       nlps_particles *state, int run_initialize,
+                       int results_every, nlps_results_cb cb, void *user,
+                       int device);
+
+/* Scalable setup: O(N) replacement of get_sourrounding_elements /
+ * fill_nodal_locality / compute_nodal_distance_local / mesh_size
+ * (Read_GramsBox.c:293-565) producing the same chain orders.  Host code.
+ * Two-call protocol: sizes first (idx pointers NULL), then fill. */
+int nlps_b200_build_locality(int ndim, int n_nodes, int n_elems, int nodes_per_elem,
+                             const int *connectivity, const double *coords,
+                             int *ring1_ptr, int *ring1_idx, int *ring2_ptr,
+                             int *ring2_idx, double *h_avg, double *delta_x);
+
+/* Stress_integration__Constitutive__ (Constitutive/Constitutive.c:18-258) over an array of
+ * independent material points (host AoS rows of T doubles); status[p] = 0 or an NLPS_ERR_* code. */
+int nlps_b200_stress_points(int ndim, const nlps_material *material, double tol_radial,
+                            int max_iter_radial, int quirk_transposed_eigvec, int n,
+                            const double *DF, const double *F_n1, const double *J_n1,
+                            const double *b_e_n, const double *eps_n, const double *kappa_n,
+                            double *stress, double *b_e_n1, double *eps_n1, double *kappa_n1,
+                            double *W, double *C_ep, int *status, int device);
+
+const char *nlps_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLPS_B200_H */

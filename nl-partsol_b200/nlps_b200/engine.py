@@ -1,0 +1,292 @@
+"""ctypes binding of include/nlps_b200.h."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from .problem import MATERIAL_TYPES, Problem
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+STAGES = dict(search=0, p2g_mass_disp=1, grid_disp=2, kin_stress=3, force=4, grid_acc=5, g2p=6)
+
+
+class Mesh(C.Structure):
+    _fields_ = [("ndim", C.c_int), ("n_nodes", C.c_int), ("coords", _dp), ("ring1_ptr", _ip),
+                ("ring1_idx", _ip), ("ring2_ptr", _ip), ("ring2_idx", _ip), ("h_avg", _dp),
+                ("delta_x", C.c_double)]
+
+
+class Load(C.Structure):
+    _fields_ = [("n_ids", C.c_int), ("dim", C.c_int), ("ids", _ip), ("dir", _ip), ("val", _dp)]
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int), ("rho", C.c_double), ("E", C.c_double), ("nu", C.c_double),
+                ("reference_pressure", C.c_double), ("kappa_0", C.c_double),
+                ("hardening_modulus", C.c_double), ("plastic_strain_0", C.c_double),
+                ("phi_frictional", C.c_double), ("psi_frictional", C.c_double),
+                ("exponent_hardening_ortiz", C.c_double), ("cohesion", C.c_double),
+                ("alpha_hardening_borja", C.c_double), ("a_hardening_borja", C.c_double * 3)]
+
+
+class Solver(C.Structure):
+    _fields_ = [("cfl", C.c_double), ("cel", C.c_double), ("initial_step", C.c_int),
+                ("num_steps", C.c_int), ("gamma_lme", C.c_double), ("tol_zero_lme", C.c_double),
+                ("tol_wrapper_lme", C.c_double), ("max_iter_lme", C.c_int),
+                ("tol_radial_returning", C.c_double), ("max_iter_radial_returning", C.c_int),
+                ("thickness", C.c_double), ("quirk_transposed_eigvec", C.c_int), ("compute_c_ep", C.c_int)]
+
+
+_PFIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "F_n1", "DF", "b_e_n", "b_e_n1", "Stress", "C_ep",
+            "J_n", "J_n1", "mass", "rho", "Vol_0", "W", "EPS_n", "EPS_n1", "Kappa_n", "Kappa_n1", "lambda",
+            "Beta")
+
+
+class Particles(C.Structure):
+    _fields_ = [("n", C.c_int)] + [(k, _dp) for k in _PFIELDS] + [("I0", _ip), ("NumberNodes", _ip),
+                                                                  ("MatIdx", _ip)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libnlps_b200.so, building it in-tree if needed.  Raises if it cannot be loaded:
+    the product path has no fallback."""
+    global _lib
+    if _lib is None:
+        so = _build.build()
+        L = C.CDLL(so)
+        L.nlps_b200_create.restype = C.c_void_p
+        L.nlps_b200_dt.restype = C.c_double
+        L.nlps_b200_version.restype = C.c_char_p
+        L.nlps_b200_launch_count.restype = C.c_longlong
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _material(t, p):
+    m = Material()
+    m.type = MATERIAL_TYPES[t]
+    (m.rho, m.E, m.nu, m.reference_pressure, m.kappa_0, m.hardening_modulus, m.plastic_strain_0,
+     m.phi_frictional, m.psi_frictional, m.exponent_hardening_ortiz, m.cohesion,
+     m.alpha_hardening_borja) = [float(v) for v in p[:12]]
+    for k in range(3):
+        m.a_hardening_borja[k] = float(p[12 + k])
+    return m
+
+
+def build_locality(ndim, coords, conn):
+    """nlps_b200_build_locality: scalable adjacency with the reference's chain orders."""
+    L = lib()
+    coords, conn = _d(coords), _i(conn)
+    nn, (ne, nne) = coords.shape[0], conn.shape
+    r1p, r2p = np.zeros(nn + 1, np.int32), np.zeros(nn + 1, np.int32)
+    h_avg = np.zeros(nn)
+    dx = C.c_double()
+    args = (ndim, nn, ne, nne, conn.ctypes.data_as(_ip), coords.ctypes.data_as(_dp))
+    assert L.nlps_b200_build_locality(*args, r1p.ctypes.data_as(_ip), None, r2p.ctypes.data_as(_ip), None,
+                                      h_avg.ctypes.data_as(_dp), C.byref(dx)) == 0
+    r1i, r2i = np.zeros(r1p[-1], np.int32), np.zeros(r2p[-1], np.int32)
+    assert L.nlps_b200_build_locality(*args, r1p.ctypes.data_as(_ip), r1i.ctypes.data_as(_ip),
+                                      r2p.ctypes.data_as(_ip), r2i.ctypes.data_as(_ip),
+                                      h_avg.ctypes.data_as(_dp), C.byref(dx)) == 0
+    return r1p, r1i, r2p, r2i, h_avg, dx.value
+
+
+class _Marshal:
+    """Keeps the numpy buffers alive that the C structs point into."""
+
+    def __init__(self, prob: Problem, quirk=-1, compute_c_ep=0, initial_step=0):
+        self.keep = []
+        k = self.keep
+        self.mesh = Mesh()
+        arrs = dict(coords=_d(prob.coords), r1p=_i(prob.r1p), r1i=_i(prob.r1i), r2p=_i(prob.r2p),
+                    r2i=_i(prob.r2i), h=_d(prob.h_avg))
+        k.append(arrs)
+        m = self.mesh
+        m.ndim, m.n_nodes = prob.ndim, prob.nn
+        m.coords = arrs["coords"].ctypes.data_as(_dp)
+        m.ring1_ptr, m.ring1_idx = arrs["r1p"].ctypes.data_as(_ip), arrs["r1i"].ctypes.data_as(_ip)
+        m.ring2_ptr, m.ring2_idx = arrs["r2p"].ctypes.data_as(_ip), arrs["r2i"].ctypes.data_as(_ip)
+        m.h_avg, m.delta_x = arrs["h"].ctypes.data_as(_dp), float(prob.dx)
+        s = prob.solver
+        self.solver = Solver(float(s["cfl"]), float(s["cel"]), int(initial_step), int(s["nsteps"]),
+                             float(s["gamma_lme"]), float(s["tol_zero"]), float(s["tol_wrapper"]),
+                             int(s["max_iter_lme"]), float(s["tol_radial"]), int(s["maxiter_radial"]),
+                             float(s.get("thickness", 1.0)), int(quirk), int(compute_c_ep))
+        self.bounds = self._loads(prob.bounds)
+        self.neumann = self._loads(prob.neumann)
+        self.gravity = _d(prob.gravity) if prob.gravity is not None else None
+        self.materials = (Material * len(prob.materials))(*[_material(t, p) for t, p in prob.materials])
+        self.state, self.host = self.particles(prob)
+
+    def _loads(self, lst):
+        arr = (Load * max(len(lst), 1))()
+        for j, b in enumerate(lst):
+            ids, di, v = _i(b["nodes"]), _i(b["dir"]), _d(b["val"])
+            self.keep.append((ids, di, v))
+            arr[j] = Load(len(ids), di.shape[0], ids.ctypes.data_as(_ip), di.ctypes.data_as(_ip),
+                          v.ctypes.data_as(_dp))
+        return arr
+
+    @staticmethod
+    def particles(prob: Problem):
+        host = {k: _d(prob.fields[k]).copy() for k in _PFIELDS if k in prob.fields}
+        host["I0"] = _i(prob.I0).copy()
+        host["MatIdx"] = _i(prob.MatIdx).copy()
+        host["NumberNodes"] = np.zeros(prob.np_, np.int32)
+        st = Particles()
+        st.n = prob.np_
+        for kname in _PFIELDS:
+            setattr(st, kname, host[kname].ctypes.data_as(_dp) if kname in host else None)
+        for kname in ("I0", "MatIdx", "NumberNodes"):
+            setattr(st, kname, host[kname].ctypes.data_as(_ip))
+        return st, host
+
+
+class Engine:
+    """Device-resident explicit NPC-FS engine (nlps_b200_create .. destroy)."""
+
+    def __init__(self, prob: Problem, device=0, quirk=-1, compute_c_ep=0):
+        L = lib()
+        self.L = L
+        self.prob = prob
+        self.m = _Marshal(prob, quirk, compute_c_ep)
+        err = C.create_string_buffer(256)
+        m = self.m
+        self.h = L.nlps_b200_create(C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds,
+                                    len(prob.neumann), m.neumann,
+                                    m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None,
+                                    len(prob.materials), m.materials, C.byref(m.state), device, err, 256)
+        if not self.h:
+            raise RuntimeError("nlps_b200_create failed: " + err.value.decode())
+        self.h = C.c_void_p(self.h)
+        self.d, self.np_, self.nn = prob.ndim, prob.np_, prob.nn
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.nlps_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def initialize_lme(self):
+        return self.L.nlps_b200_initialize_lme(self.h)
+
+    def step(self, k):
+        return self.L.nlps_b200_step(self.h, int(k))
+
+    def run(self, first, count):
+        return self.L.nlps_b200_run(self.h, int(first), int(count))
+
+    def stage(self, name, k):
+        return self.L.nlps_b200_stage(self.h, STAGES[name], int(k))
+
+    def download(self):
+        """All particle fields as a dict of numpy arrays (host layout of the reference)."""
+        st, host = self.m.state, self.m.host
+        assert self.L.nlps_b200_download(self.h, C.byref(st)) == 0
+        out = {}
+        for k, v in host.items():
+            out[k] = v.copy()
+        return out
+
+    def upload(self, fields: dict):
+        st, host = self.m.state, self.m.host
+        for k, v in fields.items():
+            if k in host:
+                host[k][...] = np.asarray(v).reshape(host[k].shape)
+        assert self.L.nlps_b200_upload(self.h, C.byref(st)) == 0
+
+    def nodal(self, which):
+        out = np.zeros((self.nn, self.d))
+        assert self.L.nlps_b200_get_nodal(self.h, which, out.ctypes.data_as(_dp)) == 0
+        return out
+
+    def active(self):
+        out = np.zeros(self.nn, np.uint8)
+        assert self.L.nlps_b200_get_active(self.h, out.ctypes.data_as(C.POINTER(C.c_ubyte))) == 0
+        return out
+
+    def lists(self):
+        cap = self.L.nlps_b200_list_capacity(self.h)
+        counts = np.zeros(self.np_, np.int32)
+        lists = np.zeros((self.np_, cap), np.int32)
+        assert self.L.nlps_b200_get_lists(self.h, counts.ctypes.data_as(_ip), lists.ctypes.data_as(_ip), cap) == 0
+        return counts, lists
+
+    def error(self):
+        c, p = C.c_int(), C.c_int()
+        self.L.nlps_b200_last_error(self.h, C.byref(c), C.byref(p))
+        return c.value, p.value
+
+    def dt(self):
+        return self.L.nlps_b200_dt(self.h)
+
+    def profile(self, on=True):
+        self.L.nlps_b200_profile(self.h, int(on))
+
+    def kernel_times(self, reset=False):
+        names = (C.c_char_p * 32)()
+        ms = (C.c_double * 32)()
+        n = (C.c_int * 32)()
+        k = self.L.nlps_b200_kernel_times(self.h, 32, names, ms, n)
+        out = {names[i].decode(): (ms[i], n[i]) for i in range(k)}
+        if reset:
+            self.L.nlps_b200_reset_kernel_times(self.h)
+        return out
+
+    def launch_count(self):
+        return int(self.L.nlps_b200_launch_count(self.h))
+
+
+def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, quirk=-1, initial_step=0):
+    """The whole scheme call with HOST buffers (nlps_b200_u_verlet).  Returns the final fields."""
+    L = lib()
+    m = _Marshal(prob, quirk, 0, initial_step)
+    rc = L.nlps_b200_u_verlet(C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds, len(prob.neumann),
+                              m.neumann, m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None,
+                              len(prob.materials), m.materials, C.byref(m.state), int(run_initialize),
+                              int(results_every), None, None, device)
+    if rc != 0:
+        raise RuntimeError("nlps_b200_u_verlet failed")
+    return {k: v.copy() for k, v in m.host.items()}
+
+
+def stress_points(ndim, mat_type, mat_params, tol_radial, maxiter_radial, DF, F_n1, J_n1, b_e_n, eps_n, kappa_n,
+                  quirk=-1, device=0):
+    """nlps_b200_stress_points: the constitutive update on arrays of material points."""
+    L = lib()
+    DF, F_n1, J_n1, b_e_n, eps_n, kappa_n = (_d(a) for a in (DF, F_n1, J_n1, b_e_n, eps_n, kappa_n))
+    n, T, dd = DF.shape[0], DF.shape[1], ndim * ndim
+    out = dict(stress=np.zeros((n, T)), b_e_n1=np.zeros((n, T)), eps_n1=np.zeros(n), kappa_n1=np.zeros(n),
+               W=np.zeros(n), C_ep=np.zeros((n, dd)), status=np.zeros(n, np.int32))
+    m = _material(mat_type, mat_params)
+    rc = L.nlps_b200_stress_points(ndim, C.byref(m), C.c_double(tol_radial), int(maxiter_radial), int(quirk), n,
+                                   DF.ctypes.data_as(_dp), F_n1.ctypes.data_as(_dp), J_n1.ctypes.data_as(_dp),
+                                   b_e_n.ctypes.data_as(_dp), eps_n.ctypes.data_as(_dp), kappa_n.ctypes.data_as(_dp),
+                                   out["stress"].ctypes.data_as(_dp), out["b_e_n1"].ctypes.data_as(_dp),
+                                   out["eps_n1"].ctypes.data_as(_dp), out["kappa_n1"].ctypes.data_as(_dp),
+                                   out["W"].ctypes.data_as(_dp), out["C_ep"].ctypes.data_as(_dp),
+                                   out["status"].ctypes.data_as(_ip), device)
+    if rc != 0:
+        raise RuntimeError("nlps_b200_stress_points failed")
+    return out
