@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the NL-PartSol explicit (NPC-FS) hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
+
+Workload (N=1): BASELINE.json configs[1] -- 2D granular column collapse, Drucker-Prager,
+10^6 particles (500x1000 particle cells x GPxElement 4) on a 3000x1250 Q4 background grid,
+LME gamma=3, explicit NPC-FS.  A "step" is one full time step over all particles.
+Prints ONE JSON line (see the keys below).  `--impl reference` times the reference's own CPU
+implementation (oracle/_ref: reference stage functions driven by the restated step loop, all
+host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "nl-partsol_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "particle-updates/sec"
+UNIT = "particle-updates/s"
+# algorithmic bytes per particle per step, 2D plastic: K0 76+4n, K1 112, K2 348, K3 128, K4 168
+ALG_BYTES_2D_PLASTIC = {"lme_update": lambda n: 76 + 4 * n, "p2g_mass_disp": lambda n: 112.0,
+                        "g2p_kin_stress": lambda n: 348.0, "p2g_force": lambda n: 128.0,
+                        "g2p_update": lambda n: 168.0}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.rows, self.proc, self.gpu = [], None, gpu
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def reference_sample(steps, warmup, threads=None, cells=(64, 128)):
+    """Time the reference's CPU path (oracle/_ref; falls back to the C port) on a bounded sample of the
+    C2 workload: same material / LME / BC set-up, cells[0] x cells[1] particle cells x 4 particles."""
+    threads = threads or os.cpu_count() or 1
+    so = os.path.join(ROOT, "oracle", "_ref", "libnlps2d_ref.so")
+    bx, by = cells
+    nsteps = steps + warmup
+    if os.path.exists(so):
+        import deckgen
+        import refharness
+        spec = deckgen.DeckSpec(nx=bx * 6, ny=by + by // 4, h=0.2 / bx, pnx=bx, pny=by, ph=0.2 / bx,
+                                porigin=(0.0, 0.0), nsteps=nsteps, cfl=0.5, cel=(1e7 / 2000.0) ** 0.5 * 1.3)
+        spec.material = deckgen.Material("Drucker-Prager", {
+            "rho": 2000.0, "E": 1e7, "nu": 0.3, "m": 1.0, "Hardening-modulus": 1.0,
+            "Reference-plastic-strain": 1e-2, "kappa-0": 1e4, "Friction-angle": 30.0, "Dilatancy-angle": 0.0})
+        tmp = tempfile.mkdtemp(prefix="nlps_bench_ref_")
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)  # the reference parser is chatty on stdout
+        try:
+            h = refharness.RefHarness(deckgen.write_deck(spec, tmp), threads=threads)
+        finally:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+            os.dup2(saved, 1)
+        npart = h.np_
+        for k in range(warmup):
+            assert h.step(k) == 0
+        t0 = time.perf_counter()
+        for k in range(warmup, nsteps):
+            assert h.step(k) == 0
+        dt = time.perf_counter() - t0
+        kind = "reference"
+        stage = h.stage_times().tolist()
+    else:
+        import oracle
+        from nlps_b200 import synthetic
+        sys.stderr.write("bench: oracle/_ref missing, timing the C port instead\n")
+        P = synthetic.column_collapse_2d(scale=bx / 500.0, nsteps=nsteps)
+        o = oracle.Oracle(P, threads=threads)
+        assert o.init_lme() == 0
+        npart = P.np_
+        for k in range(warmup):
+            assert o.step(k) == 0
+        t0 = time.perf_counter()
+        for k in range(warmup, nsteps):
+            assert o.step(k) == 0
+        dt = time.perf_counter() - t0
+        kind = "port"
+        stage = None
+    return dict(value=npart * steps / dt, unit=UNIT, cores=threads, kind=kind, ms_per_step=1e3 * dt / steps,
+                sample=f"2D DP column, {bx}x{by} particle cells x4 = {npart} particles, {steps} steps "
+                       f"(reference setup is O(Nn*Ne): full 10^6 size is out of its reach)",
+                stage_seconds_last_step=stage)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = reference_sample(args.steps, args.warmup)
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "2D granular column collapse, Drucker-Prager, explicit NPC-FS, LME gamma=3 "
+                                   "(bounded CPU sample of BASELINE configs[1])", "sample": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from nlps_b200 import engine, synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    K, Wm = args.steps, max(args.warmup, 3)
+    nsteps_total = Wm + K + 2
+    t_setup = time.perf_counter()
+    P = synthetic.column_collapse_2d(scale=args.scale, nsteps=nsteps_total)
+    eng = engine.Engine(P, device=local)
+    assert eng.initialize_lme() == 0, eng.error()
+    setup_s = time.perf_counter() - t_setup
+    npart = P.np_
+    # warm-up
+    assert eng.run(0, Wm) == 0, eng.error()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    rc, ms = eng.timed_run(Wm, K)
+    assert rc == 0, eng.error()
+    torch.cuda.synchronize()
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_particles = npart * world  # weak scaling: every rank steps its own column
+    value = total_particles * K / (ms_max * 1e-3)
+
+    # per-kernel device times (CUDA events on the engine's stream, serialised per launch)
+    counts, _ = eng.lists()
+    n_avg = float(counts.mean())
+    eng.profile(True)
+    eng.kernel_times(reset=True)
+    assert eng.run(Wm + K, 2) == 0
+    kt = eng.kernel_times()
+    eng.profile(False)
+    peak, peak_src = measured_peak()
+    per_kernel = {}
+    for name, (kms, kn) in kt.items():
+        if kn == 0:
+            continue
+        avg = kms / kn
+        d = {"ms": round(avg, 4), "launches_per_step": kn // 2}
+        if name in ALG_BYTES_2D_PLASTIC:
+            gbs = ALG_BYTES_2D_PLASTIC[name](n_avg) * npart / (avg * 1e-3) / 1e9
+            d.update(alg_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
+        per_kernel[name] = d
+    dom = max((k for k in per_kernel if "alg_gbs" in per_kernel[k]), key=lambda k: per_kernel[k]["ms"])
+    step_bytes = (832 + 4 * n_avg) * npart
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["alg_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "step_achieved_gbs": round(step_bytes * K / (ms_max * 1e-3) / 1e9, 1),
+                "step_frac": round(step_bytes * K / (ms_max * 1e-3) / 1e9 / peak, 4),
+                "neighbours_per_particle": round(n_avg, 2), "per_kernel": per_kernel}
+    eng.close()
+
+    # end to end through the scheme call with HOST buffers (create + H2D, steps, D2H of the results)
+    e2e_steps = max(K, 20)
+    P2 = synthetic.column_collapse_2d(scale=args.scale, nsteps=e2e_steps)
+    eng0 = engine.Engine(P2, device=local)       # initialise lambda/beta once (setup, as the driver does
+    assert eng0.initialize_lme() == 0            # with initialise_shapefun__MeshTools__ before the scheme)
+    f0 = eng0.download()
+    eng0.close()
+    for k in ("lambda", "Beta"):
+        P2.fields[k] = f0[k]
+    mesh_bytes = sum(a.nbytes for a in (P2.coords, P2.r1p, P2.r1i, P2.r2p, P2.r2i, P2.h_avg))
+    state_bytes = sum(v.nbytes for v in P2.fields.values()) + P2.I0.nbytes + P2.MatIdx.nbytes
+    every = 10
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    engine.u_verlet(P2, run_initialize=False, results_every=every, device=local)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    n_dl = sum(1 for k in range(e2e_steps) if k % every == 0) + 1
+    e2e = {"value": total_particles * e2e_steps / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int((mesh_bytes + state_bytes) / e2e_steps),
+           "d2h_bytes_per_step": int(state_bytes * n_dl / e2e_steps),
+           "steps": e2e_steps, "results_every": every, "seconds": round(e2e_s, 4),
+           "call": "nlps_b200_u_verlet (create+H2D, steps, D2H every 10 steps, destroy), host wall clock"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5",
+                                  "--warmup", "1"], capture_output=True, text=True, timeout=900)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as ex:  # reported baseline only, never gating
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[1]: 2D granular column collapse, Drucker-Prager, "
+                                       "explicit NPC-FS, LME gamma=3, GPxElement 4",
+                           "particles_per_gpu": npart, "background_nodes": P.nn, "scale": args.scale,
+                           "l2": "inputs larger than L2 (particle state + records ~0.7 GB per GPU)",
+                           "multi_gpu": "weak scaling, independent columns per rank" if world > 1 else "single GPU",
+                           "setup_seconds": round(setup_s, 2)},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--scale", type=float, default=1.0, help="linear scale of the C2 workload (1.0 = 10^6 particles)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

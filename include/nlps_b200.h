@@ -146,6 +146,8 @@ int nlps_b200_initialize_lme(nlps_engine *e);
 int nlps_b200_step(nlps_engine *e, int time_step);
 /* `count` consecutive steps; the error flag is polled once at the end. */
 int nlps_b200_run(nlps_engine *e, int first_step, int count);
+/* nlps_b200_run bracketed by CUDA events on the engine's stream; *ms = device time of the steps. */
+int nlps_b200_timed_run(nlps_engine *e, int first_step, int count, double *ms);
 /* One stage (stage-by-stage parity tests). */
 int nlps_b200_stage(nlps_engine *e, int stage, int time_step);
 

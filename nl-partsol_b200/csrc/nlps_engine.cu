@@ -724,6 +724,23 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
   }
 }
 
+
+// Reference roll semantics for history variables of particles whose law never writes them
+// (Neo-Hookean: b_e, EPS, Kappa): U-Verlet.c:1043-1056 COPIES n1 -> n every step, so after the
+// first step both copies hold the initial n1 value.  With the pointer-swap roll that is reproduced by
+// copying n1 -> n once, before the first swap.
+template <int D>
+__global__ void k_sync_inert(PartDev P) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.np) return;
+  if (c_mat[P.matidx[p]].type != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) return;
+  constexpr int TB = (D == 2) ? 5 : 9;
+#pragma unroll
+  for (int i = 0; i < TB; i++) P.be_n[(size_t)i * P.np + p] = P.be_n1[(size_t)i * P.np + p];
+  P.eps_n[p] = P.eps_n1[p];
+  P.kap_n[p] = P.kap_n1[p];
+}
+
 // AoS (host layout, n x cols) <-> SoA (cols x n)
 __global__ void k_aos_to_soa(const double* aos, double* soa, int n, int cols, int aos_stride, int col0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -822,6 +839,7 @@ struct nlps_engine {
   int* npart_check = nullptr;
   double neg_log_tol = 0.0, dt = 0.0;
   int has_traction = 0;
+  int inert_synced = 0;
   std::vector<void*> allocs;
   // staging for AoS <-> SoA
   double* stage = nullptr;
@@ -1002,6 +1020,10 @@ static void stage_g2p_t(nlps_engine* e, int step) {
 #define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH(e, K_G2P, kfn, nblk(e->np, 128), 128, e->mesh, e->P, e->G, sp); } break;
     CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8)
 #undef CASE_W
+  }
+  if (!e->inert_synced) {
+    k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P);
+    e->inert_synced = 1;
   }
   // roll n+1 -> n (U-Verlet.c:1043-1081) as pointer swaps
   std::swap(e->P.F_n, e->P.F_n1);
@@ -1247,6 +1269,7 @@ nlps_engine* nlps_b200_create(const nlps_mesh* mesh, const nlps_solver* solver, 
 
 int nlps_b200_upload(nlps_engine* e, const nlps_particles* in) {
   cudaSetDevice(e->device);
+  if (in->b_e_n || in->b_e_n1 || in->EPS_n || in->EPS_n1 || in->Kappa_n || in->Kappa_n1) e->inert_synced = 0;
   const int D = e->D, T = e->T, DD = D * D;
   PartDev& P = e->P;
   if (put_field(e, in->x_GC, P.x, D, D, 0) || put_field(e, in->dis, P.dis, D, D, 0) ||
@@ -1326,6 +1349,25 @@ int nlps_b200_run(nlps_engine* e, int first_step, int count) {
 }
 
 int nlps_b200_step(nlps_engine* e, int time_step) { return nlps_b200_run(e, time_step, 1); }
+
+int nlps_b200_timed_run(nlps_engine* e, int first_step, int count, double* ms) {
+  cudaSetDevice(e->device);
+  cudaEvent_t a, b;
+  CUDA_OK(cudaEventCreate(&a));
+  CUDA_OK(cudaEventCreate(&b));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  CUDA_OK(cudaEventRecord(a, e->stream));
+  for (int k = first_step; k < first_step + count; k++)
+    for (int s = NLPS_STAGE_SEARCH; s <= NLPS_STAGE_G2P; s++) enqueue_stage(e, s, k);
+  CUDA_OK(cudaEventRecord(b, e->stream));
+  CUDA_OK(cudaEventSynchronize(b));
+  float t = 0;
+  CUDA_OK(cudaEventElapsedTime(&t, a, b));
+  *ms = t;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return poll_error(e);
+}
 
 int nlps_b200_get_nodal(nlps_engine* e, int which, double* out) {
   cudaSetDevice(e->device);

@@ -197,6 +197,11 @@ class Engine:
     def run(self, first, count):
         return self.L.nlps_b200_run(self.h, int(first), int(count))
 
+    def timed_run(self, first, count):
+        ms = C.c_double()
+        rc = self.L.nlps_b200_timed_run(self.h, int(first), int(count), C.byref(ms))
+        return rc, ms.value
+
     def stage(self, name, k):
         return self.L.nlps_b200_stage(self.h, STAGES[name], int(k))
 
