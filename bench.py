@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
 
 Workload (N=1): BASELINE.json configs[1] -- 2D granular column collapse, Drucker-Prager,
-10^6 particles (500x1000 particle cells x GPxElement 4) on a 3000x1250 Q4 background grid,
+10^6 particles (354x708 particle cells x GPxElement 4) on a 2124x885 Q4 background grid,
 LME gamma=3, explicit NPC-FS.  A "step" is one full time step over all particles.
 Prints ONE JSON line (see the keys below).  `--impl reference` times the reference's own CPU
 implementation (oracle/_ref: reference stage functions driven by the restated step loop, all
@@ -122,7 +122,7 @@ def reference_sample(steps, warmup, threads=None, cells=(64, 128)):
         import oracle
         from nlps_b200 import synthetic
         sys.stderr.write("bench: oracle/_ref missing, timing the C port instead\n")
-        P = synthetic.column_collapse_2d(scale=bx / 500.0, nsteps=nsteps)
+        P = synthetic.column_collapse_2d(scale=bx / 354.0, nsteps=nsteps)
         o = oracle.Oracle(P, threads=threads)
         assert o.init_lme() == 0
         npart = P.np_

@@ -39,11 +39,12 @@ __constant__ MatParams c_mat[MAX_MATERIALS];
 
 enum KernelId {
   K_SEARCH = 0, K_NODE_FLAGS, K_SCAN1, K_SCAN2, K_SCAN3, K_FILL, K_NODE_FINISH, K_LME, K_P2G_MASS_DISP,
-  K_KIN_STRESS, K_TRACTION, K_P2G_FORCE, K_G2P, K_COUNT
+  K_GRID_DISP, K_KIN_STRESS, K_TRACTION, K_P2G_FORCE, K_GRID_ACC, K_G2P, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
     "search_closest_node", "node_flags", "scan_reduce", "scan_tops", "scan_apply", "cell_fill",
-    "node_finish", "lme_update", "p2g_mass_disp", "g2p_kin_stress", "traction", "p2g_force", "g2p_update"};
+    "node_finish", "lme_update", "p2g_mass_disp", "grid_disp_bc", "g2p_kin_stress", "traction", "p2g_force",
+    "grid_acc", "g2p_update"};
 
 // ---------------------------------------------------------------------------
 // Device views
@@ -52,6 +53,7 @@ struct MeshDev {
   const double* X;  // nn x D (row-major)
   const int *r1p, *r1i, *r2p, *r2i;
   const int *r1tp, *r1ti, *r2tp, *r2ti;  // transposed adjacency (who lists me)
+  const unsigned char* r2q;              // r2q[r2p[B]+s] = position of B inside the r2t row of node r2i[r2p[B]+s]
   const double* h_avg;
 };
 
@@ -82,7 +84,10 @@ struct GridDev {
   double *M, *dU, *F, *A;  // M: nn ; others nn x D (row-major)
   unsigned char *active, *fixed;
   int *cnt, *cursor, *cell_start, *plist, *act_list, *n_active;
-  unsigned long long *packed, *scan_blk;
+  int *occ_list, *n_occ, *act_pos, *occ_pos;
+  ulonglong2 *packed, *scan_blk;
+  double* part;  // per (active node, r2t slot): (1+D) partial sums written by the cell kernels
+  int cap;
 };
 
 struct StepParams {
@@ -156,89 +161,99 @@ __global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G,
 }
 
 // node flags: ActiveNode[A] = OR over particles with I0 in {B : A in ring1(B)} (LME.c:949-965,
-// after the reset of Shape-Functions.c:38-47); packed = cnt | active<<32 for one fused scan.
+// after the reset of Shape-Functions.c:38-47).  packed.x = cnt | occupied << 40, packed.y = active:
+// one fused exclusive scan yields cell_start, the rank of each occupied cell and of each active node.
 __global__ void __launch_bounds__(256) k_node_flags(MeshDev m, GridDev G) {
   int A = blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= m.nn) return;
   int act = 0;
   for (int q = m.r1tp[A]; q < m.r1tp[A + 1] && !act; q++) act = G.cnt[m.r1ti[q]] > 0;
   G.active[A] = (unsigned char)act;
-  G.packed[A] = (unsigned long long)(unsigned)G.cnt[A] | ((unsigned long long)act << 32);
+  unsigned long long c = (unsigned)G.cnt[A];
+  G.packed[A] = make_ulonglong2(c | ((unsigned long long)(c > 0) << 40), (unsigned long long)act);
   G.cursor[A] = 0;
 }
 
-// exclusive scan of packed (two 32-bit lanes at once), 3 phases, 2048 items per block
+__device__ __forceinline__ ulonglong2 add2(ulonglong2 a, ulonglong2 b) { return make_ulonglong2(a.x + b.x, a.y + b.y); }
+
+// exclusive scan of packed, 3 phases, 2048 items per block
 static const int SCAN_ITEMS = 2048;
-__global__ void __launch_bounds__(256) k_scan_reduce(const unsigned long long* in, unsigned long long* blk, int n) {
-  __shared__ unsigned long long sh[256];
+__global__ void __launch_bounds__(256) k_scan_reduce(const ulonglong2* in, ulonglong2* blk, int n) {
+  __shared__ ulonglong2 sh[256];
   size_t base = (size_t)blockIdx.x * SCAN_ITEMS;
-  unsigned long long s = 0;
+  ulonglong2 s = make_ulonglong2(0, 0);
   for (int i = threadIdx.x; i < SCAN_ITEMS; i += 256)
-    if (base + i < (size_t)n) s += in[base + i];
+    if (base + i < (size_t)n) s = add2(s, in[base + i]);
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    if (threadIdx.x < o) sh[threadIdx.x] = add2(sh[threadIdx.x], sh[threadIdx.x + o]);
     __syncthreads();
   }
   if (threadIdx.x == 0) blk[blockIdx.x] = sh[0];
 }
-__global__ void k_scan_tops(unsigned long long* blk, int nblk, int* n_active, int* n_particles_check) {
+__global__ void k_scan_tops(ulonglong2* blk, int nblk, int* n_active, int* n_occ, int* n_particles_check) {
   // single thread block, serial over chunks (nblk is a few thousand)
-  __shared__ unsigned long long sh[1024];
-  __shared__ unsigned long long carry;
-  if (threadIdx.x == 0) carry = 0;
+  __shared__ ulonglong2 sh[1024];
+  __shared__ ulonglong2 carry;
+  if (threadIdx.x == 0) carry = make_ulonglong2(0, 0);
   __syncthreads();
   for (int base = 0; base < nblk; base += 1024) {
     int i = base + threadIdx.x;
-    unsigned long long v = (i < nblk) ? blk[i] : 0ull;
+    ulonglong2 v = (i < nblk) ? blk[i] : make_ulonglong2(0, 0);
     sh[threadIdx.x] = v;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
-      unsigned long long t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0ull;
+      ulonglong2 t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : make_ulonglong2(0, 0);
       __syncthreads();
-      sh[threadIdx.x] += t;
+      sh[threadIdx.x] = add2(sh[threadIdx.x], t);
       __syncthreads();
     }
-    if (i < nblk) blk[i] = carry + sh[threadIdx.x] - v;
+    if (i < nblk) {
+      ulonglong2 c = carry, inc = sh[threadIdx.x];
+      blk[i] = make_ulonglong2(c.x + inc.x - v.x, c.y + inc.y - v.y);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) carry += sh[1023];
+    if (threadIdx.x == 0) carry = add2(carry, sh[1023]);
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    *n_active = (int)(carry >> 32);
-    *n_particles_check = (int)(carry & 0xffffffffu);
+    *n_active = (int)carry.y;
+    *n_occ = (int)(carry.x >> 40);
+    *n_particles_check = (int)(carry.x & 0xffffffffffull);
   }
 }
-__global__ void __launch_bounds__(256) k_scan_apply(const unsigned long long* in, const unsigned long long* blk,
-                                                    int* cell_start, int* act_pos, int n) {
-  __shared__ unsigned long long sh[256];
+__global__ void __launch_bounds__(256) k_scan_apply(const ulonglong2* in, const ulonglong2* blk, int* cell_start,
+                                                    int* occ_pos, int* act_pos, int n) {
+  __shared__ ulonglong2 sh[256];
   size_t base = (size_t)blockIdx.x * SCAN_ITEMS;
   const int per = SCAN_ITEMS / 256;
-  unsigned long long v[per], s = 0;
+  ulonglong2 v[per], s = make_ulonglong2(0, 0);
 #pragma unroll
   for (int k = 0; k < per; k++) {
     size_t i = base + (size_t)threadIdx.x * per + k;
-    v[k] = (i < (size_t)n) ? in[i] : 0ull;
-    s += v[k];
+    v[k] = (i < (size_t)n) ? in[i] : make_ulonglong2(0, 0);
+    s = add2(s, v[k]);
   }
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 1; o < 256; o <<= 1) {
-    unsigned long long t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0ull;
+    ulonglong2 t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : make_ulonglong2(0, 0);
     __syncthreads();
-    sh[threadIdx.x] += t;
+    sh[threadIdx.x] = add2(sh[threadIdx.x], t);
     __syncthreads();
   }
-  unsigned long long run = blk[blockIdx.x] + sh[threadIdx.x] - s;
+  ulonglong2 b = blk[blockIdx.x], inc = sh[threadIdx.x];
+  ulonglong2 run = make_ulonglong2(b.x + inc.x - s.x, b.y + inc.y - s.y);
 #pragma unroll
   for (int k = 0; k < per; k++) {
     size_t i = base + (size_t)threadIdx.x * per + k;
     if (i < (size_t)n) {
-      cell_start[i] = (int)(run & 0xffffffffu);
-      act_pos[i] = (int)(run >> 32);
+      cell_start[i] = (int)(run.x & 0xffffffffffull);
+      occ_pos[i] = (int)(run.x >> 40);
+      act_pos[i] = (int)run.y;
     }
-    run += v[k];
+    run = add2(run, v[k]);
   }
 }
 
@@ -251,8 +266,8 @@ __global__ void __launch_bounds__(256) k_cell_fill(PartDev P, GridDev G) {
 }
 
 // per node: sort the cell's particle ids ascending (deterministic summation order) and
-// append active nodes to the compact list.  act_pos aliases G.cursor after the fill.
-__global__ void __launch_bounds__(256) k_node_finish(MeshDev m, GridDev G, const int* act_pos) {
+// append occupied cells / active nodes to their compact lists.
+__global__ void __launch_bounds__(256) k_node_finish(MeshDev m, GridDev G) {
   int A = blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= m.nn) return;
   int n = G.cnt[A];
@@ -264,7 +279,8 @@ __global__ void __launch_bounds__(256) k_node_finish(MeshDev m, GridDev G, const
       a[j + 1] = v;
     }
   }
-  if (G.active[A]) G.act_list[act_pos[A]] = A;
+  if (n > 0) G.occ_list[G.occ_pos[A]] = A;
+  if (G.active[A]) G.act_list[G.act_pos[A]] = A;
 }
 
 // ---------------------------------------------------------------------------
@@ -395,8 +411,46 @@ __global__ void __launch_bounds__(128) k_lme(MeshDev m, PartDev P, GridDev G, St
 }
 
 // ---------------------------------------------------------------------------
-// K1 + G1, node-centric gather.  M_A = sum_p N_A m_p (U-Verlet.c:166-225);
-// DU_A = sum_p m_p N_A DU_p / M_A (U-Verlet.c:301-367); Dirichlet overwrite
+// Stage 1 (cell kernel): one WARP per occupied cell B (all particles with I0 == B), one LANE per
+// node A of the 2-ring of B.  Every lane walks the cell's particles; the particle record is the same
+// address for the whole warp (a broadcast load), so there is no scatter and no atomic.  The lane's
+// partial sums over the cell go to part[(rank(A), slot of B in A's transposed row)].
+template <int D>
+__global__ void __launch_bounds__(128) k_p2g_mass_disp(MeshDev m, PartDev P, GridDev G) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= *G.n_occ) return;
+  const int B = G.occ_list[w];
+  const int c0 = G.cell_start[B], n = G.cnt[B];
+  const int base = m.r2p[B], len = m.r2p[B + 1] - base;
+  for (int s = lane; s < len; s += 32) {
+    const int A = m.r2i[base + s];
+    if (!G.active[A]) continue;
+    double XA[D], mom[D], M = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; i++) { XA[i] = m.X[(size_t)A * D + i]; mom[i] = 0.0; }
+    for (int j = 0; j < n; j++) {
+      const double* rec = P.rec + (size_t)G.plist[c0 + j] * Rec<D>::SIZE;
+      double l[D];
+      double s2 = dist2_exact<D>(rec + Rec<D>::X, XA, l);
+      if (s2 <= rec[Rec<D>::SSTAR]) {
+        double lx = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) lx += l[i] * rec[Rec<D>::LAM + i];
+        double mN = exp(-rec[Rec<D>::BETA] * s2 + lx) * rec[Rec<D>::ZINV] * rec[Rec<D>::MASS];
+        M += mN;
+#pragma unroll
+        for (int i = 0; i < D; i++) mom[i] += mN * rec[Rec<D>::DDIS + i];
+      }
+    }
+    double* dst = G.part + ((size_t)G.act_pos[A] * G.cap + m.r2q[base + s]) * (1 + D);
+    dst[0] = M;
+#pragma unroll
+    for (int i = 0; i < D; i++) dst[1 + i] = mom[i];
+  }
+}
+
+// Stage 2 + G1 (node kernel): M_A = sum_p N_A m_p (U-Verlet.c:166-225); DU_A = sum_p m_p N_A DU_p / M_A
+// (U-Verlet.c:301-367) as a contiguous, fixed-order sum of the cell partials; Dirichlet overwrite
 // (U-Verlet.c:458-526) and restricted-DOF flags (Nodes-Tools.c:70-156).
 struct BcDev {
   const int *node_ptr, *node_bnd;  // CSR: node -> boundary ids in boundary order
@@ -407,30 +461,20 @@ struct BcDev {
 };
 
 template <int D>
-__global__ void __launch_bounds__(128) k_p2g_mass_disp(MeshDev m, PartDev P, GridDev G, BcDev bc, int step) {
+__global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev bc, int step) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *G.n_active) return;
   const int A = G.act_list[t];
-  double XA[D], mom[D], M = 0.0;
+  double mom[D], M = 0.0;
 #pragma unroll
-  for (int i = 0; i < D; i++) { XA[i] = m.X[(size_t)A * D + i]; mom[i] = 0.0; }
-  for (int q = m.r2tp[A]; q < m.r2tp[A + 1]; q++) {
-    const int B = m.r2ti[q];
-    const int c0 = G.cell_start[B], c1 = c0 + G.cnt[B];
-    for (int j = c0; j < c1; j++) {
-      const double* rec = P.rec + (size_t)G.plist[j] * Rec<D>::SIZE;
-      double l[D];
-      double s = dist2_exact<D>(rec + Rec<D>::X, XA, l);
-      if (s <= rec[Rec<D>::SSTAR]) {
-        double lx = 0.0;
+  for (int i = 0; i < D; i++) mom[i] = 0.0;
+  const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
+  const double* src = G.part + (size_t)t * G.cap * (1 + D);
+  for (int q = 0; q < nq; q++) {
+    if (G.cnt[m.r2ti[q0 + q]] == 0) continue;
+    M += src[q * (1 + D)];
 #pragma unroll
-        for (int i = 0; i < D; i++) lx += l[i] * rec[Rec<D>::LAM + i];
-        double mN = exp(-rec[Rec<D>::BETA] * s + lx) * rec[Rec<D>::ZINV] * rec[Rec<D>::MASS];
-        M += mN;
-#pragma unroll
-        for (int i = 0; i < D; i++) mom[i] += mN * rec[Rec<D>::DDIS + i];
-      }
-    }
+    for (int i = 0; i < D; i++) mom[i] += src[q * (1 + D) + 1 + i];
   }
   double dU[D];
 #pragma unroll
@@ -631,29 +675,30 @@ __global__ void k_traction(PartDev P, NeuDev nu, double thickness, int step) {
   }
 }
 
-// K3 + G2, node-centric gather: f_A = sum_p N_A (G_p l_A + t_p); a_A = g + f_A / M_A on free
-// DOFs, 0 on restricted ones (U-Verlet.c:947-958; gravity as U-Newmark-beta.c:1539-1543).
+// K3 stage 1 (cell kernel, same mapping as k_p2g_mass_disp): partial f_A over the particles of the
+// cell, f_A = sum_p N_A (G_p l_A + t_p)  ==  -V0 tau (DF^-T gradN_A) + N_A T A0.
 template <int D>
-__global__ void __launch_bounds__(128) k_p2g_force(MeshDev m, PartDev P, GridDev G, const double* grav, int nsteps,
-                                                   int step, int has_traction) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= *G.n_active) return;
-  const int A = G.act_list[t];
-  double XA[D], f[D];
+__global__ void __launch_bounds__(128) k_p2g_force(MeshDev m, PartDev P, GridDev G, int has_traction) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= *G.n_occ) return;
+  const int B = G.occ_list[w];
+  const int c0 = G.cell_start[B], n = G.cnt[B];
+  const int base = m.r2p[B], len = m.r2p[B + 1] - base;
+  for (int s = lane; s < len; s += 32) {
+    const int A = m.r2i[base + s];
+    if (!G.active[A]) continue;
+    double XA[D], f[D];
 #pragma unroll
-  for (int i = 0; i < D; i++) { XA[i] = m.X[(size_t)A * D + i]; f[i] = 0.0; }
-  for (int q = m.r2tp[A]; q < m.r2tp[A + 1]; q++) {
-    const int B = m.r2ti[q];
-    const int c0 = G.cell_start[B], c1 = c0 + G.cnt[B];
-    for (int j = c0; j < c1; j++) {
-      const double* rec = P.rec + (size_t)G.plist[j] * Rec<D>::SIZE;
+    for (int i = 0; i < D; i++) { XA[i] = m.X[(size_t)A * D + i]; f[i] = 0.0; }
+    for (int j = 0; j < n; j++) {
+      const double* rec = P.rec + (size_t)G.plist[c0 + j] * Rec<D>::SIZE;
       double l[D];
-      double s = dist2_exact<D>(rec + Rec<D>::X, XA, l);
-      if (s <= rec[Rec<D>::SSTAR]) {
+      double s2 = dist2_exact<D>(rec + Rec<D>::X, XA, l);
+      if (s2 <= rec[Rec<D>::SSTAR]) {
         double lx = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) lx += l[i] * rec[Rec<D>::LAM + i];
-        double N = exp(-rec[Rec<D>::BETA] * s + lx) * rec[Rec<D>::ZINV];
+        double N = exp(-rec[Rec<D>::BETA] * s2 + lx) * rec[Rec<D>::ZINV];
 #pragma unroll
         for (int i = 0; i < D; i++) {
           double gl = 0.0;
@@ -664,6 +709,28 @@ __global__ void __launch_bounds__(128) k_p2g_force(MeshDev m, PartDev P, GridDev
         }
       }
     }
+    double* dst = G.part + ((size_t)G.act_pos[A] * G.cap + m.r2q[base + s]) * (1 + D);
+#pragma unroll
+    for (int i = 0; i < D; i++) dst[i] = f[i];
+  }
+}
+
+// K3 stage 2 + G2 (node kernel): f_A = sum of cell partials; a_A = g + f_A / M_A on free DOFs, 0 on
+// restricted ones (U-Verlet.c:947-958; gravity as U-Newmark-beta.c:1539-1543).
+template <int D>
+__global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const double* grav, int nsteps, int step) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *G.n_active) return;
+  const int A = G.act_list[t];
+  double f[D];
+#pragma unroll
+  for (int i = 0; i < D; i++) f[i] = 0.0;
+  const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
+  const double* src = G.part + (size_t)t * G.cap * (1 + D);
+  for (int q = 0; q < nq; q++) {
+    if (G.cnt[m.r2ti[q0 + q]] == 0) continue;
+#pragma unroll
+    for (int i = 0; i < D; i++) f[i] += src[q * (1 + D) + i];
   }
   const double M = G.M[A];
   const unsigned fx = G.fixed[A];
@@ -835,10 +902,10 @@ struct nlps_engine {
   double* grav = nullptr;
   int* err = nullptr;
   int* h_err = nullptr;  // pinned
-  int* act_pos = nullptr;
   int* npart_check = nullptr;
   double neg_log_tol = 0.0, dt = 0.0;
   int has_traction = 0;
+  int max_occ = 0, max_act = 0;
   int inert_synced = 0;
   std::vector<void*> allocs;
   // staging for AoS <-> SoA
@@ -874,15 +941,21 @@ static int dev_upload(nlps_engine* e, Tp** p, const Tp* h, size_t n) {
   return 0;
 }
 
-static void transpose_csr(int nn, const int* ptr, const int* idx, std::vector<int>& tp, std::vector<int>& ti) {
+static void transpose_csr(int nn, const int* ptr, const int* idx, std::vector<int>& tp, std::vector<int>& ti,
+                          std::vector<unsigned char>* qpos = nullptr) {
   tp.assign(nn + 1, 0);
   for (int i = 0; i < nn; i++)
     for (int q = ptr[i]; q < ptr[i + 1]; q++) tp[idx[q] + 1]++;
   for (int i = 0; i < nn; i++) tp[i + 1] += tp[i];
   ti.resize(tp[nn]);
+  if (qpos) qpos->resize(ptr[nn]);
   std::vector<int> fill(tp.begin(), tp.end() - 1);
   for (int i = 0; i < nn; i++)
-    for (int q = ptr[i]; q < ptr[i + 1]; q++) ti[fill[idx[q]]++] = i;
+    for (int q = ptr[i]; q < ptr[i + 1]; q++) {
+      int A = idx[q];
+      if (qpos) (*qpos)[q] = (unsigned char)(fill[A] - tp[A]);
+      ti[fill[A]++] = i;
+    }
 }
 
 #define LAUNCH(e, id, kernel, grid, block, ...)                                 \
@@ -980,10 +1053,10 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
   LAUNCH(e, K_NODE_FLAGS, k_node_flags, nblk(nn, 256), 256, e->mesh, e->G);
   int nb = nblk(nn, SCAN_ITEMS);
   LAUNCH(e, K_SCAN1, k_scan_reduce, nb, 256, e->G.packed, e->G.scan_blk, nn);
-  LAUNCH(e, K_SCAN2, k_scan_tops, 1, 1024, e->G.scan_blk, nb, e->G.n_active, e->npart_check);
-  LAUNCH(e, K_SCAN3, k_scan_apply, nb, 256, e->G.packed, e->G.scan_blk, e->G.cell_start, e->act_pos, nn);
+  LAUNCH(e, K_SCAN2, k_scan_tops, 1, 1024, e->G.scan_blk, nb, e->G.n_active, e->G.n_occ, e->npart_check);
+  LAUNCH(e, K_SCAN3, k_scan_apply, nb, 256, e->G.packed, e->G.scan_blk, e->G.cell_start, e->G.occ_pos, e->G.act_pos, nn);
   LAUNCH(e, K_FILL, k_cell_fill, nblk(np, 256), 256, e->P, e->G);
-  LAUNCH(e, K_NODE_FINISH, k_node_finish, nblk(nn, 256), 256, e->mesh, e->G, e->act_pos);
+  LAUNCH(e, K_NODE_FINISH, k_node_finish, nblk(nn, 256), 256, e->mesh, e->G);
   StepParams sp = make_params(e, step, update_I0);
   switch (e->W) {
 #define CASE_W(w) case w: { auto kfn = k_lme<D, w>; LAUNCH(e, K_LME, kfn, nblk(np, 128), 128, e->mesh, e->P, e->G, sp, e->err, do_predictor); } break;
@@ -993,7 +1066,9 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
 }
 template <int D>
 static void stage_p2g_mass_disp_t(nlps_engine* e, int step) {
-  LAUNCH(e, K_P2G_MASS_DISP, k_p2g_mass_disp<D>, nblk(e->nn, 128), 128, e->mesh, e->P, e->G, e->bc, step);
+  // at most min(nn, np) cells are occupied; one warp per cell (surplus warps exit on n_occ)
+  LAUNCH(e, K_P2G_MASS_DISP, k_p2g_mass_disp<D>, nblk((size_t)e->max_occ * 32, 128), 128, e->mesh, e->P, e->G);
+  LAUNCH(e, K_GRID_DISP, k_grid_disp<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step);
 }
 template <int D>
 static void stage_kin_stress_t(nlps_engine* e, int step) {
@@ -1010,8 +1085,8 @@ static void stage_force_t(nlps_engine* e, int step) {
     LAUNCH(e, K_TRACTION, k_traction_clear<D>, nblk(e->np, 256), 256, e->P);
     LAUNCH(e, K_TRACTION, k_traction<D>, nblk(e->neu.n_entries, 128), 128, e->P, e->neu, e->solver.thickness, step);
   }
-  LAUNCH(e, K_P2G_FORCE, k_p2g_force<D>, nblk(e->nn, 128), 128, e->mesh, e->P, e->G, e->grav, e->solver.num_steps, step,
-         e->has_traction);
+  LAUNCH(e, K_P2G_FORCE, k_p2g_force<D>, nblk((size_t)e->max_occ * 32, 128), 128, e->mesh, e->P, e->G, e->has_traction);
+  LAUNCH(e, K_GRID_ACC, k_grid_acc<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step);
 }
 template <int D>
 static void stage_g2p_t(nlps_engine* e, int step) {
@@ -1105,11 +1180,22 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   if (dev_upload(e, &t1p, tp.data(), tp.size())) return 1;
   if (dev_upload(e, &t1i, ti.data(), ti.size())) return 1;
   CUDA_OK(cudaStreamSynchronize(e->stream));
-  transpose_csr(nn, mesh->ring2_ptr, mesh->ring2_idx, tp, ti);
+  std::vector<unsigned char> qpos;
+  transpose_csr(nn, mesh->ring2_ptr, mesh->ring2_idx, tp, ti, &qpos);
+  int maxr2t = 0, maxr1 = 0;
+  for (int i = 0; i < nn; i++) {
+    maxr2t = std::max(maxr2t, tp[i + 1] - tp[i]);
+    maxr1 = std::max(maxr1, mesh->ring1_ptr[i + 1] - mesh->ring1_ptr[i]);
+  }
+  if (maxr2t > 255) return set_err(err, err_len, "transposed 2-ring larger than 255 nodes is not supported");
+  unsigned char* dq;
   if (dev_upload(e, &t2p, tp.data(), tp.size())) return 1;
   if (dev_upload(e, &t2i, ti.data(), ti.size())) return 1;
+  if (dev_upload(e, &dq, qpos.data(), qpos.size())) return 1;
   CUDA_OK(cudaStreamSynchronize(e->stream));
-  e->mesh = MeshDev{nn, dX, r1p, r1i, r2p, r2i, t1p, t1i, t2p, t2i, dh};
+  e->mesh = MeshDev{nn, dX, r1p, r1i, r2p, r2i, t1p, t1i, t2p, t2i, dq, dh};
+  e->max_occ = (int)std::min<long long>(nn, np);
+  e->max_act = (int)std::min<long long>(nn, (long long)np * maxr1);
   // ---- grid work arrays
   GridDev& G = e->G;
   if (dev_alloc(e, &G.M, nn) || dev_alloc(e, &G.dU, (size_t)nn * D) || dev_alloc(e, &G.F, (size_t)nn * D) ||
@@ -1117,8 +1203,11 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
       dev_alloc(e, &G.cnt, nn) || dev_alloc(e, &G.cursor, nn) || dev_alloc(e, &G.cell_start, nn) ||
       dev_alloc(e, &G.plist, np) || dev_alloc(e, &G.act_list, nn) || dev_alloc(e, &G.n_active, 1) ||
       dev_alloc(e, &G.packed, nn) || dev_alloc(e, &G.scan_blk, (size_t)nblk(nn, SCAN_ITEMS) + 1) ||
-      dev_alloc(e, &e->act_pos, nn) || dev_alloc(e, &e->npart_check, 1) || dev_alloc(e, &e->err, 2))
+      dev_alloc(e, &G.act_pos, nn) || dev_alloc(e, &G.occ_pos, nn) || dev_alloc(e, &G.occ_list, e->max_occ) ||
+      dev_alloc(e, &G.n_occ, 1) || dev_alloc(e, &e->npart_check, 1) || dev_alloc(e, &e->err, 2))
     return 1;
+  G.cap = maxr2t;
+  if (dev_alloc(e, &G.part, (size_t)e->max_act * G.cap * (1 + D))) return 1;
   // ---- boundary conditions: node -> boundaries CSR (boundary order preserved)
   {
     int maxdim = 1;

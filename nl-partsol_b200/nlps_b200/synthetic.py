@@ -115,11 +115,13 @@ MN_C4 = ("Matsuoka-Nakai", [2000.0, 1e7, 0.3, 0.0, 8.0 / 3.0, 0.0, 0.0, 30.0, 0.
 
 
 def column_collapse_2d(scale=1.0, nsteps=1000):
-    """BASELINE configs[1]: 2D granular column (aspect 2) of Drucker-Prager material released in a box
-    with a fixed base and frictionless sides; scale=1 -> 500x1000 particle cells x GPx4 = 10^6
-    particles on a 3000x1250 background grid."""
-    bx, by = max(4, int(round(500 * scale))), max(8, int(round(1000 * scale)))
-    nx, ny = max(bx + 8, int(round(3000 * scale))), max(by + 4, int(round(1250 * scale)))
+    """BASELINE configs[1]: 2D granular column (aspect 2, 0.2 m x 0.4 m) of Drucker-Prager material
+    released in a box 6 column-widths wide with a fixed base and frictionless sides.  scale=1 ->
+    354 x 708 particle cells x GPxElement 4 = 1,002,528 particles (the 10^6 of BASELINE.json; SURVEY
+    8(d) C2) on a 2124 x 885 cell Q4 background grid."""
+    bx = max(4, int(round(354 * scale)))
+    by = 2 * bx
+    nx, ny = 6 * bx, by + by // 4
     h = 0.2 / bx
     return structured_problem(2, (nx, ny), h, (bx, by), (0, 0), DP_C2, nsteps, 0.5, (1e7 / 2000.0) ** 0.5 * 1.3,
                               (0.0, -9.81))

@@ -58,4 +58,7 @@ def field_scales(prob):
     dt = prob.dt()
     nat = dict(Stress=E, W=E, vel=h / dt, acc=h / dt ** 2, dis=h, D_dis=h, x_GC=1.0, C_ep=E,
                **{"lambda": 1.0 / h})
+    d = prob.ndim
+    rho = max(m[1][0] for m in prob.materials)
+    nat.update(gM=rho * h ** d, gdU=h, gF=E * h ** (d - 1), gA=h / dt ** 2, gR=E * h ** (d - 1))
     return {k: 1e-4 * v for k, v in nat.items()}
