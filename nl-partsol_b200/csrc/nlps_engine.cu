@@ -48,9 +48,17 @@ static const char* kKernelNames[K_COUNT] = {
 
 // ---------------------------------------------------------------------------
 // Device views
+// node records are padded so that one node is one or two 16-byte vector loads
+template <int D> struct NS { static constexpr int X = (D == 2) ? 2 : 4; };   // coordinates stride (doubles)
+template <int D>
+__device__ __forceinline__ void ldvec(const double* p, double* out) {
+  double2 a = *reinterpret_cast<const double2*>(p);
+  out[0] = a.x; out[1] = a.y;
+  if (D == 3) { double2 b = *reinterpret_cast<const double2*>(p + 2); out[2] = b.x; }
+}
 struct MeshDev {
   int nn;
-  const double* X;  // nn x D (row-major)
+  const double* X;  // nn x NS<D>::X (row-major, padded)
   const int *r1p, *r1i, *r2p, *r2i;
   const int *r1tp, *r1ti, *r2tp, *r2ti;  // transposed adjacency (who lists me)
   const unsigned char* r2q;              // r2q[r2p[B]+s] = position of B inside the r2t row of node r2i[r2p[B]+s]
@@ -81,7 +89,8 @@ struct PartDev {
 };
 
 struct GridDev {
-  double *M, *dU, *F, *A;  // M: nn ; others nn x D (row-major)
+  double *M, *F;  // M: nn ; F: nn x D (row-major)
+  double* UA;     // per node [dU (NS) | A (NS)]: the two nodal fields the G2P gathers read, one record
   unsigned char *active, *fixed;
   int *cnt, *cursor, *cell_start, *plist, *act_list, *n_active;
   int *occ_list, *n_occ, *act_pos, *occ_pos;
@@ -128,6 +137,29 @@ __device__ inline double sstar_from_Ra(double Ra) {
   return t;
 }
 
+
+// Neighbour iteration with 4-way memory-level parallelism: the kernels are bound by the latency of the
+// dependent gathers (mask bit -> node id -> node data), so node ids and node data of GROUPS of four
+// neighbours are requested before any of them is consumed.
+#define NLPS_GROUP 4
+template <int W>
+__device__ __forceinline__ int next_group(const MeshDev& m, int base, uint32_t* mk, int& w, int* node) {
+  int cnt = 0;
+#pragma unroll
+  for (int u = 0; u < NLPS_GROUP; u++) {
+    while (w < W && mk[w] == 0u) w++;
+    if (w < W) {
+      int b = __ffs(mk[w]) - 1;
+      mk[w] &= mk[w] - 1;
+      node[u] = m.r2i[base + w * 32 + b];
+      cnt = u + 1;
+    } else {
+      node[u] = -1;
+    }
+  }
+  return cnt;
+}
+
 // ---------------------------------------------------------------------------
 // K0a: closest node + cell histogram.   local_search__LME__ first loop (LME.c:917-944),
 // get_closest_node__MeshTools__ (Nodes-Tools.c:476-538): first strict minimum, chain order.
@@ -150,7 +182,7 @@ __global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G,
       int best = I0;
       for (int q = b0; q < b1; q++) {
         int node = m.r1i[q];
-        double dq = __dsqrt_rn(dist2_exact<D>(xp, &m.X[(size_t)node * D], l));
+        double dq = __dsqrt_rn(dist2_exact<D>(xp, &m.X[(size_t)node * NS<D>::X], l));
         if (q == b0 || dq < dmin) { dmin = dq; best = node; }
       }
       I0 = best;
@@ -309,7 +341,7 @@ __global__ void __launch_bounds__(128) k_lme(MeshDev m, PartDev P, GridDev G, St
     int node = m.r2i[base + k];
     if (!G.active[node]) continue;
     double l[D];
-    double s = dist2_exact<D>(xp, &m.X[(size_t)node * D], l);
+    double s = dist2_exact<D>(xp, &m.X[(size_t)node * NS<D>::X], l);
     if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
   }
 #pragma unroll
@@ -331,27 +363,38 @@ __global__ void __launch_bounds__(128) k_lme(MeshDev m, PartDev P, GridDev G, St
     for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
     for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
+    {
+      uint32_t mw[W];
 #pragma unroll
-    for (int w = 0; w < W; w++) {
-      uint32_t mm = mk[w];
-      while (mm) {
-        int b = __ffs(mm) - 1;
-        mm &= mm - 1;
-        int node = m.r2i[base + w * 32 + b];
-        double l[D], ll = 0.0, lx = 0.0;
+      for (int w = 0; w < W; w++) mw[w] = mk[w];
+      int wcur = 0, node[NLPS_GROUP];
+      while (next_group<W>(m, base, mw, wcur, node) > 0) {
+        double Xn[NLPS_GROUP][D];
 #pragma unroll
-        for (int i = 0; i < D; i++) {
-          l[i] = xp[i] - m.X[(size_t)node * D + i];
-          ll += l[i] * l[i];
-          lx += l[i] * lam[i];
-        }
-        double e = exp(-beta * ll + lx);
-        Z += e;
+        for (int u = 0; u < NLPS_GROUP; u++)
 #pragma unroll
-        for (int i = 0; i < D; i++) {
-          r[i] += e * l[i];
+          for (int i = 0; i < D; i++) Xn[u][i] = 0.0;
 #pragma unroll
-          for (int j = i; j < D; j++) JJ[i * D + j] += e * l[i] * l[j];
+        for (int u = 0; u < NLPS_GROUP; u++)
+          if (node[u] >= 0) ldvec<D>(&m.X[(size_t)node[u] * NS<D>::X], Xn[u]);
+#pragma unroll
+        for (int u = 0; u < NLPS_GROUP; u++) {
+          if (node[u] < 0) continue;
+          double l[D], ll = 0.0, lx = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            l[i] = xp[i] - Xn[u][i];
+            ll += l[i] * l[i];
+            lx += l[i] * lam[i];
+          }
+          double e = exp(-beta * ll + lx);
+          Z += e;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            r[i] += e * l[i];
+#pragma unroll
+            for (int j = i; j < D; j++) JJ[i * D + j] += e * l[i] * l[j];
+          }
         }
       }
     }
@@ -412,41 +455,122 @@ __global__ void __launch_bounds__(128) k_lme(MeshDev m, PartDev P, GridDev G, St
 
 // ---------------------------------------------------------------------------
 // Stage 1 (cell kernel): one WARP per occupied cell B (all particles with I0 == B), one LANE per
-// node A of the 2-ring of B.  Every lane walks the cell's particles; the particle record is the same
-// address for the whole warp (a broadcast load), so there is no scatter and no atomic.  The lane's
-// partial sums over the cell go to part[(rank(A), slot of B in A's transposed row)].
-template <int D>
-__global__ void __launch_bounds__(128) k_p2g_mass_disp(MeshDev m, PartDev P, GridDev G) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= *G.n_occ) return;
-  const int B = G.occ_list[w];
-  const int c0 = G.cell_start[B], n = G.cnt[B];
-  const int base = m.r2p[B], len = m.r2p[B + 1] - base;
-  for (int s = lane; s < len; s += 32) {
-    const int A = m.r2i[base + s];
-    if (!G.active[A]) continue;
-    double XA[D], mom[D], M = 0.0;
+// node A of the 2-ring of B (IT lanes-rounds when the ring has more than 32 nodes).  The cell's particle
+// records are staged into shared memory by the whole warp (coalesced 8-byte loads, one round trip for
+// CH particles), then every lane walks them (shared-memory broadcasts): no scatter, no atomic.  The
+// lane's partial sums over the cell go to part[(rank(A), slot of B in A's transposed row)].
+//   FORCE = false: M_A, sum m_p N_A DU_p  (U-Verlet.c:166-225, 301-367)
+//   FORCE = true : f_A = sum_p N_A (G_p l_A + t_p) == -V0 tau (DF^-T gradN_A) + N_A T A0
+//                  (U-Newmark-beta.c:1257-1374, U-Verlet.c:805-902)
+template <int D, int IT, bool FORCE>
+__global__ void __launch_bounds__(128) k_p2g_cell(MeshDev m, PartDev P, GridDev G, int has_traction) {
+  // CPW cells per warp: all their metadata, node data and particle records are requested before any
+  // is consumed (the kernel is latency-bound: ~4 particles of work per cell).
+  constexpr int CPW = (IT == 1) ? 4 : 1, CH = 8, SZ = Rec<D>::SIZE, NV = FORCE ? D : 1 + D;
+  __shared__ double sm_all[4][CPW * CH * SZ];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w0 = (blockIdx.x * 4 + wib) * CPW;
+  const int nocc = *G.n_occ;
+  if (w0 >= nocc) return;
+  double* sm = sm_all[wib];
+  // lanes 0..CPW-1 fetch the metadata of one cell each
+  int mB = 0, mc0 = 0, mn = 0, mbase = 0, mlen = 0;
+  if (lane < CPW && w0 + lane < nocc) {
+    mB = G.occ_list[w0 + lane];
+    mc0 = G.cell_start[mB];
+    mn = G.cnt[mB];
+    mbase = m.r2p[mB];
+    mlen = m.r2p[mB + 1] - mbase;
+  }
+  int c0[CPW], n[CPW], base[CPW], len[CPW];
 #pragma unroll
-    for (int i = 0; i < D; i++) { XA[i] = m.X[(size_t)A * D + i]; mom[i] = 0.0; }
-    for (int j = 0; j < n; j++) {
-      const double* rec = P.rec + (size_t)G.plist[c0 + j] * Rec<D>::SIZE;
-      double l[D];
-      double s2 = dist2_exact<D>(rec + Rec<D>::X, XA, l);
-      if (s2 <= rec[Rec<D>::SSTAR]) {
-        double lx = 0.0;
+  for (int c = 0; c < CPW; c++) {
+    c0[c] = __shfl_sync(0xffffffffu, mc0, c);
+    n[c] = __shfl_sync(0xffffffffu, mn, c);
+    base[c] = __shfl_sync(0xffffffffu, mbase, c);
+    len[c] = __shfl_sync(0xffffffffu, mlen, c);
+  }
+  double XA[CPW][IT][D], acc[CPW][IT][NV];
+  long long dst[CPW][IT];
 #pragma unroll
-        for (int i = 0; i < D; i++) lx += l[i] * rec[Rec<D>::LAM + i];
-        double mN = exp(-rec[Rec<D>::BETA] * s2 + lx) * rec[Rec<D>::ZINV] * rec[Rec<D>::MASS];
-        M += mN;
+  for (int c = 0; c < CPW; c++)
 #pragma unroll
-        for (int i = 0; i < D; i++) mom[i] += mN * rec[Rec<D>::DDIS + i];
+    for (int it = 0; it < IT; it++) {
+      const int s = lane + 32 * it;
+      dst[c][it] = -1;
+#pragma unroll
+      for (int v = 0; v < NV; v++) acc[c][it][v] = 0.0;
+#pragma unroll
+      for (int i = 0; i < D; i++) XA[c][it][i] = 0.0;
+      if (s < len[c]) {
+        const int A = m.r2i[base[c] + s];
+        if (G.active[A]) {
+          dst[c][it] = ((long long)G.act_pos[A] * G.cap + m.r2q[base[c] + s]) * (1 + D);
+#pragma unroll
+          for (int i = 0; i < D; i++) XA[c][it][i] = m.X[(size_t)A * NS<D>::X + i];
+        }
       }
     }
-    double* dst = G.part + ((size_t)G.act_pos[A] * G.cap + m.r2q[base + s]) * (1 + D);
-    dst[0] = M;
+  int nmax = 0;
 #pragma unroll
-    for (int i = 0; i < D; i++) dst[1 + i] = mom[i];
+  for (int c = 0; c < CPW; c++) nmax = max(nmax, n[c]);
+  for (int j0 = 0; j0 < nmax; j0 += CH) {
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CPW; c++) {
+      const int nc = min(CH, n[c] - j0);
+      if (nc <= 0) continue;
+      const int pid = (lane < nc) ? G.plist[c0[c] + j0 + lane] : 0;
+      for (int e0 = 0; e0 < nc * SZ; e0 += 32) {
+        const int e = e0 + lane, j = min(e / SZ, nc - 1);
+        const int pj = __shfl_sync(0xffffffffu, pid, j);
+        if (e < nc * SZ) sm[c * CH * SZ + e] = P.rec[(size_t)pj * SZ + (e - j * SZ)];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CPW; c++) {
+      const int nc = min(CH, n[c] - j0);
+#pragma unroll
+      for (int it = 0; it < IT; it++) {
+        if (dst[c][it] < 0) continue;
+        for (int j = 0; j < nc; j++) {
+          const double* rec = sm + (c * CH + j) * SZ;
+          double l[D];
+          double s2 = dist2_exact<D>(rec + Rec<D>::X, XA[c][it], l);
+          if (s2 <= rec[Rec<D>::SSTAR]) {
+            double lx = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++) lx += l[i] * rec[Rec<D>::LAM + i];
+            double N = exp(-rec[Rec<D>::BETA] * s2 + lx) * rec[Rec<D>::ZINV];
+            if (!FORCE) {
+              double mN = N * rec[Rec<D>::MASS];
+              acc[c][it][0] += mN;
+#pragma unroll
+              for (int i = 0; i < D; i++) acc[c][it][1 + i] += mN * rec[Rec<D>::DDIS + i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < D; i++) {
+                double gl = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; k++) gl += rec[Rec<D>::G + i * D + k] * l[k];
+                if (has_traction) gl += rec[Rec<D>::TRAC + i];
+                acc[c][it][i] += N * gl;
+              }
+            }
+          }
+        }
+      }
+    }
   }
+#pragma unroll
+  for (int c = 0; c < CPW; c++)
+#pragma unroll
+    for (int it = 0; it < IT; it++)
+      if (dst[c][it] >= 0) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) G.part[dst[c][it] + v] = acc[c][it][v];
+      }
 }
 
 // Stage 2 + G1 (node kernel): M_A = sum_p N_A m_p (U-Verlet.c:166-225); DU_A = sum_p m_p N_A DU_p / M_A
@@ -493,7 +617,7 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
   }
   G.M[A] = M;
 #pragma unroll
-  for (int i = 0; i < D; i++) G.dU[(size_t)A * D + i] = dU[i];
+  for (int i = 0; i < D; i++) G.UA[(size_t)A * 2 * NS<D>::X + i] = dU[i];
   G.fixed[A] = (unsigned char)fx;
 }
 
@@ -504,8 +628,10 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
 // rho /= det DF (U-Verlet.c:630-632); stress (Constitutive.c:18-258);
 // G_p = V0 tau DF^-T J^-1 so that f_A = sum_p N_A G_p l_A  ==  -V0 tau (DF^-T gradN_A)
 // (U-Newmark-beta.c:1257-1374 with Shape-Functions.c:405-448).
-template <int D, int W>
-__global__ void __launch_bounds__(128) k_kin_stress(MeshDev m, PartDev P, GridDev G, StepParams sp, int* err) {
+// MAT: compile-time material law when every particle uses the same one (keeps the Matsuoka-Nakai
+// Newton out of the register budget of the other laws); -1 = mixed, dispatched per particle.
+template <int D, int W, int MAT>
+__global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 4 : 2) k_kin_stress(MeshDev m, PartDev P, GridDev G, StepParams sp, int* err) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.np) return;
   const int np = P.np;
@@ -521,30 +647,43 @@ __global__ void __launch_bounds__(128) k_kin_stress(MeshDev m, PartDev P, GridDe
   for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < D * D; i++) { JJ[i] = 0.0; Bm[i] = 0.0; }
+  {
+    uint32_t mw[W];
 #pragma unroll
-  for (int w = 0; w < W; w++) {
-    uint32_t mm = P.mask[(size_t)w * np + p];
-    while (mm) {
-      int b = __ffs(mm) - 1;
-      mm &= mm - 1;
-      int node = m.r2i[base + w * 32 + b];
-      double l[D], ll = 0.0, lx = 0.0, du[D];
+    for (int w = 0; w < W; w++) mw[w] = P.mask[(size_t)w * np + p];
+    int wcur = 0, node[NLPS_GROUP];
+    while (next_group<W>(m, base, mw, wcur, node) > 0) {
+      double Xn[NLPS_GROUP][D], dUn[NLPS_GROUP][D];
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        l[i] = xp[i] - m.X[(size_t)node * D + i];
-        ll += l[i] * l[i];
-        lx += l[i] * lam[i];
-        du[i] = G.dU[(size_t)node * D + i];
-      }
-      double e = exp(-beta * ll + lx);
-      Z += e;
+      for (int u = 0; u < NLPS_GROUP; u++)
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        r[i] += e * l[i];
+        for (int i = 0; i < D; i++) { Xn[u][i] = 0.0; dUn[u][i] = 0.0; }
 #pragma unroll
-        for (int j = 0; j < D; j++) {
-          if (j >= i) JJ[i * D + j] += e * l[i] * l[j];
-          Bm[i * D + j] += e * du[i] * l[j];
+      for (int u = 0; u < NLPS_GROUP; u++)
+        if (node[u] >= 0) {
+          ldvec<D>(&m.X[(size_t)node[u] * NS<D>::X], Xn[u]);
+          ldvec<D>(&G.UA[(size_t)node[u] * 2 * NS<D>::X], dUn[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < NLPS_GROUP; u++) {
+        if (node[u] < 0) continue;
+        double l[D], ll = 0.0, lx = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          l[i] = xp[i] - Xn[u][i];
+          ll += l[i] * l[i];
+          lx += l[i] * lam[i];
+        }
+        double e = exp(-beta * ll + lx);
+        Z += e;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          r[i] += e * l[i];
+#pragma unroll
+          for (int j = 0; j < D; j++) {
+            if (j >= i) JJ[i * D + j] += e * l[i] * l[j];
+            Bm[i * D + j] += e * dUn[u][i] * l[j];
+          }
         }
       }
     }
@@ -592,7 +731,8 @@ __global__ void __launch_bounds__(128) k_kin_stress(MeshDev m, PartDev P, GridDe
   // constitutive update
   const MatParams& mat = c_mat[P.matidx[p]];
   double tau[T], Wp = 0.0;
-  if (mat.type == NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
+  const int mtype = (MAT >= 0) ? MAT : mat.type;
+  if (mtype == NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
     stress_neo_hookean<D>(mat, Fn1, J1, tau, Wp);
   } else {
     constexpr int TB = (D == 2) ? 5 : 9;
@@ -600,9 +740,11 @@ __global__ void __launch_bounds__(128) k_kin_stress(MeshDev m, PartDev P, GridDe
 #pragma unroll
     for (int i = 0; i < TB; i++) be[i] = P.be_n[(size_t)i * np + p];
     double eps = P.eps_n[p], kap = P.kap_n[p];
-    int st = (mat.type == NLPS_MAT_DRUCKER_PRAGER)
-                 ? stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep)
-                 : stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+    int st;
+    if (MAT == NLPS_MAT_DRUCKER_PRAGER) st = stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+    else if (MAT == NLPS_MAT_MATSUOKA_NAKAI) st = stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+    else st = (mtype == NLPS_MAT_DRUCKER_PRAGER) ? stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep)
+                                                 : stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
     if (st != 0) { latch_error(err, st, p); return; }
 #pragma unroll
     for (int i = 0; i < TB; i++) P.be_n1[(size_t)i * np + p] = be[i];
@@ -675,46 +817,6 @@ __global__ void k_traction(PartDev P, NeuDev nu, double thickness, int step) {
   }
 }
 
-// K3 stage 1 (cell kernel, same mapping as k_p2g_mass_disp): partial f_A over the particles of the
-// cell, f_A = sum_p N_A (G_p l_A + t_p)  ==  -V0 tau (DF^-T gradN_A) + N_A T A0.
-template <int D>
-__global__ void __launch_bounds__(128) k_p2g_force(MeshDev m, PartDev P, GridDev G, int has_traction) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= *G.n_occ) return;
-  const int B = G.occ_list[w];
-  const int c0 = G.cell_start[B], n = G.cnt[B];
-  const int base = m.r2p[B], len = m.r2p[B + 1] - base;
-  for (int s = lane; s < len; s += 32) {
-    const int A = m.r2i[base + s];
-    if (!G.active[A]) continue;
-    double XA[D], f[D];
-#pragma unroll
-    for (int i = 0; i < D; i++) { XA[i] = m.X[(size_t)A * D + i]; f[i] = 0.0; }
-    for (int j = 0; j < n; j++) {
-      const double* rec = P.rec + (size_t)G.plist[c0 + j] * Rec<D>::SIZE;
-      double l[D];
-      double s2 = dist2_exact<D>(rec + Rec<D>::X, XA, l);
-      if (s2 <= rec[Rec<D>::SSTAR]) {
-        double lx = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; i++) lx += l[i] * rec[Rec<D>::LAM + i];
-        double N = exp(-rec[Rec<D>::BETA] * s2 + lx) * rec[Rec<D>::ZINV];
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-          double gl = 0.0;
-#pragma unroll
-          for (int k = 0; k < D; k++) gl += rec[Rec<D>::G + i * D + k] * l[k];
-          if (has_traction) gl += rec[Rec<D>::TRAC + i];
-          f[i] += N * gl;
-        }
-      }
-    }
-    double* dst = G.part + ((size_t)G.act_pos[A] * G.cap + m.r2q[base + s]) * (1 + D);
-#pragma unroll
-    for (int i = 0; i < D; i++) dst[i] = f[i];
-  }
-}
-
 // K3 stage 2 + G2 (node kernel): f_A = sum of cell partials; a_A = g + f_A / M_A on free DOFs, 0 on
 // restricted ones (U-Verlet.c:947-958; gravity as U-Newmark-beta.c:1539-1543).
 template <int D>
@@ -738,7 +840,7 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
   for (int i = 0; i < D; i++) {
     double g = grav ? grav[(size_t)i * nsteps + step] : 0.0;
     G.F[(size_t)A * D + i] = f[i];
-    G.A[(size_t)A * D + i] = ((fx >> i) & 1u) ? 0.0 : g + f[i] / M;
+    G.UA[(size_t)A * 2 * NS<D>::X + NS<D>::X + i] = ((fx >> i) & 1u) ? 0.0 : g + f[i] / M;
   }
 }
 
@@ -756,26 +858,41 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
   for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; a[i] = 0.0; du[i] = 0.0; }
   const double beta = P.beta[p];
   double Z = 0.0;
+  {
+    uint32_t mw[W];
 #pragma unroll
-  for (int w = 0; w < W; w++) {
-    uint32_t mm = P.mask[(size_t)w * np + p];
-    while (mm) {
-      int b = __ffs(mm) - 1;
-      mm &= mm - 1;
-      int node = m.r2i[base + w * 32 + b];
-      double ll = 0.0, lx = 0.0;
+    for (int w = 0; w < W; w++) mw[w] = P.mask[(size_t)w * np + p];
+    int wcur = 0, node[NLPS_GROUP];
+    while (next_group<W>(m, base, mw, wcur, node) > 0) {
+      double Xn[NLPS_GROUP][D], An[NLPS_GROUP][D], dUn[NLPS_GROUP][D];
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        double l = xp[i] - m.X[(size_t)node * D + i];
-        ll += l * l;
-        lx += l * lam[i];
-      }
-      double e = exp(-beta * ll + lx);
-      Z += e;
+      for (int u = 0; u < NLPS_GROUP; u++)
 #pragma unroll
-      for (int i = 0; i < D; i++) {
-        a[i] += e * G.A[(size_t)node * D + i];
-        du[i] += e * G.dU[(size_t)node * D + i];
+        for (int i = 0; i < D; i++) { Xn[u][i] = 0.0; An[u][i] = 0.0; dUn[u][i] = 0.0; }
+#pragma unroll
+      for (int u = 0; u < NLPS_GROUP; u++)
+        if (node[u] >= 0) {
+          ldvec<D>(&m.X[(size_t)node[u] * NS<D>::X], Xn[u]);
+          ldvec<D>(&G.UA[(size_t)node[u] * 2 * NS<D>::X], dUn[u]);
+          ldvec<D>(&G.UA[(size_t)node[u] * 2 * NS<D>::X + NS<D>::X], An[u]);
+        }
+#pragma unroll
+      for (int u = 0; u < NLPS_GROUP; u++) {
+        if (node[u] < 0) continue;
+        double ll = 0.0, lx = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          double l = xp[i] - Xn[u][i];
+          ll += l * l;
+          lx += l * lam[i];
+        }
+        double e = exp(-beta * ll + lx);
+        Z += e;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          a[i] += e * An[u][i];
+          du[i] += e * dUn[u][i];
+        }
       }
     }
   }
@@ -845,14 +962,15 @@ __global__ void k_export_nodal(GridDev G, int nn, int D, int which, double* out)
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)nn * D) return;
   int A = (int)(i / D), k = (int)(i % D);
+  const int xs = (D == 2) ? 2 : 4;
   double v = 0.0;
   if (G.active[A]) {
     bool fx = (G.fixed[A] >> k) & 1u;
     switch (which) {
       case 0: v = G.M[A]; break;
-      case 1: v = G.dU[i]; break;
+      case 1: v = G.UA[(size_t)A * 2 * xs + k]; break;
       case 2: v = G.F[i]; break;
-      case 3: v = G.A[i]; break;
+      case 3: v = G.UA[(size_t)A * 2 * xs + xs + k]; break;
       case 4: v = fx ? G.F[i] : 0.0; break;
     }
   }
@@ -906,6 +1024,8 @@ struct nlps_engine {
   double neg_log_tol = 0.0, dt = 0.0;
   int has_traction = 0;
   int max_occ = 0, max_act = 0;
+  int cap_r2 = 0;  // largest 2-ring row
+  int uniform_mat = -1;  // material type shared by all materials, or -1
   int inert_synced = 0;
   std::vector<void*> allocs;
   // staging for AoS <-> SoA
@@ -1064,19 +1184,32 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
 #undef CASE_W
   }
 }
+template <int D, bool FORCE>
+static void launch_p2g_cell(nlps_engine* e, int id) {
+  const int it = (e->cap_r2 + 31) / 32;
+  const int grid = nblk((size_t)e->max_occ, 4 * (it == 1 ? 4 : 1));  // 4 warps per block, CPW cells per warp
+  switch (it) {
+    case 1: { auto kfn = k_p2g_cell<D, 1, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
+    case 2: { auto kfn = k_p2g_cell<D, 2, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
+    case 3: case 4: { auto kfn = k_p2g_cell<D, 4, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
+    default: { auto kfn = k_p2g_cell<D, 8, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
+  }
+}
 template <int D>
 static void stage_p2g_mass_disp_t(nlps_engine* e, int step) {
   // at most min(nn, np) cells are occupied; one warp per cell (surplus warps exit on n_occ)
-  LAUNCH(e, K_P2G_MASS_DISP, k_p2g_mass_disp<D>, nblk((size_t)e->max_occ * 32, 128), 128, e->mesh, e->P, e->G);
+  launch_p2g_cell<D, false>(e, K_P2G_MASS_DISP);
   LAUNCH(e, K_GRID_DISP, k_grid_disp<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step);
 }
 template <int D>
 static void stage_kin_stress_t(nlps_engine* e, int step) {
   StepParams sp = make_params(e, step, 1);
   switch (e->W) {
-#define CASE_W(w) case w: { auto kfn = k_kin_stress<D, w>; LAUNCH(e, K_KIN_STRESS, kfn, nblk(e->np, 128), 128, e->mesh, e->P, e->G, sp, e->err); } break;
+#define CASE_WM(w, mt) { auto kfn = k_kin_stress<D, w, mt>; LAUNCH(e, K_KIN_STRESS, kfn, nblk(e->np, 128), 128, e->mesh, e->P, e->G, sp, e->err); }
+#define CASE_W(w) case w: switch (e->uniform_mat) { case 0: CASE_WM(w, 0) break; case 1: CASE_WM(w, 1) break; case 2: CASE_WM(w, 2) break; default: CASE_WM(w, -1) break; } break;
     CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8)
 #undef CASE_W
+#undef CASE_WM
   }
 }
 template <int D>
@@ -1085,7 +1218,7 @@ static void stage_force_t(nlps_engine* e, int step) {
     LAUNCH(e, K_TRACTION, k_traction_clear<D>, nblk(e->np, 256), 256, e->P);
     LAUNCH(e, K_TRACTION, k_traction<D>, nblk(e->neu.n_entries, 128), 128, e->P, e->neu, e->solver.thickness, step);
   }
-  LAUNCH(e, K_P2G_FORCE, k_p2g_force<D>, nblk((size_t)e->max_occ * 32, 128), 128, e->mesh, e->P, e->G, e->has_traction);
+  launch_p2g_cell<D, true>(e, K_P2G_FORCE);
   LAUNCH(e, K_GRID_ACC, k_grid_acc<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step);
 }
 template <int D>
@@ -1165,11 +1298,19 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   int maxr2 = 0;
   for (int i = 0; i < nn; i++) maxr2 = std::max(maxr2, mesh->ring2_ptr[i + 1] - mesh->ring2_ptr[i]);
   e->cap = maxr2;
+  e->cap_r2 = maxr2;
   e->W = (maxr2 + 31) / 32;
   while (e->W & (e->W - 1)) e->W++;  // kernels are instantiated for 1, 2, 4, 8 mask words
   if (e->W > MAX_MASK_WORDS) return set_err(err, err_len, "2-ring larger than 256 nodes is not supported");
   double* dX; int *r1p, *r1i, *r2p, *r2i, *t1p, *t1i, *t2p, *t2i; double* dh;
-  if (dev_upload(e, &dX, mesh->coords, (size_t)nn * D)) return 1;
+  {
+    const int xs = (D == 2) ? 2 : 4;
+    std::vector<double> Xp((size_t)nn * xs, 0.0);
+    for (int i = 0; i < nn; i++)
+      for (int k = 0; k < D; k++) Xp[(size_t)i * xs + k] = mesh->coords[(size_t)i * D + k];
+    if (dev_upload(e, &dX, Xp.data(), Xp.size())) return 1;
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
   if (dev_upload(e, &r1p, mesh->ring1_ptr, (size_t)nn + 1)) return 1;
   if (dev_upload(e, &r1i, mesh->ring1_idx, (size_t)mesh->ring1_ptr[nn])) return 1;
   if (dev_upload(e, &r2p, mesh->ring2_ptr, (size_t)nn + 1)) return 1;
@@ -1198,8 +1339,8 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   e->max_act = (int)std::min<long long>(nn, (long long)np * maxr1);
   // ---- grid work arrays
   GridDev& G = e->G;
-  if (dev_alloc(e, &G.M, nn) || dev_alloc(e, &G.dU, (size_t)nn * D) || dev_alloc(e, &G.F, (size_t)nn * D) ||
-      dev_alloc(e, &G.A, (size_t)nn * D) || dev_alloc(e, &G.active, nn) || dev_alloc(e, &G.fixed, nn) ||
+  if (dev_alloc(e, &G.M, nn) || dev_alloc(e, &G.UA, (size_t)nn * 2 * (D == 2 ? 2 : 4)) || dev_alloc(e, &G.F, (size_t)nn * D) ||
+      dev_alloc(e, &G.active, nn) || dev_alloc(e, &G.fixed, nn) ||
       dev_alloc(e, &G.cnt, nn) || dev_alloc(e, &G.cursor, nn) || dev_alloc(e, &G.cell_start, nn) ||
       dev_alloc(e, &G.plist, np) || dev_alloc(e, &G.act_list, nn) || dev_alloc(e, &G.n_active, 1) ||
       dev_alloc(e, &G.packed, nn) || dev_alloc(e, &G.scan_blk, (size_t)nblk(nn, SCAN_ITEMS) + 1) ||
@@ -1291,6 +1432,9 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
                         s.a_hardening_borja[2]};
     }
     CUDA_OK(cudaMemcpyToSymbol(c_mat, hm, sizeof(hm)));
+    e->uniform_mat = hm[0].type;
+    for (int i = 1; i < n_materials; i++)
+      if (hm[i].type != hm[0].type) e->uniform_mat = -1;
   }
   // ---- particles
   PartDev& P = e->P;

@@ -1,0 +1,21 @@
+/* The three screen helpers of InOutFun/print_ScreenMessage.c, whose TU cannot be compiled without
+ * PETSc headers (it includes <petscsys.h>).  Only needed when the reference is built without PETSc. */
+#include <stdio.h>
+int ResultsTimeStep;
+void print_Status(char *Message, int Time) { (void)Time; puts(Message); }
+void print_step(int Time, int NumTimeStep, double DeltaTimeStep) {
+  printf("Step: [%i/%i] | DeltaT: %1.2e \n", Time, NumTimeStep, DeltaTimeStep);
+}
+void print_convergence_stats(int Time, int NumTimeStep, int Iter, int MaxIter, double Error0, double Error_total,
+                             double Error_relative) {
+  printf("Step [%i/%i] iter %i/%i err0 %e err %e rel %e\n", Time, NumTimeStep, Iter, MaxIter, Error0, Error_total,
+         Error_relative);
+}
+
+/* U_Static needs PETSc (Formulations/Displacements/U-Static.c); the reference driver references it
+ * unconditionally (driver-nl-partsol.c:374-377), so a PETSc-free build needs this stub. */
+struct Mesh; struct Particle;
+int U_Static() {
+  fprintf(stderr, "U_Static: this build has no PETSc\n");
+  return 1;
+}
