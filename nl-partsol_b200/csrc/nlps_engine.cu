@@ -2,13 +2,14 @@
 //
 // Design: fp64 everywhere, particle state SoA in HBM, mesh adjacency as
 // CSR in the reference's chain order.  Neighbour lists are stored as BITMASKS over the
-// 2-ring of the closest node (4 B / 16 B per particle instead of 4n B).  Particle-to-grid
-// assembly is an ATOMICS-FREE, cell-sorted gather: particles are binned by closest node
-// (I0) every step, and one thread per active node sums the contributions of the particles
-// of the cells in its 2-ring (deterministic order, no fp64 atomics -- shared-memory fp64
-// atomicAdd is a CAS loop on sm_100a).  Grid update + Dirichlet BCs are fused into the
-// node kernels; kinematics + stress update + the per-particle force operator are one
-// particle kernel; state roll is a pointer swap.
+// 2-ring of the closest node (4 B / 16 B per particle instead of 4n B).  Particles are binned by
+// closest node (I0) every step and physically re-sorted into that order every few steps.  One
+// thread block owns a run of consecutive occupied cells: it stages the 2-ring node data of its
+// cells in shared memory once, runs the per-particle work out of shared memory (no dependent
+// global gathers), and then assembles the cell's nodal sums with a warp per cell and a lane per
+// node from the shape-function weights still in shared memory: ATOMICS-FREE particle-to-grid
+// (shared-memory fp64 atomicAdd is a CAS loop on sm_100a), deterministic summation order.  Grid
+// update + Dirichlet BCs are fused into the per-node reduction kernels; state roll is a pointer swap.
 //
 // Reference citations are relative to nl-partsol/src of migmolper/NL-PartSol.
 #include <cuda_runtime.h>
@@ -38,12 +39,12 @@ static const int MAX_MASK_WORDS = 8;  // 2-ring up to 256 nodes
 __constant__ MatParams c_mat[MAX_MATERIALS];
 
 enum KernelId {
-  K_SEARCH = 0, K_NODE_FLAGS, K_SCAN1, K_SCAN2, K_SCAN3, K_FILL, K_NODE_FINISH, K_LME, K_P2G_MASS_DISP,
-  K_GRID_DISP, K_KIN_STRESS, K_TRACTION, K_P2G_FORCE, K_GRID_ACC, K_G2P, K_COUNT
+  K_SEARCH = 0, K_NODE_FLAGS, K_SCAN1, K_SCAN2, K_SCAN3, K_FILL, K_NODE_FINISH, K_REORDER, K_LME_P2G,
+  K_GRID_DISP, K_TRACTION, K_KIN_FORCE, K_GRID_ACC, K_G2P, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
     "search_closest_node", "node_flags", "scan_reduce", "scan_tops", "scan_apply", "cell_fill",
-    "node_finish", "lme_update", "p2g_mass_disp", "grid_disp_bc", "g2p_kin_stress", "traction", "p2g_force",
+    "node_finish", "reorder", "lme_p2g_mass_disp", "grid_disp_bc", "traction", "kin_stress_p2g_force",
     "grid_acc", "g2p_update"};
 
 // ---------------------------------------------------------------------------
@@ -65,26 +66,17 @@ struct MeshDev {
   const double* h_avg;
 };
 
-// AoS record read by the node-centric gather kernels.  Layout (doubles):
-// [0..D) x, [D] sstar, [D+1] beta, [D+2..2D+2) lambda, [2D+2] zinv, [2D+3] mass,
-// [2D+4..3D+4) D_dis, [3D+4 .. 3D+4+D*D) G (force operator), then D traction*area.
-template <int D>
-struct Rec {
-  static constexpr int X = 0, SSTAR = D, BETA = D + 1, LAM = D + 2, ZINV = 2 * D + 2, MASS = 2 * D + 3,
-                       DDIS = 2 * D + 4, G = 3 * D + 4, TRAC = 3 * D + 4 + D * D,
-                       SIZE = ((3 * D + 4 + D * D + D) + 1) & ~1;
-};
-
 struct PartDev {
   int np;
-  // SoA, component-major: f[c*np + p]
+  // SoA, component-major: f[c*np + p]; p is the PHYSICAL slot (cell-sorted every few steps),
+  // orig[p] the caller's particle id and inv[] its inverse.
   double *x, *dis, *ddis, *vel, *acc, *lam;
   double *beta, *mass, *vol0, *rho, *W;
   double *J_n, *J_n1, *eps_n, *eps_n1, *kap_n, *kap_n1;
   double *F_n, *F_n1, *DF, *be_n, *be_n1, *stress, *cep;
   double *Fs4, *DFs4;  // 2D slot 4 of F / DF (never touched by the kinematics, Appendix B)
-  double* rec;
-  int *I0, *nnodes, *matidx;
+  double* trac;        // D x np: Neumann traction * A0 of the current step (allocated only with loads)
+  int *I0, *nnodes, *matidx, *orig, *inv;
   uint32_t* mask;  // W words, word-major: mask[w*np + p]
 };
 
@@ -94,15 +86,74 @@ struct GridDev {
   unsigned char *active, *fixed;
   int *cnt, *cursor, *cell_start, *plist, *act_list, *n_active;
   int *occ_list, *n_occ, *act_pos, *occ_pos;
+  int4* occ_meta;   // per occupied cell (in node order): {node B, first particle slot, 2-ring base, 2-ring length}
+  int* arank;       // rank of a node among the active nodes, -1 when inactive
+  uint32_t* occm;   // per active rank: transposed-2-ring slots whose cell is occupied (w2t words, word-major)
   ulonglong2 *packed, *scan_blk;
-  double* part;  // per (active node, r2t slot): (1+D) partial sums written by the cell kernels
-  int cap;
+  double* part;     // slot-major cell partial sums: part[(q * max_act + rank) * NV + v]
+  int cap, max_act, w2t;
 };
 
 struct StepParams {
   double dt, gamma_lme, neg_log_tol, tol_wrapper, thickness;
   int max_iter_lme, nsteps, step, update_I0, W;
   ReturnMapParams rp;
+};
+
+// One thread block works on C consecutive OCCUPIED cells (a cell = all particles with the same closest
+// node I0) = one contiguous run of the cell-sorted particle order.  SL = longest 2-ring row, PCAP =
+// particles whose per-particle scratch fits in shared memory at once (longer runs go in chunks).
+struct BlockCfg { int C, SL, PCAP, threads; };
+
+struct Carve {
+  size_t off = 0;
+  __host__ __device__ size_t take(size_t bytes) { size_t o = off; off = (off + bytes + 15) & ~(size_t)15; return o; }
+};
+// shared-memory layouts, evaluated identically on host (size) and device (offsets)
+template <int D, int W, bool CACHE>
+struct LayoutA {  // k_lme_p2g
+  size_t tab, cs, base, len, B, rank, q, X, pa, zinv, mass, ddis, mask, px, plam, pbeta, total;
+  __host__ __device__ LayoutA(const BlockCfg& c) {
+    Carve k;
+    const size_t pairs = (size_t)c.C * c.SL, pc = c.PCAP;
+    tab = k.take(8 * 32);
+    cs = k.take(4 * (c.C + 1)); base = k.take(4 * c.C); len = k.take(4 * c.C); B = k.take(4 * c.C);
+    rank = k.take(4 * pairs); q = k.take(pairs); X = k.take(8 * D * pairs);
+    pa = CACHE ? k.take(8 * pc * c.SL) : 0;
+    zinv = k.take(8 * pc); mass = k.take(8 * pc); ddis = k.take(8 * D * pc); mask = k.take(4 * W * pc);
+    px = plam = pbeta = 0;
+    if (!CACHE) { px = k.take(8 * D * pc); plam = k.take(8 * D * pc); pbeta = k.take(8 * pc); }
+    total = k.off;
+  }
+};
+template <int D, int W, bool CACHE>
+struct LayoutB {  // k_kin_force
+  size_t tab, cs, base, len, B, rank, q, X, U, pa, zinv, G, px, trac, mask, plam, pbeta, total;
+  __host__ __device__ LayoutB(const BlockCfg& c) {
+    Carve k;
+    const size_t pairs = (size_t)c.C * c.SL, pc = c.PCAP;
+    tab = k.take(8 * 32);
+    cs = k.take(4 * (c.C + 1)); base = k.take(4 * c.C); len = k.take(4 * c.C); B = k.take(4 * c.C);
+    rank = k.take(4 * pairs); q = k.take(pairs); X = k.take(8 * D * pairs); U = k.take(8 * D * pairs);
+    pa = CACHE ? k.take(8 * pc * c.SL) : 0;
+    zinv = k.take(8 * pc); G = k.take(8 * D * D * pc); px = k.take(8 * D * pc); trac = k.take(8 * D * pc);
+    mask = k.take(4 * W * pc);
+    plam = pbeta = 0;
+    if (!CACHE) { plam = k.take(8 * D * pc); pbeta = k.take(8 * pc); }
+    total = k.off;
+  }
+};
+template <int D>
+struct LayoutC {  // k_g2p
+  size_t tab, cs, base, len, B, rank, X, U, A, total;
+  __host__ __device__ LayoutC(const BlockCfg& c) {
+    Carve k;
+    const size_t pairs = (size_t)c.C * c.SL;
+    tab = k.take(8 * 32);
+    cs = k.take(4 * (c.C + 1)); base = k.take(4 * c.C); len = k.take(4 * c.C); B = k.take(4 * c.C);
+    rank = k.take(4 * pairs); X = k.take(8 * D * pairs); U = k.take(8 * D * pairs); A = k.take(8 * D * pairs);
+    total = k.off;
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -137,27 +188,58 @@ __device__ inline double sstar_from_Ra(double Ra) {
   return t;
 }
 
-
-// Neighbour iteration with 4-way memory-level parallelism: the kernels are bound by the latency of the
-// dependent gathers (mask bit -> node id -> node data), so node ids and node data of GROUPS of four
-// neighbours are requested before any of them is consumed.
-#define NLPS_GROUP 4
-template <int W>
-__device__ __forceinline__ int next_group(const MeshDev& m, int base, uint32_t* mk, int& w, int* node) {
-  int cnt = 0;
+// exp() for the LME weights: exp(x) = 2^(k/32) * exp(r), k = rint(32 x / ln 2), |r| <= ln2/64, table of
+// 2^(j/32) (shared memory) times a degree-6 Taylor polynomial: 11 fp64 operations instead of libdevice's 17
+// plus constant moves, max relative error 1.94e-16 (0.9 ulp; checked against mpmath over [-700, 700]).
+// The kernels issue two of these chains per loop iteration (for_neighbour_pairs): the fp64 pipe, not the
+// latency of one dependent chain, then bounds the shape-function loops.
+__device__ const double g_exp2tab[32] = {
+    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
+    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,
+    1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,
+    1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429, 1.718619298122478,
+    1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,
+    1.9571441241754002};
+// constants in the constant bank: a DFMA takes them as a direct operand (an immediate would cost two moves each)
+__constant__ double c_fexp[8] = {46.16624130844683,        // 32 / ln 2
+                                 -0.02166084938653512,     // -ln2/32, high part (21 trailing zero bits: exact product)
+                                 -5.9631716539705866e-12,  // -ln2/32, low part
+                                 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.0};
+__device__ __forceinline__ double fexp(double x, const double* tab) {
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*c + MAGIC is rint(x*c)
+  const double kd = __fma_rn(x, c_fexp[0], MAGIC);
+  const int k = __double2loint(kd);
+  const double kf = kd - MAGIC;
+  double r = __fma_rn(kf, c_fexp[1], x);
+  r = __fma_rn(kf, c_fexp[2], r);
+  double q = __fma_rn(r, c_fexp[3], c_fexp[4]);
+  q = __fma_rn(r, q, c_fexp[5]);
+  q = __fma_rn(r, q, c_fexp[6]);
+  q = __fma_rn(r, q, 0.5);
+  q = __fma_rn(r, q, 1.0);
+  // 2^(k/32) = table entry with the exponent shifted (clamped: |x| > 708 saturates instead of wrapping;
+  // a NaN argument still gives NaN through r)
+  const int m = max(-1021, min(1022, k >> 5));
+  const double T = tab[k & 31];
+  const double Ts = __hiloint2double(__double2hiint(T) + (m << 20), __double2loint(T));
+  return __fma_rn(Ts, r * q, Ts);
+}
+// visit the set bits of a neighbour mask two at a time; `two` is false for the odd one out (k1 == k0)
+template <int W, class F>
+__device__ __forceinline__ void for_neighbour_pairs(const uint32_t* mk, F&& f) {
 #pragma unroll
-  for (int u = 0; u < NLPS_GROUP; u++) {
-    while (w < W && mk[w] == 0u) w++;
-    if (w < W) {
-      int b = __ffs(mk[w]) - 1;
-      mk[w] &= mk[w] - 1;
-      node[u] = m.r2i[base + w * 32 + b];
-      cnt = u + 1;
-    } else {
-      node[u] = -1;
+  for (int w = 0; w < W; w++) {
+    uint32_t mm = mk[w];
+    while (mm) {
+      const int b0 = __ffs(mm) - 1;
+      mm &= mm - 1;
+      const bool two = mm != 0u;
+      const int b1 = two ? __ffs(mm) - 1 : b0;
+      mm &= mm - 1;
+      f(w * 32 + b0, w * 32 + b1, two);
     }
   }
-  return cnt;
 }
 
 // ---------------------------------------------------------------------------
@@ -185,8 +267,8 @@ __global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G,
         double dq = __dsqrt_rn(dist2_exact<D>(xp, &m.X[(size_t)node * NS<D>::X], l));
         if (q == b0 || dq < dmin) { dmin = dq; best = node; }
       }
+      if (best != I0) P.I0[p] = best;
       I0 = best;
-      P.I0[p] = I0;
     }
   }
   atomicAdd(&G.cnt[I0], 1);
@@ -297,285 +379,374 @@ __global__ void __launch_bounds__(256) k_cell_fill(PartDev P, GridDev G) {
   G.plist[pos] = p;
 }
 
-// per node: sort the cell's particle ids ascending (deterministic summation order) and
-// append occupied cells / active nodes to their compact lists.
-__global__ void __launch_bounds__(256) k_node_finish(MeshDev m, GridDev G) {
+// per node: sort the cell's particles by the CALLER's particle id (summation order of the cell sums is
+// then independent of the physical particle order), append occupied cells / active nodes to their
+// compact lists, and record which slots of the node's transposed 2-ring belong to occupied cells.
+__global__ void __launch_bounds__(256) k_node_finish(MeshDev m, PartDev P, GridDev G) {
   int A = blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= m.nn) return;
   int n = G.cnt[A];
   if (n > 1) {
     int* a = G.plist + G.cell_start[A];
     for (int i = 1; i < n; i++) {
-      int v = a[i], j = i - 1;
-      while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; j--; }
+      int v = a[i], kv = P.orig[v], j = i - 1;
+      while (j >= 0 && P.orig[a[j]] > kv) { a[j + 1] = a[j]; j--; }
       a[j + 1] = v;
     }
   }
-  if (n > 0) G.occ_list[G.occ_pos[A]] = A;
-  if (G.active[A]) G.act_list[G.act_pos[A]] = A;
+  if (n > 0) {
+    G.occ_list[G.occ_pos[A]] = A;
+    const int bs = m.r2p[A];
+    G.occ_meta[G.occ_pos[A]] = make_int4(A, G.cell_start[A], bs, m.r2p[A + 1] - bs);
+  }
+  int rank = -1;
+  if (G.active[A]) {
+    rank = G.act_pos[A];
+    G.act_list[rank] = A;
+    const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
+    for (int w = 0; w < G.w2t; w++) {
+      uint32_t word = 0u;
+      for (int b = 0; b < 32; b++) {
+        int q = w * 32 + b;
+        if (q < nq && G.cnt[m.r2ti[q0 + q]] > 0) word |= 1u << b;
+      }
+      G.occm[(size_t)w * G.max_act + rank] = word;
+    }
+  }
+  G.arank[A] = rank;
+}
+
+// physical re-sort: gather every SoA field into the cell-sorted order (dst[c][t] = src[c][plist[t]])
+template <typename Tp>
+__global__ void __launch_bounds__(256) k_gather_rows(const Tp* src, Tp* dst, const int* plist, int np, int cols) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)np * cols) return;
+  int c = (int)(i / np), t = (int)(i % np);
+  dst[i] = src[(size_t)c * np + plist[t]];
+}
+__global__ void __launch_bounds__(256) k_after_sort(PartDev P, GridDev G) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.np) return;
+  G.plist[t] = t;
+  P.inv[P.orig[t]] = t;
 }
 
 // ---------------------------------------------------------------------------
-// K0: per-particle LME update.  tributary__LME__ (LME.c:1019-1099) with the PREVIOUS beta,
-// beta__LME__ (LME.c:177-185), __lambda_Newton_Rapson (LME.c:272-353), plus the explicit
-// predictor (__predictor_PARTICLES, U-Verlet.c:229-253) and the gather record.
-template <int D, int W>
-__global__ void __launch_bounds__(128) k_lme(MeshDev m, PartDev P, GridDev G, StepParams sp, int* err,
-                                             int do_predictor) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P.np) return;
-  const int np = P.np;
-  const int I0 = P.I0[p];
-  const int base = m.r2p[I0], len = m.r2p[I0 + 1] - base;
-  double xp[D], lam[D];
-#pragma unroll
-  for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
-  const double beta_old = P.beta[p];
-  const double Ra = __dsqrt_rn(__ddiv_rn(sp.neg_log_tol, beta_old));  // LME.c:1052
-  const double sstar = sstar_from_Ra(Ra);
-  uint32_t mk[W];
-#pragma unroll
-  for (int w = 0; w < W; w++) mk[w] = 0u;
-  int n = 0;
-  for (int k = 0; k < len; k++) {
-    int node = m.r2i[base + k];
-    if (!G.active[node]) continue;
-    double l[D];
-    double s = dist2_exact<D>(xp, &m.X[(size_t)node * NS<D>::X], l);
-    if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
+// block prologue shared by the three cell-block kernels
+struct Blk { int ncell, t0, t1; };
+// metadata of cell group g (C consecutive occupied cells): one global round trip
+__device__ __forceinline__ void blk_prologue(const GridDev& G, const BlockCfg& cfg, int nocc, int np, int g, int* s_cs,
+                                             int* s_base, int* s_len, int* s_B, Blk& b) {
+  const int c0 = g * cfg.C;
+  b.ncell = min(cfg.C, nocc - c0);
+  for (int i = threadIdx.x; i <= b.ncell; i += blockDim.x) {
+    if (c0 + i < nocc) {
+      const int4 mt = G.occ_meta[c0 + i];
+      s_cs[i] = mt.y;
+      if (i < b.ncell) { s_B[i] = mt.x; s_base[i] = mt.z; s_len[i] = mt.w; }
+    } else {
+      s_cs[i] = np;  // the last occupied cell ends at the last particle
+    }
   }
+  __syncthreads();
+  b.t0 = s_cs[0];
+  b.t1 = s_cs[b.ncell];
+}
+// stage the 2-ring node data of the block's cells: every (cell, slot) pair is loaded once, four pairs per
+// thread in flight (ids first, then all their data: two global round trips for the whole block); the
+// per-particle loops then run out of shared memory with no dependent global gathers.
+template <int D, bool WANT_Q, int NF>
+__device__ __forceinline__ void stage_nodes(const MeshDev& m, const GridDev& G, int SL, int ncell, const int* s_base,
+                                            const int* s_len, int* s_rank, unsigned char* s_q, double* s_X,
+                                            double* s_U, double* s_A) {
+  constexpr int U = 4;
+  const int npairs = ncell * SL;
+  for (int e0 = threadIdx.x; e0 < npairs; e0 += U * blockDim.x) {
+    int node[U], idx[U];
 #pragma unroll
-  for (int w = 0; w < W; w++) P.mask[(size_t)w * np + p] = mk[w];
-  P.nnodes[p] = n;
-  if (n < D + 1) { latch_error(err, NLPS_ERR_FEW_NEIGHBOURS, p); return; }
-  const double h = m.h_avg[I0];
-  const double beta = __ddiv_rn(sp.gamma_lme, __dmul_rn(h, h));
-  P.beta[p] = beta;
-
-  // Newton on lambda
-  int NumIter = 0;
-  double Z = 1.0;
-  bool failed = false;
-  while (NumIter <= sp.max_iter_lme) {
-    double r[D], JJ[D * D];
-    Z = 0.0;
+    for (int u = 0; u < U; u++) {
+      const int e = e0 + u * blockDim.x;
+      node[u] = -1;
+      idx[u] = 0;
+      if (e < npairs) {
+        const int c = e / SL, k = e - c * SL;
+        if (k < s_len[c]) { idx[u] = s_base[c] + k; node[u] = m.r2i[idx[u]]; }
+      }
+    }
+    // invalid pairs load node 0 (harmless) so that every load below is unconditional and independent
+    int rank[U];
+    unsigned char qv[U];
+    double2 x0[U], x1[U], u0[U], u1[U], a0[U], a1[U];
 #pragma unroll
-    for (int i = 0; i < D; i++) r[i] = 0.0;
+    for (int u = 0; u < U; u++) {
+      const int nd = max(node[u], 0);
+      const double* px = &m.X[(size_t)nd * NS<D>::X];
+      const double* pu = &G.UA[(size_t)nd * 2 * NS<D>::X];
+      rank[u] = G.arank[nd];
+      x0[u] = *reinterpret_cast<const double2*>(px);
+      if (D == 3) x1[u] = *reinterpret_cast<const double2*>(px + 2);
+      if (WANT_Q) qv[u] = m.r2q[idx[u]];
+      if (NF >= 1) {
+        u0[u] = *reinterpret_cast<const double2*>(pu);
+        if (D == 3) u1[u] = *reinterpret_cast<const double2*>(pu + 2);
+      }
+      if (NF >= 2) {
+        a0[u] = *reinterpret_cast<const double2*>(pu + NS<D>::X);
+        if (D == 3) a1[u] = *reinterpret_cast<const double2*>(pu + NS<D>::X + 2);
+      }
+    }
 #pragma unroll
-    for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
-    {
-      uint32_t mw[W];
-#pragma unroll
-      for (int w = 0; w < W; w++) mw[w] = mk[w];
-      int wcur = 0, node[NLPS_GROUP];
-      while (next_group<W>(m, base, mw, wcur, node) > 0) {
-        double Xn[NLPS_GROUP][D];
-#pragma unroll
-        for (int u = 0; u < NLPS_GROUP; u++)
-#pragma unroll
-          for (int i = 0; i < D; i++) Xn[u][i] = 0.0;
-#pragma unroll
-        for (int u = 0; u < NLPS_GROUP; u++)
-          if (node[u] >= 0) ldvec<D>(&m.X[(size_t)node[u] * NS<D>::X], Xn[u]);
-#pragma unroll
-        for (int u = 0; u < NLPS_GROUP; u++) {
-          if (node[u] < 0) continue;
-          double l[D], ll = 0.0, lx = 0.0;
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-            l[i] = xp[i] - Xn[u][i];
-            ll += l[i] * l[i];
-            lx += l[i] * lam[i];
-          }
-          double e = exp(-beta * ll + lx);
-          Z += e;
-#pragma unroll
-          for (int i = 0; i < D; i++) {
-            r[i] += e * l[i];
-#pragma unroll
-            for (int j = i; j < D; j++) JJ[i * D + j] += e * l[i] * l[j];
-          }
+    for (int u = 0; u < U; u++) {
+      const int e = e0 + u * blockDim.x;
+      if (e < npairs) {
+        s_rank[e] = (node[u] >= 0) ? rank[u] : -1;
+        if (WANT_Q) s_q[e] = qv[u];
+        double* dx = s_X + (size_t)e * D;
+        dx[0] = x0[u].x; dx[1] = x0[u].y;
+        if (D == 3) dx[2] = x1[u].x;
+        if (NF >= 1) {
+          double* du = s_U + (size_t)e * D;
+          du[0] = u0[u].x; du[1] = u0[u].y;
+          if (D == 3) du[2] = u1[u].x;
+        }
+        if (NF >= 2) {
+          double* da = s_A + (size_t)e * D;
+          da[0] = a0[u].x; da[1] = a0[u].y;
+          if (D == 3) da[2] = a1[u].x;
         }
       }
     }
-    double Zi = 1.0 / Z, nr = 0.0;
+  }
+}
+__device__ __forceinline__ int cell_of(const int* s_cs, int ncell, int t) {
+  int lo = 0, hi = ncell;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (s_cs[mid] <= t) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------
+// K0 + K1 (fused): per-particle LME update, explicit predictor, and the cell sums of the lumped mass and
+// of the mass-weighted displacement increment.
+//   particle phase (thread / particle): tributary__LME__ (LME.c:1019-1099) with the PREVIOUS beta,
+//     beta__LME__ (LME.c:177-185), __lambda_Newton_Rapson (LME.c:272-353), __predictor_PARTICLES
+//     (U-Verlet.c:229-253).  The unnormalised weights exp(-beta|l|^2 + lambda.l) of the converged
+//     evaluation stay in shared memory (CACHE) ...
+//   cell phase (warp / cell, lane / 2-ring node): ... so that M_A, sum m_p N_A DU_p (U-Verlet.c:166-225,
+//     301-367) over the cell's particles need no second evaluation and no atomics; the partials go to
+//     part[(slot of the cell in A's transposed ring, rank(A))], summed per node in a fixed order by k_grid_disp.
+template <int D, int W, bool CACHE>
+__global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg, int* err,
+                                                 int do_predictor) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const LayoutA<D, W, CACHE> L(cfg);
+  int* s_cs = (int*)(smem + L.cs); int* s_base = (int*)(smem + L.base); int* s_len = (int*)(smem + L.len);
+  int* s_rank = (int*)(smem + L.rank); unsigned char* s_q = smem + L.q; double* s_X = (double*)(smem + L.X);
+  double* s_pa = (double*)(smem + L.pa); double* s_zinv = (double*)(smem + L.zinv);
+  double* s_mass = (double*)(smem + L.mass); double* s_ddis = (double*)(smem + L.ddis);
+  uint32_t* s_mask = (uint32_t*)(smem + L.mask);
+  double* s_px = (double*)(smem + L.px); double* s_plam = (double*)(smem + L.plam); double* s_pbeta = (double*)(smem + L.pbeta);
+  double* s_tab = (double*)(smem + L.tab);
+  int* s_B = (int*)(smem + L.B);
+  if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
+  const int nocc = *G.n_occ, ngroups = (nocc + cfg.C - 1) / cfg.C;
+  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ...
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  Blk b;
+  blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
+  stage_nodes<D, true, 0>(m, G, cfg.SL, b.ncell, s_base, s_len, s_rank, s_q, s_X, nullptr, nullptr);
+  __syncthreads();
+  const int SL = cfg.SL, np = P.np;
+  for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
+    const int nb = min(cfg.PCAP, b.t1 - tb);
+    // ---- particle phase
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+      const int t = tb + j, p = G.plist[t];
+      const int ci = cell_of(s_cs, b.ncell, t);
+      const int len = s_len[ci];
+      const int* rk = s_rank + ci * SL;
+      const double* Xc = s_X + (size_t)ci * SL * D;
+      double xp[D], lam[D];
 #pragma unroll
-    for (int i = 0; i < D; i++) { r[i] *= Zi; nr += r[i] * r[i]; }
-    nr = sqrt(nr);
-    if (nr > sp.tol_wrapper) {
-#pragma unroll
-      for (int i = 0; i < D; i++)
-#pragma unroll
-        for (int j = i; j < D; j++) {
-          JJ[i * D + j] = JJ[i * D + j] * Zi - r[i] * r[j];
-          JJ[j * D + i] = JJ[i * D + j];
-        }
-      if (rcond_as_reference<D>(JJ) < 1E-8) { failed = true; latch_error(err, NLPS_ERR_SINGULAR_HESSIAN, p); break; }
-      double Ji[D * D];
-      inverse<D>(JJ, Ji);
+      for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
+      const double beta_old = P.beta[p];
+      const double mp = P.mass[p];
+      double pv[D], pa_[D];  // requested now, consumed by the predictor after the Newton loop
 #pragma unroll
       for (int i = 0; i < D; i++) {
-        double dl = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; j++) dl += Ji[i * D + j] * r[j];
-        lam[i] -= dl;
+        pv[i] = do_predictor ? P.vel[i * np + p] : P.ddis[i * np + p];
+        pa_[i] = do_predictor ? P.acc[i * np + p] : 0.0;
       }
-      NumIter++;
-    } else {
-      break;
-    }
-  }
-  if (!failed && NumIter >= sp.max_iter_lme) latch_error(err, NLPS_ERR_NEWTON_LME, p);
+      const double Ra = __dsqrt_rn(__ddiv_rn(sp.neg_log_tol, beta_old));  // LME.c:1052
+      const double sstar = sstar_from_Ra(Ra);
+      uint32_t mk[W];
 #pragma unroll
-  for (int i = 0; i < D; i++) P.lam[i * np + p] = lam[i];
-
-  // predictor + gather record
-  double* rec = P.rec + (size_t)p * Rec<D>::SIZE;
-  const double mp = P.mass[p];
-#pragma unroll
-  for (int i = 0; i < D; i++) {
-    double dd;
-    if (do_predictor) {
-      double v = P.vel[i * np + p], a = P.acc[i * np + p];
-      dd = sp.dt * v + 0.5 * (sp.dt * sp.dt) * a;
-      P.ddis[i * np + p] = dd;
-      P.vel[i * np + p] = v + (1 - 0.5) * sp.dt * a;  // gamma = 0.5, U-Verlet.c:76,248
-    } else {
-      dd = P.ddis[i * np + p];
-    }
-    rec[Rec<D>::X + i] = xp[i];
-    rec[Rec<D>::LAM + i] = lam[i];
-    rec[Rec<D>::DDIS + i] = dd;
-  }
-  rec[Rec<D>::SSTAR] = sstar;
-  rec[Rec<D>::BETA] = beta;
-  rec[Rec<D>::ZINV] = 1.0 / Z;
-  rec[Rec<D>::MASS] = mp;
-}
-
-// ---------------------------------------------------------------------------
-// Stage 1 (cell kernel): one WARP per occupied cell B (all particles with I0 == B), one LANE per
-// node A of the 2-ring of B (IT lanes-rounds when the ring has more than 32 nodes).  The cell's particle
-// records are staged into shared memory by the whole warp (coalesced 8-byte loads, one round trip for
-// CH particles), then every lane walks them (shared-memory broadcasts): no scatter, no atomic.  The
-// lane's partial sums over the cell go to part[(rank(A), slot of B in A's transposed row)].
-//   FORCE = false: M_A, sum m_p N_A DU_p  (U-Verlet.c:166-225, 301-367)
-//   FORCE = true : f_A = sum_p N_A (G_p l_A + t_p) == -V0 tau (DF^-T gradN_A) + N_A T A0
-//                  (U-Newmark-beta.c:1257-1374, U-Verlet.c:805-902)
-template <int D, int IT, bool FORCE>
-__global__ void __launch_bounds__(128) k_p2g_cell(MeshDev m, PartDev P, GridDev G, int has_traction) {
-  // CPW cells per warp: all their metadata, node data and particle records are requested before any
-  // is consumed (the kernel is latency-bound: ~4 particles of work per cell).
-  constexpr int CPW = (IT == 1) ? 4 : 1, CH = 8, SZ = Rec<D>::SIZE, NV = FORCE ? D : 1 + D;
-  __shared__ double sm_all[4][CPW * CH * SZ];
-  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int w0 = (blockIdx.x * 4 + wib) * CPW;
-  const int nocc = *G.n_occ;
-  if (w0 >= nocc) return;
-  double* sm = sm_all[wib];
-  // lanes 0..CPW-1 fetch the metadata of one cell each
-  int mB = 0, mc0 = 0, mn = 0, mbase = 0, mlen = 0;
-  if (lane < CPW && w0 + lane < nocc) {
-    mB = G.occ_list[w0 + lane];
-    mc0 = G.cell_start[mB];
-    mn = G.cnt[mB];
-    mbase = m.r2p[mB];
-    mlen = m.r2p[mB + 1] - mbase;
-  }
-  int c0[CPW], n[CPW], base[CPW], len[CPW];
-#pragma unroll
-  for (int c = 0; c < CPW; c++) {
-    c0[c] = __shfl_sync(0xffffffffu, mc0, c);
-    n[c] = __shfl_sync(0xffffffffu, mn, c);
-    base[c] = __shfl_sync(0xffffffffu, mbase, c);
-    len[c] = __shfl_sync(0xffffffffu, mlen, c);
-  }
-  double XA[CPW][IT][D], acc[CPW][IT][NV];
-  long long dst[CPW][IT];
-#pragma unroll
-  for (int c = 0; c < CPW; c++)
-#pragma unroll
-    for (int it = 0; it < IT; it++) {
-      const int s = lane + 32 * it;
-      dst[c][it] = -1;
-#pragma unroll
-      for (int v = 0; v < NV; v++) acc[c][it][v] = 0.0;
-#pragma unroll
-      for (int i = 0; i < D; i++) XA[c][it][i] = 0.0;
-      if (s < len[c]) {
-        const int A = m.r2i[base[c] + s];
-        if (G.active[A]) {
-          dst[c][it] = ((long long)G.act_pos[A] * G.cap + m.r2q[base[c] + s]) * (1 + D);
-#pragma unroll
-          for (int i = 0; i < D; i++) XA[c][it][i] = m.X[(size_t)A * NS<D>::X + i];
-        }
+      for (int w = 0; w < W; w++) mk[w] = 0u;
+      int n = 0;
+      for (int k = 0; k < len; k++) {
+        if (rk[k] < 0) continue;  // inactive node
+        double l[D];
+        const double s = dist2_exact<D>(xp, Xc + k * D, l);
+        if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
       }
-    }
-  int nmax = 0;
 #pragma unroll
-  for (int c = 0; c < CPW; c++) nmax = max(nmax, n[c]);
-  for (int j0 = 0; j0 < nmax; j0 += CH) {
-    __syncwarp();
+      for (int w = 0; w < W; w++) P.mask[(size_t)w * np + p] = mk[w];
+      P.nnodes[p] = n;
+      bool ok = true;
+      if (n < D + 1) { latch_error(err, NLPS_ERR_FEW_NEIGHBOURS, P.orig[p]); ok = false; }
+      const double h = m.h_avg[s_B[ci]];
+      const double beta = __ddiv_rn(sp.gamma_lme, __dmul_rn(h, h));
+      P.beta[p] = beta;
+      // Newton on lambda
+      int NumIter = 0;
+      double Z = 1.0;
+      while (ok && NumIter <= sp.max_iter_lme) {
+        double r[D], JJ[D * D];
+        Z = 0.0;
 #pragma unroll
-    for (int c = 0; c < CPW; c++) {
-      const int nc = min(CH, n[c] - j0);
-      if (nc <= 0) continue;
-      const int pid = (lane < nc) ? G.plist[c0[c] + j0 + lane] : 0;
-      for (int e0 = 0; e0 < nc * SZ; e0 += 32) {
-        const int e = e0 + lane, j = min(e / SZ, nc - 1);
-        const int pj = __shfl_sync(0xffffffffu, pid, j);
-        if (e < nc * SZ) sm[c * CH * SZ + e] = P.rec[(size_t)pj * SZ + (e - j * SZ)];
-      }
-    }
-    __syncwarp();
+        for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
-    for (int c = 0; c < CPW; c++) {
-      const int nc = min(CH, n[c] - j0);
+        for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
+        for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) {
+          double l0[D], l1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
 #pragma unroll
-      for (int it = 0; it < IT; it++) {
-        if (dst[c][it] < 0) continue;
-        for (int j = 0; j < nc; j++) {
-          const double* rec = sm + (c * CH + j) * SZ;
-          double l[D];
-          double s2 = dist2_exact<D>(rec + Rec<D>::X, XA[c][it], l);
-          if (s2 <= rec[Rec<D>::SSTAR]) {
-            double lx = 0.0;
-#pragma unroll
-            for (int i = 0; i < D; i++) lx += l[i] * rec[Rec<D>::LAM + i];
-            double N = exp(-rec[Rec<D>::BETA] * s2 + lx) * rec[Rec<D>::ZINV];
-            if (!FORCE) {
-              double mN = N * rec[Rec<D>::MASS];
-              acc[c][it][0] += mN;
-#pragma unroll
-              for (int i = 0; i < D; i++) acc[c][it][1 + i] += mN * rec[Rec<D>::DDIS + i];
-            } else {
-#pragma unroll
-              for (int i = 0; i < D; i++) {
-                double gl = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; k++) gl += rec[Rec<D>::G + i * D + k] * l[k];
-                if (has_traction) gl += rec[Rec<D>::TRAC + i];
-                acc[c][it][i] += N * gl;
-              }
-            }
+          for (int i = 0; i < D; i++) {
+            l0[i] = xp[i] - Xc[k0 * D + i];
+            l1[i] = xp[i] - Xc[k1 * D + i];
+            ll0 += l0[i] * l0[i];
+            ll1 += l1[i] * l1[i];
+            lx0 += l0[i] * lam[i];
+            lx1 += l1[i] * lam[i];
           }
+          const double e0 = fexp(-beta * ll0 + lx0, s_tab);
+          double e1 = fexp(-beta * ll1 + lx1, s_tab);
+          e1 = two ? e1 : 0.0;
+          if (CACHE) {
+            s_pa[(size_t)j * SL + k0] = e0;
+            if (two) s_pa[(size_t)j * SL + k1] = e1;
+          }
+          Z += e0;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            r[i] += e0 * l0[i];
+#pragma unroll
+            for (int jj = i; jj < D; jj++) JJ[i * D + jj] += e0 * l0[i] * l0[jj];
+          }
+          Z += e1;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            r[i] += e1 * l1[i];
+#pragma unroll
+            for (int jj = i; jj < D; jj++) JJ[i * D + jj] += e1 * l1[i] * l1[jj];
+          }
+        });
+        const double Zi = 1.0 / Z;
+        double nr = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; i++) { r[i] *= Zi; nr += r[i] * r[i]; }
+        nr = sqrt(nr);
+        if (nr > sp.tol_wrapper) {
+#pragma unroll
+          for (int i = 0; i < D; i++)
+#pragma unroll
+            for (int jj = i; jj < D; jj++) {
+              JJ[i * D + jj] = JJ[i * D + jj] * Zi - r[i] * r[jj];
+              JJ[jj * D + i] = JJ[i * D + jj];
+            }
+          if (rcond_as_reference<D>(JJ) < 1E-8) { ok = false; latch_error(err, NLPS_ERR_SINGULAR_HESSIAN, P.orig[p]); break; }
+          double Ji[D * D];
+          inverse<D>(JJ, Ji);
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            double dl = 0.0;
+#pragma unroll
+            for (int jj = 0; jj < D; jj++) dl += Ji[i * D + jj] * r[jj];
+            lam[i] -= dl;
+          }
+          NumIter++;
+        } else {
+          break;
         }
       }
-    }
-  }
+      if (ok && NumIter >= sp.max_iter_lme) latch_error(err, NLPS_ERR_NEWTON_LME, P.orig[p]);
 #pragma unroll
-  for (int c = 0; c < CPW; c++)
+      for (int i = 0; i < D; i++) P.lam[i * np + p] = lam[i];
+      // predictor (gamma = 0.5, U-Verlet.c:76,248)
 #pragma unroll
-    for (int it = 0; it < IT; it++)
-      if (dst[c][it] >= 0) {
-#pragma unroll
-        for (int v = 0; v < NV; v++) G.part[dst[c][it] + v] = acc[c][it][v];
+      for (int i = 0; i < D; i++) {
+        double dd;
+        if (do_predictor) {
+          const double v = pv[i], a = pa_[i];
+          dd = sp.dt * v + 0.5 * (sp.dt * sp.dt) * a;
+          P.ddis[i * np + p] = dd;
+          P.vel[i * np + p] = v + (1 - 0.5) * sp.dt * a;
+        } else {
+          dd = pv[i];
+        }
+        s_ddis[j * D + i] = dd;
+        if (!CACHE) { s_px[j * D + i] = xp[i]; s_plam[j * D + i] = lam[i]; }
       }
+      if (!CACHE) s_pbeta[j] = beta;
+      s_zinv[j] = ok ? 1.0 / Z : 0.0;
+      s_mass[j] = mp;
+#pragma unroll
+      for (int w = 0; w < W; w++) s_mask[j * W + w] = ok ? mk[w] : 0u;
+    }
+    __syncthreads();
+    // ---- cell phase: one thread per (cell, 2-ring node) pair sums over the cell's particles
+    for (int e = threadIdx.x; e < b.ncell * SL; e += blockDim.x) {
+      const int rank = s_rank[e];
+      if (rank < 0) continue;
+      const int c = e / SL, k = e - c * SL;
+      const int ja = max(s_cs[c], tb) - tb, jb = min(s_cs[c + 1], tb + nb) - tb;
+      if (ja >= jb) continue;
+      const bool first = s_cs[c] >= tb;
+      const int kw = k >> 5;
+      const uint32_t kb = 1u << (k & 31);
+      double a0 = 0.0, a[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) a[i] = 0.0;
+      for (int j = ja; j < jb; j++) {
+        if (!(s_mask[j * W + kw] & kb)) continue;
+        double N;
+        if (CACHE) {
+          N = s_pa[(size_t)j * SL + k] * s_zinv[j];
+        } else {
+          double ll = 0.0, lx = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            const double l = s_px[j * D + i] - s_X[(size_t)e * D + i];
+            ll += l * l;
+            lx += l * s_plam[j * D + i];
+          }
+          N = fexp(-s_pbeta[j] * ll + lx, s_tab) * s_zinv[j];
+        }
+        const double mN = N * s_mass[j];
+        a0 += mN;
+#pragma unroll
+        for (int i = 0; i < D; i++) a[i] += mN * s_ddis[j * D + i];
+      }
+      double* dst = G.part + ((size_t)s_q[e] * G.max_act + rank) * (1 + D);
+      if (first) {
+        dst[0] = a0;
+#pragma unroll
+        for (int i = 0; i < D; i++) dst[1 + i] = a[i];
+      } else {
+        dst[0] += a0;
+#pragma unroll
+        for (int i = 0; i < D; i++) dst[1 + i] += a[i];
+      }
+    }
+    __syncthreads();
+  }
+  }  // cell groups
 }
 
 // Stage 2 + G1 (node kernel): M_A = sum_p N_A m_p (U-Verlet.c:166-225); DU_A = sum_p m_p N_A DU_p / M_A
-// (U-Verlet.c:301-367) as a contiguous, fixed-order sum of the cell partials; Dirichlet overwrite
-// (U-Verlet.c:458-526) and restricted-DOF flags (Nodes-Tools.c:70-156).
+// (U-Verlet.c:301-367) as a fixed-order sum of the cell partials (coalesced: slot-major layout);
+// Dirichlet overwrite (U-Verlet.c:458-526) and restricted-DOF flags (Nodes-Tools.c:70-156).
 struct BcDev {
   const int *node_ptr, *node_bnd;  // CSR: node -> boundary ids in boundary order
   const int* bnd_dim;
@@ -592,13 +763,16 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
   double mom[D], M = 0.0;
 #pragma unroll
   for (int i = 0; i < D; i++) mom[i] = 0.0;
-  const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
-  const double* src = G.part + (size_t)t * G.cap * (1 + D);
-  for (int q = 0; q < nq; q++) {
-    if (G.cnt[m.r2ti[q0 + q]] == 0) continue;
-    M += src[q * (1 + D)];
+  for (int w = 0; w < G.w2t; w++) {
+    uint32_t mm = G.occm[(size_t)w * G.max_act + t];
+    while (mm) {
+      const int q = w * 32 + __ffs(mm) - 1;
+      mm &= mm - 1;
+      const double* src = G.part + ((size_t)q * G.max_act + t) * (1 + D);
+      M += src[0];
 #pragma unroll
-    for (int i = 0; i < D; i++) mom[i] += src[q * (1 + D) + 1 + i];
+      for (int i = 0; i < D; i++) mom[i] += src[1 + i];
+    }
   }
   double dU[D];
 #pragma unroll
@@ -622,173 +796,275 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
 }
 
 // ---------------------------------------------------------------------------
-// K2 (+ the particle half of K3): kinematics, stress, force operator.
-// DF = I + sum_A DU_A (x) gradN_A with gradN_a = -p_a J^-1 l_a  (compute-Strains.c:20-44,
-// LME.c:836-891); F_n1 = DF F_n (compute-Strains.c:76-105); J > 0 (U-Verlet.c:608-613);
-// rho /= det DF (U-Verlet.c:630-632); stress (Constitutive.c:18-258);
-// G_p = V0 tau DF^-T J^-1 so that f_A = sum_p N_A G_p l_A  ==  -V0 tau (DF^-T gradN_A)
-// (U-Newmark-beta.c:1257-1374 with Shape-Functions.c:405-448).
+// K2 + K3 (fused): kinematics, stress, and the cell sums of the nodal forces.
+//   particle phase: DF = I + sum_A DU_A (x) gradN_A with gradN_a = -p_a J^-1 l_a (compute-Strains.c:20-44,
+//     LME.c:836-891); F_n1 = DF F_n (compute-Strains.c:76-105); J > 0 (U-Verlet.c:608-613);
+//     rho /= det DF (U-Verlet.c:630-632); stress (Constitutive.c:18-258);
+//     G_p = V0 tau DF^-T J^-1, so that f_A = sum_p N_A (G_p l_A + t_p) == -V0 tau (DF^-T gradN_A) + N_A T A0
+//     (U-Newmark-beta.c:1257-1374 with Shape-Functions.c:405-448; tractions U-Verlet.c:805-902).
+//   cell phase: that sum over the cell's particles, weights from shared memory.
 // MAT: compile-time material law when every particle uses the same one (keeps the Matsuoka-Nakai
 // Newton out of the register budget of the other laws); -1 = mixed, dispatched per particle.
-template <int D, int W, int MAT>
-__global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 4 : 2) k_kin_stress(MeshDev m, PartDev P, GridDev G, StepParams sp, int* err) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P.np) return;
-  const int np = P.np;
+template <int D, int W, int MAT, bool CACHE>
+__global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_force(MeshDev m, PartDev P, GridDev G,
+                                                                                StepParams sp, BlockCfg cfg, int* err,
+                                                                                int has_traction) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const LayoutB<D, W, CACHE> L(cfg);
+  int* s_cs = (int*)(smem + L.cs); int* s_base = (int*)(smem + L.base); int* s_len = (int*)(smem + L.len);
+  int* s_rank = (int*)(smem + L.rank); unsigned char* s_q = smem + L.q; double* s_X = (double*)(smem + L.X);
+  double* s_U = (double*)(smem + L.U); double* s_pa = (double*)(smem + L.pa); double* s_zinv = (double*)(smem + L.zinv);
+  double* s_G = (double*)(smem + L.G); double* s_px = (double*)(smem + L.px); double* s_trac = (double*)(smem + L.trac);
+  uint32_t* s_mask = (uint32_t*)(smem + L.mask);
+  double* s_plam = (double*)(smem + L.plam); double* s_pbeta = (double*)(smem + L.pbeta);
+  double* s_tab = (double*)(smem + L.tab);
+  int* s_B = (int*)(smem + L.B);
+  if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
+  const int nocc = *G.n_occ, ngroups = (nocc + cfg.C - 1) / cfg.C;
+  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ...
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  Blk b;
+  blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
+  stage_nodes<D, true, 1>(m, G, cfg.SL, b.ncell, s_base, s_len, s_rank, s_q, s_X, s_U, nullptr);
+  __syncthreads();
+  const int SL = cfg.SL, np = P.np;
   constexpr int T = (D == 2) ? 5 : 9;
-  const int I0 = P.I0[p];
-  const int base = m.r2p[I0];
-  double xp[D], lam[D];
+  for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
+    const int nb = min(cfg.PCAP, b.t1 - tb);
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+      const int t = tb + j, p = G.plist[t];
+      const int ci = cell_of(s_cs, b.ncell, t);
+      const double* Xc = s_X + (size_t)ci * SL * D;
+      const double* Uc = s_U + (size_t)ci * SL * D;
+      double xp[D], lam[D];
 #pragma unroll
-  for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
-  const double beta = P.beta[p];
-  double Z = 0.0, r[D], JJ[D * D], Bm[D * D];
+      for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
+      const double beta = P.beta[p];
+      uint32_t mk[W];
 #pragma unroll
-  for (int i = 0; i < D; i++) r[i] = 0.0;
+      for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
+      // particle state requested now, consumed after the neighbour loop (loads overlap the loop)
+      double Fn[D * D], be[T];
 #pragma unroll
-  for (int i = 0; i < D * D; i++) { JJ[i] = 0.0; Bm[i] = 0.0; }
-  {
-    uint32_t mw[W];
+      for (int i = 0; i < D * D; i++) Fn[i] = P.F_n[(size_t)i * np + p];
+      const double rho_p = P.rho[p], V0 = P.vol0[p];
+      const int mid = P.matidx[p];
+      const bool plastic = (MAT >= 0) ? (MAT != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) : true;
+      double eps = 0.0, kap = 0.0;
+      if (plastic) {
 #pragma unroll
-    for (int w = 0; w < W; w++) mw[w] = P.mask[(size_t)w * np + p];
-    int wcur = 0, node[NLPS_GROUP];
-    while (next_group<W>(m, base, mw, wcur, node) > 0) {
-      double Xn[NLPS_GROUP][D], dUn[NLPS_GROUP][D];
+        for (int i = 0; i < T; i++) be[i] = P.be_n[(size_t)i * np + p];
+        eps = P.eps_n[p];
+        kap = P.kap_n[p];
+      }
+      double Z = 0.0, r[D], JJ[D * D], Bm[D * D];
 #pragma unroll
-      for (int u = 0; u < NLPS_GROUP; u++)
+      for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < D; i++) { Xn[u][i] = 0.0; dUn[u][i] = 0.0; }
-#pragma unroll
-      for (int u = 0; u < NLPS_GROUP; u++)
-        if (node[u] >= 0) {
-          ldvec<D>(&m.X[(size_t)node[u] * NS<D>::X], Xn[u]);
-          ldvec<D>(&G.UA[(size_t)node[u] * 2 * NS<D>::X], dUn[u]);
-        }
-#pragma unroll
-      for (int u = 0; u < NLPS_GROUP; u++) {
-        if (node[u] < 0) continue;
-        double l[D], ll = 0.0, lx = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-          l[i] = xp[i] - Xn[u][i];
-          ll += l[i] * l[i];
-          lx += l[i] * lam[i];
-        }
-        double e = exp(-beta * ll + lx);
-        Z += e;
+      for (int i = 0; i < D * D; i++) { JJ[i] = 0.0; Bm[i] = 0.0; }
+      for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) {
+        double l0[D], l1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) {
-          r[i] += e * l[i];
+          l0[i] = xp[i] - Xc[k0 * D + i];
+          l1[i] = xp[i] - Xc[k1 * D + i];
+          ll0 += l0[i] * l0[i];
+          ll1 += l1[i] * l1[i];
+          lx0 += l0[i] * lam[i];
+          lx1 += l1[i] * lam[i];
+        }
+        const double e0 = fexp(-beta * ll0 + lx0, s_tab);
+        double e1 = fexp(-beta * ll1 + lx1, s_tab);
+        e1 = two ? e1 : 0.0;
+        if (CACHE) {
+          s_pa[(size_t)j * SL + k0] = e0;
+          if (two) s_pa[(size_t)j * SL + k1] = e1;
+        }
+        Z += e0;
 #pragma unroll
-          for (int j = 0; j < D; j++) {
-            if (j >= i) JJ[i * D + j] += e * l[i] * l[j];
-            Bm[i * D + j] += e * dUn[u][i] * l[j];
+        for (int i = 0; i < D; i++) {
+          r[i] += e0 * l0[i];
+          const double eu = e0 * Uc[k0 * D + i];
+#pragma unroll
+          for (int jj = 0; jj < D; jj++) {
+            if (jj >= i) JJ[i * D + jj] += e0 * l0[i] * l0[jj];
+            Bm[i * D + jj] += eu * l0[jj];
           }
         }
+        Z += e1;
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          r[i] += e1 * l1[i];
+          const double eu = e1 * Uc[k1 * D + i];
+#pragma unroll
+          for (int jj = 0; jj < D; jj++) {
+            if (jj >= i) JJ[i * D + jj] += e1 * l1[i] * l1[jj];
+            Bm[i * D + jj] += eu * l1[jj];
+          }
+        }
+      });
+      const double Zi = 1.0 / Z;
+#pragma unroll
+      for (int i = 0; i < D; i++) r[i] *= Zi;
+#pragma unroll
+      for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int jj = i; jj < D; jj++) {
+          JJ[i * D + jj] = JJ[i * D + jj] * Zi - r[i] * r[jj];
+          JJ[jj * D + i] = JJ[i * D + jj];
+        }
+      double Ji[D * D];
+      inverse<D>(JJ, Ji);
+      double DF[D * D], Fn1[D * D];
+#pragma unroll
+      for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int jj = 0; jj < D; jj++) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) s += Bm[i * D + k] * Ji[k * D + jj];
+          DF[i * D + jj] = ((i == jj) ? 1.0 : 0.0) - s * Zi;
+        }
+#pragma unroll
+      for (int i = 0; i < D; i++)
+#pragma unroll
+        for (int jj = 0; jj < D; jj++) {
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) s += DF[i * D + k] * Fn[k * D + jj];
+          Fn1[i * D + jj] = s;
+          P.F_n1[(size_t)(i * D + jj) * np + p] = s;
+          P.DF[(size_t)(i * D + jj) * np + p] = DF[i * D + jj];
+        }
+      const double J1 = det<D>(Fn1);
+      P.J_n1[p] = J1;
+      bool ok = true;
+      double Gp[D * D];
+#pragma unroll
+      for (int i = 0; i < D * D; i++) Gp[i] = 0.0;
+      if (J1 <= 0.0) { latch_error(err, NLPS_ERR_NEGATIVE_JACOBIAN, P.orig[p]); ok = false; }
+      if (ok) {
+        const double dJ = det<D>(DF);
+        P.rho[p] = rho_p / dJ;
+        // constitutive update
+        const MatParams& mat = c_mat[mid];
+        double tau[T], Wp = 0.0;
+        const int mtype = (MAT >= 0) ? MAT : mat.type;
+        int st = 0;
+        if (mtype == NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
+          stress_neo_hookean<D>(mat, Fn1, J1, tau, Wp);
+        } else {
+          double cep[D * D];
+          if (MAT == NLPS_MAT_DRUCKER_PRAGER) st = stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+          else if (MAT == NLPS_MAT_MATSUOKA_NAKAI) st = stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+          else st = (mtype == NLPS_MAT_DRUCKER_PRAGER) ? stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep)
+                                                       : stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+          if (st != 0) { latch_error(err, st, P.orig[p]); ok = false; }
+          if (ok) {
+#pragma unroll
+            for (int i = 0; i < T; i++) P.be_n1[(size_t)i * np + p] = be[i];
+            P.eps_n1[p] = eps;
+            P.kap_n1[p] = kap;
+            if (sp.rp.want_cep)
+#pragma unroll
+              for (int i = 0; i < D * D; i++) P.cep[(size_t)i * np + p] = cep[i];
+          }
+        }
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < T; i++) P.stress[(size_t)i * np + p] = tau[i];
+          P.W[p] = Wp;
+          // force operator G = V0 * tau * DF^-T * J^-1
+          double DFi[D * D];
+          const double dd = inverse<D>(DF, DFi);
+          if (dd == 0.0) { latch_error(err, NLPS_ERR_SINGULAR_DF, P.orig[p]); ok = false; }
+          double tA[D * D];
+#pragma unroll
+          for (int i = 0; i < D; i++)
+#pragma unroll
+            for (int jj = 0; jj < D; jj++) {
+              double s = 0.0;
+#pragma unroll
+              for (int k = 0; k < D; k++) s += tau[i * D + k] * DFi[jj * D + k];  // tau * DF^-T
+              tA[i * D + jj] = s;
+            }
+#pragma unroll
+          for (int i = 0; i < D; i++)
+#pragma unroll
+            for (int jj = 0; jj < D; jj++) {
+              double s = 0.0;
+#pragma unroll
+              for (int k = 0; k < D; k++) s += tA[i * D + k] * Ji[k * D + jj];
+              Gp[i * D + jj] = V0 * s;
+            }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < D * D; i++) s_G[j * D * D + i] = Gp[i];
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        s_px[j * D + i] = xp[i];
+        s_trac[j * D + i] = has_traction ? P.trac[(size_t)i * np + p] : 0.0;
+        if (!CACHE) s_plam[j * D + i] = lam[i];
+      }
+      if (!CACHE) s_pbeta[j] = beta;
+      s_zinv[j] = ok ? Zi : 0.0;
+#pragma unroll
+      for (int w = 0; w < W; w++) s_mask[j * W + w] = ok ? mk[w] : 0u;
+    }
+    __syncthreads();
+    // ---- cell phase: f_A partials, one thread per (cell, 2-ring node) pair
+    for (int e = threadIdx.x; e < b.ncell * SL; e += blockDim.x) {
+      const int rank = s_rank[e];
+      if (rank < 0) continue;
+      const int c = e / SL, k = e - c * SL;
+      const int ja = max(s_cs[c], tb) - tb, jb = min(s_cs[c + 1], tb + nb) - tb;
+      if (ja >= jb) continue;
+      const bool first = s_cs[c] >= tb;
+      const int kw = k >> 5;
+      const uint32_t kb = 1u << (k & 31);
+      double XA[D], f[D];
+#pragma unroll
+      for (int i = 0; i < D; i++) { XA[i] = s_X[(size_t)e * D + i]; f[i] = 0.0; }
+      for (int j = ja; j < jb; j++) {
+        if (!(s_mask[j * W + kw] & kb)) continue;
+        double l[D], N;
+#pragma unroll
+        for (int i = 0; i < D; i++) l[i] = s_px[j * D + i] - XA[i];
+        if (CACHE) {
+          N = s_pa[(size_t)j * SL + k] * s_zinv[j];
+        } else {
+          double ll = 0.0, lx = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; i++) { ll += l[i] * l[i]; lx += l[i] * s_plam[j * D + i]; }
+          N = fexp(-s_pbeta[j] * ll + lx, s_tab) * s_zinv[j];
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+          double gl = s_trac[j * D + i];
+#pragma unroll
+          for (int kk = 0; kk < D; kk++) gl += s_G[j * D * D + i * D + kk] * l[kk];
+          f[i] += N * gl;
+        }
+      }
+      double* dst = G.part + ((size_t)s_q[e] * G.max_act + rank) * D;
+      if (first) {
+#pragma unroll
+        for (int i = 0; i < D; i++) dst[i] = f[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < D; i++) dst[i] += f[i];
       }
     }
+    __syncthreads();
   }
-  const double Zi = 1.0 / Z;
-#pragma unroll
-  for (int i = 0; i < D; i++) r[i] *= Zi;
-#pragma unroll
-  for (int i = 0; i < D; i++)
-#pragma unroll
-    for (int j = i; j < D; j++) {
-      JJ[i * D + j] = JJ[i * D + j] * Zi - r[i] * r[j];
-      JJ[j * D + i] = JJ[i * D + j];
-    }
-  double Ji[D * D];
-  inverse<D>(JJ, Ji);
-  double DF[D * D], Fn[D * D], Fn1[D * D];
-#pragma unroll
-  for (int i = 0; i < D; i++)
-#pragma unroll
-    for (int j = 0; j < D; j++) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < D; k++) s += Bm[i * D + k] * Ji[k * D + j];
-      DF[i * D + j] = ((i == j) ? 1.0 : 0.0) - s * Zi;
-      Fn[i * D + j] = P.F_n[(size_t)(i * D + j) * np + p];
-    }
-#pragma unroll
-  for (int i = 0; i < D; i++)
-#pragma unroll
-    for (int j = 0; j < D; j++) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < D; k++) s += DF[i * D + k] * Fn[k * D + j];
-      Fn1[i * D + j] = s;
-      P.F_n1[(size_t)(i * D + j) * np + p] = s;
-      P.DF[(size_t)(i * D + j) * np + p] = DF[i * D + j];
-    }
-  const double J1 = det<D>(Fn1);
-  P.J_n1[p] = J1;
-  if (J1 <= 0.0) { latch_error(err, NLPS_ERR_NEGATIVE_JACOBIAN, p); return; }
-  const double dJ = det<D>(DF);
-  P.rho[p] = P.rho[p] / dJ;
-
-  // constitutive update
-  const MatParams& mat = c_mat[P.matidx[p]];
-  double tau[T], Wp = 0.0;
-  const int mtype = (MAT >= 0) ? MAT : mat.type;
-  if (mtype == NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
-    stress_neo_hookean<D>(mat, Fn1, J1, tau, Wp);
-  } else {
-    constexpr int TB = (D == 2) ? 5 : 9;
-    double be[TB], cep[D * D];
-#pragma unroll
-    for (int i = 0; i < TB; i++) be[i] = P.be_n[(size_t)i * np + p];
-    double eps = P.eps_n[p], kap = P.kap_n[p];
-    int st;
-    if (MAT == NLPS_MAT_DRUCKER_PRAGER) st = stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
-    else if (MAT == NLPS_MAT_MATSUOKA_NAKAI) st = stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
-    else st = (mtype == NLPS_MAT_DRUCKER_PRAGER) ? stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep)
-                                                 : stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
-    if (st != 0) { latch_error(err, st, p); return; }
-#pragma unroll
-    for (int i = 0; i < TB; i++) P.be_n1[(size_t)i * np + p] = be[i];
-    P.eps_n1[p] = eps;
-    P.kap_n1[p] = kap;
-    if (sp.rp.want_cep)
-#pragma unroll
-      for (int i = 0; i < D * D; i++) P.cep[(size_t)i * np + p] = cep[i];
-  }
-#pragma unroll
-  for (int i = 0; i < T; i++) P.stress[(size_t)i * np + p] = tau[i];
-  P.W[p] = Wp;
-
-  // force operator G = V0 * tau * DF^-T * J^-1
-  double DFi[D * D];
-  double dd = inverse<D>(DF, DFi);
-  if (dd == 0.0) { latch_error(err, NLPS_ERR_SINGULAR_DF, p); return; }
-  const double V0 = P.vol0[p];
-  double tA[D * D];
-#pragma unroll
-  for (int i = 0; i < D; i++)
-#pragma unroll
-    for (int j = 0; j < D; j++) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < D; k++) s += tau[i * D + k] * DFi[j * D + k];  // tau * DF^-T
-      tA[i * D + j] = s;
-    }
-  double* rec = P.rec + (size_t)p * Rec<D>::SIZE;
-#pragma unroll
-  for (int i = 0; i < D; i++)
-#pragma unroll
-    for (int j = 0; j < D; j++) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < D; k++) s += tA[i * D + k] * Ji[k * D + j];
-      rec[Rec<D>::G + i * D + j] = V0 * s;
-    }
+  }  // cell groups
 }
 
 // Neumann tractions: per loaded particle t_p = sum_loads T(step) * A0_p, A0 = Vol_0 / thickness
-// in 2D (U-Verlet.c:826-869).  Written into the gather record (zero for unloaded particles).
+// in 2D (U-Verlet.c:826-869), into P.trac (zero for unloaded particles).
 struct NeuDev {
-  int n_entries;        // flattened (load, particle) pairs, load-major
+  int n_entries;        // flattened (load, particle) pairs, load-major; particle = the caller's id
   const int* part;
   const int* load;
   const int* load_dim;
@@ -797,23 +1073,15 @@ struct NeuDev {
   int maxdim, nsteps;
 };
 template <int D>
-__global__ void k_traction_clear(PartDev P) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P.np) return;
-#pragma unroll
-  for (int i = 0; i < D; i++) P.rec[(size_t)p * Rec<D>::SIZE + Rec<D>::TRAC + i] = 0.0;
-}
-template <int D>
 __global__ void k_traction(PartDev P, NeuDev nu, double thickness, int step) {
-  // serial over entries of one particle is not needed: entries of different loads may hit the same
-  // particle, so accumulate with fp64 global atomics (tiny set).
+  // entries of different loads may hit the same particle: accumulate with fp64 global atomics (tiny set)
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nu.n_entries) return;
-  int p = nu.part[e], b = nu.load[e];
+  int p = P.inv[nu.part[e]], b = nu.load[e];
   double A0 = P.vol0[p] / thickness;
   for (int k = 0; k < nu.load_dim[b] && k < D; k++) {
     size_t o = ((size_t)b * nu.maxdim + k) * nu.nsteps + step;
-    if (nu.dir[o] == 1) atomicAdd(&P.rec[(size_t)p * Rec<D>::SIZE + Rec<D>::TRAC + k], nu.val[o] * A0);
+    if (nu.dir[o] == 1) atomicAdd(&P.trac[(size_t)k * P.np + p], nu.val[o] * A0);
   }
 }
 
@@ -827,12 +1095,15 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
   double f[D];
 #pragma unroll
   for (int i = 0; i < D; i++) f[i] = 0.0;
-  const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
-  const double* src = G.part + (size_t)t * G.cap * (1 + D);
-  for (int q = 0; q < nq; q++) {
-    if (G.cnt[m.r2ti[q0 + q]] == 0) continue;
+  for (int w = 0; w < G.w2t; w++) {
+    uint32_t mm = G.occm[(size_t)w * G.max_act + t];
+    while (mm) {
+      const int q = w * 32 + __ffs(mm) - 1;
+      mm &= mm - 1;
+      const double* src = G.part + ((size_t)q * G.max_act + t) * D;
 #pragma unroll
-    for (int i = 0; i < D; i++) f[i] += src[q * (1 + D) + i];
+      for (int i = 0; i < D; i++) f[i] += src[i];
+    }
   }
   const double M = G.M[A];
   const unsigned fx = G.fixed[A];
@@ -847,65 +1118,79 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
 // K4: G2P + corrector (U-Verlet.c:963-1084).  The n+1 -> n roll of F, J, b_e, kappa, EPS is a
 // pointer swap on the host side of the engine.
 template <int D, int W>
-__global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, StepParams sp) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P.np) return;
-  const int np = P.np;
-  const int I0 = P.I0[p];
-  const int base = m.r2p[I0];
-  double xp[D], lam[D], a[D], du[D];
+__global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const LayoutC<D> L(cfg);
+  int* s_cs = (int*)(smem + L.cs); int* s_base = (int*)(smem + L.base); int* s_len = (int*)(smem + L.len);
+  int* s_rank = (int*)(smem + L.rank); double* s_X = (double*)(smem + L.X);
+  double* s_U = (double*)(smem + L.U); double* s_A = (double*)(smem + L.A);
+  double* s_tab = (double*)(smem + L.tab);
+  int* s_B = (int*)(smem + L.B);
+  if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
+  const int nocc = *G.n_occ, ngroups = (nocc + cfg.C - 1) / cfg.C;
+  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ...
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+  Blk b;
+  blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
+  stage_nodes<D, false, 2>(m, G, cfg.SL, b.ncell, s_base, s_len, s_rank, nullptr, s_X, s_U, s_A);
+  __syncthreads();
+  const int SL = cfg.SL, np = P.np;
+  for (int t = b.t0 + threadIdx.x; t < b.t1; t += blockDim.x) {
+    const int p = G.plist[t];
+    const int ci = cell_of(s_cs, b.ncell, t);
+    const double* Xc = s_X + (size_t)ci * SL * D;
+    const double* Uc = s_U + (size_t)ci * SL * D;
+    const double* Ac = s_A + (size_t)ci * SL * D;
+    double xp[D], lam[D], a[D], du[D], pvl[D], pds[D];
 #pragma unroll
-  for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; a[i] = 0.0; du[i] = 0.0; }
-  const double beta = P.beta[p];
-  double Z = 0.0;
-  {
-    uint32_t mw[W];
+    for (int i = 0; i < D; i++) {
+      xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; a[i] = 0.0; du[i] = 0.0;
+      pvl[i] = P.vel[i * np + p]; pds[i] = P.dis[i * np + p];  // consumed by the corrector after the loop
+    }
+    const double beta = P.beta[p];
+    double Z = 0.0;
+    uint32_t mk[W];
 #pragma unroll
-    for (int w = 0; w < W; w++) mw[w] = P.mask[(size_t)w * np + p];
-    int wcur = 0, node[NLPS_GROUP];
-    while (next_group<W>(m, base, mw, wcur, node) > 0) {
-      double Xn[NLPS_GROUP][D], An[NLPS_GROUP][D], dUn[NLPS_GROUP][D];
+    for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
+    for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) {
+      double ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
 #pragma unroll
-      for (int u = 0; u < NLPS_GROUP; u++)
-#pragma unroll
-        for (int i = 0; i < D; i++) { Xn[u][i] = 0.0; An[u][i] = 0.0; dUn[u][i] = 0.0; }
-#pragma unroll
-      for (int u = 0; u < NLPS_GROUP; u++)
-        if (node[u] >= 0) {
-          ldvec<D>(&m.X[(size_t)node[u] * NS<D>::X], Xn[u]);
-          ldvec<D>(&G.UA[(size_t)node[u] * 2 * NS<D>::X], dUn[u]);
-          ldvec<D>(&G.UA[(size_t)node[u] * 2 * NS<D>::X + NS<D>::X], An[u]);
-        }
-#pragma unroll
-      for (int u = 0; u < NLPS_GROUP; u++) {
-        if (node[u] < 0) continue;
-        double ll = 0.0, lx = 0.0;
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-          double l = xp[i] - Xn[u][i];
-          ll += l * l;
-          lx += l * lam[i];
-        }
-        double e = exp(-beta * ll + lx);
-        Z += e;
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-          a[i] += e * An[u][i];
-          du[i] += e * dUn[u][i];
-        }
+      for (int i = 0; i < D; i++) {
+        const double l0 = xp[i] - Xc[k0 * D + i], l1 = xp[i] - Xc[k1 * D + i];
+        ll0 += l0 * l0;
+        ll1 += l1 * l1;
+        lx0 += l0 * lam[i];
+        lx1 += l1 * lam[i];
       }
+      const double e0 = fexp(-beta * ll0 + lx0, s_tab);
+      double e1 = fexp(-beta * ll1 + lx1, s_tab);
+      e1 = two ? e1 : 0.0;
+      Z += e0;
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        a[i] += e0 * Ac[k0 * D + i];
+        du[i] += e0 * Uc[k0 * D + i];
+      }
+      Z += e1;
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+        a[i] += e1 * Ac[k1 * D + i];
+        du[i] += e1 * Uc[k1 * D + i];
+      }
+    });
+    const double Zi = 1.0 / Z;
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      const double ai = a[i] * Zi, di = du[i] * Zi;
+      P.acc[i * np + p] = ai;
+      P.ddis[i * np + p] = di;
+      P.vel[i * np + p] = pvl[i] + 0.5 * sp.dt * ai;
+      P.x[i * np + p] = xp[i] + di;
+      P.dis[i * np + p] = pds[i] + di;
     }
   }
-  const double Zi = 1.0 / Z;
-#pragma unroll
-  for (int i = 0; i < D; i++) {
-    double ai = a[i] * Zi, di = du[i] * Zi;
-    P.acc[i * np + p] = ai;
-    P.ddis[i * np + p] = di;
-    P.vel[i * np + p] += 0.5 * sp.dt * ai;
-    P.x[i * np + p] = xp[i] + di;
-    P.dis[i * np + p] += di;
-  }
+  __syncthreads();
+  }  // cell groups
 }
 
 
@@ -926,17 +1211,30 @@ __global__ void k_sync_inert(PartDev P) {
 }
 
 // AoS (host layout, n x cols) <-> SoA (cols x n)
-__global__ void k_aos_to_soa(const double* aos, double* soa, int n, int cols, int aos_stride, int col0) {
+// (row of the caller's particle orig[p]  <->  physical slot p)
+__global__ void k_aos_to_soa(const double* aos, double* soa, const int* orig, int n, int cols, int aos_stride, int col0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n * cols) return;
   int c = (int)(i / n), p = (int)(i % n);
-  soa[i] = aos[(size_t)p * aos_stride + col0 + c];
+  soa[i] = aos[(size_t)orig[p] * aos_stride + col0 + c];
 }
-__global__ void k_soa_to_aos(const double* soa, double* aos, int n, int cols, int aos_stride, int col0) {
+__global__ void k_soa_to_aos(const double* soa, double* aos, const int* orig, int n, int cols, int aos_stride, int col0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n * cols) return;
   int p = (int)(i / cols), c = (int)(i % cols);
-  aos[(size_t)p * aos_stride + col0 + c] = soa[(size_t)c * n + p];
+  aos[(size_t)orig[p] * aos_stride + col0 + c] = soa[(size_t)c * n + p];
+}
+__global__ void k_unpermute_int(const int* src, int* dst, const int* orig, int n) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[orig[p]] = src[p];
+}
+__global__ void k_permute_int(const int* src, int* dst, const int* orig, int n) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) dst[p] = src[orig[p]];
+}
+__global__ void k_iota(int* a, int* b, int n) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) { a[p] = p; b[p] = p; }
 }
 __global__ void k_fill_d(double* a, size_t n, double v) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -952,11 +1250,11 @@ __global__ void k_expand_lists(MeshDev m, PartDev P, int W, int cap, int* lists)
     while (mm) {
       int b = 31 - __clz(mm);
       mm &= ~(1u << b);
-      if (o < cap) lists[(size_t)p * cap + o] = m.r2i[base + w * 32 + b];
+      if (o < cap) lists[(size_t)P.orig[p] * cap + o] = m.r2i[base + w * 32 + b];
       o++;
     }
   }
-  for (; o < cap; o++) lists[(size_t)p * cap + o] = -1;
+  for (; o < cap; o++) lists[(size_t)P.orig[p] * cap + o] = -1;
 }
 __global__ void k_export_nodal(GridDev G, int nn, int D, int which, double* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1027,6 +1325,16 @@ struct nlps_engine {
   int cap_r2 = 0;  // largest 2-ring row
   int uniform_mat = -1;  // material type shared by all materials, or -1
   int inert_synced = 0;
+  BlockCfg cfg{};          // cells per block / 2-ring row length / particle chunk of the cell-block kernels
+  size_t smemA = 0, smemB = 0, smemC = 0;
+  int cache_pa = 1;        // keep the shape-function weights of the particle phase in shared memory (2D)
+  int smem_set[K_COUNT] = {0};
+  int reorder_every = 25;  // physical cell-sort cadence (steps); the results do not depend on it
+  int steps_since_sort = 1 << 30;
+  long long n_reorders = 0;
+  int max_smem_optin = 0;
+  int sm_count = 0, grid_override = 0;
+  int grid_k[K_COUNT] = {0};  // blocks of the persistent cell-group kernels (SMs x resident blocks)
   std::vector<void*> allocs;
   // staging for AoS <-> SoA
   double* stage = nullptr;
@@ -1093,6 +1401,31 @@ static void transpose_csr(int nn, const int* ptr, const int* idx, std::vector<in
     }                                                                           \
   } while (0)
 
+// persistent cell-group kernels: dynamic shared memory opt-in and grid = SMs x resident blocks, both
+// resolved at the first launch of the instantiation this engine uses
+#define LAUNCH_SMEM(e, id, kernel, max_blocks, block, smem_bytes, ...)                           \
+  do {                                                                                          \
+    if (!(e)->smem_set[id]) {                                                                   \
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (e)->max_smem_optin); \
+      int _nb = 1;                                                                              \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&_nb, kernel, (block), (smem_bytes));       \
+      (e)->grid_k[id] = (e)->sm_count * std::max(1, _nb);                                       \
+      if ((e)->grid_override > 0) (e)->grid_k[id] = (e)->grid_override;                         \
+      (e)->smem_set[id] = 1;                                                                    \
+    }                                                                                           \
+    if ((e)->profile) cudaEventRecord((e)->ev0, (e)->stream);                                   \
+    kernel<<<std::min((max_blocks), (e)->grid_k[id]), (block), (smem_bytes), (e)->stream>>>(__VA_ARGS__); \
+    (e)->launches++;                                                                            \
+    if ((e)->profile) {                                                                         \
+      cudaEventRecord((e)->ev1, (e)->stream);                                                   \
+      cudaEventSynchronize((e)->ev1);                                                           \
+      float _ms = 0;                                                                            \
+      cudaEventElapsedTime(&_ms, (e)->ev0, (e)->ev1);                                           \
+      (e)->k_ms[id] += _ms;                                                                     \
+      (e)->k_n[id]++;                                                                           \
+    }                                                                                           \
+  } while (0)
+
 static inline int nblk(size_t n, int b) { return (int)((n + b - 1) / b); }
 
 static StepParams make_params(nlps_engine* e, int step, int update_I0) {
@@ -1119,7 +1452,7 @@ static int put_field(nlps_engine* e, const double* h, double* d, int cols, int a
   if (!h || !d) return 0;
   size_t n = (size_t)e->np * aos_stride;
   CUDA_OK(cudaMemcpyAsync(e->stage, h, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  k_aos_to_soa<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(e->stage, d, e->np, cols, aos_stride, col0);
+  k_aos_to_soa<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(e->stage, d, e->P.orig, e->np, cols, aos_stride, col0);
   CUDA_OK(cudaStreamSynchronize(e->stream));  // host buffer may be pageable; stage is reused
   return 0;
 }
@@ -1129,9 +1462,9 @@ static int get_field(nlps_engine* e, double* h, const double* d, int cols, int a
   size_t n = (size_t)e->np * aos_stride;
   if (cols != aos_stride) {
     // partial rows (2D tensors: 4 in-plane + slot 4): assemble the whole row on the device
-    if (d_extra) k_soa_to_aos<<<nblk((size_t)e->np, 256), 256, 0, e->stream>>>(d_extra, e->stage, e->np, 1, aos_stride, cols);
+    if (d_extra) k_soa_to_aos<<<nblk((size_t)e->np, 256), 256, 0, e->stream>>>(d_extra, e->stage, e->P.orig, e->np, 1, aos_stride, cols);
   }
-  k_soa_to_aos<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(d, e->stage, e->np, cols, aos_stride, col0);
+  k_soa_to_aos<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(d, e->stage, e->P.orig, e->np, cols, aos_stride, col0);
   CUDA_OK(cudaMemcpyAsync(h, e->stage, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
   return 0;
@@ -1165,6 +1498,45 @@ static int poll_error(nlps_engine* e) {
   return 0;
 }
 
+// physical re-sort of every particle array into the cell-sorted order (plist); afterwards plist is the
+// identity.  The results do not depend on when (or whether) this runs: cells are summed in the order of
+// the caller's particle ids and everything else is per particle.
+static void reorder_particles(nlps_engine* e) {
+  const int np = e->np, D = e->D, T = e->T, DD = D * D;
+  PartDev& P = e->P;
+  const int* pl = e->G.plist;
+  if (e->profile) cudaEventRecord(e->ev0, e->stream);
+  auto gd = [&](double* f, int cols) {
+    if (!f) return;
+    k_gather_rows<double><<<nblk((size_t)np * cols, 256), 256, 0, e->stream>>>(f, e->stage, pl, np, cols);
+    cudaMemcpyAsync(f, e->stage, sizeof(double) * (size_t)np * cols, cudaMemcpyDeviceToDevice, e->stream);
+    e->launches++;
+  };
+  auto gi = [&](int* f, int cols) {
+    k_gather_rows<int><<<nblk((size_t)np * cols, 256), 256, 0, e->stream>>>(f, (int*)e->stage, pl, np, cols);
+    cudaMemcpyAsync(f, e->stage, sizeof(int) * (size_t)np * cols, cudaMemcpyDeviceToDevice, e->stream);
+    e->launches++;
+  };
+  gd(P.x, D); gd(P.dis, D); gd(P.ddis, D); gd(P.vel, D); gd(P.acc, D); gd(P.lam, D);
+  gd(P.beta, 1); gd(P.mass, 1); gd(P.vol0, 1); gd(P.rho, 1); gd(P.W, 1);
+  gd(P.J_n, 1); gd(P.J_n1, 1); gd(P.eps_n, 1); gd(P.eps_n1, 1); gd(P.kap_n, 1); gd(P.kap_n1, 1);
+  gd(P.F_n, DD); gd(P.F_n1, DD); gd(P.DF, DD); gd(P.be_n, T); gd(P.be_n1, T); gd(P.stress, T); gd(P.cep, DD);
+  gd(P.Fs4, 1); gd(P.DFs4, 1);
+  gi(P.I0, 1); gi(P.nnodes, 1); gi(P.matidx, 1); gi(P.orig, 1); gi((int*)P.mask, e->W);
+  k_after_sort<<<nblk(np, 256), 256, 0, e->stream>>>(P, e->G);
+  e->launches++;
+  if (e->profile) {
+    cudaEventRecord(e->ev1, e->stream);
+    cudaEventSynchronize(e->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->k_ms[K_REORDER] += ms;
+    e->k_n[K_REORDER]++;
+  }
+  e->steps_since_sort = 0;
+  e->n_reorders++;
+}
+
 template <int D>
 static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predictor) {
   const int np = e->np, nn = e->nn;
@@ -1176,56 +1548,47 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
   LAUNCH(e, K_SCAN2, k_scan_tops, 1, 1024, e->G.scan_blk, nb, e->G.n_active, e->G.n_occ, e->npart_check);
   LAUNCH(e, K_SCAN3, k_scan_apply, nb, 256, e->G.packed, e->G.scan_blk, e->G.cell_start, e->G.occ_pos, e->G.act_pos, nn);
   LAUNCH(e, K_FILL, k_cell_fill, nblk(np, 256), 256, e->P, e->G);
-  LAUNCH(e, K_NODE_FINISH, k_node_finish, nblk(nn, 256), 256, e->mesh, e->G);
+  LAUNCH(e, K_NODE_FINISH, k_node_finish, nblk(nn, 256), 256, e->mesh, e->P, e->G);
+  if (e->reorder_every > 0 && e->steps_since_sort >= e->reorder_every) reorder_particles(e);
+  e->steps_since_sort++;
   StepParams sp = make_params(e, step, update_I0);
-  switch (e->W) {
-#define CASE_W(w) case w: { auto kfn = k_lme<D, w>; LAUNCH(e, K_LME, kfn, nblk(np, 128), 128, e->mesh, e->P, e->G, sp, e->err, do_predictor); } break;
-    CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8)
+  const int grid = nblk((size_t)e->max_occ, e->cfg.C);
+#define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, do_predictor); }
+#define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
+  switch (e->W) { CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8) }
 #undef CASE_W
-  }
-}
-template <int D, bool FORCE>
-static void launch_p2g_cell(nlps_engine* e, int id) {
-  const int it = (e->cap_r2 + 31) / 32;
-  const int grid = nblk((size_t)e->max_occ, 4 * (it == 1 ? 4 : 1));  // 4 warps per block, CPW cells per warp
-  switch (it) {
-    case 1: { auto kfn = k_p2g_cell<D, 1, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
-    case 2: { auto kfn = k_p2g_cell<D, 2, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
-    case 3: case 4: { auto kfn = k_p2g_cell<D, 4, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
-    default: { auto kfn = k_p2g_cell<D, 8, FORCE>; LAUNCH(e, id, kfn, grid, 128, e->mesh, e->P, e->G, e->has_traction); } break;
-  }
+#undef CASE_WC
 }
 template <int D>
 static void stage_p2g_mass_disp_t(nlps_engine* e, int step) {
-  // at most min(nn, np) cells are occupied; one warp per cell (surplus warps exit on n_occ)
-  launch_p2g_cell<D, false>(e, K_P2G_MASS_DISP);
   LAUNCH(e, K_GRID_DISP, k_grid_disp<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step);
 }
 template <int D>
 static void stage_kin_stress_t(nlps_engine* e, int step) {
+  if (e->has_traction) {
+    cudaMemsetAsync(e->P.trac, 0, sizeof(double) * (size_t)e->np * D, e->stream);
+    LAUNCH(e, K_TRACTION, k_traction<D>, nblk(e->neu.n_entries, 128), 128, e->P, e->neu, e->solver.thickness, step);
+  }
   StepParams sp = make_params(e, step, 1);
-  switch (e->W) {
-#define CASE_WM(w, mt) { auto kfn = k_kin_stress<D, w, mt>; LAUNCH(e, K_KIN_STRESS, kfn, nblk(e->np, 128), 128, e->mesh, e->P, e->G, sp, e->err); }
+  const int grid = nblk((size_t)e->max_occ, e->cfg.C);
+#define CASE_WMC(w, mt, c) { auto kfn = k_kin_force<D, w, mt, c>; LAUNCH_SMEM(e, K_KIN_FORCE, kfn, grid, e->cfg.threads, e->smemB, e->mesh, e->P, e->G, sp, e->cfg, e->err, e->has_traction); }
+#define CASE_WM(w, mt) if (e->cache_pa) CASE_WMC(w, mt, true) else CASE_WMC(w, mt, false)
 #define CASE_W(w) case w: switch (e->uniform_mat) { case 0: CASE_WM(w, 0) break; case 1: CASE_WM(w, 1) break; case 2: CASE_WM(w, 2) break; default: CASE_WM(w, -1) break; } break;
-    CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8)
+  switch (e->W) { CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8) }
 #undef CASE_W
 #undef CASE_WM
-  }
+#undef CASE_WMC
 }
 template <int D>
 static void stage_force_t(nlps_engine* e, int step) {
-  if (e->has_traction) {
-    LAUNCH(e, K_TRACTION, k_traction_clear<D>, nblk(e->np, 256), 256, e->P);
-    LAUNCH(e, K_TRACTION, k_traction<D>, nblk(e->neu.n_entries, 128), 128, e->P, e->neu, e->solver.thickness, step);
-  }
-  launch_p2g_cell<D, true>(e, K_P2G_FORCE);
   LAUNCH(e, K_GRID_ACC, k_grid_acc<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step);
 }
 template <int D>
 static void stage_g2p_t(nlps_engine* e, int step) {
   StepParams sp = make_params(e, step, 1);
+  const int grid = nblk((size_t)e->max_occ, e->cfg.C);
   switch (e->W) {
-#define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH(e, K_G2P, kfn, nblk(e->np, 128), 128, e->mesh, e->P, e->G, sp); } break;
+#define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH_SMEM(e, K_G2P, kfn, grid, e->cfg.threads, e->smemC, e->mesh, e->P, e->G, sp, e->cfg); } break;
     CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8)
 #undef CASE_W
   }
@@ -1345,10 +1708,55 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
       dev_alloc(e, &G.plist, np) || dev_alloc(e, &G.act_list, nn) || dev_alloc(e, &G.n_active, 1) ||
       dev_alloc(e, &G.packed, nn) || dev_alloc(e, &G.scan_blk, (size_t)nblk(nn, SCAN_ITEMS) + 1) ||
       dev_alloc(e, &G.act_pos, nn) || dev_alloc(e, &G.occ_pos, nn) || dev_alloc(e, &G.occ_list, e->max_occ) ||
-      dev_alloc(e, &G.n_occ, 1) || dev_alloc(e, &e->npart_check, 1) || dev_alloc(e, &e->err, 2))
+      dev_alloc(e, &G.n_occ, 1) || dev_alloc(e, &e->npart_check, 1) || dev_alloc(e, &e->err, 2) ||
+      dev_alloc(e, &G.arank, nn) || dev_alloc(e, &G.occ_meta, (size_t)e->max_occ + 1))
     return 1;
   G.cap = maxr2t;
+  G.max_act = e->max_act;
+  G.w2t = (maxr2t + 31) / 32;
   if (dev_alloc(e, &G.part, (size_t)e->max_act * G.cap * (1 + D))) return 1;
+  if (dev_alloc(e, &G.occm, (size_t)e->max_act * G.w2t)) return 1;
+  // ---- cell-block kernel configuration: cells per block, shared-memory budget
+  {
+    CUDA_OK(cudaDeviceGetAttribute(&e->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device));
+    BlockCfg& c = e->cfg;
+    c.SL = maxr2;
+    c.threads = 128;
+    if (const char* s_ = getenv("NLPS_THREADS")) c.threads = std::max(32, atoi(s_) / 32 * 32);
+    e->cache_pa = (D == 2);
+    if (const char* s_ = getenv("NLPS_CACHE_PA")) e->cache_pa = atoi(s_) != 0;
+    c.C = 32;
+    if (const char* s_ = getenv("NLPS_CELLS_PER_BLOCK")) c.C = std::max(1, atoi(s_));
+    auto sizes = [&](const BlockCfg& k, size_t& a, size_t& b, size_t& g) {
+      if (D == 2) {
+        switch (e->W) {
+#define SZ_(d, w) case w: a = e->cache_pa ? LayoutA<d, w, true>(k).total : LayoutA<d, w, false>(k).total; \
+                          b = e->cache_pa ? LayoutB<d, w, true>(k).total : LayoutB<d, w, false>(k).total; break;
+          SZ_(2, 1) SZ_(2, 2) SZ_(2, 4) SZ_(2, 8)
+        }
+        g = LayoutC<2>(k).total;
+      } else {
+        switch (e->W) { SZ_(3, 1) SZ_(3, 2) SZ_(3, 4) SZ_(3, 8) }
+#undef SZ_
+        g = LayoutC<3>(k).total;
+      }
+    };
+    // keep at least two blocks per SM resident: halve the cells per block until the largest layout fits
+    const size_t budget = std::min<size_t>((size_t)e->max_smem_optin, 100 * 1024);
+    for (;;) {
+      const double ppc = std::max(1.0, (double)np / std::max(1, e->max_occ));  // particles per occupied cell (lower bound)
+      c.PCAP = std::max(32, (int)(c.C * std::max(ppc, (D == 2) ? 4.0 : 8.0) * 1.25 + 0.5));
+      if (const char* s_ = getenv("NLPS_PCAP")) c.PCAP = std::max(1, atoi(s_));
+      sizes(c, e->smemA, e->smemB, e->smemC);
+      if (std::max(e->smemA, std::max(e->smemB, e->smemC)) <= budget || c.C == 1) break;
+      c.C /= 2;
+    }
+    if (std::max(e->smemA, std::max(e->smemB, e->smemC)) > (size_t)e->max_smem_optin)
+      return set_err(err, err_len, "2-ring too large for the shared-memory staging");
+    if (const char* s_ = getenv("NLPS_REORDER_EVERY")) e->reorder_every = atoi(s_);
+    CUDA_OK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
+    if (const char* s_ = getenv("NLPS_GRID")) e->grid_override = std::max(1, atoi(s_));
+  }
   // ---- boundary conditions: node -> boundaries CSR (boundary order preserved)
   {
     int maxdim = 1;
@@ -1447,11 +1855,13 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   A_(F_n, DD) A_(F_n1, DD) A_(DF, DD) A_(be_n, TBv) A_(be_n1, TBv) A_(stress, T) A_(cep, DD)
   A_(Fs4, 1) A_(DFs4, 1)
 #undef A_
-  if (dev_alloc(e, &P.rec, (size_t)np * (D == 2 ? Rec<2>::SIZE : Rec<3>::SIZE))) return 1;
+  P.trac = nullptr;
+  if (e->has_traction && dev_alloc(e, &P.trac, (size_t)np * D)) return 1;
   if (dev_alloc(e, &P.I0, np) || dev_alloc(e, &P.nnodes, np) || dev_alloc(e, &P.matidx, np) ||
-      dev_alloc(e, &P.mask, (size_t)np * e->W))
+      dev_alloc(e, &P.orig, np) || dev_alloc(e, &P.inv, np) || dev_alloc(e, &P.mask, (size_t)np * e->W))
     return 1;
-  e->stage_doubles = (size_t)np * std::max(T, DD);
+  k_iota<<<nblk(np, 256), 256, 0, e->stream>>>(P.orig, P.inv, np);
+  e->stage_doubles = (size_t)np * std::max(std::max(T, DD), (e->W + 1) / 2);
   if (dev_alloc(e, &e->stage, e->stage_doubles)) return 1;
   // defaults as allocate_U_vars__Fields__ leaves them (identity tensors, J = 1)
   auto fill = [&](double* a, size_t n, double v) { k_fill_d<<<nblk(n, 256), 256, 0, e->stream>>>(a, n, v); };
@@ -1555,8 +1965,15 @@ int nlps_b200_download(nlps_engine* e, nlps_particles* out) {
       get_field(e, out->Kappa_n, P.kap_n, 1, 1, 0) || get_field(e, out->Kappa_n1, P.kap_n1, 1, 1, 0) ||
       get_field(e, out->Beta, P.beta, 1, 1, 0))
     return 1;
-  if (out->I0) CUDA_OK(cudaMemcpyAsync(out->I0, P.I0, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
-  if (out->NumberNodes) CUDA_OK(cudaMemcpyAsync(out->NumberNodes, P.nnodes, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
+  if (out->I0) {
+    k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(P.I0, (int*)e->stage, P.orig, e->np);
+    CUDA_OK(cudaMemcpyAsync(out->I0, e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
+  if (out->NumberNodes) {
+    k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(P.nnodes, (int*)e->stage, P.orig, e->np);
+    CUDA_OK(cudaMemcpyAsync(out->NumberNodes, e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
+  }
   CUDA_OK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -1631,8 +2048,10 @@ int nlps_b200_get_lists(nlps_engine* e, int* counts, int* lists, int cap) {
   CUDA_OK(cudaMalloc(&tmp, n * sizeof(int)));
   k_expand_lists<<<nblk(e->np, 128), 128, 0, e->stream>>>(e->mesh, e->P, e->W, cap, tmp);
   cudaError_t st = cudaMemcpyAsync(lists, tmp, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-  if (st == cudaSuccess && counts)
-    st = cudaMemcpyAsync(counts, e->P.nnodes, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream);
+  if (st == cudaSuccess && counts) {
+    k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P.nnodes, (int*)e->stage, e->P.orig, e->np);
+    st = cudaMemcpyAsync(counts, e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream);
+  }
   if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
   cudaFree(tmp);
   return st == cudaSuccess ? 0 : 1;
