@@ -103,7 +103,7 @@ struct StepParams {
 // One thread block works on C consecutive OCCUPIED cells (a cell = all particles with the same closest
 // node I0) = one contiguous run of the cell-sorted particle order.  SL = longest 2-ring row, PCAP =
 // particles whose per-particle scratch fits in shared memory at once (longer runs go in chunks).
-struct BlockCfg { int C, SL, PCAP, threads; };
+struct BlockCfg { int C, SL, PCAP, threads; unsigned magic; };  // magic = ceil(2^21 / SL): e / SL == (e * magic) >> 21 for e < C*SL (checked at create)
 
 struct Carve {
   size_t off = 0;
@@ -456,20 +456,22 @@ __device__ __forceinline__ void blk_prologue(const GridDev& G, const BlockCfg& c
 // thread in flight (ids first, then all their data: two global round trips for the whole block); the
 // per-particle loops then run out of shared memory with no dependent global gathers.
 template <int D, bool WANT_Q, int NF>
-__device__ __forceinline__ void stage_nodes(const MeshDev& m, const GridDev& G, int SL, int ncell, const int* s_base,
-                                            const int* s_len, int* s_rank, unsigned char* s_q, double* s_X,
-                                            double* s_U, double* s_A) {
+__device__ __forceinline__ void stage_nodes(const MeshDev& m, const GridDev& G, int SL, unsigned magic, int ncell,
+                                            const int* s_base, const int* s_len, int* s_rank, unsigned char* s_q,
+                                            double* s_X, double* s_U, double* s_A) {
   constexpr int U = 4;
   const int npairs = ncell * SL;
   for (int e0 = threadIdx.x; e0 < npairs; e0 += U * blockDim.x) {
-    int node[U], idx[U];
+    int node[U], idx[U], es[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int e = e0 + u * blockDim.x;
       node[u] = -1;
       idx[u] = 0;
+      es[u] = -1;
       if (e < npairs) {
-        const int c = e / SL, k = e - c * SL;
+        const int c = (int)(((unsigned)e * magic) >> 21), k = e - c * SL;
+        es[u] = e;
         if (k < s_len[c]) { idx[u] = s_base[c] + k; node[u] = m.r2i[idx[u]]; }
       }
     }
@@ -497,8 +499,8 @@ __device__ __forceinline__ void stage_nodes(const MeshDev& m, const GridDev& G, 
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int e = e0 + u * blockDim.x;
-      if (e < npairs) {
+      const int e = es[u];
+      if (e >= 0) {
         s_rank[e] = (node[u] >= 0) ? rank[u] : -1;
         if (WANT_Q) s_q[e] = qv[u];
         double* dx = s_X + (size_t)e * D;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
   Blk b;
   blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
-  stage_nodes<D, true, 0>(m, G, cfg.SL, b.ncell, s_base, s_len, s_rank, s_q, s_X, nullptr, nullptr);
+  stage_nodes<D, true, 0>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, s_q, s_X, nullptr, nullptr);
   __syncthreads();
   const int SL = cfg.SL, np = P.np;
   for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
@@ -594,6 +596,14 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
 #pragma unroll
       for (int w = 0; w < W; w++) P.mask[(size_t)w * np + p] = mk[w];
       P.nnodes[p] = n;
+      if (CACHE) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+          const int rem = len - 32 * w;
+          uint32_t nm = ~mk[w] & (rem >= 32 ? 0xffffffffu : (rem > 0 ? (1u << rem) - 1u : 0u));
+          while (nm) { s_pa[(size_t)j * SL + w * 32 + __ffs(nm) - 1] = 0.0; nm &= nm - 1; }
+        }
+      }
       bool ok = true;
       if (n < D + 1) { latch_error(err, NLPS_ERR_FEW_NEIGHBOURS, P.orig[p]); ok = false; }
       const double h = m.h_avg[s_B[ci]];
@@ -693,13 +703,22 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
       s_mass[j] = mp;
 #pragma unroll
       for (int w = 0; w < W; w++) s_mask[j * W + w] = ok ? mk[w] : 0u;
+      if (CACHE) {
+        // the cell phase sums weight * (m/Z) and weight * (m/Z) * DU_p
+        const double wgt = ok ? mp / Z : 0.0;
+        s_zinv[j] = wgt;
+#pragma unroll
+        for (int i = 0; i < D; i++) s_ddis[j * D + i] *= wgt;
+        if (!ok)
+          for (int k = 0; k < len; k++) s_pa[(size_t)j * SL + k] = 0.0;
+      }
     }
     __syncthreads();
     // ---- cell phase: one thread per (cell, 2-ring node) pair sums over the cell's particles
     for (int e = threadIdx.x; e < b.ncell * SL; e += blockDim.x) {
       const int rank = s_rank[e];
       if (rank < 0) continue;
-      const int c = e / SL, k = e - c * SL;
+      const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
       const int ja = max(s_cs[c], tb) - tb, jb = min(s_cs[c + 1], tb + nb) - tb;
       if (ja >= jb) continue;
       const bool first = s_cs[c] >= tb;
@@ -708,12 +727,16 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
       double a0 = 0.0, a[D];
 #pragma unroll
       for (int i = 0; i < D; i++) a[i] = 0.0;
-      for (int j = ja; j < jb; j++) {
-        if (!(s_mask[j * W + kw] & kb)) continue;
-        double N;
-        if (CACHE) {
-          N = s_pa[(size_t)j * SL + k] * s_zinv[j];
-        } else {
+      if (CACHE) {
+        for (int j = ja; j < jb; j++) {
+          const double pa = s_pa[(size_t)j * SL + k];
+          a0 += pa * s_zinv[j];
+#pragma unroll
+          for (int i = 0; i < D; i++) a[i] += pa * s_ddis[j * D + i];
+        }
+      } else {
+        for (int j = ja; j < jb; j++) {
+          if (!(s_mask[j * W + kw] & kb)) continue;
           double ll = 0.0, lx = 0.0;
 #pragma unroll
           for (int i = 0; i < D; i++) {
@@ -721,12 +744,11 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
             ll += l * l;
             lx += l * s_plam[j * D + i];
           }
-          N = fexp(-s_pbeta[j] * ll + lx, s_tab) * s_zinv[j];
-        }
-        const double mN = N * s_mass[j];
-        a0 += mN;
+          const double mN = fexp(-s_pbeta[j] * ll + lx, s_tab) * s_zinv[j] * s_mass[j];
+          a0 += mN;
 #pragma unroll
-        for (int i = 0; i < D; i++) a[i] += mN * s_ddis[j * D + i];
+          for (int i = 0; i < D; i++) a[i] += mN * s_ddis[j * D + i];
+        }
       }
       double* dst = G.part + ((size_t)s_q[e] * G.max_act + rank) * (1 + D);
       if (first) {
@@ -825,7 +847,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
   Blk b;
   blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
-  stage_nodes<D, true, 1>(m, G, cfg.SL, b.ncell, s_base, s_len, s_rank, s_q, s_X, s_U, nullptr);
+  stage_nodes<D, true, 1>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, s_q, s_X, s_U, nullptr);
   __syncthreads();
   const int SL = cfg.SL, np = P.np;
   constexpr int T = (D == 2) ? 5 : 9;
@@ -843,6 +865,15 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
       uint32_t mk[W];
 #pragma unroll
       for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
+      if (CACHE) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
+        const int len = s_len[ci];
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+          const int rem = len - 32 * w;
+          uint32_t nm = ~mk[w] & (rem >= 32 ? 0xffffffffu : (rem > 0 ? (1u << rem) - 1u : 0u));
+          while (nm) { s_pa[(size_t)j * SL + w * 32 + __ffs(nm) - 1] = 0.0; nm &= nm - 1; }
+        }
+      }
       // particle state requested now, consumed after the neighbour loop (loads overlap the loop)
       double Fn[D * D], be[T];
 #pragma unroll
@@ -1011,13 +1042,15 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
       s_zinv[j] = ok ? Zi : 0.0;
 #pragma unroll
       for (int w = 0; w < W; w++) s_mask[j * W + w] = ok ? mk[w] : 0u;
+      if (CACHE && !ok)
+        for (int k = 0; k < s_len[ci]; k++) s_pa[(size_t)j * SL + k] = 0.0;
     }
     __syncthreads();
     // ---- cell phase: f_A partials, one thread per (cell, 2-ring node) pair
     for (int e = threadIdx.x; e < b.ncell * SL; e += blockDim.x) {
       const int rank = s_rank[e];
       if (rank < 0) continue;
-      const int c = e / SL, k = e - c * SL;
+      const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
       const int ja = max(s_cs[c], tb) - tb, jb = min(s_cs[c + 1], tb + nb) - tb;
       if (ja >= jb) continue;
       const bool first = s_cs[c] >= tb;
@@ -1027,7 +1060,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
 #pragma unroll
       for (int i = 0; i < D; i++) { XA[i] = s_X[(size_t)e * D + i]; f[i] = 0.0; }
       for (int j = ja; j < jb; j++) {
-        if (!(s_mask[j * W + kw] & kb)) continue;
+        if (!CACHE && !(s_mask[j * W + kw] & kb)) continue;
         double l[D], N;
 #pragma unroll
         for (int i = 0; i < D; i++) l[i] = s_px[j * D + i] - XA[i];
@@ -1132,7 +1165,7 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
   Blk b;
   blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
-  stage_nodes<D, false, 2>(m, G, cfg.SL, b.ncell, s_base, s_len, s_rank, nullptr, s_X, s_U, s_A);
+  stage_nodes<D, false, 2>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, nullptr, s_X, s_U, s_A);
   __syncthreads();
   const int SL = cfg.SL, np = P.np;
   for (int t = b.t0 + threadIdx.x; t < b.t1; t += blockDim.x) {
@@ -1753,6 +1786,9 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     }
     if (std::max(e->smemA, std::max(e->smemB, e->smemC)) > (size_t)e->max_smem_optin)
       return set_err(err, err_len, "2-ring too large for the shared-memory staging");
+    c.magic = ((1u << 21) + c.SL - 1) / c.SL;
+    for (unsigned q = 0; q < (unsigned)(c.C * c.SL); q++)
+      if (((q * c.magic) >> 21) != q / c.SL) return set_err(err, err_len, "internal: pair-index division constant");
     if (const char* s_ = getenv("NLPS_REORDER_EVERY")) e->reorder_every = atoi(s_);
     CUDA_OK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
     if (const char* s_ = getenv("NLPS_GRID")) e->grid_override = std::max(1, atoi(s_));

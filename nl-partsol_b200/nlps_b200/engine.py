@@ -60,7 +60,7 @@ def lib():
     the product path has no fallback."""
     global _lib
     if _lib is None:
-        so = _build.build()
+        so = os.environ.get("NLPS_LIB") or _build.build()  # NLPS_LIB: A/B a differently built library
         L = C.CDLL(so)
         L.nlps_b200_create.restype = C.c_void_p
         L.nlps_b200_dt.restype = C.c_double
