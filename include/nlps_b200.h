@@ -40,6 +40,8 @@ extern "C" {
 #define NLPS_ERR_RETURN_MAP_DP 6       /* Drucker-Prager.c:469-482 and __eps/__kappa */
 #define NLPS_ERR_RETURN_MAP_MN 7       /* Matsuoka-Nakai.c:__solver / tangent */
 #define NLPS_ERR_SINGULAR_DF 8         /* TensorLib.c:829-905 (compute_adjunt) */
+#define NLPS_ERR_SLAB_EXCURSION 9     /* a particle left the halo band of its slab between two migrations */
+#define NLPS_ERR_SLAB_CAPACITY 10     /* migration would exceed the particle capacity of a slab */
 #define NLPS_ERR_CUDA 100
 
 /* Background mesh: the parts of `Mesh` (Types.h:631-760) the stepped path reads. */
@@ -205,6 +207,84 @@ int nlps_b200_stress_points(int ndim, const nlps_material *material, double tol_
                             const double *b_e_n, const double *eps_n, const double *kappa_n,
                             double *stress, double *b_e_n1, double *eps_n1, double *kappa_n1,
                             double *W, double *C_ep, int *status, int device);
+
+/* ---------------------------------------------------------------------------
+ * Multi-GPU: spatial slabs.  The reference is single-process (OpenMP only,
+ * driver-nl-partsol.c:192); this is new surface, one engine per GPU / process.
+ *
+ * Every slab engine holds the whole (static) background mesh and the particles whose closest
+ * node I0 lies between its two cuts along `axis`.  Per step three halo exchanges with the two
+ * neighbour slabs over the nodes within `band_cells` cells of a cut: cell occupancy (feeds
+ * Mesh.ActiveNode, LME.c:949-965), lumped mass + momentum sums (U-Verlet.c:166-225,301-367) and
+ * force sums (U-Newmark-beta.c:1257-1374); both sides then divide / apply the Dirichlet set
+ * identically, so no return broadcast is needed.  Every `migrate_every` steps particles whose I0
+ * crossed a cut move to the neighbour slab (full state row).
+ *
+ * Transport: NCCL (ncclSend/ncclRecv grouped on the engine's stream) or a caller-supplied
+ * exchange function (tests, other fabrics).  Host code distributes the NCCL id itself
+ * (torch.distributed, MPI, a file ...). */
+typedef struct nlps_msg {
+  int peer;               /* slab rank of the other side */
+  const void *send;       /* device pointers */
+  unsigned long long send_bytes;
+  void *recv;
+  unsigned long long recv_bytes;
+} nlps_msg;
+/* post all messages on CUDA stream `cuda_stream` (a cudaStream_t); 0 on success */
+typedef int (*nlps_exchange_fn)(void *user, int n_msgs, const nlps_msg *msgs, void *cuda_stream);
+typedef struct nlps_comm nlps_comm;
+int nlps_b200_comm_unique_id(char id[128]); /* ncclGetUniqueId */
+nlps_comm *nlps_b200_comm_create_nccl(const char id[128], int rank, int world, int device);
+nlps_comm *nlps_b200_comm_create_custom(int rank, int world, nlps_exchange_fn fn, void *user);
+void nlps_b200_comm_destroy(nlps_comm *c);
+/* helpers for custom transports */
+int nlps_b200_memcpy_d2d(void *dst, const void *src, unsigned long long bytes, void *cuda_stream);
+int nlps_b200_stream_sync(void *cuda_stream);
+
+typedef struct nlps_slab {
+  int rank, world;
+  int axis;               /* slab axis (0..ndim-1) */
+  const double *cuts;     /* world-1 ascending cut coordinates (between node layers) */
+  int band_cells;         /* halo half-width in cells of size delta_x (>= 4; 0 = default 6) */
+  int migrate_every;      /* steps between migrations (0 = default 10) */
+  double capacity_factor; /* particle capacity / initial count (0 = default 1.3) */
+  int n_global;           /* global particle count (ids are 0..n_global-1) */
+  const int *global_id;   /* id of every row of `state`, or NULL: row index == global id */
+  nlps_comm *comm;
+} nlps_slab;
+
+/* Host planning: slab axis (longest extent of the cloud when axis < 0) and world-1 cuts that
+ * balance the particle counts, each placed midway between two node layers. */
+int nlps_b200_slab_cuts(const nlps_mesh *mesh, int n, const int *I0, int world, int axis,
+                        int *axis_out, double *cuts_out);
+/* Which slab owns a particle whose closest node is I0 (host). */
+int nlps_b200_slab_owner(const nlps_mesh *mesh, int axis, int world, const double *cuts, int I0);
+/* Node ids within band_cells*delta_x of cut (ascending ids): the halo both neighbours exchange.
+ * ids may be NULL (count only). */
+int nlps_b200_slab_halo_nodes(const nlps_mesh *mesh, int axis, double cut, int band_cells, int *ids);
+
+/* nlps_b200_create for one slab: keeps the rows of `state` this slab owns. */
+nlps_engine *nlps_b200_create_slab(const nlps_mesh *mesh, const nlps_solver *solver,
+                                   int n_bounds, const nlps_load *bounds,
+                                   int n_neumann, const nlps_load *neumann,
+                                   const double *gravity, int n_materials,
+                                   const nlps_material *materials,
+                                   const nlps_particles *state, const nlps_slab *slab,
+                                   int device, char *err, int err_len);
+int nlps_b200_local_count(nlps_engine *e);
+/* compact download: rows 0..local_count-1 of `out` (out->n >= local_count) and their global ids */
+int nlps_b200_download_local(nlps_engine *e, nlps_particles *out, int *ids);
+/* move particles that crossed a cut now (also runs every migrate_every steps inside run) */
+int nlps_b200_migrate(nlps_engine *e);
+long long nlps_b200_migrated_count(nlps_engine *e); /* particles received so far */
+/* The scheme call for one slab; `state` rows are indexed by global id on return (rows of other
+ * slabs untouched) when slab->global_id == NULL, compact (download_local order) otherwise. */
+int nlps_b200_u_verlet_slab(const nlps_mesh *mesh, const nlps_solver *solver,
+                            int n_bounds, const nlps_load *bounds, int n_neumann,
+                            const nlps_load *neumann, const double *gravity,
+                            int n_materials, const nlps_material *materials,
+                            nlps_particles *state, const nlps_slab *slab, int run_initialize,
+                            int results_every, nlps_results_cb cb, void *user, int device);
 
 const char *nlps_b200_version(void);
 

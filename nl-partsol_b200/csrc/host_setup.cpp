@@ -164,3 +164,65 @@ extern "C" int nlps_b200_build_locality(int ndim, int n_nodes, int n_elems, int 
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Spatial-slab planning.  The reference has no multi-process path; these are the host
+// decisions every slab must take identically: the slab axis, the cuts, who owns a particle (by the
+// coordinate of its closest node I0) and which nodes two neighbour slabs exchange.
+extern "C" int nlps_b200_slab_cuts(const nlps_mesh* mesh, int n, const int* I0, int world, int axis, int* axis_out,
+                                   double* cuts_out) {
+  const int d = mesh->ndim;
+  if (world < 1 || n < 1 || axis >= d) return 1;
+  for (int p = 0; p < n; p++)
+    if (I0[p] < 0 || I0[p] >= mesh->n_nodes) return 1;
+  if (axis < 0) {  // longest extent of the cloud of closest nodes
+    double best = -1.0;
+    for (int k = 0; k < d; k++) {
+      double lo = 1e300, hi = -1e300;
+      for (int p = 0; p < n; p++) {
+        const double c = mesh->coords[(size_t)I0[p] * d + k];
+        lo = std::min(lo, c);
+        hi = std::max(hi, c);
+      }
+      if (hi - lo > best) { best = hi - lo; axis = k; }
+    }
+  }
+  if (axis_out) *axis_out = axis;
+  std::vector<double> c(n);
+  for (int p = 0; p < n; p++) c[p] = mesh->coords[(size_t)I0[p] * d + axis];
+  std::sort(c.begin(), c.end());
+  double prev_cut = -1e300;
+  for (int g = 1; g < world; g++) {
+    size_t k = (size_t)((double)g * n / world);
+    if (k >= (size_t)n) k = n - 1;
+    double q = c[k];
+    // first layer of this slab = q; the cut sits midway to the previous distinct layer
+    auto it = std::lower_bound(c.begin(), c.end(), q);
+    double below = (it == c.begin()) ? q - mesh->delta_x : *(it - 1);
+    double cut = 0.5 * (q + below);
+    if (!(cut > prev_cut)) return 2;  // more slabs than node layers with particles
+    cuts_out[g - 1] = cut;
+    prev_cut = cut;
+  }
+  return 0;
+}
+
+extern "C" int nlps_b200_slab_owner(const nlps_mesh* mesh, int axis, int world, const double* cuts, int I0) {
+  const double c = mesh->coords[(size_t)I0 * mesh->ndim + axis];
+  int g = 0;
+  while (g < world - 1 && c >= cuts[g]) g++;
+  return g;
+}
+
+extern "C" int nlps_b200_slab_halo_nodes(const nlps_mesh* mesh, int axis, double cut, int band_cells, int* ids) {
+  const double w = band_cells * mesh->delta_x * (1.0 + 1e-9);
+  int n = 0;
+  for (int i = 0; i < mesh->n_nodes; i++) {
+    const double c = mesh->coords[(size_t)i * mesh->ndim + axis];
+    if (fabs(c - cut) <= w) {
+      if (ids) ids[n] = i;
+      n++;
+    }
+  }
+  return n;
+}

@@ -13,6 +13,8 @@
 //
 // Reference citations are relative to nl-partsol/src of migmolper/NL-PartSol.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time (see nccl_api)
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -40,12 +42,12 @@ __constant__ MatParams c_mat[MAX_MATERIALS];
 
 enum KernelId {
   K_SEARCH = 0, K_NODE_FLAGS, K_SCAN1, K_SCAN2, K_SCAN3, K_FILL, K_NODE_FINISH, K_REORDER, K_LME_P2G,
-  K_GRID_DISP, K_TRACTION, K_KIN_FORCE, K_GRID_ACC, K_G2P, K_COUNT
+  K_GRID_DISP, K_TRACTION, K_KIN_FORCE, K_GRID_ACC, K_G2P, K_HALO, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
     "search_closest_node", "node_flags", "scan_reduce", "scan_tops", "scan_apply", "cell_fill",
     "node_finish", "reorder", "lme_p2g_mass_disp", "grid_disp_bc", "traction", "kin_stress_p2g_force",
-    "grid_acc", "g2p_update"};
+    "grid_acc", "g2p_update", "halo_exchange"};
 
 // ---------------------------------------------------------------------------
 // Device views
@@ -67,9 +69,10 @@ struct MeshDev {
 };
 
 struct PartDev {
-  int np;
-  // SoA, component-major: f[c*np + p]; p is the PHYSICAL slot (cell-sorted every few steps),
-  // orig[p] the caller's particle id and inv[] its inverse.
+  int np;  // particles held by this engine (changes when particles migrate between slabs)
+  int ld;  // leading dimension of the SoA arrays = capacity (np <= ld)
+  // SoA, component-major: f[c*ld + p]; p is the PHYSICAL slot (cell-sorted every few steps),
+  // orig[p] the caller's (global) particle id and inv[] its inverse (-1: not held by this slab).
   double *x, *dis, *ddis, *vel, *acc, *lam;
   double *beta, *mass, *vol0, *rho, *W;
   double *J_n, *J_n1, *eps_n, *eps_n1, *kap_n, *kap_n1;
@@ -82,6 +85,8 @@ struct PartDev {
 
 struct GridDev {
   double *M, *F;  // M: nn ; F: nn x D (row-major)
+  double* MOM;    // nn x D: sum m N DU_p before the division by M (kept for the slab halo sums)
+  unsigned char* rocc;  // cell occupied by particles of a NEIGHBOUR slab (multi-GPU), zero otherwise
   double* UA;     // per node [dU (NS) | A (NS)]: the two nodal fields the G2P gathers read, one record
   unsigned char *active, *fixed;
   int *cnt, *cursor, *cell_start, *plist, *act_list, *n_active;
@@ -99,6 +104,10 @@ struct StepParams {
   int max_iter_lme, nsteps, step, update_I0, W;
   ReturnMapParams rp;
 };
+
+// slab view of the kernels: ownership interval [own_lo, own_hi) of closest-node coordinates along `axis`
+// and the wider interval [lo, hi] a particle may roam between two migrations (halo band minus 3.5 cells)
+struct SlabDev { int on, axis; double lo, hi, own_lo, own_hi; };
 
 // One thread block works on C consecutive OCCUPIED cells (a cell = all particles with the same closest
 // node I0) = one contiguous run of the cell-sorted particle order.  SL = longest 2-ring row, PCAP =
@@ -246,7 +255,7 @@ __device__ __forceinline__ void for_neighbour_pairs(const uint32_t* mk, F&& f) {
 // K0a: closest node + cell histogram.   local_search__LME__ first loop (LME.c:917-944),
 // get_closest_node__MeshTools__ (Nodes-Tools.c:476-538): first strict minimum, chain order.
 template <int D>
-__global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G, int update_I0) {
+__global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G, int update_I0, SlabDev sl, int* err) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.np) return;
   int I0 = P.I0[p];
@@ -254,9 +263,9 @@ __global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G,
     double nd = 0.0, xp[D];
 #pragma unroll
     for (int i = 0; i < D; i++) {
-      double dd = P.dis[i * P.np + p];
+      double dd = P.dis[i * P.ld + p];
       nd = __dadd_rn(nd, __dmul_rn(dd, dd));
-      xp[i] = P.x[i * P.np + p];
+      xp[i] = P.x[i * P.ld + p];
     }
     if (nd > 0.0) {  // norm__MatrixLib__(dis) > 0  (LME.c:924)
       int b0 = m.r1p[I0], b1 = m.r1p[I0 + 1];
@@ -271,6 +280,10 @@ __global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G,
       I0 = best;
     }
   }
+  if (sl.on) {
+    const double c = m.X[(size_t)I0 * NS<D>::X + sl.axis];
+    if (c < sl.lo || c > sl.hi) latch_error(err, NLPS_ERR_SLAB_EXCURSION, P.orig[p]);
+  }
   atomicAdd(&G.cnt[I0], 1);
 }
 
@@ -281,7 +294,10 @@ __global__ void __launch_bounds__(256) k_node_flags(MeshDev m, GridDev G) {
   int A = blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= m.nn) return;
   int act = 0;
-  for (int q = m.r1tp[A]; q < m.r1tp[A + 1] && !act; q++) act = G.cnt[m.r1ti[q]] > 0;
+  for (int q = m.r1tp[A]; q < m.r1tp[A + 1] && !act; q++) {
+    const int B = m.r1ti[q];
+    act = G.cnt[B] > 0 || G.rocc[B];
+  }
   G.active[A] = (unsigned char)act;
   unsigned long long c = (unsigned)G.cnt[A];
   G.packed[A] = make_ulonglong2(c | ((unsigned long long)(c > 0) << 40), (unsigned long long)act);
@@ -418,11 +434,11 @@ __global__ void __launch_bounds__(256) k_node_finish(MeshDev m, PartDev P, GridD
 
 // physical re-sort: gather every SoA field into the cell-sorted order (dst[c][t] = src[c][plist[t]])
 template <typename Tp>
-__global__ void __launch_bounds__(256) k_gather_rows(const Tp* src, Tp* dst, const int* plist, int np, int cols) {
+__global__ void __launch_bounds__(256) k_gather_rows(const Tp* src, Tp* dst, const int* plist, int np, int ld, int cols) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)np * cols) return;
   int c = (int)(i / np), t = (int)(i % np);
-  dst[i] = src[(size_t)c * np + plist[t]];
+  dst[(size_t)c * ld + t] = src[(size_t)c * ld + plist[t]];
 }
 __global__ void __launch_bounds__(256) k_after_sort(PartDev P, GridDev G) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -560,7 +576,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
   blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
   stage_nodes<D, true, 0>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, s_q, s_X, nullptr, nullptr);
   __syncthreads();
-  const int SL = cfg.SL, np = P.np;
+  const int SL = cfg.SL, np = P.ld;  // np: SoA stride
   for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
     const int nb = min(cfg.PCAP, b.t1 - tb);
     // ---- particle phase
@@ -777,7 +793,9 @@ struct BcDev {
   int maxdim, nsteps, nb;
 };
 
-template <int D>
+// MODE 0: everything (single slab).  MODE 1: sums only, M and MOM stored (the slab halo exchange adds the
+// neighbour slabs' sums on the shared nodes).  MODE 2: division + Dirichlet from the stored sums.
+template <int D, int MODE>
 __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev bc, int step) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *G.n_active) return;
@@ -785,7 +803,12 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
   double mom[D], M = 0.0;
 #pragma unroll
   for (int i = 0; i < D; i++) mom[i] = 0.0;
-  for (int w = 0; w < G.w2t; w++) {
+  if (MODE == 2) {
+    M = G.M[A];
+#pragma unroll
+    for (int i = 0; i < D; i++) mom[i] = G.MOM[(size_t)A * D + i];
+  }
+  for (int w = 0; MODE != 2 && w < G.w2t; w++) {
     uint32_t mm = G.occm[(size_t)w * G.max_act + t];
     while (mm) {
       const int q = w * 32 + __ffs(mm) - 1;
@@ -795,6 +818,12 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
 #pragma unroll
       for (int i = 0; i < D; i++) mom[i] += src[1 + i];
     }
+  }
+  if (MODE == 1) {
+    G.M[A] = M;
+#pragma unroll
+    for (int i = 0; i < D; i++) G.MOM[(size_t)A * D + i] = mom[i];
+    return;
   }
   double dU[D];
 #pragma unroll
@@ -849,7 +878,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
   blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
   stage_nodes<D, true, 1>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, s_q, s_X, s_U, nullptr);
   __syncthreads();
-  const int SL = cfg.SL, np = P.np;
+  const int SL = cfg.SL, np = P.ld;  // np: SoA stride
   constexpr int T = (D == 2) ? 5 : 9;
   for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
     const int nb = min(cfg.PCAP, b.t1 - tb);
@@ -1111,24 +1140,25 @@ __global__ void k_traction(PartDev P, NeuDev nu, double thickness, int step) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nu.n_entries) return;
   int p = P.inv[nu.part[e]], b = nu.load[e];
+  if (p < 0) return;  // the particle lives in another slab
   double A0 = P.vol0[p] / thickness;
   for (int k = 0; k < nu.load_dim[b] && k < D; k++) {
     size_t o = ((size_t)b * nu.maxdim + k) * nu.nsteps + step;
-    if (nu.dir[o] == 1) atomicAdd(&P.trac[(size_t)k * P.np + p], nu.val[o] * A0);
+    if (nu.dir[o] == 1) atomicAdd(&P.trac[(size_t)k * P.ld + p], nu.val[o] * A0);
   }
 }
 
 // K3 stage 2 + G2 (node kernel): f_A = sum of cell partials; a_A = g + f_A / M_A on free DOFs, 0 on
 // restricted ones (U-Verlet.c:947-958; gravity as U-Newmark-beta.c:1539-1543).
-template <int D>
+template <int D, int MODE>
 __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const double* grav, int nsteps, int step) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *G.n_active) return;
   const int A = G.act_list[t];
   double f[D];
 #pragma unroll
-  for (int i = 0; i < D; i++) f[i] = 0.0;
-  for (int w = 0; w < G.w2t; w++) {
+  for (int i = 0; i < D; i++) f[i] = (MODE == 2) ? G.F[(size_t)A * D + i] : 0.0;
+  for (int w = 0; MODE != 2 && w < G.w2t; w++) {
     uint32_t mm = G.occm[(size_t)w * G.max_act + t];
     while (mm) {
       const int q = w * 32 + __ffs(mm) - 1;
@@ -1137,6 +1167,11 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
 #pragma unroll
       for (int i = 0; i < D; i++) f[i] += src[i];
     }
+  }
+  if (MODE == 1) {
+#pragma unroll
+    for (int i = 0; i < D; i++) G.F[(size_t)A * D + i] = f[i];
+    return;
   }
   const double M = G.M[A];
   const unsigned fx = G.fixed[A];
@@ -1167,7 +1202,7 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
   blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
   stage_nodes<D, false, 2>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, nullptr, s_X, s_U, s_A);
   __syncthreads();
-  const int SL = cfg.SL, np = P.np;
+  const int SL = cfg.SL, np = P.ld;  // np: SoA stride
   for (int t = b.t0 + threadIdx.x; t < b.t1; t += blockDim.x) {
     const int p = G.plist[t];
     const int ci = cell_of(s_cs, b.ncell, t);
@@ -1238,32 +1273,132 @@ __global__ void k_sync_inert(PartDev P) {
   if (c_mat[P.matidx[p]].type != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) return;
   constexpr int TB = (D == 2) ? 5 : 9;
 #pragma unroll
-  for (int i = 0; i < TB; i++) P.be_n[(size_t)i * P.np + p] = P.be_n1[(size_t)i * P.np + p];
+  for (int i = 0; i < TB; i++) P.be_n[(size_t)i * P.ld + p] = P.be_n1[(size_t)i * P.ld + p];
   P.eps_n[p] = P.eps_n1[p];
   P.kap_n[p] = P.kap_n1[p];
 }
 
-// AoS (host layout, n x cols) <-> SoA (cols x n)
-// (row of the caller's particle orig[p]  <->  physical slot p)
-__global__ void k_aos_to_soa(const double* aos, double* soa, const int* orig, int n, int cols, int aos_stride, int col0) {
+// ---------------------------------------------------------------------------
+// Slab halo (multi-GPU): every slab keeps the nodes within a band of its cuts; the sums of
+// the shared nodes are exchanged with the neighbour slab and added.  which: 0 = cell occupancy (-> remote
+// occupancy flags, feeds ActiveNode), 1 = lumped mass + momentum sums, 2 = force sums.
+template <int D>
+__global__ void k_halo_pack(GridDev G, const int* ids, int n, int which, double* buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int A = ids[i];
+  if (which == 0) {
+    buf[i] = G.cnt[A] > 0 ? 1.0 : 0.0;
+  } else if (which == 1) {
+    const bool act = G.active[A];
+    buf[(size_t)i * (1 + D)] = act ? G.M[A] : 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) buf[(size_t)i * (1 + D) + 1 + k] = act ? G.MOM[(size_t)A * D + k] : 0.0;
+  } else {
+    const bool act = G.active[A];
+#pragma unroll
+    for (int k = 0; k < D; k++) buf[(size_t)i * D + k] = act ? G.F[(size_t)A * D + k] : 0.0;
+  }
+}
+template <int D>
+__global__ void k_halo_add(GridDev G, const int* ids, int n, int which, const double* buf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int A = ids[i];
+  if (which == 0) {
+    G.rocc[A] = (unsigned char)(buf[i] != 0.0);  // the bands of the two cuts are disjoint: plain overwrite
+  } else if (which == 1) {
+    if (!G.active[A]) return;
+    G.M[A] += buf[(size_t)i * (1 + D)];
+#pragma unroll
+    for (int k = 0; k < D; k++) G.MOM[(size_t)A * D + k] += buf[(size_t)i * (1 + D) + 1 + k];
+  } else {
+    if (!G.active[A]) return;
+#pragma unroll
+    for (int k = 0; k < D; k++) G.F[(size_t)A * D + k] += buf[(size_t)i * D + k];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Migration between slabs: particles whose closest node crossed a cut move to the neighbour.
+template <int D>
+__global__ void __launch_bounds__(256) k_mig_mark(MeshDev m, PartDev P, SlabDev sl, int* dest, int* cnt) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  int d = -1;
+  if (p < P.np) {
+    const double c = m.X[(size_t)P.I0[p] * NS<D>::X + sl.axis];
+    d = (c < sl.own_lo) ? 1 : ((c >= sl.own_hi) ? 2 : 0);
+    dest[p] = d;
+  }
+  const int n0 = __syncthreads_count(d == 0), n1 = __syncthreads_count(d == 1), n2 = __syncthreads_count(d == 2);
+  if (threadIdx.x == 0) {
+    if (n0) atomicAdd(&cnt[0], n0);
+    if (n1) atomicAdd(&cnt[1], n1);
+    if (n2) atomicAdd(&cnt[2], n2);
+  }
+}
+// permutation: stayers first, then the particles bound for the lower slab, then for the upper slab
+__global__ void __launch_bounds__(256) k_mig_perm(int np, const int* dest, int* cnt, int* perm) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const int d = dest[p];
+  const int base = (d == 0) ? 0 : ((d == 1) ? cnt[0] : cnt[0] + cnt[1]);
+  perm[base + atomicAdd(&cnt[3 + d], 1)] = p;
+}
+struct MigCol { void* base; int is_int; int pad; unsigned long long off; };  // off: byte offset of the column per buffered row
+// rows [row0, row0 + nrows) of every column <-> buffer (column c at buf + off_c * nrows)
+__global__ void __launch_bounds__(256) k_mig_copy(const MigCol* tab, int ncols, int row0, int nrows, unsigned char* buf, int unpack) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)ncols * nrows) return;
+  const int c = (int)(i / nrows), r = (int)(i % nrows);
+  const MigCol col = tab[c];
+  if (col.is_int) {
+    int* a = (int*)col.base + row0 + r;
+    int* b = (int*)(buf + col.off * nrows) + r;
+    if (unpack) *a = *b; else *b = *a;
+  } else {
+    double* a = (double*)col.base + row0 + r;
+    double* b = (double*)(buf + col.off * nrows) + r;
+    if (unpack) *a = *b; else *b = *a;
+  }
+}
+__global__ void __launch_bounds__(256) k_mig_inv(PartDev P, int row0, int nrows, int value_is_slot) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  P.inv[P.orig[row0 + r]] = value_is_slot ? row0 + r : -1;
+}
+__global__ void k_fill_i(int* a, size_t n, int v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+__global__ void k_set_inv(const int* orig, int* inv, int n) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) inv[orig[p]] = p;
+}
+
+// AoS (host layout, rows x cols) <-> SoA (cols x ld)
+// (row rowmap[p] of the AoS buffer <-> physical slot p; rowmap == nullptr: row p)
+__global__ void k_aos_to_soa(const double* aos, double* soa, const int* rowmap, int n, int ld, int cols, int aos_stride, int col0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n * cols) return;
   int c = (int)(i / n), p = (int)(i % n);
-  soa[i] = aos[(size_t)orig[p] * aos_stride + col0 + c];
+  const int row = rowmap ? rowmap[p] : p;
+  soa[(size_t)c * ld + p] = aos[(size_t)row * aos_stride + col0 + c];
 }
-__global__ void k_soa_to_aos(const double* soa, double* aos, const int* orig, int n, int cols, int aos_stride, int col0) {
+__global__ void k_soa_to_aos(const double* soa, double* aos, const int* rowmap, int n, int ld, int cols, int aos_stride, int col0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n * cols) return;
   int p = (int)(i / cols), c = (int)(i % cols);
-  aos[(size_t)orig[p] * aos_stride + col0 + c] = soa[(size_t)c * n + p];
+  const int row = rowmap ? rowmap[p] : p;
+  aos[(size_t)row * aos_stride + col0 + c] = soa[(size_t)c * ld + p];
 }
-__global__ void k_unpermute_int(const int* src, int* dst, const int* orig, int n) {
+__global__ void k_unpermute_int(const int* src, int* dst, const int* rowmap, int n) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) dst[orig[p]] = src[p];
+  if (p < n) dst[rowmap ? rowmap[p] : p] = src[p];
 }
-__global__ void k_permute_int(const int* src, int* dst, const int* orig, int n) {
+__global__ void k_permute_int(const int* src, int* dst, const int* rowmap, int n) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n) dst[p] = src[orig[p]];
+  if (p < n) dst[p] = src[rowmap ? rowmap[p] : p];
 }
 __global__ void k_iota(int* a, int* b, int n) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1274,20 +1409,21 @@ __global__ void k_fill_d(double* a, size_t n, double v) {
   if (i < n) a[i] = v;
 }
 // expand bitmask lists to the reference's ListNodes order (reverse of acceptance order)
-__global__ void k_expand_lists(MeshDev m, PartDev P, int W, int cap, int* lists) {
+__global__ void k_expand_lists(MeshDev m, PartDev P, int W, int cap, int* lists, int compact) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.np) return;
   int base = m.r2p[P.I0[p]], o = 0;
+  const size_t row = compact ? p : P.orig[p];
   for (int w = W - 1; w >= 0; w--) {
-    uint32_t mm = P.mask[(size_t)w * P.np + p];
+    uint32_t mm = P.mask[(size_t)w * P.ld + p];
     while (mm) {
       int b = 31 - __clz(mm);
       mm &= ~(1u << b);
-      if (o < cap) lists[(size_t)P.orig[p] * cap + o] = m.r2i[base + w * 32 + b];
+      if (o < cap) lists[row * cap + o] = m.r2i[base + w * 32 + b];
       o++;
     }
   }
-  for (; o < cap; o++) lists[(size_t)P.orig[p] * cap + o] = -1;
+  for (; o < cap; o++) lists[row * cap + o] = -1;
 }
 __global__ void k_export_nodal(GridDev G, int nn, int D, int which, double* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1380,7 +1516,93 @@ struct nlps_engine {
   int k_n[K_COUNT] = {0};
   long long launches = 0;
   int last_code = 0, last_particle = -1;
+  // ---- spatial slab (multi-GPU); slab_on == 0: the engine owns every particle
+  int slab_on = 0, rank = 0, world = 1, axis = 0, band_cells = 6, migrate_every = 10, n_global = 0;
+  int steps_since_migration = 0;
+  long long n_migrated_in = 0;
+  double cut_lo = -1e300, cut_hi = 1e300;  // ownership interval of closest-node coordinates [cut_lo, cut_hi)
+  nlps_comm* comm = nullptr;
+  struct HaloSide {
+    int peer = -1, n = 0;
+    int* ids = nullptr;            // device, ascending node ids, identical on both sides of the cut
+    double *sbuf = nullptr, *rbuf = nullptr;  // n x (1 + D)
+  } side[2];                        // 0: lower neighbour, 1: upper neighbour
+  int* mig_dest = nullptr;          // per particle: 0 stay, 1 to the lower slab, 2 to the upper slab
+  int* mig_cnt = nullptr;           // device [8]: counts stay/low/up, cursors, received low/up
+  int* h_mig = nullptr;             // pinned [8]
+  unsigned char *mig_sbuf[2] = {nullptr, nullptr}, *mig_rbuf[2] = {nullptr, nullptr};
+  int mig_cap = 0;                  // rows per migration buffer
+  MigCol* mig_tab = nullptr;
+  double solver_dx = 0.0;           // Mesh.DeltaX
+  std::vector<int> h_ids;           // host copy of P.orig (slab I/O)
+  std::vector<double> h_rows;       // host staging of compact rows (slab I/O)
 };
+
+// ---------------------------------------------------------------------------
+// NCCL is bound with dlopen at the first use, not at link time: a process that also hosts PyTorch must end
+// up with ONE libnccl.so.2 (the dynamic linker deduplicates by soname), and it has to be the newer one
+// PyTorch ships; linking would pin the system copy as soon as this library is loaded.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static int tried = 0;
+  if (!tried) {
+    tried = 1;
+    const char* names[] = {getenv("NLPS_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm) continue;
+      api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (api.h) {
+#define SYM_(f) *(void**)(&api.f) = dlsym(api.h, "nccl" #f)
+      SYM_(GetUniqueId); SYM_(CommInitRank); SYM_(CommDestroy); SYM_(GroupStart); SYM_(GroupEnd); SYM_(Send); SYM_(Recv);
+      SYM_(GetErrorString);
+#undef SYM_
+      if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.GroupStart || !api.GroupEnd || !api.Send ||
+          !api.Recv || !api.GetErrorString)
+        api.h = nullptr;
+    }
+    if (!api.h) fprintf(stderr, "nlps_b200: libnccl.so.2 not found (set NLPS_NCCL_LIB)\n");
+  }
+  return api.h ? &api : nullptr;
+}
+
+// Transports of the slab exchanges
+struct nlps_comm {
+  int rank = 0, world = 1, is_nccl = 0;
+  ncclComm_t nccl = nullptr;
+  nlps_exchange_fn fn = nullptr;
+  void* user = nullptr;
+};
+static int comm_exchange(nlps_comm* c, int n, const nlps_msg* msgs, cudaStream_t stream) {
+  if (!c) return n ? 1 : 0;
+  if (!c->is_nccl) return c->fn(c->user, n, msgs, (void*)stream);  // also with n == 0: collective transports count calls
+  if (n == 0) return 0;
+  NcclApi* N = nccl_api();
+  ncclResult_t r = N->GroupStart();
+  for (int i = 0; i < n && r == ncclSuccess; i++) {
+    if (msgs[i].send_bytes) r = N->Send(msgs[i].send, msgs[i].send_bytes, ncclChar, msgs[i].peer, c->nccl, stream);
+    if (r == ncclSuccess && msgs[i].recv_bytes) r = N->Recv(msgs[i].recv, msgs[i].recv_bytes, ncclChar, msgs[i].peer, c->nccl, stream);
+  }
+  ncclResult_t r2 = N->GroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess) {
+    fprintf(stderr, "nlps_b200: NCCL exchange failed: %s\n", N->GetErrorString(r != ncclSuccess ? r : r2));
+    return 1;
+  }
+  return 0;
+}
+
 
 template <typename Tp>
 static int dev_alloc(nlps_engine* e, Tp** p, size_t n) {
@@ -1480,25 +1702,65 @@ static StepParams make_params(nlps_engine* e, int step, int update_I0) {
   return sp;
 }
 
-// AoS host -> SoA device for one field (cols columns starting at col0 of an aos_stride-wide row)
-static int put_field(nlps_engine* e, const double* h, double* d, int cols, int aos_stride, int col0) {
-  if (!h || !d) return 0;
-  size_t n = (size_t)e->np * aos_stride;
+// host copy of the global ids of the particles in slot order (slab I/O)
+static int refresh_ids(nlps_engine* e) {
+  e->h_ids.resize(e->np);
+  if (e->np) CUDA_OK(cudaMemcpyAsync(e->h_ids.data(), e->P.orig, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+// AoS host -> SoA device for one field (cols columns starting at col0 of an aos_stride-wide row).
+// rows: how the host buffer is indexed -- 0: by the caller's particle id (whole buffer copied, rows picked on the
+// device), 1: by global id, gathered on the host (slab engines hold a subset), 2: compact, row = slot.
+static int put_field(nlps_engine* e, const double* h, double* d, int cols, int aos_stride, int col0, int rows = 0) {
+  if (!h || !d || e->np == 0) return 0;
+  const size_t n = (size_t)e->np * aos_stride;
+  const int* rowmap = e->P.orig;
+  if (rows == 1) {
+    e->h_rows.resize(n);
+    for (int p = 0; p < e->np; p++) memcpy(&e->h_rows[(size_t)p * aos_stride], h + (size_t)e->h_ids[p] * aos_stride, sizeof(double) * aos_stride);
+    h = e->h_rows.data();
+    rowmap = nullptr;
+  } else if (rows == 2) {
+    rowmap = nullptr;
+  }
   CUDA_OK(cudaMemcpyAsync(e->stage, h, n * sizeof(double), cudaMemcpyHostToDevice, e->stream));
-  k_aos_to_soa<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(e->stage, d, e->P.orig, e->np, cols, aos_stride, col0);
+  k_aos_to_soa<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(e->stage, d, rowmap, e->np, e->P.ld, cols, aos_stride, col0);
   CUDA_OK(cudaStreamSynchronize(e->stream));  // host buffer may be pageable; stage is reused
   return 0;
 }
 static int get_field(nlps_engine* e, double* h, const double* d, int cols, int aos_stride, int col0,
-                     const double* d_extra = nullptr) {
-  if (!h || !d) return 0;
-  size_t n = (size_t)e->np * aos_stride;
+                     const double* d_extra = nullptr, int rows = 0) {
+  if (!h || !d || e->np == 0) return 0;
+  const size_t n = (size_t)e->np * aos_stride;
+  const int* rowmap = rows == 0 ? e->P.orig : nullptr;
   if (cols != aos_stride) {
     // partial rows (2D tensors: 4 in-plane + slot 4): assemble the whole row on the device
-    if (d_extra) k_soa_to_aos<<<nblk((size_t)e->np, 256), 256, 0, e->stream>>>(d_extra, e->stage, e->P.orig, e->np, 1, aos_stride, cols);
+    if (d_extra) k_soa_to_aos<<<nblk((size_t)e->np, 256), 256, 0, e->stream>>>(d_extra, e->stage, rowmap, e->np, e->P.ld, 1, aos_stride, cols);
   }
-  k_soa_to_aos<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(d, e->stage, e->P.orig, e->np, cols, aos_stride, col0);
+  k_soa_to_aos<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(d, e->stage, rowmap, e->np, e->P.ld, cols, aos_stride, col0);
+  if (rows == 1) {
+    e->h_rows.resize(n);
+    CUDA_OK(cudaMemcpyAsync(e->h_rows.data(), e->stage, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    for (int p = 0; p < e->np; p++) memcpy(h + (size_t)e->h_ids[p] * aos_stride, &e->h_rows[(size_t)p * aos_stride], sizeof(double) * aos_stride);
+    return 0;
+  }
   CUDA_OK(cudaMemcpyAsync(h, e->stage, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+static int get_ints(nlps_engine* e, int* h, const int* d, int rows) {
+  if (!h || e->np == 0) return 0;
+  k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(d, (int*)e->stage, rows == 0 ? e->P.orig : nullptr, e->np);
+  if (rows == 1) {
+    std::vector<int> tmp(e->np);
+    CUDA_OK(cudaMemcpyAsync(tmp.data(), e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    for (int p = 0; p < e->np; p++) h[e->h_ids[p]] = tmp[p];
+    return 0;
+  }
+  CUDA_OK(cudaMemcpyAsync(h, e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -1531,23 +1793,24 @@ static int poll_error(nlps_engine* e) {
   return 0;
 }
 
-// physical re-sort of every particle array into the cell-sorted order (plist); afterwards plist is the
+// physical re-sort of every particle array into the order given by plist; afterwards plist is the
 // identity.  The results do not depend on when (or whether) this runs: cells are summed in the order of
 // the caller's particle ids and everything else is per particle.
 static void reorder_particles(nlps_engine* e) {
-  const int np = e->np, D = e->D, T = e->T, DD = D * D;
+  const int np = e->np, ld = e->P.ld, D = e->D, T = e->T, DD = D * D;
   PartDev& P = e->P;
   const int* pl = e->G.plist;
+  if (np == 0) { e->steps_since_sort = 0; return; }
   if (e->profile) cudaEventRecord(e->ev0, e->stream);
   auto gd = [&](double* f, int cols) {
     if (!f) return;
-    k_gather_rows<double><<<nblk((size_t)np * cols, 256), 256, 0, e->stream>>>(f, e->stage, pl, np, cols);
-    cudaMemcpyAsync(f, e->stage, sizeof(double) * (size_t)np * cols, cudaMemcpyDeviceToDevice, e->stream);
+    k_gather_rows<double><<<nblk((size_t)np * cols, 256), 256, 0, e->stream>>>(f, e->stage, pl, np, ld, cols);
+    cudaMemcpy2DAsync(f, sizeof(double) * ld, e->stage, sizeof(double) * ld, sizeof(double) * np, cols, cudaMemcpyDeviceToDevice, e->stream);
     e->launches++;
   };
   auto gi = [&](int* f, int cols) {
-    k_gather_rows<int><<<nblk((size_t)np * cols, 256), 256, 0, e->stream>>>(f, (int*)e->stage, pl, np, cols);
-    cudaMemcpyAsync(f, e->stage, sizeof(int) * (size_t)np * cols, cudaMemcpyDeviceToDevice, e->stream);
+    k_gather_rows<int><<<nblk((size_t)np * cols, 256), 256, 0, e->stream>>>(f, (int*)e->stage, pl, np, ld, cols);
+    cudaMemcpy2DAsync(f, sizeof(int) * ld, e->stage, sizeof(int) * ld, sizeof(int) * np, cols, cudaMemcpyDeviceToDevice, e->stream);
     e->launches++;
   };
   gd(P.x, D); gd(P.dis, D); gd(P.ddis, D); gd(P.vel, D); gd(P.acc, D); gd(P.lam, D);
@@ -1570,63 +1833,206 @@ static void reorder_particles(nlps_engine* e) {
   e->n_reorders++;
 }
 
+static SlabDev slab_dev(const nlps_engine* e) {
+  SlabDev sl{};
+  sl.on = e->slab_on;
+  sl.axis = e->axis;
+  const double roam = (e->band_cells - 3.5) * e->solver_dx;
+  sl.own_lo = e->cut_lo; sl.own_hi = e->cut_hi;
+  sl.lo = e->cut_lo - roam; sl.hi = e->cut_hi + roam;
+  return sl;
+}
+
+// ---------------------------------------------------------------------------
+// Slab halo exchange over the nodes within the band of each cut.  which: 0 occupancy, 1 M + momentum, 2 forces.
+template <int D>
+static int halo_exchange(nlps_engine* e, int which) {
+  if (!e->slab_on) return 0;
+  const int per = (which == 0) ? 1 : ((which == 1) ? 1 + D : D);
+  nlps_msg msgs[2];
+  int nm = 0;
+  if (e->profile) cudaEventRecord(e->ev0, e->stream);
+  for (int s_ = 0; s_ < 2; s_++) {
+    auto& h = e->side[s_];
+    if (h.peer < 0 || h.n == 0) continue;
+    k_halo_pack<D><<<nblk(h.n, 256), 256, 0, e->stream>>>(e->G, h.ids, h.n, which, h.sbuf);
+    e->launches++;
+    const unsigned long long bytes = sizeof(double) * (unsigned long long)h.n * per;
+    msgs[nm++] = nlps_msg{h.peer, h.sbuf, bytes, h.rbuf, bytes};
+  }
+  int rc = comm_exchange(e->comm, nm, msgs, e->stream);
+  for (int s_ = 0; s_ < 2 && !rc; s_++) {
+    auto& h = e->side[s_];
+    if (h.peer < 0 || h.n == 0) continue;
+    k_halo_add<D><<<nblk(h.n, 256), 256, 0, e->stream>>>(e->G, h.ids, h.n, which, h.rbuf);
+    e->launches++;
+  }
+  if (e->profile) {
+    cudaEventRecord(e->ev1, e->stream);
+    cudaEventSynchronize(e->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    e->k_ms[K_HALO] += ms;
+    e->k_n[K_HALO]++;
+  }
+  if (rc) e->last_code = NLPS_ERR_CUDA;
+  return rc;
+}
+
+// Migration: mark, permute (stayers first), ship the tails to the neighbour slabs, append what arrives.
+template <int D>
+static int migrate_t(nlps_engine* e) {
+  if (!e->slab_on) return 0;
+  PartDev& P = e->P;
+  const int np = e->np, ld = P.ld, T = e->T, DD = D * D;
+  const SlabDev sl = slab_dev(e);
+  cudaMemsetAsync(e->mig_cnt, 0, sizeof(int) * 16, e->stream);
+  if (np) k_mig_mark<D><<<nblk(np, 256), 256, 0, e->stream>>>(e->mesh, P, sl, e->mig_dest, e->mig_cnt);
+  // counts to the neighbours (slot 6: to lower, 7: to upper; 8: from lower, 9: from upper)
+  cudaMemcpyAsync(e->mig_cnt + 6, e->mig_cnt + 1, sizeof(int) * 2, cudaMemcpyDeviceToDevice, e->stream);
+  nlps_msg msgs[2];
+  int nm = 0;
+  for (int s_ = 0; s_ < 2; s_++)
+    if (e->side[s_].peer >= 0) msgs[nm++] = nlps_msg{e->side[s_].peer, e->mig_cnt + 6 + s_, sizeof(int), e->mig_cnt + 8 + s_, sizeof(int)};
+  if (comm_exchange(e->comm, nm, msgs, e->stream)) return 1;
+  CUDA_OK(cudaMemcpyAsync(e->h_mig, e->mig_cnt, sizeof(int) * 16, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  const int n_stay = e->h_mig[0], n_out[2] = {e->h_mig[1], e->h_mig[2]}, n_in[2] = {e->h_mig[8], e->h_mig[9]};
+  e->steps_since_migration = 0;
+  if ((n_out[0] && e->side[0].peer < 0) || (n_out[1] && e->side[1].peer < 0)) {
+    fprintf(stderr, "nlps_b200: slab %d: particles left the outer end of the slab range\n", e->rank);
+    e->last_code = NLPS_ERR_SLAB_EXCURSION;
+    return 1;
+  }
+  const int np_new = n_stay + n_in[0] + n_in[1];
+  if (np_new > ld || std::max(std::max(n_out[0], n_out[1]), std::max(n_in[0], n_in[1])) > e->mig_cap) {
+    fprintf(stderr, "nlps_b200: slab %d: migration exceeds the capacity (%d rows, %d per message)\n", e->rank, ld, e->mig_cap);
+    e->last_code = NLPS_ERR_SLAB_CAPACITY;
+    return 1;
+  }
+  const bool any = n_out[0] + n_out[1] + n_in[0] + n_in[1] > 0;
+  if (n_out[0] + n_out[1]) {
+    k_mig_perm<<<nblk(np, 256), 256, 0, e->stream>>>(np, e->mig_dest, e->mig_cnt, e->G.plist);
+    reorder_particles(e);
+    k_mig_inv<<<nblk(n_out[0] + n_out[1], 256), 256, 0, e->stream>>>(P, n_stay, n_out[0] + n_out[1], 0);
+  }
+  // column table of the travelling state (doubles first, then ints)
+  std::vector<MigCol> tab;
+  unsigned long long off = 0;
+  auto addd = [&](double* f, int cols) { for (int c = 0; c < cols; c++) { tab.push_back(MigCol{f + (size_t)c * ld, 0, 0, off}); off += 8; } };
+  auto addi = [&](int* f, int cols) { for (int c = 0; c < cols; c++) { tab.push_back(MigCol{f + (size_t)c * ld, 1, 0, off}); off += 4; } };
+  addd(P.x, D); addd(P.dis, D); addd(P.ddis, D); addd(P.vel, D); addd(P.acc, D); addd(P.lam, D);
+  addd(P.beta, 1); addd(P.mass, 1); addd(P.vol0, 1); addd(P.rho, 1); addd(P.W, 1);
+  addd(P.J_n, 1); addd(P.J_n1, 1); addd(P.eps_n, 1); addd(P.eps_n1, 1); addd(P.kap_n, 1); addd(P.kap_n1, 1);
+  addd(P.F_n, DD); addd(P.F_n1, DD); addd(P.DF, DD); addd(P.be_n, T); addd(P.be_n1, T); addd(P.stress, T); addd(P.cep, DD);
+  addd(P.Fs4, 1); addd(P.DFs4, 1);
+  addi(P.I0, 1); addi(P.nnodes, 1); addi(P.matidx, 1); addi(P.orig, 1); addi((int*)P.mask, e->W);
+  const unsigned long long row_bytes = off;
+  const int ncols = (int)tab.size();
+  if (any) {
+    CUDA_OK(cudaMemcpyAsync(e->mig_tab, tab.data(), sizeof(MigCol) * ncols, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));  // tab is a host temporary
+  }
+  nm = 0;
+  int row0 = n_stay;
+  for (int s_ = 0; s_ < 2; s_++) {
+    if (e->side[s_].peer < 0) continue;
+    if (n_out[s_]) k_mig_copy<<<nblk((size_t)ncols * n_out[s_], 256), 256, 0, e->stream>>>(e->mig_tab, ncols, row0, n_out[s_], e->mig_sbuf[s_], 0);
+    row0 += n_out[s_];
+    if (n_out[s_] || n_in[s_])
+      msgs[nm++] = nlps_msg{e->side[s_].peer, e->mig_sbuf[s_], row_bytes * n_out[s_], e->mig_rbuf[s_], row_bytes * n_in[s_]};
+  }
+  if (comm_exchange(e->comm, nm, msgs, e->stream)) return 1;
+  if (!any) return 0;
+  row0 = n_stay;
+  for (int s_ = 0; s_ < 2; s_++) {
+    if (e->side[s_].peer < 0 || !n_in[s_]) continue;
+    k_mig_copy<<<nblk((size_t)ncols * n_in[s_], 256), 256, 0, e->stream>>>(e->mig_tab, ncols, row0, n_in[s_], e->mig_rbuf[s_], 1);
+    row0 += n_in[s_];
+  }
+  e->np = np_new;
+  P.np = np_new;
+  if (n_in[0] + n_in[1]) k_mig_inv<<<nblk(n_in[0] + n_in[1], 256), 256, 0, e->stream>>>(P, n_stay, n_in[0] + n_in[1], 1);
+  e->n_migrated_in += n_in[0] + n_in[1];
+  e->steps_since_sort = 1 << 30;  // cell-sort the new population at the next search
+  e->launches += 6;
+  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
 template <int D>
 static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predictor) {
+  if (e->slab_on && update_I0 && e->migrate_every > 0 && e->steps_since_migration >= e->migrate_every) migrate_t<D>(e);
+  e->steps_since_migration++;
   const int np = e->np, nn = e->nn;
   cudaMemsetAsync(e->G.cnt, 0, sizeof(int) * nn, e->stream);
-  LAUNCH(e, K_SEARCH, k_search<D>, nblk(np, 256), 256, e->mesh, e->P, e->G, update_I0);
+  if (np) LAUNCH(e, K_SEARCH, k_search<D>, nblk(np, 256), 256, e->mesh, e->P, e->G, update_I0, slab_dev(e), e->err);
+  halo_exchange<D>(e, 0);
   LAUNCH(e, K_NODE_FLAGS, k_node_flags, nblk(nn, 256), 256, e->mesh, e->G);
   int nb = nblk(nn, SCAN_ITEMS);
   LAUNCH(e, K_SCAN1, k_scan_reduce, nb, 256, e->G.packed, e->G.scan_blk, nn);
   LAUNCH(e, K_SCAN2, k_scan_tops, 1, 1024, e->G.scan_blk, nb, e->G.n_active, e->G.n_occ, e->npart_check);
   LAUNCH(e, K_SCAN3, k_scan_apply, nb, 256, e->G.packed, e->G.scan_blk, e->G.cell_start, e->G.occ_pos, e->G.act_pos, nn);
-  LAUNCH(e, K_FILL, k_cell_fill, nblk(np, 256), 256, e->P, e->G);
+  if (np) LAUNCH(e, K_FILL, k_cell_fill, nblk(np, 256), 256, e->P, e->G);
   LAUNCH(e, K_NODE_FINISH, k_node_finish, nblk(nn, 256), 256, e->mesh, e->P, e->G);
   if (e->reorder_every > 0 && e->steps_since_sort >= e->reorder_every) reorder_particles(e);
   e->steps_since_sort++;
   StepParams sp = make_params(e, step, update_I0);
-  const int grid = nblk((size_t)e->max_occ, e->cfg.C);
+  const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, do_predictor); }
 #define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
-  switch (e->W) { CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8) }
+#define CASE_WF(w) case w: CASE_WC(w, false) break;
+  // instantiated: 2D with 1-2 mask words (weights cached or not), 3D with 4-8 words (no weight cache)
+  if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_WF(4) CASE_WF(8) } }
+#undef CASE_WF
 #undef CASE_W
 #undef CASE_WC
 }
 template <int D>
 static void stage_p2g_mass_disp_t(nlps_engine* e, int step) {
-  LAUNCH(e, K_GRID_DISP, k_grid_disp<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step);
+  if (!e->slab_on) {
+    { auto kf = k_grid_disp<D, 0>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step); }
+  } else {
+    { auto kf = k_grid_disp<D, 1>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step); }
+    halo_exchange<D>(e, 1);
+    { auto kf = k_grid_disp<D, 2>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step); }
+  }
 }
 template <int D>
 static void stage_kin_stress_t(nlps_engine* e, int step) {
   if (e->has_traction) {
-    cudaMemsetAsync(e->P.trac, 0, sizeof(double) * (size_t)e->np * D, e->stream);
+    cudaMemsetAsync(e->P.trac, 0, sizeof(double) * (size_t)e->P.ld * D, e->stream);
     LAUNCH(e, K_TRACTION, k_traction<D>, nblk(e->neu.n_entries, 128), 128, e->P, e->neu, e->solver.thickness, step);
   }
   StepParams sp = make_params(e, step, 1);
-  const int grid = nblk((size_t)e->max_occ, e->cfg.C);
+  const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_WMC(w, mt, c) { auto kfn = k_kin_force<D, w, mt, c>; LAUNCH_SMEM(e, K_KIN_FORCE, kfn, grid, e->cfg.threads, e->smemB, e->mesh, e->P, e->G, sp, e->cfg, e->err, e->has_traction); }
-#define CASE_WM(w, mt) if (e->cache_pa) CASE_WMC(w, mt, true) else CASE_WMC(w, mt, false)
+#define CASE_WM(w, mt) if (D == 2 && e->cache_pa) CASE_WMC(w, mt, (D == 2)) else CASE_WMC(w, mt, false)
 #define CASE_W(w) case w: switch (e->uniform_mat) { case 0: CASE_WM(w, 0) break; case 1: CASE_WM(w, 1) break; case 2: CASE_WM(w, 2) break; default: CASE_WM(w, -1) break; } break;
-  switch (e->W) { CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8) }
+  if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_W(4) CASE_W(8) } }
 #undef CASE_W
 #undef CASE_WM
 #undef CASE_WMC
 }
 template <int D>
 static void stage_force_t(nlps_engine* e, int step) {
-  LAUNCH(e, K_GRID_ACC, k_grid_acc<D>, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step);
+  if (!e->slab_on) {
+    { auto kf = k_grid_acc<D, 0>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step); }
+  } else {
+    { auto kf = k_grid_acc<D, 1>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step); }
+    halo_exchange<D>(e, 2);
+    { auto kf = k_grid_acc<D, 2>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step); }
+  }
 }
 template <int D>
 static void stage_g2p_t(nlps_engine* e, int step) {
   StepParams sp = make_params(e, step, 1);
-  const int grid = nblk((size_t)e->max_occ, e->cfg.C);
-  switch (e->W) {
+  const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH_SMEM(e, K_G2P, kfn, grid, e->cfg.threads, e->smemC, e->mesh, e->P, e->G, sp, e->cfg); } break;
-    CASE_W(1) CASE_W(2) CASE_W(4) CASE_W(8)
+  if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_W(4) CASE_W(8) } }
 #undef CASE_W
-  }
   if (!e->inert_synced) {
-    k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P);
+    if (e->np) k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P);
     e->inert_synced = 1;
   }
   // roll n+1 -> n (U-Verlet.c:1043-1081) as pointer swaps
@@ -1660,6 +2066,7 @@ void nlps_b200_destroy(nlps_engine* e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_err) cudaFreeHost(e->h_err);
+  if (e->h_mig) cudaFreeHost(e->h_mig);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1672,18 +2079,50 @@ static int set_err(char* err, int len, const char* msg) {
   return 1;
 }
 
+static int upload_impl(nlps_engine* e, const nlps_particles* in, int rows);
 static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds,
                        const nlps_load* bounds, int n_neumann, const nlps_load* neumann, const double* gravity,
-                       int n_materials, const nlps_material* materials, const nlps_particles* st, char* err,
-                       int err_len) {
-  const int D = mesh->ndim, nn = mesh->n_nodes, np = st->n;
+                       int n_materials, const nlps_material* materials, const nlps_particles* st,
+                       const nlps_slab* slab, char* err, int err_len) {
+  const int D = mesh->ndim, nn = mesh->n_nodes;
+  if (D != 2 && D != 3) return set_err(err, err_len, "ndim must be 2 or 3");
+  if (!st->x_GC || !st->mass || !st->Vol_0 || !st->rho || !st->I0 || !st->MatIdx)
+    return set_err(err, err_len, "x_GC, mass, Vol_0, rho, I0 and MatIdx are mandatory");
+  for (int p = 0; p < st->n; p++)
+    if (st->I0[p] < 0 || st->I0[p] >= nn) return set_err(err, err_len, "I0 out of range");
+  // ---- which rows of `state` this engine holds
+  std::vector<int> rows;  // state rows held (slab engines only)
+  int np = st->n, ld = st->n;
+  e->n_global = st->n;
+  e->solver_dx = mesh->delta_x;
+  if (slab) {
+    if (slab->world < 1 || slab->rank < 0 || slab->rank >= slab->world || slab->axis < 0 || slab->axis >= D)
+      return set_err(err, err_len, "bad slab description");
+    if (slab->world > 1 && (!slab->cuts || !slab->comm)) return set_err(err, err_len, "slabs need cuts and a communicator");
+    e->slab_on = 1;
+    e->rank = slab->rank; e->world = slab->world; e->axis = slab->axis; e->comm = slab->comm;
+    e->band_cells = slab->band_cells > 0 ? slab->band_cells : 6;
+    if (e->band_cells < 4) return set_err(err, err_len, "band_cells must be >= 4");
+    e->migrate_every = slab->migrate_every > 0 ? slab->migrate_every : 10;
+    e->n_global = slab->global_id ? slab->n_global : st->n;
+    if (e->n_global < st->n && !slab->global_id) return set_err(err, err_len, "n_global smaller than the state");
+    e->cut_lo = slab->rank > 0 ? slab->cuts[slab->rank - 1] : -1e300;
+    e->cut_hi = slab->rank < slab->world - 1 ? slab->cuts[slab->rank] : 1e300;
+    if (slab->rank > 0 && slab->rank < slab->world - 1 && !(e->cut_hi - e->cut_lo > 2.0 * e->band_cells * mesh->delta_x))
+      return set_err(err, err_len, "slab narrower than two halo bands");
+    for (int p = 0; p < st->n; p++) {
+      if (slab->global_id && (slab->global_id[p] < 0 || slab->global_id[p] >= e->n_global))
+        return set_err(err, err_len, "global particle id out of range");
+      if (nlps_b200_slab_owner(mesh, slab->axis, slab->world, slab->cuts, st->I0[p]) == slab->rank) rows.push_back(p);
+    }
+    np = (int)rows.size();
+    const double capf = slab->capacity_factor > 1.0 ? slab->capacity_factor : 1.3;
+    ld = (int)(capf * std::max<double>(np, (double)e->n_global / slab->world)) + 1024;
+  }
   e->D = D; e->T = (D == 2) ? 5 : 9; e->TB = e->T; e->nn = nn; e->np = np;
   e->solver = *solver;
   if (e->solver.quirk_transposed_eigvec < 0) e->solver.quirk_transposed_eigvec = (D == 2) ? 1 : 0;
-  if (D != 2 && D != 3) return set_err(err, err_len, "ndim must be 2 or 3");
   if (n_materials < 1 || n_materials > MAX_MATERIALS) return set_err(err, err_len, "1..8 materials supported");
-  if (!st->x_GC || !st->mass || !st->Vol_0 || !st->rho || !st->I0 || !st->MatIdx)
-    return set_err(err, err_len, "x_GC, mass, Vol_0, rho, I0 and MatIdx are mandatory");
   CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&e->ev0));
   CUDA_OK(cudaEventCreate(&e->ev1));
@@ -1697,7 +2136,9 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   e->cap_r2 = maxr2;
   e->W = (maxr2 + 31) / 32;
   while (e->W & (e->W - 1)) e->W++;  // kernels are instantiated for 1, 2, 4, 8 mask words
-  if (e->W > MAX_MASK_WORDS) return set_err(err, err_len, "2-ring larger than 256 nodes is not supported");
+  if (D == 3 && e->W < 4) e->W = 4;
+  if (e->W > MAX_MASK_WORDS || (D == 2 && e->W > 2))
+    return set_err(err, err_len, "2-ring larger than 64 (2D) / 256 (3D) nodes is not supported");
   double* dX; int *r1p, *r1i, *r2p, *r2i, *t1p, *t1i, *t2p, *t2i; double* dh;
   {
     const int xs = (D == 2) ? 2 : 4;
@@ -1731,14 +2172,15 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   if (dev_upload(e, &dq, qpos.data(), qpos.size())) return 1;
   CUDA_OK(cudaStreamSynchronize(e->stream));
   e->mesh = MeshDev{nn, dX, r1p, r1i, r2p, r2i, t1p, t1i, t2p, t2i, dq, dh};
-  e->max_occ = (int)std::min<long long>(nn, np);
-  e->max_act = (int)std::min<long long>(nn, (long long)np * maxr1);
+  e->max_occ = (int)std::min<long long>(nn, std::max(ld, 1));
+  e->max_act = (int)std::min<long long>(nn, (long long)std::max(ld, 1) * maxr1);
   // ---- grid work arrays
   GridDev& G = e->G;
   if (dev_alloc(e, &G.M, nn) || dev_alloc(e, &G.UA, (size_t)nn * 2 * (D == 2 ? 2 : 4)) || dev_alloc(e, &G.F, (size_t)nn * D) ||
       dev_alloc(e, &G.active, nn) || dev_alloc(e, &G.fixed, nn) ||
       dev_alloc(e, &G.cnt, nn) || dev_alloc(e, &G.cursor, nn) || dev_alloc(e, &G.cell_start, nn) ||
-      dev_alloc(e, &G.plist, np) || dev_alloc(e, &G.act_list, nn) || dev_alloc(e, &G.n_active, 1) ||
+      dev_alloc(e, &G.MOM, (size_t)nn * D) || dev_alloc(e, &G.rocc, nn) ||
+      dev_alloc(e, &G.plist, ld) || dev_alloc(e, &G.act_list, nn) || dev_alloc(e, &G.n_active, 1) ||
       dev_alloc(e, &G.packed, nn) || dev_alloc(e, &G.scan_blk, (size_t)nblk(nn, SCAN_ITEMS) + 1) ||
       dev_alloc(e, &G.act_pos, nn) || dev_alloc(e, &G.occ_pos, nn) || dev_alloc(e, &G.occ_list, e->max_occ) ||
       dev_alloc(e, &G.n_occ, 1) || dev_alloc(e, &e->npart_check, 1) || dev_alloc(e, &e->err, 2) ||
@@ -1757,7 +2199,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     c.threads = 128;
     if (const char* s_ = getenv("NLPS_THREADS")) c.threads = std::max(32, atoi(s_) / 32 * 32);
     e->cache_pa = (D == 2);
-    if (const char* s_ = getenv("NLPS_CACHE_PA")) e->cache_pa = atoi(s_) != 0;
+    if (const char* s_ = getenv("NLPS_CACHE_PA")) e->cache_pa = (D == 2) && atoi(s_) != 0;
     c.C = 32;
     if (const char* s_ = getenv("NLPS_CELLS_PER_BLOCK")) c.C = std::max(1, atoi(s_));
     auto sizes = [&](const BlockCfg& k, size_t& a, size_t& b, size_t& g) {
@@ -1777,7 +2219,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     // keep at least two blocks per SM resident: halve the cells per block until the largest layout fits
     const size_t budget = std::min<size_t>((size_t)e->max_smem_optin, 100 * 1024);
     for (;;) {
-      const double ppc = std::max(1.0, (double)np / std::max(1, e->max_occ));  // particles per occupied cell (lower bound)
+      const double ppc = std::max(1.0, (double)std::max(np, 1) / std::max(1, e->max_occ));  // particles per occupied cell (lower bound)
       c.PCAP = std::max(32, (int)(c.C * std::max(ppc, (D == 2) ? 4.0 : 8.0) * 1.25 + 0.5));
       if (const char* s_ = getenv("NLPS_PCAP")) c.PCAP = std::max(1, atoi(s_));
       sizes(c, e->smemA, e->smemB, e->smemC);
@@ -1837,7 +2279,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     for (int b = 0; b < n_neumann; b++) {
       dims[b] = neumann[b].dim;
       for (int j = 0; j < neumann[b].n_ids; j++) {
-        if (neumann[b].ids[j] < 0 || neumann[b].ids[j] >= np) return set_err(err, err_len, "Neumann particle id out of range");
+        if (neumann[b].ids[j] < 0 || neumann[b].ids[j] >= e->n_global) return set_err(err, err_len, "Neumann particle id out of range");
         part[o] = neumann[b].ids[j]; load[o] = b; o++;
       }
     }
@@ -1883,8 +2325,9 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   // ---- particles
   PartDev& P = e->P;
   P.np = np;
+  P.ld = ld;
   const int T = e->T, DD = D * D, TBv = (D == 2) ? 5 : 9;
-#define A_(f, c) if (dev_alloc(e, &P.f, (size_t)np * (c))) return 1;
+#define A_(f, c) if (dev_alloc(e, &P.f, (size_t)ld * (c))) return 1;
   A_(x, D) A_(dis, D) A_(ddis, D) A_(vel, D) A_(acc, D) A_(lam, D)
   A_(beta, 1) A_(mass, 1) A_(vol0, 1) A_(rho, 1) A_(W, 1)
   A_(J_n, 1) A_(J_n1, 1) A_(eps_n, 1) A_(eps_n1, 1) A_(kap_n, 1) A_(kap_n1, 1)
@@ -1892,41 +2335,89 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   A_(Fs4, 1) A_(DFs4, 1)
 #undef A_
   P.trac = nullptr;
-  if (e->has_traction && dev_alloc(e, &P.trac, (size_t)np * D)) return 1;
-  if (dev_alloc(e, &P.I0, np) || dev_alloc(e, &P.nnodes, np) || dev_alloc(e, &P.matidx, np) ||
-      dev_alloc(e, &P.orig, np) || dev_alloc(e, &P.inv, np) || dev_alloc(e, &P.mask, (size_t)np * e->W))
+  if (e->has_traction && dev_alloc(e, &P.trac, (size_t)ld * D)) return 1;
+  if (dev_alloc(e, &P.I0, ld) || dev_alloc(e, &P.nnodes, ld) || dev_alloc(e, &P.matidx, ld) ||
+      dev_alloc(e, &P.orig, ld) || dev_alloc(e, &P.inv, std::max(e->n_global, 1)) || dev_alloc(e, &P.mask, (size_t)ld * e->W))
     return 1;
-  k_iota<<<nblk(np, 256), 256, 0, e->stream>>>(P.orig, P.inv, np);
-  e->stage_doubles = (size_t)np * std::max(std::max(T, DD), (e->W + 1) / 2);
+  e->stage_doubles = (size_t)std::max(ld, 1) * std::max(std::max(T, DD), (e->W + 1) / 2);
   if (dev_alloc(e, &e->stage, e->stage_doubles)) return 1;
   // defaults as allocate_U_vars__Fields__ leaves them (identity tensors, J = 1)
-  auto fill = [&](double* a, size_t n, double v) { k_fill_d<<<nblk(n, 256), 256, 0, e->stream>>>(a, n, v); };
+  auto fill = [&](double* a, size_t n, double v) { if (n) k_fill_d<<<nblk(n, 256), 256, 0, e->stream>>>(a, n, v); };
   for (int i = 0; i < D; i++) {
-    fill(P.F_n + (size_t)(i * D + i) * np, np, 1.0);
-    fill(P.F_n1 + (size_t)(i * D + i) * np, np, 1.0);
-    fill(P.DF + (size_t)(i * D + i) * np, np, 1.0);
-    fill(P.be_n + (size_t)(i * D + i) * np, np, 1.0);
-    fill(P.be_n1 + (size_t)(i * D + i) * np, np, 1.0);
+    fill(P.F_n + (size_t)(i * D + i) * ld, ld, 1.0);
+    fill(P.F_n1 + (size_t)(i * D + i) * ld, ld, 1.0);
+    fill(P.DF + (size_t)(i * D + i) * ld, ld, 1.0);
+    fill(P.be_n + (size_t)(i * D + i) * ld, ld, 1.0);
+    fill(P.be_n1 + (size_t)(i * D + i) * ld, ld, 1.0);
   }
-  if (D == 2) { fill(P.be_n + (size_t)4 * np, np, 1.0); fill(P.be_n1 + (size_t)4 * np, np, 1.0); }
-  fill(P.Fs4, np, 1.0); fill(P.DFs4, np, 1.0);
-  fill(P.J_n, np, 1.0); fill(P.J_n1, np, 1.0);
-  CUDA_OK(cudaStreamSynchronize(e->stream));
-  if (nlps_b200_upload(e, st)) return 1;
-  CUDA_OK(cudaMemcpyAsync(P.I0, st->I0, sizeof(int) * np, cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaMemcpyAsync(P.matidx, st->MatIdx, sizeof(int) * np, cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaStreamSynchronize(e->stream));
-  for (int p = 0; p < np; p++)
+  if (D == 2) { fill(P.be_n + (size_t)4 * ld, ld, 1.0); fill(P.be_n1 + (size_t)4 * ld, ld, 1.0); }
+  fill(P.Fs4, ld, 1.0); fill(P.DFs4, ld, 1.0);
+  fill(P.J_n, ld, 1.0); fill(P.J_n1, ld, 1.0);
+  for (int p = 0; p < st->n; p++)
     if (st->MatIdx[p] < 0 || st->MatIdx[p] >= n_materials) return set_err(err, err_len, "MatIdx out of range");
-  for (int p = 0; p < np; p++)
-    if (st->I0[p] < 0 || st->I0[p] >= nn) return set_err(err, err_len, "I0 out of range");
+  if (!e->slab_on) {
+    k_iota<<<nblk(std::max(np, 1), 256), 256, 0, e->stream>>>(P.orig, P.inv, np);
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    if (upload_impl(e, st, 0)) return 1;
+    CUDA_OK(cudaMemcpyAsync(P.I0, st->I0, sizeof(int) * np, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(P.matidx, st->MatIdx, sizeof(int) * np, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+  }
+  // ---- slab engine: gather the held rows on the host, ids = global ids
+  {
+    e->h_ids = rows;  // state-row indices: upload_impl(rows = 1) gathers by them
+    if (upload_impl(e, st, 1)) return 1;
+    std::vector<int> i0(std::max(np, 1)), mi(std::max(np, 1)), gid(std::max(np, 1));
+    for (int p = 0; p < np; p++) {
+      i0[p] = st->I0[rows[p]];
+      mi[p] = st->MatIdx[rows[p]];
+      gid[p] = slab->global_id ? slab->global_id[rows[p]] : rows[p];
+    }
+    CUDA_OK(cudaMemcpyAsync(P.I0, i0.data(), sizeof(int) * np, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(P.matidx, mi.data(), sizeof(int) * np, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(P.orig, gid.data(), sizeof(int) * np, cudaMemcpyHostToDevice, e->stream));
+    k_fill_i<<<nblk(std::max(e->n_global, 1), 256), 256, 0, e->stream>>>(P.inv, (size_t)e->n_global, -1);
+    if (np) k_set_inv<<<nblk(np, 256), 256, 0, e->stream>>>(P.orig, P.inv, np);
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->h_ids = gid;
+    e->h_ids.resize(np);
+  }
+  // ---- halo node lists (identical on both sides of a cut) and exchange buffers
+  for (int s_ = 0; s_ < 2; s_++) {
+    const int peer = s_ == 0 ? e->rank - 1 : e->rank + 1;
+    if (peer < 0 || peer >= e->world) continue;
+    const double cut = s_ == 0 ? e->cut_lo : e->cut_hi;
+    const int n = nlps_b200_slab_halo_nodes(mesh, e->axis, cut, e->band_cells, nullptr);
+    std::vector<int> ids(std::max(n, 1));
+    nlps_b200_slab_halo_nodes(mesh, e->axis, cut, e->band_cells, ids.data());
+    auto& h = e->side[s_];
+    h.peer = peer;
+    h.n = n;
+    if (dev_upload(e, &h.ids, ids.data(), (size_t)n) || dev_alloc(e, &h.sbuf, (size_t)n * (1 + D)) ||
+        dev_alloc(e, &h.rbuf, (size_t)n * (1 + D)))
+      return 1;
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
+  // ---- migration buffers
+  {
+    const size_t row_bytes = 8 * (size_t)(6 * D + 11 + 4 * DD + 3 * T + 2) + 4 * (size_t)(4 + e->W);
+    e->mig_cap = std::max(4096, ld / 8);
+    if (dev_alloc(e, &e->mig_dest, ld) || dev_alloc(e, &e->mig_cnt, 16) || dev_alloc(e, &e->mig_tab, 256)) return 1;
+    for (int s_ = 0; s_ < 2; s_++)
+      if (e->side[s_].peer >= 0 &&
+          (dev_alloc(e, &e->mig_sbuf[s_], row_bytes * e->mig_cap) || dev_alloc(e, &e->mig_rbuf[s_], row_bytes * e->mig_cap)))
+        return 1;
+    CUDA_OK(cudaMallocHost(&e->h_mig, 16 * sizeof(int)));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
   return 0;
 }
 
-nlps_engine* nlps_b200_create(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
-                              int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
-                              const nlps_material* materials, const nlps_particles* state, int device, char* err,
-                              int err_len) {
+static nlps_engine* create_any(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
+                               int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
+                               const nlps_material* materials, const nlps_particles* state, const nlps_slab* slab,
+                               int device, char* err, int err_len) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_err(err, err_len, "no CUDA device: this library has no CPU fallback");
@@ -1938,81 +2429,171 @@ nlps_engine* nlps_b200_create(const nlps_mesh* mesh, const nlps_solver* solver, 
   }
   nlps_engine* e = new nlps_engine();
   e->device = device;
-  if (create_impl(e, mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, err,
-                  err_len)) {
+  if (create_impl(e, mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, slab,
+                  err, err_len)) {
     nlps_b200_destroy(e);
     return nullptr;
   }
   return e;
 }
 
-int nlps_b200_upload(nlps_engine* e, const nlps_particles* in) {
-  cudaSetDevice(e->device);
+nlps_engine* nlps_b200_create(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
+                              int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
+                              const nlps_material* materials, const nlps_particles* state, int device, char* err,
+                              int err_len) {
+  return create_any(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, nullptr,
+                    device, err, err_len);
+}
+
+nlps_engine* nlps_b200_create_slab(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds,
+                                   const nlps_load* bounds, int n_neumann, const nlps_load* neumann,
+                                   const double* gravity, int n_materials, const nlps_material* materials,
+                                   const nlps_particles* state, const nlps_slab* slab, int device, char* err,
+                                   int err_len) {
+  if (!slab) {
+    set_err(err, err_len, "nlps_b200_create_slab: slab description missing");
+    return nullptr;
+  }
+  return create_any(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, slab,
+                    device, err, err_len);
+}
+
+static int upload_impl(nlps_engine* e, const nlps_particles* in, int rows) {
   if (in->b_e_n || in->b_e_n1 || in->EPS_n || in->EPS_n1 || in->Kappa_n || in->Kappa_n1) e->inert_synced = 0;
   const int D = e->D, T = e->T, DD = D * D;
   PartDev& P = e->P;
-  if (put_field(e, in->x_GC, P.x, D, D, 0) || put_field(e, in->dis, P.dis, D, D, 0) ||
-      put_field(e, in->D_dis, P.ddis, D, D, 0) || put_field(e, in->vel, P.vel, D, D, 0) ||
-      put_field(e, in->acc, P.acc, D, D, 0) || put_field(e, in->lambda, P.lam, D, D, 0))
+  if (put_field(e, in->x_GC, P.x, D, D, 0, rows) || put_field(e, in->dis, P.dis, D, D, 0, rows) ||
+      put_field(e, in->D_dis, P.ddis, D, D, 0, rows) || put_field(e, in->vel, P.vel, D, D, 0, rows) ||
+      put_field(e, in->acc, P.acc, D, D, 0, rows) || put_field(e, in->lambda, P.lam, D, D, 0, rows))
     return 1;
-  if (put_field(e, in->F_n, P.F_n, DD, T, 0) || put_field(e, in->F_n1, P.F_n1, DD, T, 0) ||
-      put_field(e, in->DF, P.DF, DD, T, 0))
+  if (put_field(e, in->F_n, P.F_n, DD, T, 0, rows) || put_field(e, in->F_n1, P.F_n1, DD, T, 0, rows) ||
+      put_field(e, in->DF, P.DF, DD, T, 0, rows))
     return 1;
   if (D == 2) {
-    if (put_field(e, in->F_n, P.Fs4, 1, T, 4) || put_field(e, in->DF, P.DFs4, 1, T, 4)) return 1;
+    if (put_field(e, in->F_n, P.Fs4, 1, T, 4, rows) || put_field(e, in->DF, P.DFs4, 1, T, 4, rows)) return 1;
   }
-  if (put_field(e, in->b_e_n, P.be_n, T, T, 0) || put_field(e, in->b_e_n1, P.be_n1, T, T, 0) ||
-      put_field(e, in->Stress, P.stress, T, T, 0) || put_field(e, in->C_ep, P.cep, DD, DD, 0))
+  if (put_field(e, in->b_e_n, P.be_n, T, T, 0, rows) || put_field(e, in->b_e_n1, P.be_n1, T, T, 0, rows) ||
+      put_field(e, in->Stress, P.stress, T, T, 0, rows) || put_field(e, in->C_ep, P.cep, DD, DD, 0, rows))
     return 1;
-  if (put_field(e, in->J_n, P.J_n, 1, 1, 0) || put_field(e, in->J_n1, P.J_n1, 1, 1, 0) ||
-      put_field(e, in->mass, P.mass, 1, 1, 0) || put_field(e, in->rho, P.rho, 1, 1, 0) ||
-      put_field(e, in->Vol_0, P.vol0, 1, 1, 0) || put_field(e, in->W, P.W, 1, 1, 0) ||
-      put_field(e, in->EPS_n, P.eps_n, 1, 1, 0) || put_field(e, in->EPS_n1, P.eps_n1, 1, 1, 0) ||
-      put_field(e, in->Kappa_n, P.kap_n, 1, 1, 0) || put_field(e, in->Kappa_n1, P.kap_n1, 1, 1, 0) ||
-      put_field(e, in->Beta, P.beta, 1, 1, 0))
+  if (put_field(e, in->J_n, P.J_n, 1, 1, 0, rows) || put_field(e, in->J_n1, P.J_n1, 1, 1, 0, rows) ||
+      put_field(e, in->mass, P.mass, 1, 1, 0, rows) || put_field(e, in->rho, P.rho, 1, 1, 0, rows) ||
+      put_field(e, in->Vol_0, P.vol0, 1, 1, 0, rows) || put_field(e, in->W, P.W, 1, 1, 0, rows) ||
+      put_field(e, in->EPS_n, P.eps_n, 1, 1, 0, rows) || put_field(e, in->EPS_n1, P.eps_n1, 1, 1, 0, rows) ||
+      put_field(e, in->Kappa_n, P.kap_n, 1, 1, 0, rows) || put_field(e, in->Kappa_n1, P.kap_n1, 1, 1, 0, rows) ||
+      put_field(e, in->Beta, P.beta, 1, 1, 0, rows))
     return 1;
+  return 0;
+}
+
+int nlps_b200_upload(nlps_engine* e, const nlps_particles* in) {
+  cudaSetDevice(e->device);
+  if (!e->slab_on) return upload_impl(e, in, 0);
+  if (refresh_ids(e)) return 1;  // rows of `in` are indexed by global id
+  return upload_impl(e, in, 1);
+}
+
+static int download_impl(nlps_engine* e, nlps_particles* out, int rows) {
+  const int D = e->D, T = e->T, DD = D * D;
+  PartDev& P = e->P;
+  if (get_field(e, out->x_GC, P.x, D, D, 0, nullptr, rows) || get_field(e, out->dis, P.dis, D, D, 0, nullptr, rows) ||
+      get_field(e, out->D_dis, P.ddis, D, D, 0, nullptr, rows) || get_field(e, out->vel, P.vel, D, D, 0, nullptr, rows) ||
+      get_field(e, out->acc, P.acc, D, D, 0, nullptr, rows) || get_field(e, out->lambda, P.lam, D, D, 0, nullptr, rows))
+    return 1;
+  if (D == 2) {
+    if (get_field(e, out->F_n, P.F_n, DD, T, 0, P.Fs4, rows) || get_field(e, out->F_n1, P.F_n1, DD, T, 0, P.Fs4, rows) ||
+        get_field(e, out->DF, P.DF, DD, T, 0, P.DFs4, rows))
+      return 1;
+  } else {
+    if (get_field(e, out->F_n, P.F_n, DD, T, 0, nullptr, rows) || get_field(e, out->F_n1, P.F_n1, DD, T, 0, nullptr, rows) ||
+        get_field(e, out->DF, P.DF, DD, T, 0, nullptr, rows))
+      return 1;
+  }
+  if (get_field(e, out->b_e_n, P.be_n, T, T, 0, nullptr, rows) || get_field(e, out->b_e_n1, P.be_n1, T, T, 0, nullptr, rows) ||
+      get_field(e, out->Stress, P.stress, T, T, 0, nullptr, rows) || get_field(e, out->C_ep, P.cep, DD, DD, 0, nullptr, rows))
+    return 1;
+  if (get_field(e, out->J_n, P.J_n, 1, 1, 0, nullptr, rows) || get_field(e, out->J_n1, P.J_n1, 1, 1, 0, nullptr, rows) ||
+      get_field(e, out->mass, P.mass, 1, 1, 0, nullptr, rows) || get_field(e, out->rho, P.rho, 1, 1, 0, nullptr, rows) ||
+      get_field(e, out->Vol_0, P.vol0, 1, 1, 0, nullptr, rows) || get_field(e, out->W, P.W, 1, 1, 0, nullptr, rows) ||
+      get_field(e, out->EPS_n, P.eps_n, 1, 1, 0, nullptr, rows) || get_field(e, out->EPS_n1, P.eps_n1, 1, 1, 0, nullptr, rows) ||
+      get_field(e, out->Kappa_n, P.kap_n, 1, 1, 0, nullptr, rows) || get_field(e, out->Kappa_n1, P.kap_n1, 1, 1, 0, nullptr, rows) ||
+      get_field(e, out->Beta, P.beta, 1, 1, 0, nullptr, rows))
+    return 1;
+  if (get_ints(e, out->I0, P.I0, rows) || get_ints(e, out->NumberNodes, P.nnodes, rows)) return 1;
   return 0;
 }
 
 int nlps_b200_download(nlps_engine* e, nlps_particles* out) {
   cudaSetDevice(e->device);
-  const int D = e->D, T = e->T, DD = D * D;
-  PartDev& P = e->P;
-  if (get_field(e, out->x_GC, P.x, D, D, 0) || get_field(e, out->dis, P.dis, D, D, 0) ||
-      get_field(e, out->D_dis, P.ddis, D, D, 0) || get_field(e, out->vel, P.vel, D, D, 0) ||
-      get_field(e, out->acc, P.acc, D, D, 0) || get_field(e, out->lambda, P.lam, D, D, 0))
+  if (!e->slab_on) return download_impl(e, out, 0);
+  if (out->n < e->n_global) {
+    fprintf(stderr, "nlps_b200_download: slab engines write rows by global id: out->n must be n_global\n");
     return 1;
-  if (D == 2) {
-    if (get_field(e, out->F_n, P.F_n, DD, T, 0, P.Fs4) || get_field(e, out->F_n1, P.F_n1, DD, T, 0, P.Fs4) ||
-        get_field(e, out->DF, P.DF, DD, T, 0, P.DFs4))
-      return 1;
-  } else {
-    if (get_field(e, out->F_n, P.F_n, DD, T, 0) || get_field(e, out->F_n1, P.F_n1, DD, T, 0) ||
-        get_field(e, out->DF, P.DF, DD, T, 0))
-      return 1;
   }
-  if (get_field(e, out->b_e_n, P.be_n, T, T, 0) || get_field(e, out->b_e_n1, P.be_n1, T, T, 0) ||
-      get_field(e, out->Stress, P.stress, T, T, 0) || get_field(e, out->C_ep, P.cep, DD, DD, 0))
-    return 1;
-  if (get_field(e, out->J_n, P.J_n, 1, 1, 0) || get_field(e, out->J_n1, P.J_n1, 1, 1, 0) ||
-      get_field(e, out->mass, P.mass, 1, 1, 0) || get_field(e, out->rho, P.rho, 1, 1, 0) ||
-      get_field(e, out->Vol_0, P.vol0, 1, 1, 0) || get_field(e, out->W, P.W, 1, 1, 0) ||
-      get_field(e, out->EPS_n, P.eps_n, 1, 1, 0) || get_field(e, out->EPS_n1, P.eps_n1, 1, 1, 0) ||
-      get_field(e, out->Kappa_n, P.kap_n, 1, 1, 0) || get_field(e, out->Kappa_n1, P.kap_n1, 1, 1, 0) ||
-      get_field(e, out->Beta, P.beta, 1, 1, 0))
-    return 1;
-  if (out->I0) {
-    k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(P.I0, (int*)e->stage, P.orig, e->np);
-    CUDA_OK(cudaMemcpyAsync(out->I0, e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
+  if (refresh_ids(e)) return 1;
+  return download_impl(e, out, 1);
+}
+
+int nlps_b200_local_count(nlps_engine* e) { return e->np; }
+
+int nlps_b200_download_local(nlps_engine* e, nlps_particles* out, int* ids) {
+  cudaSetDevice(e->device);
+  if (out->n < e->np) return 1;
+  if (refresh_ids(e)) return 1;
+  if (ids) memcpy(ids, e->h_ids.data(), sizeof(int) * e->np);
+  // compact rows in slot order (MatIdx is not part of download(): fetch it here for completeness of a row)
+  if (out->MatIdx && e->np) {
+    CUDA_OK(cudaMemcpyAsync(out->MatIdx, e->P.matidx, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
   }
-  if (out->NumberNodes) {
-    k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(P.nnodes, (int*)e->stage, P.orig, e->np);
-    CUDA_OK(cudaMemcpyAsync(out->NumberNodes, e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream));
-  }
-  CUDA_OK(cudaStreamSynchronize(e->stream));
+  return download_impl(e, out, 2);
+}
+
+int nlps_b200_migrate(nlps_engine* e) {
+  cudaSetDevice(e->device);
+  int rc = (e->D == 2) ? migrate_t<2>(e) : migrate_t<3>(e);
+  return rc ? 1 : poll_error(e);
+}
+long long nlps_b200_migrated_count(nlps_engine* e) { return e->n_migrated_in; }
+
+int nlps_b200_comm_unique_id(char id[128]) {
+  ncclUniqueId u;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  NcclApi* N = nccl_api();
+  if (!N || N->GetUniqueId(&u) != ncclSuccess) return 1;
+  memcpy(id, &u, 128);
   return 0;
 }
+nlps_comm* nlps_b200_comm_create_nccl(const char id[128], int rank, int world, int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  nlps_comm* c = new nlps_comm();
+  c->rank = rank; c->world = world; c->is_nccl = 1;
+  NcclApi* N = nccl_api();
+  ncclResult_t r = N ? N->CommInitRank(&c->nccl, world, u, rank) : ncclSystemError;
+  if (r != ncclSuccess) {
+    fprintf(stderr, "nlps_b200_comm_create_nccl: %s\n", N ? N->GetErrorString(r) : "NCCL library not available");
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+nlps_comm* nlps_b200_comm_create_custom(int rank, int world, nlps_exchange_fn fn, void* user) {
+  if (!fn) return nullptr;
+  nlps_comm* c = new nlps_comm();
+  c->rank = rank; c->world = world; c->fn = fn; c->user = user;
+  return c;
+}
+void nlps_b200_comm_destroy(nlps_comm* c) {
+  if (!c) return;
+  if (c->is_nccl && c->nccl) nccl_api()->CommDestroy(c->nccl);
+  delete c;
+}
+int nlps_b200_memcpy_d2d(void* dst, const void* src, unsigned long long bytes, void* cuda_stream) {
+  if (!bytes) return 0;
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream) == cudaSuccess ? 0 : 1;
+}
+int nlps_b200_stream_sync(void* cuda_stream) { return cudaStreamSynchronize((cudaStream_t)cuda_stream) == cudaSuccess ? 0 : 1; }
 
 int nlps_b200_initialize_lme(nlps_engine* e) {
   cudaSetDevice(e->device);
@@ -2079,16 +2660,26 @@ int nlps_b200_list_capacity(nlps_engine* e) { return e->cap; }
 
 int nlps_b200_get_lists(nlps_engine* e, int* counts, int* lists, int cap) {
   cudaSetDevice(e->device);
+  if (e->np == 0) return 0;
   int* tmp = nullptr;
   size_t n = (size_t)e->np * cap;
   CUDA_OK(cudaMalloc(&tmp, n * sizeof(int)));
-  k_expand_lists<<<nblk(e->np, 128), 128, 0, e->stream>>>(e->mesh, e->P, e->W, cap, tmp);
-  cudaError_t st = cudaMemcpyAsync(lists, tmp, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-  if (st == cudaSuccess && counts) {
-    k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P.nnodes, (int*)e->stage, e->P.orig, e->np);
-    st = cudaMemcpyAsync(counts, e->stage, sizeof(int) * e->np, cudaMemcpyDeviceToHost, e->stream);
+  k_expand_lists<<<nblk(e->np, 128), 128, 0, e->stream>>>(e->mesh, e->P, e->W, cap, tmp, e->slab_on);
+  cudaError_t st = cudaSuccess;
+  if (!e->slab_on) {
+    st = cudaMemcpyAsync(lists, tmp, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+    if (st == cudaSuccess && counts && get_ints(e, counts, e->P.nnodes, 0)) st = cudaErrorUnknown;
+  } else {  // rows of the caller's arrays are indexed by global id
+    std::vector<int> h(n);
+    st = cudaMemcpyAsync(h.data(), tmp, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+    if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
+    if (st == cudaSuccess && refresh_ids(e)) st = cudaErrorUnknown;
+    if (st == cudaSuccess) {
+      for (int p = 0; p < e->np; p++) memcpy(lists + (size_t)e->h_ids[p] * cap, &h[(size_t)p * cap], sizeof(int) * cap);
+      if (counts && get_ints(e, counts, e->P.nnodes, 1)) st = cudaErrorUnknown;
+    }
   }
-  if (st == cudaSuccess) st = cudaStreamSynchronize(e->stream);
   cudaFree(tmp);
   return st == cudaSuccess ? 0 : 1;
 }
@@ -2115,14 +2706,16 @@ void nlps_b200_reset_kernel_times(nlps_engine* e) {
 }
 long long nlps_b200_launch_count(nlps_engine* e) { return e->launches; }
 
-int nlps_b200_u_verlet(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
+static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
                        int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
-                       const nlps_material* materials, nlps_particles* state, int run_initialize, int results_every,
-                       nlps_results_cb cb, void* user, int device) {
+                       const nlps_material* materials, nlps_particles* state, const nlps_slab* slab, int run_initialize,
+                       int results_every, nlps_results_cb cb, void* user, int device) {
   char msg[256];
-  nlps_engine* e = nlps_b200_create(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials,
-                                    state, device, msg, sizeof(msg));
+  nlps_engine* e = create_any(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state,
+                              slab, device, msg, sizeof(msg));
   if (!e) return 1;
+  const bool compact = slab && slab->global_id;
+  auto fetch = [&]() { return compact ? nlps_b200_download_local(e, state, nullptr) : nlps_b200_download(e, state); };
   int status = 0;
   if (run_initialize) status = nlps_b200_initialize_lme(e);
   int k = solver->initial_step;
@@ -2135,13 +2728,31 @@ int nlps_b200_u_verlet(const nlps_mesh* mesh, const nlps_solver* solver, int n_b
     status = nlps_b200_run(e, k, chunk);
     k += chunk;
     if (!status && results_every > 0 && ((k - 1) % results_every == 0)) {
-      status = nlps_b200_download(e, state);
+      status = fetch();
       if (!status && cb) cb(k - 1, user);
     }
   }
-  if (!status) status = nlps_b200_download(e, state);
+  if (!status) status = fetch();
+  if (compact) state->n = e->np;
   nlps_b200_destroy(e);
   return status;
+}
+
+int nlps_b200_u_verlet(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
+                       int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
+                       const nlps_material* materials, nlps_particles* state, int run_initialize, int results_every,
+                       nlps_results_cb cb, void* user, int device) {
+  return scheme_call(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, nullptr,
+                     run_initialize, results_every, cb, user, device);
+}
+
+int nlps_b200_u_verlet_slab(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
+                            int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
+                            const nlps_material* materials, nlps_particles* state, const nlps_slab* slab,
+                            int run_initialize, int results_every, nlps_results_cb cb, void* user, int device) {
+  if (!slab) return 1;
+  return scheme_call(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, slab,
+                     run_initialize, results_every, cb, user, device);
 }
 
 int nlps_b200_stress_points(int ndim, const nlps_material* material, double tol_radial, int max_iter_radial,

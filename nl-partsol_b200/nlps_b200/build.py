@@ -23,7 +23,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp,-O2", "-shared", "-o", SO] + SRCS + ["-lgomp"]
+           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fopenmp,-O2", "-shared", "-o", SO] + SRCS + ["-lgomp", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

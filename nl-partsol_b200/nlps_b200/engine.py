@@ -52,6 +52,19 @@ class Particles(C.Structure):
                                                                   ("MatIdx", _ip)]
 
 
+class Msg(C.Structure):
+    _fields_ = [("peer", C.c_int), ("send", C.c_void_p), ("send_bytes", C.c_ulonglong), ("recv", C.c_void_p),
+                ("recv_bytes", C.c_ulonglong)]
+
+
+class Slab(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("axis", C.c_int), ("cuts", _dp), ("band_cells", C.c_int),
+                ("migrate_every", C.c_int), ("capacity_factor", C.c_double), ("n_global", C.c_int),
+                ("global_id", _ip), ("comm", C.c_void_p)]
+
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(Msg), C.c_void_p)
+
 _lib = None
 
 
@@ -66,6 +79,14 @@ def lib():
         L.nlps_b200_dt.restype = C.c_double
         L.nlps_b200_version.restype = C.c_char_p
         L.nlps_b200_launch_count.restype = C.c_longlong
+        L.nlps_b200_create_slab.restype = C.c_void_p
+        L.nlps_b200_comm_create_nccl.restype = C.c_void_p
+        L.nlps_b200_comm_create_custom.restype = C.c_void_p
+        L.nlps_b200_comm_create_custom.argtypes = [C.c_int, C.c_int, EXCHANGE_FN, C.c_void_p]
+        L.nlps_b200_comm_destroy.argtypes = [C.c_void_p]
+        L.nlps_b200_memcpy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_void_p]
+        L.nlps_b200_stream_sync.argtypes = [C.c_void_p]
+        L.nlps_b200_migrated_count.restype = C.c_longlong
         _lib = L
     return _lib
 
@@ -105,6 +126,125 @@ def build_locality(ndim, coords, conn):
                                       r2p.ctypes.data_as(_ip), r2i.ctypes.data_as(_ip),
                                       h_avg.ctypes.data_as(_dp), C.byref(dx)) == 0
     return r1p, r1i, r2p, r2i, h_avg, dx.value
+
+
+def _mesh_struct(prob: Problem):
+    arrs = dict(coords=_d(prob.coords), r1p=_i(prob.r1p), r1i=_i(prob.r1i), r2p=_i(prob.r2p),
+                r2i=_i(prob.r2i), h=_d(prob.h_avg))
+    m = Mesh()
+    m.ndim, m.n_nodes = prob.ndim, prob.nn
+    m.coords = arrs["coords"].ctypes.data_as(_dp)
+    m.ring1_ptr, m.ring1_idx = arrs["r1p"].ctypes.data_as(_ip), arrs["r1i"].ctypes.data_as(_ip)
+    m.ring2_ptr, m.ring2_idx = arrs["r2p"].ctypes.data_as(_ip), arrs["r2i"].ctypes.data_as(_ip)
+    m.h_avg, m.delta_x = arrs["h"].ctypes.data_as(_dp), float(prob.dx)
+    return m, arrs
+
+
+# ---- spatial slabs: host planning, identical on every rank ------------------------
+def slab_cuts(prob: Problem, world, axis=-1, I0=None):
+    """nlps_b200_slab_cuts: (axis, cuts[world-1]) balancing the particle counts."""
+    m, keep = _mesh_struct(prob)
+    I0 = _i(prob.I0 if I0 is None else I0)
+    ax = C.c_int()
+    cuts = np.zeros(max(world - 1, 1))
+    rc = lib().nlps_b200_slab_cuts(C.byref(m), len(I0), I0.ctypes.data_as(_ip), int(world), int(axis), C.byref(ax),
+                                   cuts.ctypes.data_as(_dp))
+    if rc != 0:
+        raise RuntimeError(f"nlps_b200_slab_cuts failed ({rc})")
+    return ax.value, cuts[:world - 1].copy()
+
+
+def slab_owner(prob: Problem, axis, cuts, I0=None):
+    """Owner slab of every particle (vectorised twin of nlps_b200_slab_owner)."""
+    I0 = prob.I0 if I0 is None else I0
+    return np.searchsorted(np.asarray(cuts), prob.coords[I0, axis], side="right").astype(np.int32)
+
+
+def slab_halo_nodes(prob: Problem, axis, cut, band_cells=6):
+    m, keep = _mesh_struct(prob)
+    L = lib()
+    n = L.nlps_b200_slab_halo_nodes(C.byref(m), int(axis), C.c_double(cut), int(band_cells), None)
+    ids = np.zeros(max(n, 1), np.int32)
+    L.nlps_b200_slab_halo_nodes(C.byref(m), int(axis), C.c_double(cut), int(band_cells), ids.ctypes.data_as(_ip))
+    return ids[:n]
+
+
+class NcclComm:
+    """NCCL transport; the id travels through torch.distributed (any backend) -- plumbing only."""
+
+    def __init__(self, rank, world, device):
+        import torch
+        import torch.distributed as dist
+        L = lib()
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            assert L.nlps_b200_comm_unique_id(buf) == 0
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda(device)
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        self.h = C.c_void_p(L.nlps_b200_comm_create_nccl(raw, int(rank), int(world), int(device)))
+        if not self.h:
+            raise RuntimeError("nlps_b200_comm_create_nccl failed")
+
+    def close(self):
+        if self.h:
+            lib().nlps_b200_comm_destroy(self.h)
+            self.h = None
+
+
+class ThreadComm:
+    """Loopback transport for several slab engines inside ONE process (one thread per slab, any
+    number of GPUs -- also all on the same one): device-to-device copies behind a barrier.
+    Used by the single-GPU tests of the multi-slab path."""
+
+    class _Shared:
+        def __init__(self, world):
+            import threading
+            self.world = world
+            self.barrier = threading.Barrier(world)
+            self.box = {}
+
+    @staticmethod
+    def group(world):
+        sh = ThreadComm._Shared(world)
+        return [ThreadComm(sh, r) for r in range(world)]
+
+    def __init__(self, shared, rank):
+        L = lib()
+        self.sh, self.rank = shared, rank
+
+        def xchg(user, n, msgs, stream):
+            try:
+                sh = self.sh
+                L.nlps_b200_stream_sync(stream)
+                for k in range(n):
+                    sh.box[(rank, msgs[k].peer)] = (msgs[k].send, msgs[k].send_bytes)
+                sh.barrier.wait(timeout=120)
+                for k in range(n):
+                    src, nb = sh.box[(msgs[k].peer, rank)]
+                    if nb != msgs[k].recv_bytes:
+                        return 1
+                    if L.nlps_b200_memcpy_d2d(msgs[k].recv, src, nb, stream) != 0:
+                        return 1
+                L.nlps_b200_stream_sync(stream)
+                sh.barrier.wait(timeout=120)
+                return 0
+            except Exception:  # a broken barrier must not hang the other slabs
+                try:
+                    self.sh.barrier.abort()
+                except Exception:
+                    pass
+                return 1
+
+        self._cb = EXCHANGE_FN(xchg)
+        self.h = C.c_void_p(L.nlps_b200_comm_create_custom(rank, shared.world, self._cb, None))
+
+    def close(self):
+        if self.h:
+            lib().nlps_b200_comm_destroy(self.h)
+            self.h = None
 
 
 class _Marshal:
@@ -161,21 +301,29 @@ class _Marshal:
 class Engine:
     """Device-resident explicit NPC-FS engine (nlps_b200_create .. destroy)."""
 
-    def __init__(self, prob: Problem, device=0, quirk=-1, compute_c_ep=0):
+    def __init__(self, prob: Problem, device=0, quirk=-1, compute_c_ep=0, slab=None):
+        """slab: None, or dict(rank, world, axis, cuts, comm[, band_cells, migrate_every, capacity_factor,
+        global_id, n_global]) -- this engine then keeps the particles of `prob` its slab owns."""
         L = lib()
         self.L = L
         self.prob = prob
         self.m = _Marshal(prob, quirk, compute_c_ep)
         err = C.create_string_buffer(256)
         m = self.m
-        self.h = L.nlps_b200_create(C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds,
-                                    len(prob.neumann), m.neumann,
-                                    m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None,
-                                    len(prob.materials), m.materials, C.byref(m.state), device, err, 256)
+        args = (C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds, len(prob.neumann), m.neumann,
+                m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None, len(prob.materials), m.materials,
+                C.byref(m.state))
+        self.slab = None
+        if slab is None:
+            self.h = L.nlps_b200_create(*args, device, err, 256)
+        else:
+            self.slab = make_slab(slab, prob.np_, m.keep)
+            self.h = L.nlps_b200_create_slab(*args, C.byref(self.slab), device, err, 256)
         if not self.h:
             raise RuntimeError("nlps_b200_create failed: " + err.value.decode())
         self.h = C.c_void_p(self.h)
         self.d, self.np_, self.nn = prob.ndim, prob.np_, prob.nn
+        self.compact = slab is not None and slab.get("global_id") is not None
 
     def close(self):
         if getattr(self, "h", None):
@@ -213,6 +361,24 @@ class Engine:
         for k, v in host.items():
             out[k] = v.copy()
         return out
+
+    def local_count(self):
+        return int(self.L.nlps_b200_local_count(self.h))
+
+    def download_local(self):
+        """Compact rows of the particles this slab holds + their global ids."""
+        n = self.local_count()
+        st, host = self.m.state, self.m.host
+        assert st.n >= n, "host buffers smaller than the slab population"
+        ids = np.zeros(max(n, 1), np.int32)
+        assert self.L.nlps_b200_download_local(self.h, C.byref(st), ids.ctypes.data_as(_ip)) == 0
+        return {k: v[:n].copy() for k, v in host.items()}, ids[:n].copy()
+
+    def migrate(self):
+        return self.L.nlps_b200_migrate(self.h)
+
+    def migrated_count(self):
+        return int(self.L.nlps_b200_migrated_count(self.h))
 
     def upload(self, fields: dict):
         st, host = self.m.state, self.m.host
@@ -263,17 +429,36 @@ class Engine:
         return int(self.L.nlps_b200_launch_count(self.h))
 
 
-def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, quirk=-1, initial_step=0):
-    """The whole scheme call with HOST buffers (nlps_b200_u_verlet).  Returns the final fields."""
+def make_slab(slab: dict, n_state, keep: list):
+    cuts = _d(slab.get("cuts", np.zeros(0)))
+    gid = slab.get("global_id")
+    gid = _i(gid) if gid is not None else None
+    keep.append((cuts, gid))
+    comm = slab.get("comm")
+    return Slab(int(slab["rank"]), int(slab["world"]), int(slab["axis"]),
+                cuts.ctypes.data_as(_dp) if len(cuts) else None, int(slab.get("band_cells", 0)),
+                int(slab.get("migrate_every", 0)), float(slab.get("capacity_factor", 0.0)),
+                int(slab.get("n_global", n_state)), gid.ctypes.data_as(_ip) if gid is not None else None,
+                comm.h if comm is not None else None)
+
+
+def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, quirk=-1, initial_step=0, slab=None):
+    """The whole scheme call with HOST buffers (nlps_b200_u_verlet[_slab]).  Returns the final fields
+    (slab engines: rows of other slabs keep their input values; with global_id: compact rows)."""
     L = lib()
     m = _Marshal(prob, quirk, 0, initial_step)
-    rc = L.nlps_b200_u_verlet(C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds, len(prob.neumann),
-                              m.neumann, m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None,
-                              len(prob.materials), m.materials, C.byref(m.state), int(run_initialize),
-                              int(results_every), None, None, device)
+    args = (C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds, len(prob.neumann),
+            m.neumann, m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None,
+            len(prob.materials), m.materials, C.byref(m.state))
+    if slab is None:
+        rc = L.nlps_b200_u_verlet(*args, int(run_initialize), int(results_every), None, None, device)
+    else:
+        sl = make_slab(slab, prob.np_, m.keep)
+        rc = L.nlps_b200_u_verlet_slab(*args, C.byref(sl), int(run_initialize), int(results_every), None, None, device)
     if rc != 0:
         raise RuntimeError("nlps_b200_u_verlet failed")
-    return {k: v.copy() for k, v in m.host.items()}
+    n = m.state.n
+    return {k: v[:n].copy() for k, v in m.host.items()}
 
 
 def stress_points(ndim, mat_type, mat_params, tol_radial, maxiter_radial, DF, F_n1, J_n1, b_e_n, eps_n, kappa_n,

@@ -155,6 +155,16 @@ class Oracle:
         self.L.orc_get_nodal(self.h, which, out.ctypes.data_as(_dp))
         return out
 
+    def set_nodal(self, which, arr):
+        a = _d(arr)
+        self.L.orc_set_nodal(self.h, which, a.ctypes.data_as(_dp))
+
+    def search_closest(self):
+        return self.L.orc_search_closest(self.h)
+
+    def search_lists(self):
+        return self.L.orc_search_lists(self.h, None)
+
     def init_lme(self):
         return self.L.orc_init_lme(self.h)
 

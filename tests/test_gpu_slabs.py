@@ -1,0 +1,137 @@
+"""Multi-slab engine against the single-slab engine, through the C ABI.
+
+Single GPU: the slabs run as threads of this process and exchange through the custom-transport
+hook of the ABI (device-to-device copies behind a barrier) -- the same kernels, halo lists,
+migration and buffers as with NCCL.  With >= 2 GPUs the NCCL transport is exercised through
+torchrun.  Bar: integer outputs bit-exact, fields <= 1e-10 (the nodal sums of the shared nodes are
+added in a different order than on one slab)."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from nlps_b200 import engine
+from slabcases import COMPARE, merge, moving_block, sinking_column
+from util import assert_close, field_scales
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_single(P, nsteps):
+    eng = engine.Engine(P, device=0)
+    assert eng.initialize_lme() == 0
+    assert eng.run(0, nsteps) == 0, eng.error()
+    f = eng.download()
+    counts, lists = eng.lists()
+    act = eng.active()
+    eng.close()
+    return f, counts, lists, act
+
+
+def run_slabs_threads(P, nsteps, world, migrate_every, device=0):
+    axis, cuts = engine.slab_cuts(P, world)
+    comms = engine.ThreadComm.group(world)
+    res, errs = [None] * world, []
+
+    def work(r):
+        try:
+            eng = engine.Engine(P, device=device, slab=dict(rank=r, world=world, axis=axis, cuts=cuts, comm=comms[r],
+                                                            migrate_every=migrate_every))
+            n0 = eng.local_count()
+            assert eng.initialize_lme() == 0, eng.error()
+            assert eng.run(0, nsteps) == 0, eng.error()
+            f, ids = eng.download_local()
+            counts, lists = eng.lists()
+            res[r] = (f, ids, counts, lists, n0, eng.migrated_count(), eng.active())
+            eng.close()
+        except BaseException as ex:  # noqa: BLE001 -- release the other slabs, then report
+            errs.append((r, ex))
+            comms[r].sh.barrier.abort()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(600)
+    for c in comms:
+        c.close()
+    assert not errs, errs
+    return res, axis, cuts
+
+
+def compare(P, single, res):
+    f1, c1, l1, act1 = single
+    m = merge([r[:4] for r in res], P.np_)
+    assert np.array_equal(m["I0"], f1["I0"])
+    assert np.array_equal(m["NumberNodes"], f1["NumberNodes"])
+    assert np.array_equal(m["_counts"], c1) and np.array_equal(m["_lists"], l1)
+    sc = field_scales(P)
+    for k in COMPARE:
+        assert_close(m[k], f1[k], "slabs vs single: " + k, scale=sc.get(k))
+    act = np.zeros_like(act1)
+    for r in res:
+        act |= r[6]
+    assert np.array_equal(act, act1)   # union of the slabs' ActiveNode views == Mesh.ActiveNode
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_moving_block_slabs_match_single(world):
+    nsteps = 60
+    P = moving_block(nsteps=nsteps)
+    single = run_single(P, nsteps)
+    res, axis, cuts = run_slabs_threads(P, nsteps, world, migrate_every=4)
+    assert axis == 0
+    assert sum(r[5] for r in res) > 100, "the block must have crossed the cuts"
+    compare(P, single, res)
+    # the populations moved downstream
+    assert res[-1][0]["x_GC"].shape[0] > res[-1][4]
+
+
+def test_plastic_column_slabs_match_single():
+    nsteps = 50
+    P = sinking_column(nsteps=nsteps)
+    single = run_single(P, nsteps)
+    assert (single[0]["EPS_n"] > 0).sum() > 50
+    res, axis, cuts = run_slabs_threads(P, nsteps, 2, migrate_every=3)
+    assert axis == 1
+    assert sum(r[5] for r in res) > 0
+    compare(P, single, res)
+
+
+def test_excursion_is_latched():
+    """Without migration a particle eventually leaves the band its slab may roam in: error 9."""
+    nsteps = 60
+    P = moving_block(nsteps=nsteps)
+    axis, cuts = engine.slab_cuts(P, 2)
+    comms = engine.ThreadComm.group(2)
+    codes = [None, None]
+
+    def work(r):
+        eng = engine.Engine(P, device=0, slab=dict(rank=r, world=2, axis=axis, cuts=cuts, comm=comms[r],
+                                                   migrate_every=10 ** 6))
+        eng.initialize_lme()
+        rc = eng.run(0, nsteps)
+        codes[r] = (rc, eng.error()[0])
+        eng.close()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(600)
+    assert (1, 9) in codes, codes
+
+
+def test_slabs_nccl_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29741", os.path.join(ROOT, "tests", "workers", "slab_nccl_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "NCCL slabs OK" in out.stdout
