@@ -171,16 +171,29 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     K, Wm = args.steps, max(args.warmup, 3)
     nsteps_total = Wm + K + 2
     t_setup = time.perf_counter()
-    P = synthetic.column_collapse_2d(scale=args.scale, nsteps=nsteps_total)
-    eng = engine.Engine(P, device=local)
+    comm = slab = None
+    if world == 1:
+        P = synthetic.column_collapse_2d(scale=args.scale, nsteps=nsteps_total)
+        eng = engine.Engine(P, device=local)
+        total_particles = P.np_
+    else:
+        # weak scaling over spatial slabs: the column is `world` times taller, one slab of by rows per GPU,
+        # halo sums + migration over NCCL; every rank builds only its sub-mesh and particles
+        P, slab = synthetic.column_slab_2d(rank, world, scale=args.scale, nsteps=nsteps_total)
+        comm = engine.NcclComm(rank, world, local)
+        slab = dict(slab, comm=comm, migrate_every=10)
+        eng = engine.Engine(P, device=local, slab=slab)
+        total_particles = slab["n_global"]
     assert eng.initialize_lme() == 0, eng.error()
     setup_s = time.perf_counter() - t_setup
-    npart = P.np_
+    npart = eng.local_count() if world > 1 else P.np_
     # warm-up
     assert eng.run(0, Wm) == 0, eng.error()
     sampler = ClockSampler(local)
@@ -198,11 +211,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    total_particles = npart * world  # weak scaling: every rank steps its own column
     value = total_particles * K / (ms_max * 1e-3)
 
     # per-kernel device times (CUDA events on the engine's stream, serialised per launch)
-    counts, _ = eng.lists()
+    if world == 1:
+        counts, _ = eng.lists()
+    else:
+        counts = eng.download_local()[0]["NumberNodes"]
     n_avg = float(counts.mean())
     eng.profile(True)
     eng.kernel_times(reset=True)
@@ -237,20 +252,33 @@ def run_ours(args):
 
     # end to end through the scheme call with HOST buffers (create + H2D, steps, D2H of the results)
     e2e_steps = max(K, 20)
-    P2 = synthetic.column_collapse_2d(scale=args.scale, nsteps=e2e_steps)
-    eng0 = engine.Engine(P2, device=local)       # initialise lambda/beta once (setup, as the driver does
-    assert eng0.initialize_lme() == 0            # with initialise_shapefun__MeshTools__ before the scheme)
-    f0 = eng0.download()
-    eng0.close()
-    for k in ("lambda", "Beta"):
-        P2.fields[k] = f0[k]
+    if world == 1:
+        P2 = synthetic.column_collapse_2d(scale=args.scale, nsteps=e2e_steps)
+        eng0 = engine.Engine(P2, device=local)       # initialise lambda/beta once (setup, as the driver does
+        assert eng0.initialize_lme() == 0            # with initialise_shapefun__MeshTools__ before the scheme)
+        f0 = eng0.download()
+        eng0.close()
+        for k in ("lambda", "Beta"):
+            P2.fields[k] = f0[k]
+        slab2 = None
+    else:
+        P2, slab2 = synthetic.column_slab_2d(rank, world, scale=args.scale, nsteps=e2e_steps)
+        slab2 = dict(slab2, comm=comm, migrate_every=10)
+        eng0 = engine.Engine(P2, device=local, slab=slab2)
+        assert eng0.initialize_lme() == 0
+        f0, ids0 = eng0.download_local()
+        eng0.close()
+        order = np.argsort(slab2["global_id"])
+        rows = order[np.searchsorted(slab2["global_id"][order], ids0)]
+        for k in ("lambda", "Beta"):
+            P2.fields[k][rows] = f0[k]
     mesh_bytes = sum(a.nbytes for a in (P2.coords, P2.r1p, P2.r1i, P2.r2p, P2.r2i, P2.h_avg))
     state_bytes = sum(v.nbytes for v in P2.fields.values()) + P2.I0.nbytes + P2.MatIdx.nbytes
     every = 10
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    engine.u_verlet(P2, run_initialize=False, results_every=every, device=local)
+    engine.u_verlet(P2, run_initialize=False, results_every=every, device=local, slab=slab2)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -258,8 +286,8 @@ def run_ours(args):
     e2e_s = float(te.item())
     n_dl = sum(1 for k in range(e2e_steps) if k % every == 0) + 1
     e2e = {"value": total_particles * e2e_steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int((mesh_bytes + state_bytes) / e2e_steps),
-           "d2h_bytes_per_step": int(state_bytes * n_dl / e2e_steps),
+           "h2d_bytes_per_step": int(world * (mesh_bytes + state_bytes) / e2e_steps),
+           "d2h_bytes_per_step": int(world * state_bytes * n_dl / e2e_steps),
            "steps": e2e_steps, "results_every": every, "seconds": round(e2e_s, 4),
            "call": "nlps_b200_u_verlet (create+H2D, steps, D2H every 10 steps, destroy), host wall clock"}
 
@@ -279,11 +307,15 @@ def run_ours(args):
                                        "explicit NPC-FS, LME gamma=3, GPxElement 4",
                            "particles_per_gpu": npart, "background_nodes": P.nn, "scale": args.scale,
                            "l2": "inputs larger than L2 (particle state + records ~0.7 GB per GPU)",
-                           "multi_gpu": "weak scaling, independent columns per rank" if world > 1 else "single GPU",
+                           "multi_gpu": (f"weak scaling over {world} spatial slabs along y (column {world}x taller): "
+                                         "NCCL halo sums of occupancy / mass+momentum / forces every step, "
+                                         "particle migration every 10 steps") if world > 1 else "single GPU",
                            "setup_seconds": round(setup_s, 2)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu}
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -250,6 +250,9 @@ typedef struct nlps_slab {
   double capacity_factor; /* particle capacity / initial count (0 = default 1.3) */
   int n_global;           /* global particle count (ids are 0..n_global-1) */
   const int *global_id;   /* id of every row of `state`, or NULL: row index == global id */
+  int node_id_offset;     /* sub-mesh slabs: global node id = local node id + node_id_offset (the sub-mesh is
+                             a contiguous id range of the global mesh, e.g. whole rows / planes of a structured
+                             grid); 0 when every slab holds the whole mesh.  Used when particles migrate. */
   nlps_comm *comm;
 } nlps_slab;
 
@@ -278,13 +281,16 @@ int nlps_b200_download_local(nlps_engine *e, nlps_particles *out, int *ids);
 int nlps_b200_migrate(nlps_engine *e);
 long long nlps_b200_migrated_count(nlps_engine *e); /* particles received so far */
 /* The scheme call for one slab; `state` rows are indexed by global id on return (rows of other
- * slabs untouched) when slab->global_id == NULL, compact (download_local order) otherwise. */
+ * slabs untouched) when slab->global_id == NULL; otherwise compact (download_local order): state->n
+ * becomes the number of particles the slab holds at the end and ids_out (may be NULL, room for the
+ * input state->n... capacity rows) receives their global ids. */
 int nlps_b200_u_verlet_slab(const nlps_mesh *mesh, const nlps_solver *solver,
                             int n_bounds, const nlps_load *bounds, int n_neumann,
                             const nlps_load *neumann, const double *gravity,
                             int n_materials, const nlps_material *materials,
-                            nlps_particles *state, const nlps_slab *slab, int run_initialize,
-                            int results_every, nlps_results_cb cb, void *user, int device);
+                            nlps_particles *state, const nlps_slab *slab, int *ids_out,
+                            int run_initialize, int results_every, nlps_results_cb cb, void *user,
+                            int device);
 
 const char *nlps_b200_version(void);
 

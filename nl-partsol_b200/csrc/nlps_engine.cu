@@ -1347,7 +1347,9 @@ __global__ void __launch_bounds__(256) k_mig_perm(int np, const int* dest, int* 
 }
 struct MigCol { void* base; int is_int; int pad; unsigned long long off; };  // off: byte offset of the column per buffered row
 // rows [row0, row0 + nrows) of every column <-> buffer (column c at buf + off_c * nrows)
-__global__ void __launch_bounds__(256) k_mig_copy(const MigCol* tab, int ncols, int row0, int nrows, unsigned char* buf, int unpack) {
+// (is_int == 2: a node id -- travels as a GLOBAL id: + node_offset on the way out, - node_offset on the way in)
+__global__ void __launch_bounds__(256) k_mig_copy(const MigCol* tab, int ncols, int row0, int nrows, unsigned char* buf, int unpack,
+                                                  int node_offset) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)ncols * nrows) return;
   const int c = (int)(i / nrows), r = (int)(i % nrows);
@@ -1355,7 +1357,8 @@ __global__ void __launch_bounds__(256) k_mig_copy(const MigCol* tab, int ncols, 
   if (col.is_int) {
     int* a = (int*)col.base + row0 + r;
     int* b = (int*)(buf + col.off * nrows) + r;
-    if (unpack) *a = *b; else *b = *a;
+    const int shift = (col.is_int == 2) ? node_offset : 0;
+    if (unpack) *a = *b - shift; else *b = *a + shift;
   } else {
     double* a = (double*)col.base + row0 + r;
     double* b = (double*)(buf + col.off * nrows) + r;
@@ -1534,6 +1537,7 @@ struct nlps_engine {
   int mig_cap = 0;                  // rows per migration buffer
   MigCol* mig_tab = nullptr;
   double solver_dx = 0.0;           // Mesh.DeltaX
+  int node_offset = 0;              // global node id = local id + node_offset (sub-mesh slabs)
   std::vector<int> h_ids;           // host copy of P.orig (slab I/O)
   std::vector<double> h_rows;       // host staging of compact rows (slab I/O)
 };
@@ -1926,7 +1930,8 @@ static int migrate_t(nlps_engine* e) {
   addd(P.J_n, 1); addd(P.J_n1, 1); addd(P.eps_n, 1); addd(P.eps_n1, 1); addd(P.kap_n, 1); addd(P.kap_n1, 1);
   addd(P.F_n, DD); addd(P.F_n1, DD); addd(P.DF, DD); addd(P.be_n, T); addd(P.be_n1, T); addd(P.stress, T); addd(P.cep, DD);
   addd(P.Fs4, 1); addd(P.DFs4, 1);
-  addi(P.I0, 1); addi(P.nnodes, 1); addi(P.matidx, 1); addi(P.orig, 1); addi((int*)P.mask, e->W);
+  addi(P.I0, 1); tab.back().is_int = 2;
+  addi(P.nnodes, 1); addi(P.matidx, 1); addi(P.orig, 1); addi((int*)P.mask, e->W);
   const unsigned long long row_bytes = off;
   const int ncols = (int)tab.size();
   if (any) {
@@ -1937,7 +1942,7 @@ static int migrate_t(nlps_engine* e) {
   int row0 = n_stay;
   for (int s_ = 0; s_ < 2; s_++) {
     if (e->side[s_].peer < 0) continue;
-    if (n_out[s_]) k_mig_copy<<<nblk((size_t)ncols * n_out[s_], 256), 256, 0, e->stream>>>(e->mig_tab, ncols, row0, n_out[s_], e->mig_sbuf[s_], 0);
+    if (n_out[s_]) k_mig_copy<<<nblk((size_t)ncols * n_out[s_], 256), 256, 0, e->stream>>>(e->mig_tab, ncols, row0, n_out[s_], e->mig_sbuf[s_], 0, e->node_offset);
     row0 += n_out[s_];
     if (n_out[s_] || n_in[s_])
       msgs[nm++] = nlps_msg{e->side[s_].peer, e->mig_sbuf[s_], row_bytes * n_out[s_], e->mig_rbuf[s_], row_bytes * n_in[s_]};
@@ -1947,7 +1952,7 @@ static int migrate_t(nlps_engine* e) {
   row0 = n_stay;
   for (int s_ = 0; s_ < 2; s_++) {
     if (e->side[s_].peer < 0 || !n_in[s_]) continue;
-    k_mig_copy<<<nblk((size_t)ncols * n_in[s_], 256), 256, 0, e->stream>>>(e->mig_tab, ncols, row0, n_in[s_], e->mig_rbuf[s_], 1);
+    k_mig_copy<<<nblk((size_t)ncols * n_in[s_], 256), 256, 0, e->stream>>>(e->mig_tab, ncols, row0, n_in[s_], e->mig_rbuf[s_], 1, e->node_offset);
     row0 += n_in[s_];
   }
   e->np = np_new;
@@ -2104,6 +2109,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     e->band_cells = slab->band_cells > 0 ? slab->band_cells : 6;
     if (e->band_cells < 4) return set_err(err, err_len, "band_cells must be >= 4");
     e->migrate_every = slab->migrate_every > 0 ? slab->migrate_every : 10;
+    e->node_offset = slab->node_id_offset;
     e->n_global = slab->global_id ? slab->n_global : st->n;
     if (e->n_global < st->n && !slab->global_id) return set_err(err, err_len, "n_global smaller than the state");
     e->cut_lo = slab->rank > 0 ? slab->cuts[slab->rank - 1] : -1e300;
@@ -2708,14 +2714,25 @@ long long nlps_b200_launch_count(nlps_engine* e) { return e->launches; }
 
 static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
                        int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
-                       const nlps_material* materials, nlps_particles* state, const nlps_slab* slab, int run_initialize,
-                       int results_every, nlps_results_cb cb, void* user, int device) {
+                       const nlps_material* materials, nlps_particles* state, const nlps_slab* slab, int* ids_out,
+                       int run_initialize, int results_every, nlps_results_cb cb, void* user, int device) {
   char msg[256];
   nlps_engine* e = create_any(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state,
                               slab, device, msg, sizeof(msg));
   if (!e) return 1;
   const bool compact = slab && slab->global_id;
-  auto fetch = [&]() { return compact ? nlps_b200_download_local(e, state, nullptr) : nlps_b200_download(e, state); };
+  const int n_in = state->n;
+  auto fetch = [&]() {
+    if (!compact) return nlps_b200_download(e, state);
+    if (e->np > n_in) {
+      fprintf(stderr, "nlps_b200_u_verlet_slab: the slab now holds %d particles, the caller's buffers %d rows\n", e->np, n_in);
+      return 1;
+    }
+    state->n = n_in;
+    int rc = nlps_b200_download_local(e, state, ids_out);
+    state->n = e->np;
+    return rc;
+  };
   int status = 0;
   if (run_initialize) status = nlps_b200_initialize_lme(e);
   int k = solver->initial_step;
@@ -2733,7 +2750,6 @@ static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_b
     }
   }
   if (!status) status = fetch();
-  if (compact) state->n = e->np;
   nlps_b200_destroy(e);
   return status;
 }
@@ -2743,16 +2759,16 @@ int nlps_b200_u_verlet(const nlps_mesh* mesh, const nlps_solver* solver, int n_b
                        const nlps_material* materials, nlps_particles* state, int run_initialize, int results_every,
                        nlps_results_cb cb, void* user, int device) {
   return scheme_call(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, nullptr,
-                     run_initialize, results_every, cb, user, device);
+                     nullptr, run_initialize, results_every, cb, user, device);
 }
 
 int nlps_b200_u_verlet_slab(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
                             int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
-                            const nlps_material* materials, nlps_particles* state, const nlps_slab* slab,
+                            const nlps_material* materials, nlps_particles* state, const nlps_slab* slab, int* ids_out,
                             int run_initialize, int results_every, nlps_results_cb cb, void* user, int device) {
   if (!slab) return 1;
   return scheme_call(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state, slab,
-                     run_initialize, results_every, cb, user, device);
+                     ids_out, run_initialize, results_every, cb, user, device);
 }
 
 int nlps_b200_stress_points(int ndim, const nlps_material* material, double tol_radial, int max_iter_radial,

@@ -60,7 +60,7 @@ class Msg(C.Structure):
 class Slab(C.Structure):
     _fields_ = [("rank", C.c_int), ("world", C.c_int), ("axis", C.c_int), ("cuts", _dp), ("band_cells", C.c_int),
                 ("migrate_every", C.c_int), ("capacity_factor", C.c_double), ("n_global", C.c_int),
-                ("global_id", _ip), ("comm", C.c_void_p)]
+                ("global_id", _ip), ("node_id_offset", C.c_int), ("comm", C.c_void_p)]
 
 
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(Msg), C.c_void_p)
@@ -368,11 +368,16 @@ class Engine:
     def download_local(self):
         """Compact rows of the particles this slab holds + their global ids."""
         n = self.local_count()
-        st, host = self.m.state, self.m.host
-        assert st.n >= n, "host buffers smaller than the slab population"
+        host = {k: np.zeros((max(n, 1),) + v.shape[1:], v.dtype) for k, v in self.m.host.items()}
+        st = Particles()
+        st.n = max(n, 1)
+        for k in _PFIELDS:
+            setattr(st, k, host[k].ctypes.data_as(_dp) if k in host else None)
+        for k in ("I0", "MatIdx", "NumberNodes"):
+            setattr(st, k, host[k].ctypes.data_as(_ip))
         ids = np.zeros(max(n, 1), np.int32)
         assert self.L.nlps_b200_download_local(self.h, C.byref(st), ids.ctypes.data_as(_ip)) == 0
-        return {k: v[:n].copy() for k, v in host.items()}, ids[:n].copy()
+        return {k: v[:n] for k, v in host.items()}, ids[:n].copy()
 
     def migrate(self):
         return self.L.nlps_b200_migrate(self.h)
@@ -439,7 +444,7 @@ def make_slab(slab: dict, n_state, keep: list):
                 cuts.ctypes.data_as(_dp) if len(cuts) else None, int(slab.get("band_cells", 0)),
                 int(slab.get("migrate_every", 0)), float(slab.get("capacity_factor", 0.0)),
                 int(slab.get("n_global", n_state)), gid.ctypes.data_as(_ip) if gid is not None else None,
-                comm.h if comm is not None else None)
+                int(slab.get("node_offset", 0)), comm.h if comm is not None else None)
 
 
 def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, quirk=-1, initial_step=0, slab=None):
@@ -454,11 +459,16 @@ def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, qui
         rc = L.nlps_b200_u_verlet(*args, int(run_initialize), int(results_every), None, None, device)
     else:
         sl = make_slab(slab, prob.np_, m.keep)
-        rc = L.nlps_b200_u_verlet_slab(*args, C.byref(sl), int(run_initialize), int(results_every), None, None, device)
+        ids = np.zeros(max(prob.np_, 1), np.int32)
+        rc = L.nlps_b200_u_verlet_slab(*args, C.byref(sl), ids.ctypes.data_as(_ip), int(run_initialize),
+                                       int(results_every), None, None, device)
     if rc != 0:
         raise RuntimeError("nlps_b200_u_verlet failed")
     n = m.state.n
-    return {k: v[:n].copy() for k, v in m.host.items()}
+    out = {k: v[:n].copy() for k, v in m.host.items()}
+    if slab is not None and slab.get("global_id") is not None:
+        out["_ids"] = ids[:n].copy()
+    return out
 
 
 def stress_points(ndim, mat_type, mat_params, tol_radial, maxiter_radial, DF, F_n1, J_n1, b_e_n, eps_n, kappa_n,

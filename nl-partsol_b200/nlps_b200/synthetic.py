@@ -16,16 +16,19 @@ from .problem import Problem
 _G = 1.0 / np.sqrt(3.0)
 
 
-def _grid(nx, ny, nz, h, origin):
+def _grid(nx, ny, nz, h, origin, cell_offset=(0, 0, 0)):
+    """cell_offset: index of the grid's first node in a larger (global) grid; coordinates are
+    (index + offset) * h so that a sub-grid reproduces the global coordinates bit for bit."""
     if nz is None:
-        ii, jj = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="xy")
+        ii, jj = np.meshgrid(np.arange(nx + 1) + cell_offset[0], np.arange(ny + 1) + cell_offset[1], indexing="xy")
         coords = np.stack([origin[0] + ii.ravel() * h, origin[1] + jj.ravel() * h], axis=1)
         e = np.arange(nx * ny)
         i, j = e % nx, e // nx
         n1 = j * (nx + 1) + i
         conn = np.stack([n1, n1 + 1, n1 + 1 + (nx + 1), n1 + (nx + 1)], axis=1).astype(np.int32)
     else:
-        kk, jj, ii = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+        kk, jj, ii = np.meshgrid(np.arange(nz + 1) + cell_offset[2], np.arange(ny + 1) + cell_offset[1],
+                                 np.arange(nx + 1) + cell_offset[0], indexing="ij")
         coords = np.stack([origin[0] + ii.ravel() * h, origin[1] + jj.ravel() * h, origin[2] + kk.ravel() * h], axis=1)
         e = np.arange(nx * ny * nz)
         i, j, k = e % nx, (e // nx) % ny, e // (nx * ny)
@@ -39,13 +42,14 @@ def _grid(nx, ny, nz, h, origin):
 
 def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, material, nsteps, cfl, cel,
                        gravity, gamma_lme=3.0, fixed=("bottom",), rollers=("left", "right"), jitter=0.0,
-                       seed=20261018, tol_radial=None, maxiter_radial=None, bc_scale=None):
+                       seed=20261018, tol_radial=None, maxiter_radial=None, bc_scale=None, cell_offset=(0, 0, 0)):
     """Block of block_cells particle cells (one particle cell = one background cell, GPxElement 4 / 8)
-    placed at block_origin_cell inside a grid of grid_cells cells of size h."""
+    placed at block_origin_cell inside a grid of grid_cells cells of size h.  cell_offset places the
+    grid inside a larger global one (sub-mesh of one slab); block_origin_cell stays LOCAL."""
     d = ndim
     nx, ny = grid_cells[0], grid_cells[1]
     nz = grid_cells[2] if d == 3 else None
-    coords, conn = _grid(nx, ny, nz, h, (0.0,) * d)
+    coords, conn = _grid(nx, ny, nz, h, (0.0,) * d, cell_offset)
     r1p, r1i, r2p, r2i, h_avg, dx = engine.build_locality(d, coords, conn)
     mtype, mpar = material
     if tol_radial is None:  # globals set by the last material parsed (F10-iv)
@@ -88,7 +92,8 @@ def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, mate
     else:
         xi = np.array([[sx_, sy_, sz_] for sz_ in (_G, -_G) for sy_ in (_G, -_G) for sx_ in (_G, -_G)])
     gp = xi.shape[0]
-    cen = np.stack([(ei + 0.5) * h, (ej + 0.5) * h] + ([(ek + 0.5) * h] if d == 3 else []), axis=1)
+    co = cell_offset
+    cen = np.stack([(ei + co[0] + 0.5) * h, (ej + co[1] + 0.5) * h] + ([(ek + co[2] + 0.5) * h] if d == 3 else []), axis=1)
     x = (cen[:, None, :] + 0.5 * h * xi[None, :, :]).reshape(-1, d)
     if jitter > 0.0:
         x = x + np.random.default_rng(seed).uniform(-jitter * h, jitter * h, x.shape)
@@ -101,7 +106,7 @@ def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, mate
         # closest node of the containing cell
         c = np.floor(x / h).astype(np.int64)
         f = x / h - c
-        rn = c + (f > 0.5)
+        rn = c + (f > 0.5) - np.asarray(co[:d])
         I0 = ((rn[:, 2] if d == 3 else 0) * (nxn * nyn) + rn[:, 1] * nxn + rn[:, 0]).astype(np.int32)
     vol = np.full(x.shape[0], h ** d / gp)
     P.init_fields(x, vol, np.zeros(x.shape[0], np.int32))
@@ -139,3 +144,35 @@ def cube_3d(cells=24, nsteps=100, material=NH_C1, gamma_lme=6.0):
     return structured_problem(3, (cells + 4, cells + 4, cells + 4), 1.0 / cells, (cells, cells, cells), (2, 2, 0),
                               material, nsteps, 0.5, cel, (0.0, 0.0, -9.81), gamma_lme=gamma_lme,
                               rollers=("left", "right", "front", "back"))
+
+
+def column_slab_2d(rank, world, scale=1.0, nsteps=1000, band_cells=6):
+    """Weak-scaling version of column_collapse_2d for `world` slabs stacked along y: the column is
+    `world` times taller (2 * bx * world particle-cell rows), every slab gets the rows
+    [rank * by, (rank + 1) * by) plus one extra row either side (the engine keeps what the slab owns),
+    on a SUB-MESH that reaches band_cells + 2 cells beyond its cuts -- per-rank memory and setup stay
+    constant.  Node coordinates are (global index) * h: identical bits on every rank.
+    Returns (Problem, slab dict for engine.Engine(..., slab=...))."""
+    bx = max(4, int(round(354 * scale)))
+    by = 2 * bx
+    nx = 6 * bx
+    h = 0.2 / bx
+    tot_rows = by * world
+    ny_glob = tot_rows + by // 4
+    pad = band_cells + 2
+    j0 = max(0, rank * by - pad)                        # first cell row of the sub-mesh
+    j1 = min(ny_glob, (rank + 1) * by + pad) if rank < world - 1 else ny_glob
+    c0 = max(0, rank * by - 1) if rank > 0 else 0      # particle-cell rows generated here
+    c1 = min(tot_rows, (rank + 1) * by + 1) if rank < world - 1 else tot_rows
+    P = structured_problem(2, (nx, j1 - j0), h, (bx, c1 - c0), (0, c0 - j0), DP_C2, nsteps, 0.5,
+                           (1e7 / 2000.0) ** 0.5 * 1.3, (0.0, -9.81), fixed=("bottom",) if j0 == 0 else (),
+                           cell_offset=(0, j0, 0))
+    # global particle ids: (global cell index) * 4 + Gauss point; cells are numbered row-major
+    e = np.arange(bx * (c1 - c0))
+    gcell = (e // bx + c0) * bx + e % bx
+    gid = (gcell[:, None] * 4 + np.arange(4)[None, :]).ravel().astype(np.int32)
+    # a particle in cell row j has its closest node on row j or j + 1: slab r owns node rows (r*by, (r+1)*by]
+    cuts = np.array([(r * by + 0.5) * h for r in range(1, world)])
+    slab = dict(rank=rank, world=world, axis=1, cuts=cuts, band_cells=band_cells, global_id=gid,
+                n_global=4 * bx * tot_rows, node_offset=j0 * (nx + 1))
+    return P, slab

@@ -32,20 +32,28 @@ def run_single(P, nsteps):
     return f, counts, lists, act
 
 
-def run_slabs_threads(P, nsteps, world, migrate_every, device=0):
-    axis, cuts = engine.slab_cuts(P, world)
+def run_slabs_threads(P, nsteps, world, migrate_every, device=0, per_rank=None):
+    """per_rank: [(Problem, slab dict)] when every slab brings its own sub-mesh and particles."""
+    axis, cuts = engine.slab_cuts(P, world) if per_rank is None else (per_rank[0][1]["axis"], per_rank[0][1]["cuts"])
     comms = engine.ThreadComm.group(world)
     res, errs = [None] * world, []
 
     def work(r):
         try:
-            eng = engine.Engine(P, device=device, slab=dict(rank=r, world=world, axis=axis, cuts=cuts, comm=comms[r],
-                                                            migrate_every=migrate_every))
+            if per_rank is None:
+                eng = engine.Engine(P, device=device, slab=dict(rank=r, world=world, axis=axis, cuts=cuts,
+                                                                comm=comms[r], migrate_every=migrate_every))
+            else:
+                eng = engine.Engine(per_rank[r][0], device=device,
+                                    slab=dict(per_rank[r][1], comm=comms[r], migrate_every=migrate_every))
             n0 = eng.local_count()
             assert eng.initialize_lme() == 0, eng.error()
             assert eng.run(0, nsteps) == 0, eng.error()
             f, ids = eng.download_local()
-            counts, lists = eng.lists()
+            if per_rank is None:
+                counts, lists = eng.lists()
+            else:  # compact population: lists by local node ids -> global ids, rows scattered by particle id
+                counts, lists = local_lists(eng, per_rank[r][1], ids, P.np_)
             res[r] = (f, ids, counts, lists, n0, eng.migrated_count(), eng.active())
             eng.close()
         except BaseException as ex:  # noqa: BLE001 -- release the other slabs, then report
@@ -63,7 +71,23 @@ def run_slabs_threads(P, nsteps, world, migrate_every, device=0):
     return res, axis, cuts
 
 
-def compare(P, single, res):
+def local_lists(eng, slab, ids, n_global):
+    """neighbour lists of a sub-mesh slab in the global frame (node ids + offset, rows by particle id)"""
+    import ctypes as C
+    n = eng.local_count()
+    cap = eng.L.nlps_b200_list_capacity(eng.h)
+    # get_lists of a slab engine indexes rows by global id: hand it global-size arrays
+    counts = np.zeros(n_global, np.int32)
+    lists = np.full((n_global, cap), -7, np.int32)
+    ip = C.POINTER(C.c_int)
+    assert eng.L.nlps_b200_get_lists(eng.h, counts.ctypes.data_as(ip), lists.ctypes.data_as(ip), cap) == 0
+    rows = lists[ids]
+    rows[rows >= 0] += slab["node_offset"]
+    lists[ids] = rows
+    return counts, lists
+
+
+def compare(P, single, res, check_active=True):
     f1, c1, l1, act1 = single
     m = merge([r[:4] for r in res], P.np_)
     assert np.array_equal(m["I0"], f1["I0"])
@@ -72,10 +96,11 @@ def compare(P, single, res):
     sc = field_scales(P)
     for k in COMPARE:
         assert_close(m[k], f1[k], "slabs vs single: " + k, scale=sc.get(k))
-    act = np.zeros_like(act1)
-    for r in res:
-        act |= r[6]
-    assert np.array_equal(act, act1)   # union of the slabs' ActiveNode views == Mesh.ActiveNode
+    if check_active:
+        act = np.zeros_like(act1)
+        for r in res:
+            act |= r[6]
+        assert np.array_equal(act, act1)   # union of the slabs' ActiveNode views == Mesh.ActiveNode
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -100,6 +125,31 @@ def test_plastic_column_slabs_match_single():
     assert axis == 1
     assert sum(r[5] for r in res) > 0
     compare(P, single, res)
+
+
+def test_submesh_slabs_match_global_engine():
+    """The weak-scaling set-up of bench.py: every slab builds only its sub-mesh (cut +- band) and its own
+    particles with global ids; three slabs reproduce the engine that holds the whole tall column."""
+    from nlps_b200 import synthetic
+    world, scale, nsteps = 3, 0.06, 40
+    bx = max(4, int(round(354 * scale)))
+    by = 2 * bx
+    G = synthetic.structured_problem(2, (6 * bx, by * world + by // 4), 0.2 / bx, (bx, by * world), (0, 0),
+                                     synthetic.DP_C2, nsteps, 0.5, (1e7 / 2000.0) ** 0.5 * 1.3, (0.0, -9.81))
+    G.fields["vel"][:, 1] = -0.12 * G.solver["cel"]
+    per_rank = []
+    for r in range(world):
+        Pr, sl = synthetic.column_slab_2d(r, world, scale=scale, nsteps=nsteps)
+        Pr.fields["vel"][:, 1] = -0.12 * Pr.solver["cel"]
+        per_rank.append((Pr, sl))
+    single = run_single(G, nsteps)
+    assert (single[0]["EPS_n"] > 0).sum() > 20
+    res, axis, cuts = run_slabs_threads(G, nsteps, world, migrate_every=3, per_rank=per_rank)
+    # I0 of a sub-mesh slab is a local node id
+    for r, (Pr, sl) in zip(res, per_rank):
+        r[0]["I0"] = r[0]["I0"] + sl["node_offset"]
+    assert sum(r[5] for r in res) > 0
+    compare(G, single, res, check_active=False)
 
 
 def test_excursion_is_latched():
