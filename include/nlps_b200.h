@@ -42,6 +42,7 @@ extern "C" {
 #define NLPS_ERR_SINGULAR_DF 8         /* TensorLib.c:829-905 (compute_adjunt) */
 #define NLPS_ERR_SLAB_EXCURSION 9     /* a particle left the halo band of its slab between two migrations */
 #define NLPS_ERR_SLAB_CAPACITY 10     /* migration would exceed the particle capacity of a slab */
+#define NLPS_ERR_CSR_PATTERN 11       /* implicit: a particle couples two nodes outside the tangent pattern */
 #define NLPS_ERR_CUDA 100
 
 /* Background mesh: the parts of `Mesh` (Types.h:631-760) the stepped path reads. */
@@ -291,6 +292,49 @@ int nlps_b200_u_verlet_slab(const nlps_mesh *mesh, const nlps_solver *solver,
                             nlps_particles *state, const nlps_slab *slab, int *ids_out,
                             int run_initialize, int results_every, nlps_results_cb cb, void *user,
                             int device);
+
+/* ---------------------------------------------------------------------------
+ * Implicit scheme: "Newmark-beta-Finite-Strains" -> PetscErrorCode U_Newmark_Beta(Mesh, Particle,
+ * Time_Int_Params) (Formulations/Displacements/U-Newmark-beta.c:130-425).  The PETSc objects of
+ * the reference (Vec/Mat/IS/SNES/KSP/PC, :220-425) are replaced by device vectors over the active
+ * nodes, a block-CSR tangent and a hand-written Jacobi-PCG; the nonlinear driver is Newton with
+ * step halving.  Tangent: Neo-Hookean-Wriggers (Neo-Hookean.c:89-141).  Single slab. */
+typedef struct nlps_newmark {
+  double beta, gamma;      /* Time_Int_Params.beta_Newmark_beta / gamma_Newmark_beta */
+  double tol;              /* TOL_Newmark_beta: rtol; atol = 100 * tol (U-Newmark-beta.c:171-172) */
+  int max_iter;            /* MaxIter (Newton) */
+  int use_explicit_trial;  /* Use_explicit_trial (:879-957) */
+  double pcg_rtol;         /* |r| <= pcg_rtol |b|   (0 = 1e-8; PETSc's default would be 1e-5) */
+  int pcg_max_iter;        /* 0 = 10000 (PETSc default) */
+} nlps_newmark;
+typedef struct nlps_newmark_stats {
+  int newton_iters;        /* of the last step */
+  int n_rows, nnz_blocks;  /* block rows (active nodes) and d x d blocks of the last pattern */
+  long long pcg_iters_total, assemblies_total, residual_evals_total;
+  double residual0, residual; /* |R| before / after the last step's Newton loop */
+  double ms_assemble, ms_pcg, ms_residual; /* accumulated device times */
+} nlps_newmark_stats;
+int nlps_b200_newmark_setup(nlps_engine *e, const nlps_newmark *prm);
+int nlps_b200_newmark_step(nlps_engine *e, int time_step);  /* one pass of the loop :192-425 */
+int nlps_b200_newmark_run(nlps_engine *e, int first_step, int count);
+int nlps_b200_newmark_stats(nlps_engine *e, nlps_newmark_stats *out);
+/* stage-level entry points (parity tests): search + lumped mass + v_n, a_n + pattern + initial guess */
+int nlps_b200_newmark_begin(nlps_engine *e, int time_step);
+/* which: 0 v_n, 1 a_n, 2 dU (current iterate), 3 residual; out is n_nodes x ndim (full grid) */
+int nlps_b200_newmark_get(nlps_engine *e, int which, double *out);
+/* __lagrangian_evaluation (:970-1050) at dU (n_nodes x ndim; NULL = current iterate) */
+int nlps_b200_newmark_residual(nlps_engine *e, int time_step, const double *dU, double *R);
+/* __jacobian_evaluation (:1646-1830) at the state of the last residual evaluation, as block CSR over
+ * the active nodes, without alpha_1 M and without the Dirichlet rows/columns (applied in the
+ * operator).  Two calls: sizes first (arrays NULL), then fill. */
+int nlps_b200_newmark_tangent(nlps_engine *e, int *n_rows, int *nnz_blocks, int *row_nodes,
+                              int *row_ptr, int *col_nodes, double *vals);
+int nlps_b200_u_newmark_beta(const nlps_mesh *mesh, const nlps_solver *solver,
+                             const nlps_newmark *newmark, int n_bounds, const nlps_load *bounds,
+                             int n_neumann, const nlps_load *neumann, const double *gravity,
+                             int n_materials, const nlps_material *materials,
+                             nlps_particles *state, int run_initialize, int results_every,
+                             nlps_results_cb cb, void *user, int device);
 
 const char *nlps_b200_version(void);
 

@@ -103,6 +103,10 @@ struct StepParams {
   double dt, gamma_lme, neg_log_tol, tol_wrapper, thickness;
   int max_iter_lme, nsteps, step, update_I0, W;
   ReturnMapParams rp;
+  // implicit scheme (U-Newmark-beta.c): project `proj` (D x ld SoA) instead of D_dis, keep the neighbour lists and
+  // beta of the search already done this step, leave the density alone in the kinematics
+  const double* proj;
+  int reuse_lists, implicit;
 };
 
 // slab view of the kernels: ownership interval [own_lo, own_hi) of closest-node coordinates along `axis`
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
       double pv[D], pa_[D];  // requested now, consumed by the predictor after the Newton loop
 #pragma unroll
       for (int i = 0; i < D; i++) {
-        pv[i] = do_predictor ? P.vel[i * np + p] : P.ddis[i * np + p];
+        pv[i] = do_predictor ? P.vel[i * np + p] : (sp.proj ? sp.proj[i * np + p] : P.ddis[i * np + p]);
         pa_[i] = do_predictor ? P.acc[i * np + p] : 0.0;
       }
       const double Ra = __dsqrt_rn(__ddiv_rn(sp.neg_log_tol, beta_old));  // LME.c:1052
@@ -603,15 +607,20 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
 #pragma unroll
       for (int w = 0; w < W; w++) mk[w] = 0u;
       int n = 0;
-      for (int k = 0; k < len; k++) {
-        if (rk[k] < 0) continue;  // inactive node
-        double l[D];
-        const double s = dist2_exact<D>(xp, Xc + k * D, l);
-        if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
-      }
+      if (sp.reuse_lists) {
 #pragma unroll
-      for (int w = 0; w < W; w++) P.mask[(size_t)w * np + p] = mk[w];
-      P.nnodes[p] = n;
+        for (int w = 0; w < W; w++) { mk[w] = P.mask[(size_t)w * np + p]; n += __popc(mk[w]); }
+      } else {
+        for (int k = 0; k < len; k++) {
+          if (rk[k] < 0) continue;  // inactive node
+          double l[D];
+          const double s = dist2_exact<D>(xp, Xc + k * D, l);
+          if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) P.mask[(size_t)w * np + p] = mk[w];
+        P.nnodes[p] = n;
+      }
       if (CACHE) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
 #pragma unroll
         for (int w = 0; w < W; w++) {
@@ -623,8 +632,8 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
       bool ok = true;
       if (n < D + 1) { latch_error(err, NLPS_ERR_FEW_NEIGHBOURS, P.orig[p]); ok = false; }
       const double h = m.h_avg[s_B[ci]];
-      const double beta = __ddiv_rn(sp.gamma_lme, __dmul_rn(h, h));
-      P.beta[p] = beta;
+      const double beta = sp.reuse_lists ? beta_old : __ddiv_rn(sp.gamma_lme, __dmul_rn(h, h));
+      if (!sp.reuse_lists) P.beta[p] = beta;
       // Newton on lambda
       int NumIter = 0;
       double Z = 1.0;
@@ -1005,7 +1014,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
       if (J1 <= 0.0) { latch_error(err, NLPS_ERR_NEGATIVE_JACOBIAN, P.orig[p]); ok = false; }
       if (ok) {
         const double dJ = det<D>(DF);
-        P.rho[p] = rho_p / dJ;
+        if (!sp.implicit) P.rho[p] = rho_p / dJ;  // the implicit scheme updates rho once, after convergence
         // constitutive update
         const MatParams& mat = c_mat[mid];
         double tau[T], Wp = 0.0;
@@ -1478,6 +1487,8 @@ __global__ void k_stress_points(int n, int mat, ReturnMapParams rp, const double
 
 // ---------------------------------------------------------------------------
 // Host-side engine
+struct ImplicitCtx;
+static void implicit_free(nlps_engine* e);
 struct nlps_engine {
   int D = 2, T = 5, TB = 5, W = 1, np = 0, nn = 0, device = 0, cap = 0;
   nlps_solver solver{};
@@ -1538,6 +1549,8 @@ struct nlps_engine {
   MigCol* mig_tab = nullptr;
   double solver_dx = 0.0;           // Mesh.DeltaX
   int node_offset = 0;              // global node id = local id + node_offset (sub-mesh slabs)
+  int implicit_on = 0;              // inside an implicit (Newmark-beta) step: kinematics leave rho alone
+  struct ImplicitCtx* imp = nullptr;
   std::vector<int> h_ids;           // host copy of P.orig (slab I/O)
   std::vector<double> h_rows;       // host staging of compact rows (slab I/O)
 };
@@ -1703,6 +1716,9 @@ static StepParams make_params(nlps_engine* e, int step, int update_I0) {
   sp.rp.max_iter = e->solver.max_iter_radial_returning;
   sp.rp.quirk_rows = e->solver.quirk_transposed_eigvec;
   sp.rp.want_cep = e->solver.compute_c_ep;
+  sp.proj = nullptr;
+  sp.reuse_lists = 0;
+  sp.implicit = 0;
   return sp;
 }
 
@@ -1965,8 +1981,25 @@ static int migrate_t(nlps_engine* e) {
   return 0;
 }
 
+// proj != nullptr: implicit scheme, project that field instead of D_dis; lists_only_reuse: skip the whole search
+// (second projection of the same step) and reuse lists, beta and lambda
 template <int D>
-static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predictor) {
+static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predictor, const double* proj = nullptr,
+                           int reuse = 0) {
+  if (reuse) {
+    StepParams sp = make_params(e, step, update_I0);
+    sp.proj = proj;
+    sp.reuse_lists = 1;
+    const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
+#define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, 0); }
+#define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
+#define CASE_WF(w) case w: CASE_WC(w, false) break;
+    if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_WF(4) CASE_WF(8) } }
+#undef CASE_WF
+#undef CASE_W
+#undef CASE_WC
+    return;
+  }
   if (e->slab_on && update_I0 && e->migrate_every > 0 && e->steps_since_migration >= e->migrate_every) migrate_t<D>(e);
   e->steps_since_migration++;
   const int np = e->np, nn = e->nn;
@@ -1983,6 +2016,7 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
   if (e->reorder_every > 0 && e->steps_since_sort >= e->reorder_every) reorder_particles(e);
   e->steps_since_sort++;
   StepParams sp = make_params(e, step, update_I0);
+  sp.proj = proj;
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, do_predictor); }
 #define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
@@ -2010,6 +2044,7 @@ static void stage_kin_stress_t(nlps_engine* e, int step) {
     LAUNCH(e, K_TRACTION, k_traction<D>, nblk(e->neu.n_entries, 128), 128, e->P, e->neu, e->solver.thickness, step);
   }
   StepParams sp = make_params(e, step, 1);
+  sp.implicit = e->implicit_on;
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_WMC(w, mt, c) { auto kfn = k_kin_force<D, w, mt, c>; LAUNCH_SMEM(e, K_KIN_FORCE, kfn, grid, e->cfg.threads, e->smemB, e->mesh, e->P, e->G, sp, e->cfg, e->err, e->has_traction); }
 #define CASE_WM(w, mt) if (D == 2 && e->cache_pa) CASE_WMC(w, mt, (D == 2)) else CASE_WMC(w, mt, false)
@@ -2069,6 +2104,7 @@ void nlps_b200_destroy(nlps_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  implicit_free(e);
   for (void* p : e->allocs) cudaFree(p);
   if (e->h_err) cudaFreeHost(e->h_err);
   if (e->h_mig) cudaFreeHost(e->h_mig);
@@ -2826,3 +2862,5 @@ int nlps_b200_stress_points(int ndim, const nlps_material* material, double tol_
 }
 
 }  // extern "C"
+
+#include "nlps_implicit.inl"

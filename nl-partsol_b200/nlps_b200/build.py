@@ -7,7 +7,7 @@ import subprocess
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(PKG, "libnlps_b200.so")
 SRCS = [os.path.join(PKG, "csrc", f) for f in ("nlps_engine.cu", "host_setup.cpp")]
-DEPS = SRCS + [os.path.join(PKG, "csrc", "nlps_device.cuh"),
+DEPS = SRCS + [os.path.join(PKG, "csrc", "nlps_device.cuh"), os.path.join(PKG, "csrc", "nlps_implicit.inl"),
                os.path.join(PKG, "..", "include", "nlps_b200.h")]
 
 

@@ -63,6 +63,18 @@ class Slab(C.Structure):
                 ("global_id", _ip), ("node_id_offset", C.c_int), ("comm", C.c_void_p)]
 
 
+class Newmark(C.Structure):
+    _fields_ = [("beta", C.c_double), ("gamma", C.c_double), ("tol", C.c_double), ("max_iter", C.c_int),
+                ("use_explicit_trial", C.c_int), ("pcg_rtol", C.c_double), ("pcg_max_iter", C.c_int)]
+
+
+class NewmarkStats(C.Structure):
+    _fields_ = [("newton_iters", C.c_int), ("n_rows", C.c_int), ("nnz_blocks", C.c_int),
+                ("pcg_iters_total", C.c_longlong), ("assemblies_total", C.c_longlong),
+                ("residual_evals_total", C.c_longlong), ("residual0", C.c_double), ("residual", C.c_double),
+                ("ms_assemble", C.c_double), ("ms_pcg", C.c_double), ("ms_residual", C.c_double)]
+
+
 EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(Msg), C.c_void_p)
 
 _lib = None
@@ -384,6 +396,51 @@ class Engine:
 
     def migrated_count(self):
         return int(self.L.nlps_b200_migrated_count(self.h))
+
+    # ---- implicit Newmark-beta (nlps_b200_newmark_*)
+    def newmark_setup(self, beta=0.25, gamma=0.5, tol=1e-10, max_iter=10, explicit_trial=False, pcg_rtol=0.0,
+                      pcg_max_iter=0):
+        prm = Newmark(beta, gamma, tol, int(max_iter), int(explicit_trial), pcg_rtol, int(pcg_max_iter))
+        return self.L.nlps_b200_newmark_setup(self.h, C.byref(prm))
+
+    def newmark_step(self, k):
+        return self.L.nlps_b200_newmark_step(self.h, int(k))
+
+    def newmark_run(self, first, count):
+        return self.L.nlps_b200_newmark_run(self.h, int(first), int(count))
+
+    def newmark_stats(self):
+        st = NewmarkStats()
+        assert self.L.nlps_b200_newmark_stats(self.h, C.byref(st)) == 0
+        return {k: getattr(st, k) for k, _ in NewmarkStats._fields_}
+
+    def newmark_begin(self, k):
+        return self.L.nlps_b200_newmark_begin(self.h, int(k))
+
+    def newmark_get(self, which):
+        out = np.zeros((self.nn, self.d))
+        assert self.L.nlps_b200_newmark_get(self.h, dict(Vn=0, An=1, dU=2, R=3)[which], out.ctypes.data_as(_dp)) == 0
+        return out
+
+    def newmark_residual(self, k, dU=None):
+        R = np.zeros((self.nn, self.d))
+        du = _d(dU) if dU is not None else None
+        rc = self.L.nlps_b200_newmark_residual(self.h, int(k), du.ctypes.data_as(_dp) if du is not None else None,
+                                               R.ctypes.data_as(_dp))
+        return rc, R
+
+    def newmark_tangent(self):
+        """(row_nodes, row_ptr, col_nodes, vals[nnz, d, d]) of the tangent at the last residual state."""
+        nr, nz = C.c_int(), C.c_int()
+        assert self.L.nlps_b200_newmark_tangent(self.h, C.byref(nr), C.byref(nz), None, None, None, None) == 0
+        rows = np.zeros(nr.value, np.int32)
+        rp = np.zeros(nr.value + 1, np.int32)
+        cols = np.zeros(max(nz.value, 1), np.int32)
+        vals = np.zeros((max(nz.value, 1), self.d, self.d))
+        assert self.L.nlps_b200_newmark_tangent(self.h, C.byref(nr), C.byref(nz), rows.ctypes.data_as(_ip),
+                                                rp.ctypes.data_as(_ip), cols.ctypes.data_as(_ip),
+                                                vals.ctypes.data_as(_dp)) == 0
+        return rows, rp, cols[:nz.value], vals[:nz.value]
 
     def upload(self, fields: dict):
         st, host = self.m.state, self.m.host

@@ -165,6 +165,42 @@ class Oracle:
     def search_lists(self):
         return self.L.orc_search_lists(self.h, None)
 
+    # ---- implicit Newmark-beta restatement (parity unpinned: no PETSc here)
+    def newmark_setup(self, beta=0.25, gamma=0.5, tol=1e-10, max_iter=10, explicit_trial=False):
+        self.L.orc_newmark_setup(self.h, ctypes.c_double(beta), ctypes.c_double(gamma), ctypes.c_double(tol),
+                                 int(max_iter), int(explicit_trial))
+
+    def newmark_begin(self, step):
+        return self.L.orc_newmark_begin(self.h, int(step))
+
+    def newmark_residual(self, step, dU):
+        dU = _d(dU)
+        R = np.zeros_like(dU)
+        st = self.L.orc_newmark_residual(self.h, int(step), dU.ctypes.data_as(_dp), R.ctypes.data_as(_dp))
+        return st, R
+
+    def newmark_tangent(self):
+        nd = self.prob.nn * self.d
+        K = np.zeros((nd, nd))
+        st = self.L.orc_newmark_tangent(self.h, K.ctypes.data_as(_dp))
+        return st, K
+
+    def newmark_step(self, step):
+        return self.L.orc_newmark_step(self.h, int(step))
+
+    def newmark_iters(self):
+        return self.L.orc_newmark_iters()
+
+    def newmark_get(self, which):
+        out = np.zeros((self.prob.nn, self.d))
+        self.L.orc_newmark_get(self.h, dict(Vn=0, An=1, dU=2, R=3)[which], out.ctypes.data_as(_dp))
+        return out
+
+    def fixed(self):
+        out = np.zeros((self.prob.nn, self.d), np.uint8)
+        self.L.orc_get_fixed(self.h, out.ctypes.data_as(_up))
+        return out
+
     def init_lme(self):
         return self.L.orc_init_lme(self.h)
 

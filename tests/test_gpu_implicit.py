@@ -1,0 +1,103 @@
+"""Implicit Newmark-beta on the device against the CPU restatement, through the C ABI:
+stage by stage (nodal v_n/a_n, initial guess, residual, tangent entries) and converged time steps.
+The oracle solves its Newton systems with dense LU, the engine with Jacobi-PCG on a block-CSR tangent:
+converged states are compared, with the tolerance the nonlinear solve supports."""
+import numpy as np
+import pytest
+
+import oracle
+from nlps_b200 import engine, synthetic
+from util import assert_close, field_scales
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "block2d": lambda n: synthetic.block_2d(cells=8, nsteps=n),
+    "cube3d": lambda n: synthetic.cube_3d(cells=3, nsteps=n),
+}
+
+
+def _pair(case, nsteps, cfl, tol=1e-12, explicit_trial=False):
+    P = CASES[case](nsteps)
+    P.solver["cfl"] = cfl
+    o = oracle.Oracle(P)
+    assert o.init_lme() == 0
+    o.newmark_setup(tol=tol, max_iter=25, explicit_trial=explicit_trial)
+    eng = engine.Engine(P, device=0)
+    assert eng.initialize_lme() == 0
+    assert eng.newmark_setup(tol=tol, max_iter=25, explicit_trial=explicit_trial, pcg_rtol=1e-13) == 0
+    return P, o, eng
+
+
+def dense_from_csr(eng, P, o, a1):
+    rows, rp, cols, vals = eng.newmark_tangent()
+    d = P.ndim
+    nd = P.nn * d
+    K = np.zeros((nd, nd))
+    for t, A in enumerate(rows):
+        for q in range(rp[t], rp[t + 1]):
+            B = cols[q]
+            K[A * d:(A + 1) * d, B * d:(B + 1) * d] += vals[q]
+    K[np.arange(nd), np.arange(nd)] += a1 * o.nodal(0).ravel()
+    dead = ((o.active()[:, None] == 0) | (o.fixed() != 0)).ravel()
+    K[dead, :] = 0.0
+    K[:, dead] = 0.0
+    K[dead, dead] = 1.0
+    return K, rows, rp
+
+
+@pytest.mark.parametrize("case", ["block2d", "cube3d"])
+def test_stages_match_the_oracle(case):
+    P, o, eng = _pair(case, 4, 4.0, explicit_trial=True)
+    # one converged step first, so that F_n != I and the state is not trivial
+    assert o.newmark_step(0) == 0 and eng.newmark_step(0) == 0, eng.error()
+    sc = field_scales(P)
+    assert o.newmark_begin(1) == 0 and eng.newmark_begin(1) == 0
+    assert np.array_equal(eng.active(), o.active())
+    h, dt = P.dx, P.dt()
+    for which, scale in (("Vn", h / dt), ("An", h / dt ** 2), ("dU", h)):
+        assert_close(eng.newmark_get(which), o.newmark_get(which), f"{case} {which}", rtol=1e-9, scale=1e-5 * scale)
+    dU = o.newmark_get("dU")
+    st, Ro = o.newmark_residual(1, dU)
+    rc, Rg = eng.newmark_residual(1, dU)
+    assert st == 0 and rc == 0
+    fscale = sc["gF"] / 1e-4                       # natural force scale E h^(d-1)
+    assert np.abs(Rg - Ro).max() <= 1e-10 * max(np.abs(Ro).max(), 1e-4 * fscale)
+    # tangent: every entry of the oracle's dense matrix
+    st, Ko = o.newmark_tangent()
+    beta = 0.25
+    Kg, rows, rp = dense_from_csr(eng, P, o, 1.0 / (beta * dt * dt))
+    assert st == 0
+    assert np.abs(Kg - Ko).max() <= 1e-10 * np.abs(Ko).max()
+    assert np.array_equal(rows, np.nonzero(o.active())[0])
+    assert rp[-1] < len(rows) ** 2 or len(rows) < 40   # sparse
+    eng.close()
+
+
+@pytest.mark.parametrize("case,cfl", [("block2d", 5.0), ("cube3d", 5.0)])
+def test_converged_steps_match_the_oracle(case, cfl):
+    nsteps = 6
+    P, o, eng = _pair(case, nsteps, cfl)
+    for k in range(nsteps):
+        assert o.newmark_step(k) == 0, o.error()
+        assert eng.newmark_step(k) == 0, eng.error()
+        st = eng.newmark_stats()
+        assert st["newton_iters"] <= 8 and st["residual"] <= max(100 * 1e-12, 1e-12 * st["residual0"]) * 10
+    f = eng.download()
+    sc = field_scales(P)
+    # both Newton loops stop at |R| <= 1e-12 |R0|: the states agree to the conditioning of the tangent times that
+    for name in ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "lambda"):
+        assert_close(f[name], o.field(name), f"{case} {name}", rtol=1e-8, scale=sc.get(name))
+    assert np.array_equal(f["I0"], o.ints("I0"))
+    counts, lists = eng.lists()
+    assert np.array_equal(lists, o.lists())
+    s = eng.newmark_stats()
+    assert s["pcg_iters_total"] > 0 and s["assemblies_total"] >= nsteps
+    eng.close()
+
+
+def test_implicit_refuses_what_is_not_built():
+    P = synthetic.column_collapse_2d(scale=0.03, nsteps=2)   # Drucker-Prager: no tangent restated
+    eng = engine.Engine(P, device=0)
+    assert eng.newmark_setup() != 0
+    eng.close()
