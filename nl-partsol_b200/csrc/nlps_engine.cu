@@ -21,6 +21,9 @@
 #include <string.h>
 
 #include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <string>
 #include <vector>
 
@@ -453,6 +456,12 @@ __global__ void __launch_bounds__(256) k_after_sort(PartDev P, GridDev G) {
 
 // ---------------------------------------------------------------------------
 // block prologue shared by the three cell-block kernels
+#ifndef NLPS_STAGE_U
+#define NLPS_STAGE_U 4
+#endif
+#ifndef NLPS_STAGE_U_G2P
+#define NLPS_STAGE_U_G2P 4
+#endif
 struct Blk { int ncell, t0, t1; };
 // metadata of cell group g (C consecutive occupied cells): one global round trip
 __device__ __forceinline__ void blk_prologue(const GridDev& G, const BlockCfg& cfg, int nocc, int np, int g, int* s_cs,
@@ -479,7 +488,8 @@ template <int D, bool WANT_Q, int NF>
 __device__ __forceinline__ void stage_nodes(const MeshDev& m, const GridDev& G, int SL, unsigned magic, int ncell,
                                             const int* s_base, const int* s_len, int* s_rank, unsigned char* s_q,
                                             double* s_X, double* s_U, double* s_A) {
-  constexpr int U = 4;
+  // pairs in flight per thread (7 = one sweep of the usual block, measured no faster than 4 and costs registers)
+  constexpr int U = (NF == 2) ? NLPS_STAGE_U_G2P : NLPS_STAGE_U;
   const int npairs = ncell * SL;
   for (int e0 = threadIdx.x; e0 < npairs; e0 += U * blockDim.x) {
     int node[U], idx[U], es[U];
@@ -1641,21 +1651,42 @@ static int dev_upload(nlps_engine* e, Tp** p, const Tp* h, size_t n) {
   return 0;
 }
 
+// transposed adjacency (who lists me), rows in ascending source order; qpos[q] = position of entry q inside the
+// transposed row of idx[q].  Threads own disjoint ranges of DESTINATION nodes and each scans the whole
+// adjacency: no atomics, the same order as the serial algorithm whatever the thread count.
 static void transpose_csr(int nn, const int* ptr, const int* idx, std::vector<int>& tp, std::vector<int>& ti,
                           std::vector<unsigned char>* qpos = nullptr) {
   tp.assign(nn + 1, 0);
-  for (int i = 0; i < nn; i++)
-    for (int q = ptr[i]; q < ptr[i + 1]; q++) tp[idx[q] + 1]++;
-  for (int i = 0; i < nn; i++) tp[i + 1] += tp[i];
-  ti.resize(tp[nn]);
-  if (qpos) qpos->resize(ptr[nn]);
-  std::vector<int> fill(tp.begin(), tp.end() - 1);
-  for (int i = 0; i < nn; i++)
-    for (int q = ptr[i]; q < ptr[i + 1]; q++) {
-      int A = idx[q];
-      if (qpos) (*qpos)[q] = (unsigned char)(fill[A] - tp[A]);
-      ti[fill[A]++] = i;
+  const long long nnz = ptr[nn];
+  if (qpos) qpos->resize(nnz);
+#pragma omp parallel
+  {
+    int nt = 1, me = 0;
+#ifdef _OPENMP
+    nt = omp_get_num_threads();
+    me = omp_get_thread_num();
+#endif
+    const int a0 = (int)((long long)nn * me / nt), a1 = (int)((long long)nn * (me + 1) / nt);
+    for (long long q = 0; q < nnz; q++) {
+      const int A = idx[q];
+      if (A >= a0 && A < a1) tp[A + 1]++;
     }
+#pragma omp barrier
+#pragma omp single
+    {
+      for (int i = 0; i < nn; i++) tp[i + 1] += tp[i];
+      ti.resize(tp[nn]);
+    }
+    std::vector<int> fill(tp.begin() + a0, tp.begin() + a1);
+    for (int i = 0; i < nn; i++)
+      for (int q = ptr[i]; q < ptr[i + 1]; q++) {
+        const int A = idx[q];
+        if (A < a0 || A >= a1) continue;
+        int& f = fill[A - a0];
+        if (qpos) (*qpos)[q] = (unsigned char)(f - tp[A]);
+        ti[f++] = i;
+      }
+  }
 }
 
 #define LAUNCH(e, id, kernel, grid, block, ...)                                 \

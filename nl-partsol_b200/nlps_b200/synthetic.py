@@ -176,3 +176,23 @@ def column_slab_2d(rank, world, scale=1.0, nsteps=1000, band_cells=6):
     slab = dict(rank=rank, world=world, axis=1, cuts=cuts, band_cells=band_cells, global_id=gid,
                 n_global=4 * bx * tot_rows, node_offset=j0 * (nx + 1))
     return P, slab
+
+
+def beam_3d(cells_per_unit=8, nsteps=20, gamma_lme=6.0, E=1e7, cfl=10.0, traction=-2.0e3):
+    """BASELINE configs[4] shape: cantilever 8 x 1 x 1 on an H8 grid, GPxElement 8,
+    Neo-Hookean, clamped at x = 0 (left face), tip traction on the last particle-cell layer ramped over
+    the run; implicit Newmark-beta with dt = cfl x the explicit limit.  cells_per_unit = 32 -> 2.1e6
+    particles."""
+    c = cells_per_unit
+    mat = ("Neo-Hookean-Wriggers", [1000.0, E, 0.3] + [0.0] * 13)
+    cel = (E / 1000.0) ** 0.5 * 1.3
+    P = structured_problem(3, (8 * c + 4, c + 4, c + 4), 1.0 / c, (8 * c, c, c), (0, 2, 2), mat, nsteps, cfl, cel,
+                           (0.0, 0.0, 0.0), gamma_lme=gamma_lme, fixed=("left",), rollers=())
+    x = P.fields["x_GC"]
+    tip = np.nonzero(x[:, 0] > 8.0 - 1.0 / c)[0].astype(np.int32)
+    dr = np.zeros((3, nsteps), np.int32)
+    dr[2, :] = 1
+    val = np.zeros((3, nsteps))
+    val[2, :] = traction * np.minimum(1.0, (np.arange(nsteps) + 1) / max(nsteps, 1))
+    P.neumann.append(dict(nodes=tip, dir=dr, val=val))
+    return P
