@@ -62,6 +62,17 @@ __device__ __forceinline__ void ldvec(const double* p, double* out) {
   out[0] = a.x; out[1] = a.y;
   if (D == 3) { double2 b = *reinterpret_cast<const double2*>(p + 2); out[2] = b.x; }
 }
+// D doubles from shared memory: one 16-byte load in 2D (the staged node arrays are 16-byte aligned, stride 2)
+template <int D>
+__device__ __forceinline__ void ldsvec(const double* p, double* out) {
+  if constexpr (D == 2) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    out[0] = a.x; out[1] = a.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < D; i++) out[i] = p[i];
+  }
+}
 struct MeshDev {
   int nn;
   const double* X;  // nn x NS<D>::X (row-major, padded)
@@ -257,6 +268,27 @@ __device__ __forceinline__ void for_neighbour_pairs(const uint32_t* mk, F&& f) {
     }
   }
 }
+
+// 2D: walk ALL slots of the cell's 2-ring in order, two at a time, with weight 0 for the slots that are not
+// neighbours: the lanes of a warp that sit in the same cell then read the same shared-memory words in the same
+// instruction (broadcast: one wavefront instead of one per lane -- the LSU data pipe is the busiest unit of these
+// kernels, profiles/r01_ncu_full_c2_v5.txt) and the bit scanning disappears; the price is 25 instead of ~22 exp
+// evaluations, which the fp64 pipe (16-25 % busy) absorbs.  3D (125 slots, ~40 neighbours) keeps the bit iteration.
+template <int D, int W, class F>
+__device__ __forceinline__ void for_slots(const uint32_t* mk, int len, F&& f) {
+  if constexpr (D == 2 && W == 1) {
+    const uint32_t m = mk[0];
+    for (int k = 0; k < len; k += 2) {
+      const bool has1 = k + 1 < len;
+      const double w0 = ((m >> k) & 1u) ? 1.0 : 0.0;
+      const double w1 = (has1 && ((m >> (k + 1)) & 1u)) ? 1.0 : 0.0;
+      f(k, has1 ? k + 1 : k, w0, w1);
+    }
+  } else {
+    for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) { f(k0, k1, 1.0, two ? 1.0 : 0.0); });
+  }
+}
+template <int D, int W> struct DenseSlots { static constexpr bool value = (D == 2 && W == 1); };
 
 // ---------------------------------------------------------------------------
 // K0a: closest node + cell histogram.   local_search__LME__ first loop (LME.c:917-944),
@@ -631,7 +663,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
         for (int w = 0; w < W; w++) P.mask[(size_t)w * np + p] = mk[w];
         P.nnodes[p] = n;
       }
-      if (CACHE) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
+      if (CACHE && !DenseSlots<D, W>::value) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
 #pragma unroll
         for (int w = 0; w < W; w++) {
           const int rem = len - 32 * w;
@@ -654,23 +686,24 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
         for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
-        for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) {
-          double l0[D], l1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
+        for_slots<D, W>(mk, len, [&](int k0, int k1, double w0, double w1) {
+          double l0[D], l1[D], X0[D], X1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
+          ldsvec<D>(Xc + k0 * D, X0);
+          ldsvec<D>(Xc + k1 * D, X1);
 #pragma unroll
           for (int i = 0; i < D; i++) {
-            l0[i] = xp[i] - Xc[k0 * D + i];
-            l1[i] = xp[i] - Xc[k1 * D + i];
+            l0[i] = xp[i] - X0[i];
+            l1[i] = xp[i] - X1[i];
             ll0 += l0[i] * l0[i];
             ll1 += l1[i] * l1[i];
             lx0 += l0[i] * lam[i];
             lx1 += l1[i] * lam[i];
           }
-          const double e0 = fexp(-beta * ll0 + lx0, s_tab);
-          double e1 = fexp(-beta * ll1 + lx1, s_tab);
-          e1 = two ? e1 : 0.0;
+          const double e0 = fexp(-beta * ll0 + lx0, s_tab) * w0;
+          const double e1 = fexp(-beta * ll1 + lx1, s_tab) * w1;
           if (CACHE) {
             s_pa[(size_t)j * SL + k0] = e0;
-            if (two) s_pa[(size_t)j * SL + k1] = e1;
+            if (k1 != k0) s_pa[(size_t)j * SL + k1] = e1;
           }
           Z += e0;
 #pragma unroll
@@ -913,7 +946,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
       uint32_t mk[W];
 #pragma unroll
       for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
-      if (CACHE) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
+      if (CACHE && !DenseSlots<D, W>::value) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
         const int len = s_len[ci];
 #pragma unroll
         for (int w = 0; w < W; w++) {
@@ -941,29 +974,32 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
       for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
       for (int i = 0; i < D * D; i++) { JJ[i] = 0.0; Bm[i] = 0.0; }
-      for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) {
-        double l0[D], l1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
+      for_slots<D, W>(mk, s_len[ci], [&](int k0, int k1, double w0, double w1) {
+        double l0[D], l1[D], X0[D], X1[D], U0[D], U1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
+        ldsvec<D>(Xc + k0 * D, X0);
+        ldsvec<D>(Xc + k1 * D, X1);
+        ldsvec<D>(Uc + k0 * D, U0);
+        ldsvec<D>(Uc + k1 * D, U1);
 #pragma unroll
         for (int i = 0; i < D; i++) {
-          l0[i] = xp[i] - Xc[k0 * D + i];
-          l1[i] = xp[i] - Xc[k1 * D + i];
+          l0[i] = xp[i] - X0[i];
+          l1[i] = xp[i] - X1[i];
           ll0 += l0[i] * l0[i];
           ll1 += l1[i] * l1[i];
           lx0 += l0[i] * lam[i];
           lx1 += l1[i] * lam[i];
         }
-        const double e0 = fexp(-beta * ll0 + lx0, s_tab);
-        double e1 = fexp(-beta * ll1 + lx1, s_tab);
-        e1 = two ? e1 : 0.0;
+        const double e0 = fexp(-beta * ll0 + lx0, s_tab) * w0;
+        const double e1 = fexp(-beta * ll1 + lx1, s_tab) * w1;
         if (CACHE) {
           s_pa[(size_t)j * SL + k0] = e0;
-          if (two) s_pa[(size_t)j * SL + k1] = e1;
+          if (k1 != k0) s_pa[(size_t)j * SL + k1] = e1;
         }
         Z += e0;
 #pragma unroll
         for (int i = 0; i < D; i++) {
           r[i] += e0 * l0[i];
-          const double eu = e0 * Uc[k0 * D + i];
+          const double eu = e0 * U0[i];
 #pragma unroll
           for (int jj = 0; jj < D; jj++) {
             if (jj >= i) JJ[i * D + jj] += e0 * l0[i] * l0[jj];
@@ -974,7 +1010,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
 #pragma unroll
         for (int i = 0; i < D; i++) {
           r[i] += e1 * l1[i];
-          const double eu = e1 * Uc[k1 * D + i];
+          const double eu = e1 * U1[i];
 #pragma unroll
           for (int jj = 0; jj < D; jj++) {
             if (jj >= i) JJ[i * D + jj] += e1 * l1[i] * l1[jj];
@@ -1239,30 +1275,35 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
     uint32_t mk[W];
 #pragma unroll
     for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
-    for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) {
-      double ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
+    for_slots<D, W>(mk, s_len[ci], [&](int k0, int k1, double w0, double w1) {
+      double X0[D], X1[D], U0[D], U1[D], A0[D], A1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
+      ldsvec<D>(Xc + k0 * D, X0);
+      ldsvec<D>(Xc + k1 * D, X1);
+      ldsvec<D>(Uc + k0 * D, U0);
+      ldsvec<D>(Uc + k1 * D, U1);
+      ldsvec<D>(Ac + k0 * D, A0);
+      ldsvec<D>(Ac + k1 * D, A1);
 #pragma unroll
       for (int i = 0; i < D; i++) {
-        const double l0 = xp[i] - Xc[k0 * D + i], l1 = xp[i] - Xc[k1 * D + i];
+        const double l0 = xp[i] - X0[i], l1 = xp[i] - X1[i];
         ll0 += l0 * l0;
         ll1 += l1 * l1;
         lx0 += l0 * lam[i];
         lx1 += l1 * lam[i];
       }
-      const double e0 = fexp(-beta * ll0 + lx0, s_tab);
-      double e1 = fexp(-beta * ll1 + lx1, s_tab);
-      e1 = two ? e1 : 0.0;
+      const double e0 = fexp(-beta * ll0 + lx0, s_tab) * w0;
+      const double e1 = fexp(-beta * ll1 + lx1, s_tab) * w1;
       Z += e0;
 #pragma unroll
       for (int i = 0; i < D; i++) {
-        a[i] += e0 * Ac[k0 * D + i];
-        du[i] += e0 * Uc[k0 * D + i];
+        a[i] += e0 * A0[i];
+        du[i] += e0 * U0[i];
       }
       Z += e1;
 #pragma unroll
       for (int i = 0; i < D; i++) {
-        a[i] += e1 * Ac[k1 * D + i];
-        du[i] += e1 * Uc[k1 * D + i];
+        a[i] += e1 * A1[i];
+        du[i] += e1 * U1[i];
       }
     });
     const double Zi = 1.0 / Z;

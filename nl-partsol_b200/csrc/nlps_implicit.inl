@@ -16,7 +16,8 @@
 //
 // Scope: Neo-Hookean-Wriggers tangent (BASELINE configs[4]); single slab.
 
-static const int IMP_NPART = 296;  // blocks of the reduction kernels = length of the partial-sum arrays (2 x 148 SMs)
+static const int IMP_NPART = 296;   // blocks of the vector kernels = length of their partial-sum arrays (2 x 148 SMs)
+static const int IMP_NSPMV = 1184;  // blocks of the SpMV (8 x 148 SMs x 8 warps: the row gathers need the warps to hide latency)
 
 struct ImplicitCtx {
   nlps_newmark prm{};
@@ -30,7 +31,7 @@ struct ImplicitCtx {
   double *Vn = nullptr, *An = nullptr, *dU = nullptr, *R = nullptr, *delta = nullptr, *trial = nullptr, *Rt = nullptr;
   double *r = nullptr, *z = nullptr, *p = nullptr, *Ap = nullptr, *diag = nullptr;
   unsigned char* fx = nullptr;
-  double* part = nullptr;    // [5][IMP_NPART]: 0 pAp, 1-2 rz (ping-pong), 3 rr, 4 scratch (|R|^2)
+  double* part = nullptr;    // [4][IMP_NPART]: 0-1 rz (ping-pong), 2 rr, 3 scratch (|R|^2); then pAp[IMP_NSPMV]
   double* h_part = nullptr;  // pinned
   std::vector<void*> allocs;
   int newton_iters = 0;
@@ -131,9 +132,9 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   __syncthreads();
   return s;  // valid in thread 0
 }
-__device__ __forceinline__ double sum_partials(const double* part) {  // fixed order: identical in every block
+__device__ __forceinline__ double sum_partials(const double* part, int n = IMP_NPART) {  // fixed order: identical in every block
   double s = 0.0;
-  for (int i = 0; i < IMP_NPART; i++) s += part[i];
+  for (int i = 0; i < n; i++) s += part[i];
   return s;
 }
 
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(256) k_pcg_update1(const int* n_active, int D,
                                                      double* z, double* part_rz_new, double* part_rr) {
   __shared__ double sh[8];
   const int n = *n_active * D;
-  const double pAp = sum_partials(part_pAp), rz = sum_partials(part_rz_cur);
+  const double pAp = sum_partials(part_pAp, IMP_NSPMV), rz = sum_partials(part_rz_cur);
   const double alpha = (pAp != 0.0) ? rz / pAp : 0.0;
   double a = 0.0, c = 0.0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -580,11 +581,11 @@ static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
       imp_alloc(e, &c->An, nv) || imp_alloc(e, &c->dU, nv) || imp_alloc(e, &c->R, nv) || imp_alloc(e, &c->delta, nv) ||
       imp_alloc(e, &c->trial, nv) || imp_alloc(e, &c->Rt, nv) || imp_alloc(e, &c->r, nv) || imp_alloc(e, &c->z, nv) ||
       imp_alloc(e, &c->p, nv) || imp_alloc(e, &c->Ap, nv) || imp_alloc(e, &c->diag, nv) || imp_alloc(e, &c->fx, e->max_act) ||
-      imp_alloc(e, &c->part, 5 * IMP_NPART))
+      imp_alloc(e, &c->part, 4 * IMP_NPART + IMP_NSPMV))
     return 1;
   CUDA_OK(cudaMemcpyAsync(c->cpl_ptr, cp.data(), sizeof(int) * (nn + 1), cudaMemcpyHostToDevice, e->stream));
   CUDA_OK(cudaMemcpyAsync(c->cpl_idx, ci.data(), sizeof(int) * tot, cudaMemcpyHostToDevice, e->stream));
-  CUDA_OK(cudaMallocHost(&c->h_part, sizeof(double) * 5 * IMP_NPART));
+  CUDA_OK(cudaMallocHost(&c->h_part, sizeof(double) * IMP_NPART));
   CUDA_OK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -665,24 +666,24 @@ template <int D>
 static int imp_pcg_t(nlps_engine* e, const double* b, double* x) {
   ImplicitCtx* c = e->imp;
   const int* na = e->G.n_active;
-  double* part_pAp = c->part;
-  double* part_rz[2] = {c->part + IMP_NPART, c->part + 2 * IMP_NPART};
-  double* part_rr = c->part + 3 * IMP_NPART;
+  double* part_pAp = c->part + 4 * IMP_NPART;
+  double* part_rz[2] = {c->part, c->part + IMP_NPART};
+  double* part_rr = c->part + 2 * IMP_NPART;
   k_pcg_init<<<IMP_NPART, 256, 0, e->stream>>>(na, D, b, c->diag, x, c->r, c->z, c->p, part_rz[0], part_rr);
-  const double bnorm = imp_norm(e, 3);
+  const double bnorm = imp_norm(e, 2);
   if (bnorm == 0.0) return 0;
   const double target = c->prm.pcg_rtol * bnorm;
   int it = 0;
   const int check = 8;
   while (it < c->prm.pcg_max_iter) {
     for (int k = 0; k < check; k++, it++) {
-      k_bsr_spmv<D><<<IMP_NPART, 256, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->p, c->Ap, part_pAp);
+      k_bsr_spmv<D><<<IMP_NSPMV, 256, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->p, c->Ap, part_pAp);
       k_pcg_update1<<<IMP_NPART, 256, 0, e->stream>>>(na, D, part_pAp, part_rz[it & 1], c->p, c->Ap, c->diag, x, c->r, c->z,
                                                      part_rz[(it + 1) & 1], part_rr);
       k_pcg_update2<<<IMP_NPART, 256, 0, e->stream>>>(na, D, part_rz[it & 1], part_rz[(it + 1) & 1], c->z, c->p);
     }
     e->launches += 3 * check;
-    const double rn = imp_norm(e, 3);
+    const double rn = imp_norm(e, 2);
     if (!(rn == rn)) return -it;  // NaN: breakdown
     if (rn <= target) { c->pcg_iters += it; return it; }
   }
@@ -700,8 +701,8 @@ static int imp_step_t(nlps_engine* e, int step) {
   auto tock = [&](double& acc) { cudaEventRecord(t1, e->stream); cudaEventSynchronize(t1); float ms = 0; cudaEventElapsedTime(&ms, t0, t1); acc += ms; };
   imp_begin_t<D>(e, step);
   tick();
-  imp_residual_t<D>(e, step, c->dU, c->R, 4);
-  double rn = imp_norm(e, 4);
+  imp_residual_t<D>(e, step, c->dU, c->R, 3);
+  double rn = imp_norm(e, 3);
   tock(c->ms_residual);
   if (poll_error(e)) return 1;
   c->res0 = rn;
@@ -724,14 +725,14 @@ static int imp_step_t(nlps_engine* e, int step) {
     bool ok = false;
     for (int ls = 0; ls < 8; ls++, lam *= 0.5) {
       k_vec_axpy<<<IMP_NPART, 256, 0, e->stream>>>(na, D, c->dU, lam, c->delta, c->trial);
-      imp_residual_t<D>(e, step, c->trial, c->Rt, 4);
-      rt = imp_norm(e, 4);
+      imp_residual_t<D>(e, step, c->trial, c->Rt, 3);
+      rt = imp_norm(e, 3);
       if (rt < rn) { ok = true; break; }
     }
     if (!ok) {
       k_vec_axpy<<<IMP_NPART, 256, 0, e->stream>>>(na, D, c->dU, 1.0, c->delta, c->trial);
-      imp_residual_t<D>(e, step, c->trial, c->Rt, 4);
-      rt = imp_norm(e, 4);
+      imp_residual_t<D>(e, step, c->trial, c->Rt, 3);
+      rt = imp_norm(e, 3);
     }
     tock(c->ms_residual);
     if (poll_error(e)) { status = 1; break; }
@@ -842,7 +843,7 @@ int nlps_b200_newmark_residual(nlps_engine* e, int time_step, const double* dU, 
     CUDA_OK(cudaStreamSynchronize(e->stream));
     cudaFree(tmp);
   }
-  if (e->D == 2) imp_residual_t<2>(e, time_step, c->dU, c->R, 4); else imp_residual_t<3>(e, time_step, c->dU, c->R, 4);
+  if (e->D == 2) imp_residual_t<2>(e, time_step, c->dU, c->R, 3); else imp_residual_t<3>(e, time_step, c->dU, c->R, 3);
   if (poll_error(e)) return 1;
   return R ? nlps_b200_newmark_get(e, 3, R) : 0;
 }

@@ -152,6 +152,21 @@ def test_submesh_slabs_match_global_engine():
     compare(G, single, res, check_active=False)
 
 
+def test_cube_3d_slabs_match_single():
+    """3D (4 mask words, 125-node rings): Neo-Hookean cube drifting along x through two cuts."""
+    from nlps_b200 import synthetic
+    nsteps = 40
+    P = synthetic.structured_problem(3, (44, 10, 10), 1.0 / 8, (32, 6, 6), (4, 2, 2), synthetic.NH_C1, nsteps, 0.5,
+                                     (1e6 / 1000.0) ** 0.5 * 1.3, (0.0, 0.0, -9.81), gamma_lme=6.0, fixed=("bottom",),
+                                     rollers=())
+    z = P.fields["x_GC"][:, 2]
+    P.fields["vel"][:, 0] = 0.3 * P.solver["cel"] * (1.0 + 0.2 * (z - z.min()))
+    single = run_single(P, nsteps)
+    res, axis, cuts = run_slabs_threads(P, nsteps, 2, migrate_every=4)
+    assert axis == 0 and sum(r[5] for r in res) > 100
+    compare(P, single, res)
+
+
 def test_excursion_is_latched():
     """Without migration a particle eventually leaves the band its slab may roam in: error 9."""
     nsteps = 60
