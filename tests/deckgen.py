@@ -58,6 +58,7 @@ class DeckSpec:
         ("Right", "right", {"V.x": 0.0, "V.y": None}, "CONSTANT_CURVE"),
     ])
     out_every: int = 1000000
+    solver_extra: dict = field(default_factory=dict)   # e.g. Beta-Newmark-beta, TOL-Newmark-beta, Max-Iter
 
 
 def background_nodes(spec: DeckSpec):
@@ -127,6 +128,8 @@ def write_deck(spec: DeckSpec, outdir: str) -> str:
     lines.append(f"  CFL={spec.cfl!r}")
     lines.append(f"  Cel={spec.cel!r}")
     lines.append(f"  N={spec.nsteps}")
+    for k, v in spec.solver_extra.items():
+        lines.append(f"  {k}={v!r}")
     lines.append("}")
     lines.append("generate-gravity-field-constant")
     lines.append("{")

@@ -42,3 +42,42 @@ def test_reference_driver_with_b200_scheme(tmp_path):
         assert files, f"no VTK for step {cp - 1}"
         x = _points(files[0])
         assert np.abs(x - tr[f"s{cp}_x_GC"]).max() <= 1e-10 * np.abs(tr[f"s{cp}_x_GC"]).max()
+
+
+@pytest.mark.gpu
+def test_reference_driver_with_b200_implicit_scheme(tmp_path):
+    """`NLPS-Solver (Type=Newmark-beta-Finite-Strains)`: the reference driver (compiled with -DUSE_PETSC against
+    stand-in headers, no PETSc library) dispatches to U_Newmark_Beta, which here is the B200 shim.  The VTK
+    positions are compared with the CPU restatement of the scheme (oracle, dense LU) on the same problem."""
+    if not os.path.exists(BIN):
+        pytest.skip("drop-in binary not built (needs /root/reference at build time)")
+    import deckgen
+    import make_golden
+    import oracle
+    from util import load_problem
+    nsteps, cfl, tol = 6, 4.0, 1e-12
+    spec = make_golden.spec_for("nh")
+    spec.scheme = "Newmark-beta-Finite-Strains"
+    spec.nsteps, spec.cfl, spec.out_every = nsteps, cfl, 1
+    spec.solver_extra = {"Beta-Newmark-beta": 0.25, "Gamma-Newmark-beta": 0.5, "TOL-Newmark-beta": tol, "Max-Iter": 25,
+                         "Epsilon": 0.0}
+    deckgen.write_deck(spec, str(tmp_path))
+    r = subprocess.run([BIN, "--FORMULATION-U", "-f", "deck.nlp"], cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "abnormally" not in r.stdout + r.stderr
+    P = load_problem("nh")                      # the same deck as the reference's own setup produced it
+    P.solver["cfl"], P.solver["nsteps"] = cfl, nsteps
+    for b in P.bounds:
+        b["dir"], b["val"] = b["dir"][:, :nsteps], b["val"][:, :nsteps]
+    P.gravity = P.gravity[:, :nsteps]
+    o = oracle.Oracle(P)
+    assert o.init_lme() == 0
+    o.newmark_setup(tol=tol, max_iter=25)
+    for k in range(nsteps):
+        assert o.newmark_step(k) == 0, o.error()
+        files = glob.glob(os.path.join(str(tmp_path), "Results", f"*_{k}.vtk"))
+        assert files, f"no VTK for step {k}"
+        x = _points(files[0])
+        assert np.abs(x - o.field("x_GC")).max() <= 1e-8 * np.abs(o.field("x_GC")).max(), k
+    assert np.abs(o.field("dis")).max() > 1e-6
