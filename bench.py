@@ -60,6 +60,56 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+class NvmlSampler:
+    """SM clock and clock-event (throttle) reasons read through NVML every few milliseconds during the timed
+    region -- the same quantities as the recipe's nvidia-smi line, fine enough for a region of tens of ms."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, gpu=0, period=0.004):
+        self.gpu, self.period, self.sm, self.mask, self.ok = gpu, period, [], 0, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu]) if vis and vis.split(",")[gpu].isdigit() else gpu
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def start(self):
+        self.stop_flag = False
+        if not self.ok:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self.stop_flag = True
+        if not self.ok:
+            return None
+        self.t.join(1.0)
+        if not self.sm:
+            return None
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max,
+                "reasons": sorted(v for k, v in self.REASONS.items() if self.mask & k), "samples": len(self.sm),
+                "source": "nvml"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -206,7 +256,8 @@ def run_ours(args):
     npart = eng.local_count() if world > 1 else P.np_
     # warm-up
     assert eng.run(0, Wm) == 0, eng.error()
-    sampler = ClockSampler(local)
+    sampler, sampler2 = NvmlSampler(local), ClockSampler(local)
+    sampler2.start()
     sampler.start()
     if world > 1:
         dist.barrier()
@@ -217,6 +268,9 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches = eng.launch_count() - l0
     clocks = sampler.stop()
+    clocks2 = sampler2.stop()
+    if clocks is None:
+        clocks = clocks2
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -293,7 +347,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    engine.u_verlet(P2, run_initialize=False, results_every=every, device=local, slab=slab2)
+    engine.u_verlet(P2, run_initialize=False, results_every=every, device=local, slab=slab2, inplace=True)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -338,7 +392,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--scale", type=float, default=1.0, help="linear scale of the C2 workload (1.0 = 10^6 particles)")

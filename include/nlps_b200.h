@@ -336,6 +336,11 @@ int nlps_b200_u_newmark_beta(const nlps_mesh *mesh, const nlps_solver *solver,
                              nlps_particles *state, int run_initialize, int results_every,
                              nlps_results_cb cb, void *user, int device);
 
+/* Engines take their device memory from the device's stream-ordered pool and leave it cached there on
+ * destroy (a second scheme call in the same process then skips cudaMalloc/cudaFree); this returns the cached
+ * memory to the driver.  NLPS_POOL=0 in the environment disables the pool. */
+int nlps_b200_trim(int device);
+
 const char *nlps_b200_version(void);
 
 #ifdef __cplusplus

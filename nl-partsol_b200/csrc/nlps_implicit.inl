@@ -42,7 +42,7 @@ struct ImplicitCtx {
 
 static void implicit_free(nlps_engine* e) {
   if (!e->imp) return;
-  for (void* p : e->imp->allocs) cudaFree(p);
+  for (void* p : e->imp->allocs) pool_free(p, e->stream);
   if (e->imp->h_part) cudaFreeHost(e->imp->h_part);
   delete e->imp;
   e->imp = nullptr;
@@ -51,7 +51,7 @@ static void implicit_free(nlps_engine* e) {
 template <typename Tp>
 static int imp_alloc(nlps_engine* e, Tp** p, size_t n) {
   void* q = nullptr;
-  cudaError_t st = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(Tp));
+  cudaError_t st = pool_malloc(&q, std::max<size_t>(n, 1) * sizeof(Tp), e->stream);
   if (st != cudaSuccess) {
     fprintf(stderr, "nlps_b200 (implicit): cudaMalloc(%zu) failed: %s\n", n * sizeof(Tp), cudaGetErrorString(st));
     return 1;

@@ -262,7 +262,7 @@ class ThreadComm:
 class _Marshal:
     """Keeps the numpy buffers alive that the C structs point into."""
 
-    def __init__(self, prob: Problem, quirk=-1, compute_c_ep=0, initial_step=0):
+    def __init__(self, prob: Problem, quirk=-1, compute_c_ep=0, initial_step=0, copy=True):
         self.keep = []
         k = self.keep
         self.mesh = Mesh()
@@ -284,7 +284,7 @@ class _Marshal:
         self.neumann = self._loads(prob.neumann)
         self.gravity = _d(prob.gravity) if prob.gravity is not None else None
         self.materials = (Material * len(prob.materials))(*[_material(t, p) for t, p in prob.materials])
-        self.state, self.host = self.particles(prob)
+        self.state, self.host = self.particles(prob, copy)
 
     def _loads(self, lst):
         arr = (Load * max(len(lst), 1))()
@@ -296,10 +296,13 @@ class _Marshal:
         return arr
 
     @staticmethod
-    def particles(prob: Problem):
-        host = {k: _d(prob.fields[k]).copy() for k in _PFIELDS if k in prob.fields}
-        host["I0"] = _i(prob.I0).copy()
-        host["MatIdx"] = _i(prob.MatIdx).copy()
+    def particles(prob: Problem, copy=True):
+        """copy=False: the C side reads and writes the Problem's own arrays, as the reference's scheme functions
+        do with the driver's buffers (arrays must already be contiguous float64 / int32)."""
+        cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        host = {k: cp(_d(prob.fields[k])) for k in _PFIELDS if k in prob.fields}
+        host["I0"] = cp(_i(prob.I0))
+        host["MatIdx"] = cp(_i(prob.MatIdx))
         host["NumberNodes"] = np.zeros(prob.np_, np.int32)
         st = Particles()
         st.n = prob.np_
@@ -504,11 +507,12 @@ def make_slab(slab: dict, n_state, keep: list):
                 int(slab.get("node_offset", 0)), comm.h if comm is not None else None)
 
 
-def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, quirk=-1, initial_step=0, slab=None):
+def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, quirk=-1, initial_step=0, slab=None,
+             inplace=False):
     """The whole scheme call with HOST buffers (nlps_b200_u_verlet[_slab]).  Returns the final fields
     (slab engines: rows of other slabs keep their input values; with global_id: compact rows)."""
     L = lib()
-    m = _Marshal(prob, quirk, 0, initial_step)
+    m = _Marshal(prob, quirk, 0, initial_step, copy=not inplace)
     args = (C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds, len(prob.neumann),
             m.neumann, m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None,
             len(prob.materials), m.materials, C.byref(m.state))
@@ -522,7 +526,7 @@ def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, qui
     if rc != 0:
         raise RuntimeError("nlps_b200_u_verlet failed")
     n = m.state.n
-    out = {k: v[:n].copy() for k, v in m.host.items()}
+    out = {k: (v[:n] if inplace else v[:n].copy()) for k, v in m.host.items()}
     if slab is not None and slab.get("global_id") is not None:
         out["_ids"] = ids[:n].copy()
     return out
