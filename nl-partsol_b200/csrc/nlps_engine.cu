@@ -45,11 +45,11 @@ static const int MAX_MASK_WORDS = 8;  // 2-ring up to 256 nodes
 __constant__ MatParams c_mat[MAX_MATERIALS];
 
 enum KernelId {
-  K_SEARCH = 0, K_NODE_FLAGS, K_SCAN1, K_SCAN2, K_SCAN3, K_FILL, K_NODE_FINISH, K_REORDER, K_LME_P2G,
+  K_SEARCH = 0, K_MARK, K_NODE_FLAGS, K_SCAN1, K_SCAN2, K_SCAN3, K_FILL, K_NODE_FINISH, K_REORDER, K_LME_P2G,
   K_GRID_DISP, K_TRACTION, K_KIN_FORCE, K_GRID_ACC, K_G2P, K_HALO, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
-    "search_closest_node", "node_flags", "scan_reduce", "scan_tops", "scan_apply", "cell_fill",
+    "search_closest_node", "mark_live_blocks", "node_flags", "scan_reduce", "scan_tops", "scan_apply", "cell_fill",
     "node_finish", "reorder", "lme_p2g_mass_disp", "grid_disp_bc", "traction", "kin_stress_p2g_force",
     "grid_acc", "g2p_update", "halo_exchange"};
 
@@ -110,6 +110,10 @@ struct GridDev {
   int* arank;       // rank of a node among the active nodes, -1 when inactive
   uint32_t* occm;   // per active rank: transposed-2-ring slots whose cell is occupied (w2t words, word-major)
   ulonglong2 *packed, *scan_blk;
+  // per block of 256 node ids: holds an occupied cell (set by the search) / lies in the 2-ring of one (this step,
+  // previous step) / must be processed by the node kernels this step (= dirty now or last step: leaving blocks are
+  // visited once more so that their flags return to zero)
+  unsigned char *occ_blk, *dirty_cur, *dirty_prev, *live;
   double* part;     // slot-major cell partial sums: part[(q * max_act + rank) * NV + v]
   int cap, max_act, w2t;
 };
@@ -325,12 +329,35 @@ __global__ void __launch_bounds__(256) k_search(MeshDev m, PartDev P, GridDev G,
     if (c < sl.lo || c > sl.hi) latch_error(err, NLPS_ERR_SLAB_EXCURSION, P.orig[p]);
   }
   atomicAdd(&G.cnt[I0], 1);
+  G.occ_blk[I0 >> 8] = 1;
+}
+
+// Only the node blocks within the 2-ring of an occupied cell can change: the node kernels below skip the rest
+// (the benchmark grid is 6x wider than the column; 4/5 of its nodes never see a particle).
+__global__ void __launch_bounds__(256) k_mark(MeshDev m, GridDev G) {
+  if (!G.occ_blk[blockIdx.x]) return;
+  const int A = blockIdx.x * 256 + threadIdx.x;
+  if (A >= m.nn) return;
+  if (G.cnt[A] > 0 || G.rocc[A]) {
+    // test before set: thousands of threads mark the same few bytes (the stale read is a benign race)
+    for (int q = m.r2p[A]; q < m.r2p[A + 1]; q++) { const int b = m.r2i[q] >> 8; if (!G.dirty_cur[b]) G.dirty_cur[b] = 1; }
+    for (int q = m.r1p[A]; q < m.r1p[A + 1]; q++) { const int b = m.r1i[q] >> 8; if (!G.dirty_cur[b]) G.dirty_cur[b] = 1; }
+    if (!G.dirty_cur[A >> 8]) G.dirty_cur[A >> 8] = 1;
+  }
+}
+__global__ void __launch_bounds__(256) k_live(GridDev G, int nblocks) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  G.live[b] = G.dirty_cur[b] | G.dirty_prev[b];
+  G.dirty_prev[b] = 0;  // becomes dirty_cur of the next step
+  G.occ_blk[b] = 0;
 }
 
 // node flags: ActiveNode[A] = OR over particles with I0 in {B : A in ring1(B)} (LME.c:949-965,
 // after the reset of Shape-Functions.c:38-47).  packed.x = cnt | occupied << 40, packed.y = active:
 // one fused exclusive scan yields cell_start, the rank of each occupied cell and of each active node.
 __global__ void __launch_bounds__(256) k_node_flags(MeshDev m, GridDev G) {
+  if (!G.live[blockIdx.x]) return;
   int A = blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= m.nn) return;
   int act = 0;
@@ -348,12 +375,24 @@ __device__ __forceinline__ ulonglong2 add2(ulonglong2 a, ulonglong2 b) { return 
 
 // exclusive scan of packed, 3 phases, 2048 items per block
 static const int SCAN_ITEMS = 2048;
-__global__ void __launch_bounds__(256) k_scan_reduce(const ulonglong2* in, ulonglong2* blk, int n) {
+// live (optional): one flag per 256 items; a chunk of SCAN_ITEMS whose flags are all clear holds only zeros
+__device__ __forceinline__ bool chunk_live(const unsigned char* live, int chunk, int n) {
+  if (!live) return true;
+  const int b0 = chunk * (SCAN_ITEMS / 256), nb = (n + 255) / 256;
+  unsigned v = 0;
+  for (int k = 0; k < SCAN_ITEMS / 256 && b0 + k < nb; k++) v |= live[b0 + k];
+  return v != 0;
+}
+__global__ void __launch_bounds__(256) k_scan_reduce(const ulonglong2* in, ulonglong2* blk, int n, const unsigned char* live = nullptr) {
   __shared__ ulonglong2 sh[256];
+  if (!chunk_live(live, blockIdx.x, n)) {
+    if (threadIdx.x == 0) blk[blockIdx.x] = make_ulonglong2(0, 0);
+    return;
+  }
   size_t base = (size_t)blockIdx.x * SCAN_ITEMS;
   ulonglong2 s = make_ulonglong2(0, 0);
   for (int i = threadIdx.x; i < SCAN_ITEMS; i += 256)
-    if (base + i < (size_t)n) s = add2(s, in[base + i]);
+    if (base + i < (size_t)n && (!live || live[(base + i) >> 8])) s = add2(s, in[base + i]);
   sh[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -394,15 +433,18 @@ __global__ void k_scan_tops(ulonglong2* blk, int nblk, int* n_active, int* n_occ
   }
 }
 __global__ void __launch_bounds__(256) k_scan_apply(const ulonglong2* in, const ulonglong2* blk, int* cell_start,
-                                                    int* occ_pos, int* act_pos, int n) {
+                                                    int* occ_pos, int* act_pos, int n, const unsigned char* live = nullptr) {
   __shared__ ulonglong2 sh[256];
+  if (!chunk_live(live, blockIdx.x, n)) return;  // nobody reads the positions of nodes outside the live blocks
   size_t base = (size_t)blockIdx.x * SCAN_ITEMS;
   const int per = SCAN_ITEMS / 256;
   ulonglong2 v[per], s = make_ulonglong2(0, 0);
+  // a thread's `per` items lie in one block of 256 (per divides 256): clean blocks are neither read nor written
+  const bool on = !live || live[(base + (size_t)threadIdx.x * per) >> 8];
 #pragma unroll
   for (int k = 0; k < per; k++) {
     size_t i = base + (size_t)threadIdx.x * per + k;
-    v[k] = (i < (size_t)n) ? in[i] : make_ulonglong2(0, 0);
+    v[k] = (on && i < (size_t)n) ? in[i] : make_ulonglong2(0, 0);
     s = add2(s, v[k]);
   }
   sh[threadIdx.x] = s;
@@ -418,7 +460,7 @@ __global__ void __launch_bounds__(256) k_scan_apply(const ulonglong2* in, const 
 #pragma unroll
   for (int k = 0; k < per; k++) {
     size_t i = base + (size_t)threadIdx.x * per + k;
-    if (i < (size_t)n) {
+    if (on && i < (size_t)n) {
       cell_start[i] = (int)(run.x & 0xffffffffffull);
       occ_pos[i] = (int)(run.x >> 40);
       act_pos[i] = (int)run.y;
@@ -439,6 +481,7 @@ __global__ void __launch_bounds__(256) k_cell_fill(PartDev P, GridDev G) {
 // then independent of the physical particle order), append occupied cells / active nodes to their
 // compact lists, and record which slots of the node's transposed 2-ring belong to occupied cells.
 __global__ void __launch_bounds__(256) k_node_finish(MeshDev m, PartDev P, GridDev G) {
+  if (!G.live[blockIdx.x]) return;
   int A = blockIdx.x * blockDim.x + threadIdx.x;
   if (A >= m.nn) return;
   int n = G.cnt[A];
@@ -1368,6 +1411,7 @@ __global__ void k_halo_add(GridDev G, const int* ids, int n, int which, const do
   const int A = ids[i];
   if (which == 0) {
     G.rocc[A] = (unsigned char)(buf[i] != 0.0);  // the bands of the two cuts are disjoint: plain overwrite
+    if (buf[i] != 0.0) G.occ_blk[A >> 8] = 1;
   } else if (which == 1) {
     if (!G.active[A]) return;
     G.M[A] += buf[(size_t)i * (1 + D)];
@@ -2188,11 +2232,14 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
   cudaMemsetAsync(e->G.cnt, 0, sizeof(int) * nn, e->stream);
   if (np) LAUNCH(e, K_SEARCH, k_search<D>, nblk(np, 256), 256, e->mesh, e->P, e->G, update_I0, slab_dev(e), e->err);
   halo_exchange<D>(e, 0);
+  std::swap(e->G.dirty_cur, e->G.dirty_prev);
+  LAUNCH(e, K_MARK, k_mark, nblk(nn, 256), 256, e->mesh, e->G);
+  LAUNCH(e, K_MARK, k_live, nblk(nblk(nn, 256), 256), 256, e->G, nblk(nn, 256));
   LAUNCH(e, K_NODE_FLAGS, k_node_flags, nblk(nn, 256), 256, e->mesh, e->G);
   int nb = nblk(nn, SCAN_ITEMS);
-  LAUNCH(e, K_SCAN1, k_scan_reduce, nb, 256, e->G.packed, e->G.scan_blk, nn);
+  LAUNCH(e, K_SCAN1, k_scan_reduce, nb, 256, e->G.packed, e->G.scan_blk, nn, e->G.live);
   LAUNCH(e, K_SCAN2, k_scan_tops, 1, 1024, e->G.scan_blk, nb, e->G.n_active, e->G.n_occ, e->npart_check);
-  LAUNCH(e, K_SCAN3, k_scan_apply, nb, 256, e->G.packed, e->G.scan_blk, e->G.cell_start, e->G.occ_pos, e->G.act_pos, nn);
+  LAUNCH(e, K_SCAN3, k_scan_apply, nb, 256, e->G.packed, e->G.scan_blk, e->G.cell_start, e->G.occ_pos, e->G.act_pos, nn, e->G.live);
   if (np) LAUNCH(e, K_FILL, k_cell_fill, nblk(np, 256), 256, e->P, e->G);
   LAUNCH(e, K_NODE_FINISH, k_node_finish, nblk(nn, 256), 256, e->mesh, e->P, e->G);
   if (e->reorder_every > 0 && e->steps_since_sort >= e->reorder_every) reorder_particles(e);
@@ -2425,6 +2472,8 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
       dev_alloc(e, &G.active, nn) || dev_alloc(e, &G.fixed, nn) ||
       dev_alloc(e, &G.cnt, nn) || dev_alloc(e, &G.cursor, nn) || dev_alloc(e, &G.cell_start, nn) ||
       dev_alloc(e, &G.MOM, (size_t)nn * D) || dev_alloc(e, &G.rocc, nn) ||
+      dev_alloc(e, &G.occ_blk, (size_t)nblk(nn, 256) + 1) || dev_alloc(e, &G.dirty_cur, (size_t)nblk(nn, 256) + 1) ||
+      dev_alloc(e, &G.dirty_prev, (size_t)nblk(nn, 256) + 1) || dev_alloc(e, &G.live, (size_t)nblk(nn, 256) + 1) ||
       dev_alloc(e, &G.plist, ld) || dev_alloc(e, &G.act_list, nn) || dev_alloc(e, &G.n_active, 1) ||
       dev_alloc(e, &G.packed, nn) || dev_alloc(e, &G.scan_blk, (size_t)nblk(nn, SCAN_ITEMS) + 1) ||
       dev_alloc(e, &G.act_pos, nn) || dev_alloc(e, &G.occ_pos, nn) || dev_alloc(e, &G.occ_list, e->max_occ) ||
