@@ -1424,6 +1424,86 @@ __global__ void k_halo_add(GridDev G, const int* ids, int n, int which, const do
   }
 }
 
+// Peer-memory halo exchange (one process per GPU, neighbours' buffers mapped with CUDA IPC): the push kernel packs
+// the band values of BOTH sides and stores them straight into the neighbours' receive buffers over NVLink, the last
+// block to finish publishes the arrival counters; the pull kernel waits for the neighbours' counters and adds.
+// A push never waits, so the pair cannot deadlock; the wait is bounded (about 2 s) and latches NLPS_ERR_CUDA.
+struct HaloP2P {
+  const int* ids[2];
+  int n[2];
+  double* peer_rbuf[2];               // where my values go (offset for this exchange kind already applied)
+  unsigned long long* peer_flag[2];   // the neighbour's counter for this kind
+  const double* my_rbuf[2];
+  const unsigned long long* my_flag[2];
+};
+template <int D>
+__device__ __forceinline__ void halo_values(const GridDev& G, int A, int which, double* v) {
+  if (which == 0) {
+    v[0] = G.cnt[A] > 0 ? 1.0 : 0.0;
+  } else if (which == 1) {
+    const bool act = G.active[A];
+    v[0] = act ? G.M[A] : 0.0;
+#pragma unroll
+    for (int k = 0; k < D; k++) v[1 + k] = act ? G.MOM[(size_t)A * D + k] : 0.0;
+  } else {
+    const bool act = G.active[A];
+#pragma unroll
+    for (int k = 0; k < D; k++) v[k] = act ? G.F[(size_t)A * D + k] : 0.0;
+  }
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_halo_push(GridDev G, HaloP2P h, int which, unsigned long long seq, unsigned int* done) {
+  const int per = (which == 0) ? 1 : ((which == 1) ? 1 + D : D);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s_ = (i < h.n[0]) ? 0 : 1, j = (s_ == 0) ? i : i - h.n[0];
+  if (j < h.n[s_]) {
+    double v[1 + D];
+    halo_values<D>(G, h.ids[s_][j], which, v);
+    for (int k = 0; k < per; k++) h.peer_rbuf[s_][(size_t)j * per + k] = v[k];
+  }
+  __threadfence_system();  // my stores are visible to the peer before the counter can be
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(done, 1u);
+    if (ticket == gridDim.x - 1) {
+      *done = 0u;
+      __threadfence_system();
+      for (int t = 0; t < 2; t++)
+        if (h.n[t] > 0) *((volatile unsigned long long*)h.peer_flag[t]) = seq;
+    }
+  }
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_halo_pull(GridDev G, HaloP2P h, int which, unsigned long long seq, int* err) {
+  const int per = (which == 0) ? 1 : ((which == 1) ? 1 + D : D);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s_ = (i < h.n[0]) ? 0 : 1, j = (s_ == 0) ? i : i - h.n[0];
+  if (j >= h.n[s_]) return;
+  const volatile unsigned long long* f = (const volatile unsigned long long*)h.my_flag[s_];
+  const long long t0 = clock64();
+  while (*f < seq) {
+    if (clock64() - t0 > 4000000000ll) { latch_error(err, NLPS_ERR_CUDA, -1); return; }
+    __nanosleep(64);
+  }
+  __threadfence_system();
+  const double* buf = h.my_rbuf[s_] + (size_t)j * per;
+  const int A = h.ids[s_][j];
+  if (which == 0) {
+    const bool on = ((const volatile double*)buf)[0] != 0.0;
+    G.rocc[A] = (unsigned char)on;
+    if (on) G.occ_blk[A >> 8] = 1;
+  } else if (which == 1) {
+    if (!G.active[A]) return;
+    G.M[A] += ((const volatile double*)buf)[0];
+#pragma unroll
+    for (int k = 0; k < D; k++) G.MOM[(size_t)A * D + k] += ((const volatile double*)buf)[1 + k];
+  } else {
+    if (!G.active[A]) return;
+#pragma unroll
+    for (int k = 0; k < D; k++) G.F[(size_t)A * D + k] += ((const volatile double*)buf)[k];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Migration between slabs: particles whose closest node crossed a cut move to the neighbour.
 template <int D>
@@ -1635,7 +1715,16 @@ struct nlps_engine {
     int peer = -1, n = 0;
     int* ids = nullptr;            // device, ascending node ids, identical on both sides of the cut
     double *sbuf = nullptr, *rbuf = nullptr;  // n x (1 + D)
+    // peer-memory path (NVLink stores into the neighbour's buffers, no NCCL launch): 3 receive buffers (one per
+    // exchange kind) + 3 arrival counters in MY memory, and the neighbour's, mapped through CUDA IPC
+    double* p2p_rbuf = nullptr;               // mine: 3 x n x (1 + D), cudaMalloc (IPC needs it)
+    unsigned long long* p2p_flag = nullptr;   // mine: [4]
+    double* peer_rbuf = nullptr;              // the neighbour's p2p_rbuf (of its side facing me)
+    unsigned long long* peer_flag = nullptr;
   } side[2];                        // 0: lower neighbour, 1: upper neighbour
+  int p2p_on = 0;
+  unsigned long long halo_seq[3] = {0, 0, 0};
+  unsigned int* p2p_done = nullptr;  // device counter of the push kernel's last-block election
   int* mig_dest = nullptr;          // per particle: 0 stay, 1 to the lower slab, 2 to the upper slab
   int* mig_cnt = nullptr;           // device [8]: counts stay/low/up, cursors, received low/up
   int* h_mig = nullptr;             // pinned [8]
@@ -2098,6 +2187,37 @@ static int halo_exchange(nlps_engine* e, int which) {
   nlps_msg msgs[2];
   int nm = 0;
   if (e->profile) cudaEventRecord(e->ev0, e->stream);
+  if (e->p2p_on) {
+    HaloP2P h{};
+    const unsigned long long seq = ++e->halo_seq[which];
+    int tot = 0;
+    for (int s_ = 0; s_ < 2; s_++) {
+      auto& sd = e->side[s_];
+      const bool on = sd.peer >= 0 && sd.n > 0;
+      h.ids[s_] = sd.ids;
+      h.n[s_] = on ? sd.n : 0;
+      const size_t off = (size_t)which * sd.n * (1 + D);
+      h.peer_rbuf[s_] = on ? sd.peer_rbuf + off : nullptr;
+      h.peer_flag[s_] = on ? sd.peer_flag + which : nullptr;
+      h.my_rbuf[s_] = on ? sd.p2p_rbuf + off : nullptr;
+      h.my_flag[s_] = on ? sd.p2p_flag + which : nullptr;
+      tot += h.n[s_];
+    }
+    if (tot > 0) {
+      k_halo_push<D><<<nblk(tot, 256), 256, 0, e->stream>>>(e->G, h, which, seq, e->p2p_done);
+      k_halo_pull<D><<<nblk(tot, 256), 256, 0, e->stream>>>(e->G, h, which, seq, e->err);
+      e->launches += 2;
+    }
+    if (e->profile) {
+      cudaEventRecord(e->ev1, e->stream);
+      cudaEventSynchronize(e->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+      e->k_ms[K_HALO] += ms;
+      e->k_n[K_HALO]++;
+    }
+    return 0;
+  }
   for (int s_ = 0; s_ < 2; s_++) {
     auto& h = e->side[s_];
     if (h.peer < 0 || h.n == 0) continue;
@@ -2341,6 +2461,13 @@ void nlps_b200_destroy(nlps_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   implicit_free(e);
+  for (int s_ = 0; s_ < 2; s_++) {
+    auto& h = e->side[s_];
+    if (h.peer_rbuf) cudaIpcCloseMemHandle(h.peer_rbuf);
+    if (h.peer_flag) cudaIpcCloseMemHandle(h.peer_flag);
+    if (h.p2p_rbuf) cudaFree(h.p2p_rbuf);
+    if (h.p2p_flag) cudaFree(h.p2p_flag);
+  }
   for (void* p : e->allocs) pool_free(p, e->stream);
   if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->h_err) cudaFreeHost(e->h_err);
@@ -2708,6 +2835,69 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
         return 1;
     CUDA_OK(cudaMallocHost(&e->h_mig, 16 * sizeof(int)));
     CUDA_OK(cudaStreamSynchronize(e->stream));
+  }
+  // ---- peer-memory halo path (NVLink stores through CUDA IPC mappings): needs the NCCL transport (the handles
+  // travel over it) and one process per GPU; any failure leaves the NCCL path in place
+  if (e->comm && e->comm->is_nccl && e->world > 1 && !(getenv("NLPS_P2P") && atoi(getenv("NLPS_P2P")) == 0)) {
+    struct Blob { cudaIpcMemHandle_t buf, flag; int ok; int pad; };
+    Blob mine[2], theirs[2];
+    memset(mine, 0, sizeof(mine));
+    memset(theirs, 0, sizeof(theirs));
+    bool ok = true;
+    for (int s_ = 0; s_ < 2 && ok; s_++) {
+      auto& h = e->side[s_];
+      if (h.peer < 0) continue;
+      const size_t nb = sizeof(double) * 3 * (size_t)std::max(h.n, 1) * (1 + D);
+      ok = cudaMalloc(&h.p2p_rbuf, nb) == cudaSuccess && cudaMalloc(&h.p2p_flag, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+           cudaMemset(h.p2p_rbuf, 0, nb) == cudaSuccess && cudaMemset(h.p2p_flag, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine[s_].buf, h.p2p_rbuf) == cudaSuccess &&
+           cudaIpcGetMemHandle(&mine[s_].flag, h.p2p_flag) == cudaSuccess;
+      mine[s_].ok = ok ? 1 : 0;
+    }
+    // exchange the handles with the two neighbours over the transport (device bounce buffers)
+    Blob *d_mine = nullptr, *d_theirs = nullptr;
+    if (dev_alloc(e, &d_mine, 2) || dev_alloc(e, &d_theirs, 2)) return 1;
+    CUDA_OK(cudaMemcpyAsync(d_mine, mine, sizeof(mine), cudaMemcpyHostToDevice, e->stream));
+    nlps_msg msgs[2];
+    int nm = 0;
+    for (int s_ = 0; s_ < 2; s_++)
+      if (e->side[s_].peer >= 0) msgs[nm++] = nlps_msg{e->side[s_].peer, d_mine + s_, sizeof(Blob), d_theirs + s_, sizeof(Blob)};
+    if (comm_exchange(e->comm, nm, msgs, e->stream)) return 1;
+    CUDA_OK(cudaMemcpyAsync(theirs, d_theirs, sizeof(theirs), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    for (int s_ = 0; s_ < 2; s_++) {
+      auto& h = e->side[s_];
+      if (h.peer < 0) continue;
+      if (!mine[s_].ok || !theirs[s_].ok) { ok = false; continue; }
+      if (cudaIpcOpenMemHandle((void**)&h.peer_rbuf, theirs[s_].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle((void**)&h.peer_flag, theirs[s_].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+      }
+    }
+    // everybody must take the same path: the verdict travels along the chain of slabs (world - 1 rounds of
+    // neighbour exchanges of min(mine, theirs) reach every rank)
+    int *d_v = nullptr, *d_g = nullptr;
+    if (dev_alloc(e, &d_v, 2) || dev_alloc(e, &d_g, 2)) return 1;
+    int verdict = ok ? 1 : 0;
+    for (int round = 0; round < e->world - 1; round++) {
+      int v2[2] = {verdict, verdict}, got[2] = {1, 1};
+      CUDA_OK(cudaMemcpyAsync(d_v, v2, sizeof(v2), cudaMemcpyHostToDevice, e->stream));
+      nm = 0;
+      for (int s_ = 0; s_ < 2; s_++)
+        if (e->side[s_].peer >= 0) msgs[nm++] = nlps_msg{e->side[s_].peer, d_v + s_, sizeof(int), d_g + s_, sizeof(int)};
+      if (comm_exchange(e->comm, nm, msgs, e->stream)) return 1;
+      CUDA_OK(cudaMemcpyAsync(got, d_g, sizeof(got), cudaMemcpyDeviceToHost, e->stream));
+      CUDA_OK(cudaStreamSynchronize(e->stream));
+      for (int s_ = 0; s_ < 2; s_++)
+        if (e->side[s_].peer >= 0) verdict = std::min(verdict, got[s_]);
+    }
+    if (!verdict) {
+      if (e->rank == 0) fprintf(stderr, "nlps_b200: peer-memory halo path unavailable, using NCCL send/recv\n");
+      return 0;  // buffers and mappings are released by destroy
+    }
+    if (dev_alloc(e, &e->p2p_done, 4)) return 1;
+    e->p2p_on = 1;
   }
   return 0;
 }
