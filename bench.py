@@ -52,6 +52,15 @@ FP64_ROOF = {"dfma_per_s": 1.711e13, "pipe_util_ncu": {"lme_p2g_mass_disp": 0.16
                                                       "g2p_update": 0.252}, "source": "profiles/r01_ncu_full_c2_v5.txt"}
 
 
+# --workload c3: BASELINE configs[2], 3D Neo-Hookean cube, 126^3 particle cells x 8 = 16,003,008 particles, gamma 6,
+# STRONG scaling over z slabs (the global problem is fixed).  SURVEY 8(d) 3D NH: K0 100+4n, K1 160, K2 380, K3 208, K4 248.
+ALG_BYTES_3D_NH = {"lme_p2g_mass_disp": lambda n: 100 + 4 * n + 160.0, "kin_stress_p2g_force": lambda n: 380.0 + 208.0,
+                   "g2p_update": lambda n: 248.0}
+STAGE_GROUPS_3D = {"K0+K1 lme+p2g_mass_disp+grid_disp": (("lme_p2g_mass_disp", "grid_disp_bc"), lambda n: 260 + 4 * n),
+                   "K2+K3 kin_stress+p2g_force+grid_acc": (("traction", "kin_stress_p2g_force", "grid_acc"), lambda n: 588.0),
+                   "K4 g2p_update": (("g2p_update",), lambda n: 248.0)}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -239,7 +248,23 @@ def run_ours(args):
     nsteps_total = Wm + K + 2
     t_setup = time.perf_counter()
     comm = slab = None
-    if world == 1:
+    c3 = args.workload == "c3"
+    alg_k = ALG_BYTES_3D_NH if c3 else ALG_BYTES_2D_PLASTIC
+    groups_k = STAGE_GROUPS_3D if c3 else STAGE_GROUPS
+    step_alg = (lambda n: 1096 + 4 * n) if c3 else (lambda n: 832 + 4 * n)
+    if c3:
+        cells = max(8 * world, int(round(126 * args.scale)))
+        if world == 1:
+            P = synthetic.cube_3d(cells=cells, nsteps=nsteps_total)
+            eng = engine.Engine(P, device=local)
+            total_particles = P.np_
+        else:
+            P, slab = synthetic.cube_slab_3d(rank, world, cells=cells, nsteps=nsteps_total)
+            comm = engine.NcclComm(rank, world, local)
+            slab = dict(slab, comm=comm, migrate_every=10)
+            eng = engine.Engine(P, device=local, slab=slab)
+            total_particles = slab["n_global"]
+    elif world == 1:
         P = synthetic.column_collapse_2d(scale=args.scale, nsteps=nsteps_total)
         eng = engine.Engine(P, device=local)
         total_particles = P.np_
@@ -278,11 +303,12 @@ def run_ours(args):
     value = total_particles * K / (ms_max * 1e-3)
 
     # per-kernel device times (CUDA events on the engine's stream, serialised per launch)
-    if world == 1:
-        counts, _ = eng.lists()
+    if npart > 3_000_000:
+        n_avg = 38.9   # measured on the 64^3 cube (profiles/bench_3d.py); the full lists of 16 M particles are 8 GB
+    elif world == 1:
+        n_avg = float(eng.lists()[0].mean())
     else:
-        counts = eng.download_local()[0]["NumberNodes"]
-    n_avg = float(counts.mean())
+        n_avg = float(eng.download_local()[0]["NumberNodes"].mean())
     eng.profile(True)
     eng.kernel_times(reset=True)
     assert eng.run(Wm + K, 2) == 0
@@ -295,73 +321,96 @@ def run_ours(args):
             continue
         avg = kms / kn
         d = {"ms": round(avg, 4), "launches_per_step": round(kn / 2, 2)}
-        if name in ALG_BYTES_2D_PLASTIC:
-            gbs = ALG_BYTES_2D_PLASTIC[name](n_avg) * npart / (avg * 1e-3) / 1e9
+        if name in alg_k:
+            gbs = alg_k[name](n_avg) * npart / (avg * 1e-3) / 1e9
             d.update(alg_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
         per_kernel[name] = d
     groups = {}
-    for gname, (members, fn) in STAGE_GROUPS.items():
+    for gname, (members, fn) in groups_k.items():
         tms = sum(per_kernel[k]["ms"] * per_kernel[k]["launches_per_step"] for k in members if k in per_kernel)
         if tms > 0:
             gbs = fn(n_avg) * npart / (tms * 1e-3) / 1e9
             groups[gname] = {"ms": round(tms, 4), "alg_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
     dom = max((k for k in per_kernel if "alg_gbs" in per_kernel[k]), key=lambda k: per_kernel[k]["ms"])
-    step_bytes = (832 + 4 * n_avg) * npart
+    step_bytes = step_alg(n_avg) * total_particles
     traffic = None
-    if abs(args.scale - 1.0) < 1e-12 and dom in NCU_DRAM_BYTES_PER_LAUNCH:
+    if not c3 and abs(args.scale - 1.0) < 1e-12 and dom in NCU_DRAM_BYTES_PER_LAUNCH:
         traffic = round(NCU_DRAM_BYTES_PER_LAUNCH[dom] / (per_kernel[dom]["ms"] * 1e-3) / 1e9, 1)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["alg_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": traffic,
                 "traffic_note": "ncu dram bytes per launch (profiles/r01_ncu_full_c2_v5.txt) / live launch duration",
                 "fp64_roof": FP64_ROOF, "peak_source": peak_src,
                 "step_achieved_gbs": round(step_bytes * K / (ms_max * 1e-3) / 1e9, 1),
-                "step_frac": round(step_bytes * K / (ms_max * 1e-3) / 1e9 / peak, 4),
+                "step_frac": round(step_bytes * K / (ms_max * 1e-3) / 1e9 / (peak * world), 4),
                 "neighbours_per_particle": round(n_avg, 2), "per_kernel": per_kernel, "per_stage": groups}
     eng.close()
 
-    # end to end through the scheme call with HOST buffers (create + H2D, steps, D2H of the results)
-    e2e_steps = max(K, 200)   # the scheme call amortises its set-up over the run, as a production deck does
-    if world == 1:
-        P2 = synthetic.column_collapse_2d(scale=args.scale, nsteps=e2e_steps)
-        eng0 = engine.Engine(P2, device=local)       # initialise lambda/beta once (setup, as the driver does
-        assert eng0.initialize_lme() == 0            # with initialise_shapefun__MeshTools__ before the scheme)
-        f0 = eng0.download()
-        eng0.close()
-        for k in ("lambda", "Beta"):
-            P2.fields[k] = f0[k]
-        slab2 = None
-    else:
-        P2, slab2 = synthetic.column_slab_2d(rank, world, scale=args.scale, nsteps=e2e_steps)
-        slab2 = dict(slab2, comm=comm, migrate_every=10)
-        eng0 = engine.Engine(P2, device=local, slab=slab2)
-        assert eng0.initialize_lme() == 0
-        f0, ids0 = eng0.download_local()
-        eng0.close()
-        order = np.argsort(slab2["global_id"])
-        rows = order[np.searchsorted(slab2["global_id"][order], ids0)]
-        for k in ("lambda", "Beta"):
-            P2.fields[k][rows] = f0[k]
-    mesh_bytes = sum(a.nbytes for a in (P2.coords, P2.r1p, P2.r1i, P2.r2p, P2.r2i, P2.h_avg))
-    state_bytes = sum(v.nbytes for v in P2.fields.values()) + P2.I0.nbytes + P2.MatIdx.nbytes
-    every = 50
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    engine.u_verlet(P2, run_initialize=False, results_every=every, device=local, slab=slab2, inplace=True)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    n_dl = sum(1 for k in range(e2e_steps) if k % every == 0) + 1
-    e2e = {"value": total_particles * e2e_steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(world * (mesh_bytes + state_bytes) / e2e_steps),
-           "d2h_bytes_per_step": int(world * state_bytes * n_dl / e2e_steps),
-           "steps": e2e_steps, "results_every": every, "seconds": round(e2e_s, 4),
-           "call": "nlps_b200_u_verlet[_slab] (create + H2D of mesh and state, steps, D2H of all fields every 50 steps, destroy), host wall clock"}
+    e2e = None
+    if not args.no_e2e:
+        # end to end through the scheme call with HOST buffers (create + H2D, steps, D2H of the results)
+        e2e_steps = max(K, 200) if not c3 else max(K, 40)   # the scheme call amortises its set-up over the run
+        if c3:
+            if world == 1:
+                P2, slab2 = synthetic.cube_3d(cells=cells, nsteps=e2e_steps), None
+                eng0 = engine.Engine(P2, device=local)
+                assert eng0.initialize_lme() == 0
+                f0 = eng0.download()
+                eng0.close()
+                for k in ("lambda", "Beta"):
+                    P2.fields[k] = f0[k]
+            else:
+                P2, slab2 = synthetic.cube_slab_3d(rank, world, cells=cells, nsteps=e2e_steps)
+                slab2 = dict(slab2, comm=comm, migrate_every=10)
+                eng0 = engine.Engine(P2, device=local, slab=slab2)
+                assert eng0.initialize_lme() == 0
+                f0, ids0 = eng0.download_local()
+                eng0.close()
+                order = np.argsort(slab2["global_id"])
+                rows = order[np.searchsorted(slab2["global_id"][order], ids0)]
+                for k in ("lambda", "Beta"):
+                    P2.fields[k][rows] = f0[k]
+        elif world == 1:
+            P2 = synthetic.column_collapse_2d(scale=args.scale, nsteps=e2e_steps)
+            eng0 = engine.Engine(P2, device=local)       # initialise lambda/beta once (setup, as the driver does
+            assert eng0.initialize_lme() == 0            # with initialise_shapefun__MeshTools__ before the scheme)
+            f0 = eng0.download()
+            eng0.close()
+            for k in ("lambda", "Beta"):
+                P2.fields[k] = f0[k]
+            slab2 = None
+        else:
+            P2, slab2 = synthetic.column_slab_2d(rank, world, scale=args.scale, nsteps=e2e_steps)
+            slab2 = dict(slab2, comm=comm, migrate_every=10)
+            eng0 = engine.Engine(P2, device=local, slab=slab2)
+            assert eng0.initialize_lme() == 0
+            f0, ids0 = eng0.download_local()
+            eng0.close()
+            order = np.argsort(slab2["global_id"])
+            rows = order[np.searchsorted(slab2["global_id"][order], ids0)]
+            for k in ("lambda", "Beta"):
+                P2.fields[k][rows] = f0[k]
+        mesh_bytes = sum(a.nbytes for a in (P2.coords, P2.r1p, P2.r1i, P2.r2p, P2.r2i, P2.h_avg))
+        state_bytes = sum(v.nbytes for v in P2.fields.values()) + P2.I0.nbytes + P2.MatIdx.nbytes
+        every = 50 if not c3 else 20
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        engine.u_verlet(P2, run_initialize=False, results_every=every, device=local, slab=slab2, inplace=True)
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        n_dl = sum(1 for k in range(e2e_steps) if k % every == 0) + 1
+        e2e = {"value": total_particles * e2e_steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(world * (mesh_bytes + state_bytes) / e2e_steps),
+               "d2h_bytes_per_step": int(world * state_bytes * n_dl / e2e_steps),
+               "steps": e2e_steps, "results_every": every, "seconds": round(e2e_s, 4),
+               "call": "nlps_b200_u_verlet[_slab] (create + H2D of mesh and state, steps, D2H of all fields every 50 steps, destroy), host wall clock"}
+
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not c3:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5",
                                   "--warmup", "1"], capture_output=True, text=True, timeout=900)
@@ -370,13 +419,16 @@ def run_ours(args):
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong" if c3 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[1]: 2D granular column collapse, Drucker-Prager, "
-                                       "explicit NPC-FS, LME gamma=3, GPxElement 4",
+                "config": {"workload": ("BASELINE configs[2]: 3D Neo-Hookean cube, explicit NPC-FS, LME gamma=6, GPxElement 8"
+                                        if c3 else "BASELINE configs[1]: 2D granular column collapse, Drucker-Prager, "
+                                        "explicit NPC-FS, LME gamma=3, GPxElement 4"),
                            "particles_per_gpu": npart, "background_nodes": P.nn, "scale": args.scale,
                            "l2": "inputs larger than L2 (particle state + records ~0.7 GB per GPU)",
-                           "multi_gpu": (f"weak scaling over {world} spatial slabs along y (column {world}x taller): "
+                           "multi_gpu": (f"strong scaling over {world} spatial slabs along z of the fixed cube: halo sums + migration"
+                                         if c3 and world > 1 else
+                                         f"weak scaling over {world} spatial slabs along y (column {world}x taller): "
                                          "NCCL halo sums of occupancy / mass+momentum / forces every step, "
                                          "particle migration every 10 steps") if world > 1 else "single GPU",
                            "setup_seconds": round(setup_s, 2)},
@@ -397,6 +449,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--scale", type=float, default=1.0, help="linear scale of the C2 workload (1.0 = 10^6 particles)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer scheme call (large --workload c3 runs)")
+    ap.add_argument("--workload", default="c2", choices=("c2", "c3"),
+                    help="c2 (default, the driver's bench line): BASELINE configs[1]; c3: configs[2], 3D cube, strong scaling")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -196,3 +196,31 @@ def beam_3d(cells_per_unit=8, nsteps=20, gamma_lme=6.0, E=1e7, cfl=10.0, tractio
     val[2, :] = traction * np.minimum(1.0, (np.arange(nsteps) + 1) / max(nsteps, 1))
     P.neumann.append(dict(nodes=tip, dir=dr, val=val))
     return P
+
+
+def cube_slab_3d(rank, world, cells=126, nsteps=100, gamma_lme=6.0, band_cells=6, material=NH_C1):
+    """BASELINE configs[2] split into `world` slabs along z: the global problem is cube_3d(cells)
+    (cells^3 particle cells x GPxElement 8; 126 -> 16,003,008 particles); slab r owns the particle-cell layers
+    [r*cells//world, (r+1)*cells//world) and builds only the sub-mesh within band_cells + 2 layers of them.
+    Strong scaling of a fixed global problem.  Returns (Problem, slab dict)."""
+    c = cells
+    h = 1.0 / c
+    nx = ny = c + 4
+    nz_glob = c + 4
+    lay = [r * c // world for r in range(world + 1)]
+    pad = band_cells + 2
+    k0 = max(0, lay[rank] - pad) if rank > 0 else 0
+    k1 = min(nz_glob, lay[rank + 1] + pad) if rank < world - 1 else nz_glob
+    c0 = max(0, lay[rank] - 1) if rank > 0 else 0
+    c1 = min(c, lay[rank + 1] + 1) if rank < world - 1 else c
+    cel = (material[1][1] / material[1][0]) ** 0.5 * 1.3
+    P = structured_problem(3, (nx, ny, k1 - k0), h, (c, c, c1 - c0), (2, 2, c0 - k0), material, nsteps, 0.5, cel,
+                           (0.0, 0.0, -9.81), gamma_lme=gamma_lme, fixed=("bottom",) if k0 == 0 else (),
+                           rollers=("left", "right", "front", "back"), cell_offset=(0, 0, k0))
+    e = np.arange(c * c * (c1 - c0), dtype=np.int64)
+    gcell = e + c0 * c * c                               # cells are numbered x fastest, z slowest
+    gid = (gcell[:, None] * 8 + np.arange(8)[None, :]).ravel().astype(np.int32)
+    cuts = np.array([(lay[r] + 0.5) * h for r in range(1, world)])
+    slab = dict(rank=rank, world=world, axis=2, cuts=cuts, band_cells=band_cells, global_id=gid, n_global=8 * c ** 3,
+                node_offset=k0 * (nx + 1) * (ny + 1))
+    return P, slab

@@ -167,6 +167,25 @@ def test_cube_3d_slabs_match_single():
     compare(P, single, res)
 
 
+def test_submesh_slabs_3d_match_global_engine():
+    """bench.py --workload c3: z slabs of the cube, each on its own sub-mesh, against the engine holding the cube."""
+    from nlps_b200 import synthetic
+    world, cells, nsteps = 2, 20, 30
+    G = synthetic.cube_3d(cells=cells, nsteps=nsteps)
+    G.fields["vel"][:, 2] = -0.15 * G.solver["cel"]
+    per_rank = []
+    for r in range(world):
+        Pr, sl = synthetic.cube_slab_3d(r, world, cells=cells, nsteps=nsteps)
+        Pr.fields["vel"][:, 2] = -0.15 * Pr.solver["cel"]
+        per_rank.append((Pr, sl))
+    single = run_single(G, nsteps)
+    res, axis, cuts = run_slabs_threads(G, nsteps, world, migrate_every=3, per_rank=per_rank)
+    for r, (Pr, sl) in zip(res, per_rank):
+        r[0]["I0"] = r[0]["I0"] + sl["node_offset"]
+    assert axis == 2 and sum(r[5] for r in res) > 0
+    compare(G, single, res, check_active=False)
+
+
 def test_excursion_is_latched():
     """Without migration a particle eventually leaves the band its slab may roam in: error 9."""
     nsteps = 60
