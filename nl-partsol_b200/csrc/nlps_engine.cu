@@ -3194,6 +3194,29 @@ void nlps_b200_reset_kernel_times(nlps_engine* e) {
 }
 long long nlps_b200_launch_count(nlps_engine* e) { return e->launches; }
 
+// Page-lock the caller's field buffers for the duration of a scheme call: the D2H copies before every results
+// step then run at PCIe/C2C speed instead of through the driver's pageable bounce buffers.  Best effort.
+static void pin_state(const nlps_particles* st, int D, int T, bool on, std::vector<void*>& pinned) {
+  if (!on) {
+    for (void* p : pinned) cudaHostUnregister(p);
+    pinned.clear();
+    return;
+  }
+  const size_t n = (size_t)st->n;
+  auto reg = [&](const void* p, size_t bytes) {
+    if (!p || bytes < (1u << 20)) return;
+    if (cudaHostRegister((void*)p, bytes, cudaHostRegisterDefault) == cudaSuccess) pinned.push_back((void*)p);
+    else cudaGetLastError();
+  };
+  const double* vec[] = {st->x_GC, st->dis, st->D_dis, st->vel, st->acc, st->lambda};
+  for (const double* p : vec) reg(p, n * D * 8);
+  const double* ten[] = {st->F_n, st->F_n1, st->DF, st->b_e_n, st->b_e_n1, st->Stress};
+  for (const double* p : ten) reg(p, n * T * 8);
+  reg(st->C_ep, n * D * D * 8);
+  const double* sca[] = {st->J_n, st->J_n1, st->mass, st->rho, st->Vol_0, st->W, st->EPS_n, st->EPS_n1, st->Kappa_n, st->Kappa_n1, st->Beta};
+  for (const double* p : sca) reg(p, n * 8);
+}
+
 static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_bounds, const nlps_load* bounds,
                        int n_neumann, const nlps_load* neumann, const double* gravity, int n_materials,
                        const nlps_material* materials, nlps_particles* state, const nlps_slab* slab, int* ids_out,
@@ -3202,9 +3225,14 @@ static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_b
   const bool timing = getenv("NLPS_TIMING") != nullptr;
   auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
   double t_create = now(), t_run = 0.0, t_io = 0.0;
+  std::vector<void*> pinned;
+  // registering costs about as much as ten pageable downloads (measured: +0.12 s / -0.022 s per download at 10^6
+  // particles), so only long output sequences pay for it
+  if (results_every > 0 && (solver->num_steps - solver->initial_step) / results_every >= 12 && !getenv("NLPS_NO_PIN"))
+    pin_state(state, mesh->ndim, mesh->ndim == 2 ? 5 : 9, true, pinned);
   nlps_engine* e = create_any(mesh, solver, n_bounds, bounds, n_neumann, neumann, gravity, n_materials, materials, state,
                               slab, device, msg, sizeof(msg));
-  if (!e) return 1;
+  if (!e) { pin_state(state, 0, 0, false, pinned); return 1; }
   t_create = now() - t_create;
   const bool compact = slab && slab->global_id;
   const int n_in = state->n;
@@ -3244,6 +3272,7 @@ static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_b
   t_io += now() - t0;
   t0 = now();
   nlps_b200_destroy(e);
+  pin_state(state, 0, 0, false, pinned);
   if (timing)
     fprintf(stderr, "nlps_b200 scheme call: create %.3f s, steps %.3f s, downloads %.3f s, destroy %.3f s\n", t_create, t_run, t_io,
             now() - t0);
