@@ -135,7 +135,7 @@ struct SlabDev { int on, axis; double lo, hi, own_lo, own_hi; };
 // One thread block works on C consecutive OCCUPIED cells (a cell = all particles with the same closest
 // node I0) = one contiguous run of the cell-sorted particle order.  SL = longest 2-ring row, PCAP =
 // particles whose per-particle scratch fits in shared memory at once (longer runs go in chunks).
-struct BlockCfg { int C, SL, PCAP, threads; unsigned magic; };  // magic = ceil(2^21 / SL): e / SL == (e * magic) >> 21 for e < C*SL (checked at create)
+struct BlockCfg { int C, SL, PCAP, threads; unsigned magic; int NCA, NCB; };  // NCA / NCB: compact weight cache entries per particle in k_lme_p2g / k_kin_force (0 = none)  // magic = ceil(2^21 / SL): e / SL == (e * magic) >> 21 for e < C*SL (checked at create)
 
 struct Carve {
   size_t off = 0;
@@ -144,7 +144,7 @@ struct Carve {
 // shared-memory layouts, evaluated identically on host (size) and device (offsets)
 template <int D, int W, bool CACHE>
 struct LayoutA {  // k_lme_p2g
-  size_t tab, cs, base, len, B, rank, q, X, pa, zinv, mass, ddis, mask, px, plam, pbeta, total;
+  size_t tab, cs, base, len, B, rank, q, X, pa, zinv, mass, ddis, mask, px, plam, pbeta, cw, pre, ovf, total;
   __host__ __device__ LayoutA(const BlockCfg& c) {
     Carve k;
     const size_t pairs = (size_t)c.C * c.SL, pc = c.PCAP;
@@ -155,6 +155,11 @@ struct LayoutA {  // k_lme_p2g
     zinv = k.take(8 * pc); mass = k.take(8 * pc); ddis = k.take(8 * D * pc); mask = k.take(4 * W * pc);
     px = plam = pbeta = 0;
     if (!CACHE) { px = k.take(8 * D * pc); plam = k.take(8 * D * pc); pbeta = k.take(8 * pc); }
+    // compact weight cache (3D): the weights of a particle's neighbours in ascending slot order + the prefix
+    // popcounts of its mask words, so that the cell phase finds weight(j, k) without another exp
+    cw = pre = 0;
+    ovf = k.take(16);
+    if (!CACHE && c.NCA > 0) { cw = k.take(8 * pc * c.NCA); pre = k.take(pc * W); }
     total = k.off;
   }
 };
@@ -656,6 +661,9 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
   double* s_mass = (double*)(smem + L.mass); double* s_ddis = (double*)(smem + L.ddis);
   uint32_t* s_mask = (uint32_t*)(smem + L.mask);
   double* s_px = (double*)(smem + L.px); double* s_plam = (double*)(smem + L.plam); double* s_pbeta = (double*)(smem + L.pbeta);
+  double* s_cw = (double*)(smem + L.cw); unsigned char* s_pre = smem + L.pre;
+  const int NC = CACHE ? 0 : cfg.NCA;
+  int& s_ovf = *(int*)(smem + L.ovf);  // a particle of the chunk has more neighbours than the compact cache holds: recompute
   double* s_tab = (double*)(smem + L.tab);
   int* s_B = (int*)(smem + L.B);
   if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
@@ -669,6 +677,8 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
   const int SL = cfg.SL, np = P.ld;  // np: SoA stride
   for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
     const int nb = min(cfg.PCAP, b.t1 - tb);
+    if (threadIdx.x == 0) s_ovf = 0;
+    __syncthreads();
     // ---- particle phase
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
       const int t = tb + j, p = G.plist[t];
@@ -730,6 +740,8 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
         for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
+        int ord = 0;  // ordinal of the neighbour in ascending slot order (compact cache)
+        const bool keep = !CACHE && NC > 0 && n <= NC;
         for_slots<D, W>(mk, len, [&](int k0, int k1, double w0, double w1) {
           double l0[D], l1[D], X0[D], X1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
           ldsvec<D>(Xc + k0 * D, X0);
@@ -748,6 +760,11 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
           if (CACHE) {
             s_pa[(size_t)j * SL + k0] = e0;
             if (k1 != k0) s_pa[(size_t)j * SL + k1] = e1;
+          }
+          if (keep) {
+            s_cw[(size_t)j * NC + ord] = e0;
+            if (k1 != k0) s_cw[(size_t)j * NC + ord + 1] = e1;
+            ord += (k1 != k0) ? 2 : 1;  // a mask word with an odd number of bits ends on a single
           }
           Z += e0;
 #pragma unroll
@@ -811,6 +828,12 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
         if (!CACHE) { s_px[j * D + i] = xp[i]; s_plam[j * D + i] = lam[i]; }
       }
       if (!CACHE) s_pbeta[j] = beta;
+      if (!CACHE && NC > 0) {
+        if (n > NC) s_ovf = 1;
+        int acc = 0;
+#pragma unroll
+        for (int w = 0; w < W; w++) { s_pre[j * W + w] = (unsigned char)acc; acc += __popc(mk[w]); }
+      }
       s_zinv[j] = ok ? 1.0 / Z : 0.0;
       s_mass[j] = mp;
 #pragma unroll
@@ -847,16 +870,24 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
           for (int i = 0; i < D; i++) a[i] += pa * s_ddis[j * D + i];
         }
       } else {
+        const bool use_cw = NC > 0 && !s_ovf;
         for (int j = ja; j < jb; j++) {
-          if (!(s_mask[j * W + kw] & kb)) continue;
-          double ll = 0.0, lx = 0.0;
+          const uint32_t mw = s_mask[j * W + kw];
+          if (!(mw & kb)) continue;
+          double wexp;
+          if (use_cw) {
+            wexp = s_cw[(size_t)j * NC + s_pre[j * W + kw] + __popc(mw & (kb - 1u))];
+          } else {
+            double ll = 0.0, lx = 0.0;
 #pragma unroll
-          for (int i = 0; i < D; i++) {
-            const double l = s_px[j * D + i] - s_X[(size_t)e * D + i];
-            ll += l * l;
-            lx += l * s_plam[j * D + i];
+            for (int i = 0; i < D; i++) {
+              const double l = s_px[j * D + i] - s_X[(size_t)e * D + i];
+              ll += l * l;
+              lx += l * s_plam[j * D + i];
+            }
+            wexp = fexp(-s_pbeta[j] * ll + lx, s_tab);
           }
-          const double mN = fexp(-s_pbeta[j] * ll + lx, s_tab) * s_zinv[j] * s_mass[j];
+          const double mN = wexp * s_zinv[j] * s_mass[j];
           a0 += mN;
 #pragma unroll
           for (int i = 0; i < D; i++) a[i] += mN * s_ddis[j * D + i];
@@ -2623,6 +2654,11 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     if (const char* s_ = getenv("NLPS_CACHE_PA")) e->cache_pa = (D == 2) && atoi(s_) != 0;
     c.C = 32;
     if (const char* s_ = getenv("NLPS_CELLS_PER_BLOCK")) c.C = std::max(1, atoi(s_));
+    // compact weight cache of the 3D cell phase of k_lme_p2g (NLPS_NCA=48 covers gamma = 6, n ~ 39-45; chunks holding
+    // a particle with more neighbours recompute).  OFF by default: measured on the 64^3 cube it saves the exp of the
+    // cell phase but its 25-33 KB of shared memory cost more in resident warps (4.31 -> 4.68 ms at 48, 5.63 at 64).
+    c.NCA = c.NCB = 0;
+    if (const char* s_ = getenv("NLPS_NCA")) c.NCA = (D == 3) ? std::max(0, atoi(s_)) : 0;
     auto sizes = [&](const BlockCfg& k, size_t& a, size_t& b, size_t& g) {
       if (D == 2) {
         switch (e->W) {
