@@ -30,6 +30,9 @@ struct ImplicitCtx {
   ulonglong2 *packed = nullptr, *scan_blk = nullptr;
   double *Vn = nullptr, *An = nullptr, *dU = nullptr, *R = nullptr, *delta = nullptr, *trial = nullptr, *Rt = nullptr;
   double *r = nullptr, *z = nullptr, *p = nullptr, *Ap = nullptr, *diag = nullptr;
+  double *bv = nullptr, *bs = nullptr, *bt = nullptr, *by = nullptr, *brh = nullptr;  // BiCGStab: v, s, t, y, r^
+  double* part2 = nullptr;   // BiCGStab partials: rho[2], rr (IMP_NPART each), then rv[2], ts[2], tt[2] (IMP_NSPMV each)
+  int plastic = 0;           // some material has an elastoplastic tangent: unsymmetric operator
   unsigned char* fx = nullptr;
   double* part = nullptr;    // [4][IMP_NPART]: 0-1 rz (ping-pong), 2 rr, 3 scratch (|R|^2); then pAp[IMP_NSPMV]
   double* h_part = nullptr;  // pinned
@@ -198,7 +201,11 @@ __device__ __forceinline__ int csr_find(const int* cols, int lo, int hi, int key
 // Tangent values, one warp per particle (U-Newmark-beta.c:1646-1830 with compute_stiffness_density_Neo_Hookean,
 // Neo-Hookean.c:89-141):  K_AB += V0 [ c0 g1_A (x) g1_B + G (g_B . b_n g_A) I + c1 g1_B (x) g1_A ],
 // g = grad N at t_n, g1 = DF^-T g, b_n = F_n F_n^T, c0 = lambda J^2, c1 = G - lambda (J^2 - 1)/2, J = J_n1.
-template <int D, int W>
+// EP: elastoplastic laws (Drucker-Prager, Matsuoka-Nakai) use compute_stiffness_elastoplastic__Constitutive__
+// (Constitutive/Plasticity/Elastoplastic-Tangent-Matrix.c:42-160): spectral form with C_ep of the return mapping, the
+// eigen-pairs of b_e_n1 and the eigenvalues of tau, plus the geometric term -tau (g1_B (x) g1_A); unsymmetric when the
+// flow rule is not associated, hence BiCGStab below.  The law is read per particle (mixed clouds work).
+template <int D, int W, bool EP>
 __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridDev G, const int* row_ptr, const int* cols, double* vals,
                                                      int* err) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -303,6 +310,62 @@ __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridD
     const double Gm = mat.E / (2 * (1 + mat.nu)), lm = mat.nu * mat.E / ((1 - mat.nu * 2) * (1 + mat.nu));
     const double J = P.J_n1[p], V0 = P.vol0[p];
     const double c0 = V0 * lm * J * J, c1 = V0 * (Gm - 0.5 * lm * (J * J - 1.0)), cg = V0 * Gm;
+    if (EP && mat.type != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
+      double be[DD], ta[DD], cep[DD], lb[3], ev[9], lT[3], evT[9];
+#pragma unroll
+      for (int i = 0; i < DD; i++) {
+        be[i] = P.be_n1[(size_t)i * np + p];
+        ta[i] = P.stress[(size_t)i * np + p];
+        cep[i] = P.cep[(size_t)i * np + p];
+      }
+      if (D == 2) { dsyev2_dev(be[0], be[1], be[3], lb, ev); dsyev2_dev(ta[0], ta[1], ta[3], lT, evT); }
+      else { jacobi3_dev(be, lb, ev); jacobi3_dev(ta, lT, evT); }
+      for (int q = lane; q < n * n; q += 32) {
+        const int a = q / n, b = q - a * n;
+        const double* u = s_g + (size_t)a * 3 * D + D;  // g1 of node A (dN_alpha_n1)
+        const double* v = s_g + (size_t)b * 3 * D + D;  // g1 of node B (dN_beta_n1)
+        double Kd[DD], ue[D], ve[D];
+#pragma unroll
+        for (int i = 0; i < DD; i++) Kd[i] = 0.0;
+#pragma unroll
+        for (int A = 0; A < D; A++) {
+          ue[A] = 0.0; ve[A] = 0.0;
+#pragma unroll
+          for (int i = 0; i < D; i++) { ue[A] += u[i] * ev[A + i * D]; ve[A] += v[i] * ev[A + i * D]; }
+        }
+#pragma unroll
+        for (int A = 0; A < D; A++)
+#pragma unroll
+          for (int B = 0; B < D; B++) {
+            const double C = cep[A * D + B];
+            const bool geo = (A != B) && fabs(lb[B] - lb[A]) > 1E-14;
+            const double rat = geo ? 0.5 * ((lT[B] - lT[A]) / (lb[B] - lb[A])) : 0.0;
+#pragma unroll
+            for (int i = 0; i < D; i++)
+#pragma unroll
+              for (int j = 0; j < D; j++) {
+                Kd[i * D + j] += C * (ue[A] * ve[B]) * ev[A + i * D] * ev[B + j * D];
+                if (geo)
+                  Kd[i * D + j] += rat * (lb[B] * (ue[B] * ve[B]) * (ev[A + i * D] * ev[A + j * D]) +
+                                          lb[A] * (ue[B] * ve[A]) * (ev[A + i * D] * ev[B + j * D]));
+              }
+          }
+#pragma unroll
+        for (int i = 0; i < D; i++)
+#pragma unroll
+          for (int j = 0; j < D; j++)
+#pragma unroll
+            for (int k = 0; k < D; k++) Kd[i * D + j] += -ta[i * D + k] * (v[k] * u[j]);
+        const int row = s_rank[a];
+        const int pos = csr_find(cols, row_ptr[row], row_ptr[row + 1], s_rank[b]);
+        if (pos < 0) { latch_error(err, NLPS_ERR_CSR_PATTERN, P.orig[p]); continue; }
+        double* dst = vals + (size_t)pos * DD;
+#pragma unroll
+        for (int i = 0; i < DD; i++) atomicAdd(&dst[i], V0 * Kd[i]);
+      }
+      __syncwarp();
+      continue;
+    }
     for (int q = lane; q < n * n; q += 32) {
       const int a = q / n, b = q - a * n;
       const double* ga = s_g + (size_t)a * 3 * D;
@@ -342,14 +405,16 @@ __global__ void __launch_bounds__(128) k_bsr_diag(GridDev G, const int* row_ptr,
 // y = (K + alpha_1 M) x with the Dirichlet rows and columns replaced by the identity (MatZeroRowsColumnsIS,
 // U-Newmark-beta.c:1828), one warp per block row, lanes over the scalar entries of the row (coalesced);
 // part_out[block] = partial sum of x.y
+// part_w[block] = partial sum of w.y (w = x for CG), part_yy[block] (optional) of y.y
 template <int D>
 __global__ void __launch_bounds__(256) k_bsr_spmv(GridDev G, const int* row_ptr, const int* cols, const double* vals,
-                                                  const unsigned char* fxr, double a1, const double* x, double* y, double* part_out) {
+                                                  const unsigned char* fxr, double a1, const double* x, double* y,
+                                                  const double* w, double* part_out, double* part_yy) {
   __shared__ double sh[8];
   constexpr int DD = D * D;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int nact = *G.n_active;
-  double dot = 0.0;
+  double dot = 0.0, dyy = 0.0;
   for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < nact; t += gridDim.x * wpb) {
     const int q0 = row_ptr[t], nent = (row_ptr[t + 1] - q0) * DD;
     const double* v = vals + (size_t)q0 * DD;
@@ -375,12 +440,17 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(GridDev G, const int* row_ptr,
         const double xi = x[(size_t)t * D + i];
         const double yi = ((fx >> i) & 1u) ? xi : acc[i] + a1 * M * xi;
         y[(size_t)t * D + i] = yi;
-        dot += xi * yi;
+        dot += w[(size_t)t * D + i] * yi;
+        dyy += yi * yi;
       }
     }
   }
   const double s = block_sum(dot, sh);
   if (threadIdx.x == 0) part_out[blockIdx.x] = s;
+  if (part_yy) {
+    const double s2 = block_sum(dyy, sh);
+    if (threadIdx.x == 0) part_yy[blockIdx.x] = s2;
+  }
 }
 
 // PCG vector kernels; every scalar is re-summed from the partial arrays in a fixed order by every block
@@ -423,6 +493,68 @@ __global__ void __launch_bounds__(256) k_pcg_update2(const int* n_active, int D,
   const double rz = sum_partials(part_rz_cur), rzn = sum_partials(part_rz_new);
   const double beta = (rz != 0.0) ? rzn / rz : 0.0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) p[k] = z[k] + beta * p[k];
+}
+// Jacobi-preconditioned BiCGStab for the unsymmetric elastoplastic tangents; scalars as in the PCG: every block
+// re-sums the per-block partials of the previous kernels in a fixed order (q = parity of the iteration)
+__device__ __forceinline__ double safe_div(double a, double b) { return b != 0.0 ? a / b : 0.0; }
+struct BiParts {  // [2] = ping-pong by iteration parity
+  double *rho[2], *rv[2], *ts[2], *tt[2], *rr;
+};
+__global__ void __launch_bounds__(256) k_bi_init(const int* n_active, int D, const double* b, double* x, double* r, double* rhat,
+                                                 double* part_rho0, double* part_rr) {
+  __shared__ double sh[8];
+  const int n = *n_active * D;
+  double a = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const double bv = b[k];
+    x[k] = 0.0; r[k] = bv; rhat[k] = bv;
+    a += bv * bv;
+  }
+  const double s = block_sum(a, sh);
+  if (threadIdx.x == 0) { part_rho0[blockIdx.x] = s; part_rr[blockIdx.x] = s; }
+}
+__global__ void __launch_bounds__(256) k_bi_p(const int* n_active, int D, BiParts P_, int it, const double* r, const double* v,
+                                              const double* diag, double* p, double* y) {
+  const int n = *n_active * D, q = it & 1, pq = q ^ 1;
+  double beta = 0.0, omega_prev = 0.0;
+  if (it > 0) {
+    const double rho = sum_partials(P_.rho[q]), rho_prev = sum_partials(P_.rho[pq]);
+    const double alpha_prev = safe_div(rho_prev, sum_partials(P_.rv[pq], IMP_NSPMV));
+    omega_prev = safe_div(sum_partials(P_.ts[pq], IMP_NSPMV), sum_partials(P_.tt[pq], IMP_NSPMV));
+    beta = safe_div(rho, rho_prev) * safe_div(alpha_prev, omega_prev);
+  }
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const double pv = (it > 0) ? r[k] + beta * (p[k] - omega_prev * v[k]) : r[k];
+    p[k] = pv;
+    y[k] = pv / diag[k];
+  }
+}
+__global__ void __launch_bounds__(256) k_bi_s(const int* n_active, int D, BiParts P_, int it, const double* r, const double* v,
+                                              const double* diag, double* s, double* z) {
+  const int n = *n_active * D, q = it & 1;
+  const double alpha = safe_div(sum_partials(P_.rho[q]), sum_partials(P_.rv[q], IMP_NSPMV));
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const double sv = r[k] - alpha * v[k];
+    s[k] = sv;
+    z[k] = sv / diag[k];
+  }
+}
+__global__ void __launch_bounds__(256) k_bi_x(const int* n_active, int D, BiParts P_, int it, const double* y, const double* z,
+                                              const double* s, const double* t, const double* rhat, double* x, double* r) {
+  __shared__ double sh[8];
+  const int n = *n_active * D, q = it & 1;
+  const double alpha = safe_div(sum_partials(P_.rho[q]), sum_partials(P_.rv[q], IMP_NSPMV));
+  const double omega = safe_div(sum_partials(P_.ts[q], IMP_NSPMV), sum_partials(P_.tt[q], IMP_NSPMV));
+  double a = 0.0, c = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    x[k] += alpha * y[k] + omega * z[k];
+    const double rv = s[k] - omega * t[k];
+    r[k] = rv;
+    a += rhat[k] * rv;
+    c += rv * rv;
+  }
+  const double s1 = block_sum(a, sh), s2 = block_sum(c, sh);
+  if (threadIdx.x == 0) { P_.rho[q ^ 1][blockIdx.x] = s1; P_.rr[blockIdx.x] = s2; }
 }
 // out = a + s * b ; out = -a
 __global__ void __launch_bounds__(256) k_vec_axpy(const int* n_active, int D, const double* a, double s, const double* b, double* out) {
@@ -508,13 +640,15 @@ static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
     fprintf(stderr, "nlps_b200_newmark_setup: the implicit scheme runs on a single slab\n");
     return 1;
   }
-  if (e->uniform_mat != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
-    fprintf(stderr, "nlps_b200_newmark_setup: only the Neo-Hookean-Wriggers tangent (Neo-Hookean.c:89-141) is built\n");
+  if (!(prm->beta > 0.0) || !(prm->gamma > 0.0)) {  // a1 = 1/(beta dt^2): explicit central differences are U_Verlet's job
+    fprintf(stderr, "nlps_b200_newmark_setup: beta and gamma must be positive (beta=%g gamma=%g)\n", prm->beta, prm->gamma);
     return 1;
   }
   e->imp = new ImplicitCtx();
   ImplicitCtx* c = e->imp;
   c->prm = *prm;
+  c->plastic = e->uniform_mat != NLPS_MAT_NEO_HOOKEAN_WRIGGERS;
+  if (c->plastic) e->solver.compute_c_ep = 1;  // the elastoplastic tangent reads Phi.C_ep (Constitutive.c:330-355)
   if (c->prm.pcg_rtol <= 0.0) c->prm.pcg_rtol = 1e-8;
   if (c->prm.pcg_max_iter <= 0) c->prm.pcg_max_iter = 10000;
   const double dt = e->dt, b = prm->beta, g = prm->gamma;
@@ -582,6 +716,9 @@ static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
       imp_alloc(e, &c->trial, nv) || imp_alloc(e, &c->Rt, nv) || imp_alloc(e, &c->r, nv) || imp_alloc(e, &c->z, nv) ||
       imp_alloc(e, &c->p, nv) || imp_alloc(e, &c->Ap, nv) || imp_alloc(e, &c->diag, nv) || imp_alloc(e, &c->fx, e->max_act) ||
       imp_alloc(e, &c->part, 4 * IMP_NPART + IMP_NSPMV))
+    return 1;
+  if (c->plastic && (imp_alloc(e, &c->bv, nv) || imp_alloc(e, &c->bs, nv) || imp_alloc(e, &c->bt, nv) || imp_alloc(e, &c->by, nv) ||
+                     imp_alloc(e, &c->brh, nv) || imp_alloc(e, &c->part2, 3 * IMP_NPART + 6 * IMP_NSPMV)))
     return 1;
   CUDA_OK(cudaMemcpyAsync(c->cpl_ptr, cp.data(), sizeof(int) * (nn + 1), cudaMemcpyHostToDevice, e->stream));
   CUDA_OK(cudaMemcpyAsync(c->cpl_idx, ci.data(), sizeof(int) * tot, cudaMemcpyHostToDevice, e->stream));
@@ -651,9 +788,11 @@ static int imp_assemble_t(nlps_engine* e) {
     kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err);
   };
   if constexpr (D == 2) {
-    if (e->W == 1) launch(k_assemble_nh<2, 1>, 1); else launch(k_assemble_nh<2, 2>, 2);
+    if (c->plastic) { if (e->W == 1) launch(k_assemble_nh<2, 1, true>, 1); else launch(k_assemble_nh<2, 2, true>, 2); }
+    else { if (e->W == 1) launch(k_assemble_nh<2, 1, false>, 1); else launch(k_assemble_nh<2, 2, false>, 2); }
   } else {
-    if (e->W == 4) launch(k_assemble_nh<3, 4>, 4); else launch(k_assemble_nh<3, 8>, 8);
+    if (c->plastic) { if (e->W == 4) launch(k_assemble_nh<3, 4, true>, 4); else launch(k_assemble_nh<3, 8, true>, 8); }
+    else { if (e->W == 4) launch(k_assemble_nh<3, 4, false>, 4); else launch(k_assemble_nh<3, 8, false>, 8); }
   }
   k_bsr_diag<D><<<nblk(e->max_act, 128), 128, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->diag);
   e->launches += 2;
@@ -677,7 +816,7 @@ static int imp_pcg_t(nlps_engine* e, const double* b, double* x) {
   const int check = 8;
   while (it < c->prm.pcg_max_iter) {
     for (int k = 0; k < check; k++, it++) {
-      k_bsr_spmv<D><<<IMP_NSPMV, 256, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->p, c->Ap, part_pAp);
+      k_bsr_spmv<D><<<IMP_NSPMV, 256, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->p, c->Ap, c->p, part_pAp, nullptr);
       k_pcg_update1<<<IMP_NPART, 256, 0, e->stream>>>(na, D, part_pAp, part_rz[it & 1], c->p, c->Ap, c->diag, x, c->r, c->z,
                                                      part_rz[(it + 1) & 1], part_rr);
       k_pcg_update2<<<IMP_NPART, 256, 0, e->stream>>>(na, D, part_rz[it & 1], part_rz[(it + 1) & 1], c->z, c->p);
@@ -685,6 +824,45 @@ static int imp_pcg_t(nlps_engine* e, const double* b, double* x) {
     e->launches += 3 * check;
     const double rn = imp_norm(e, 2);
     if (!(rn == rn)) return -it;  // NaN: breakdown
+    if (rn <= target) { c->pcg_iters += it; return it; }
+  }
+  c->pcg_iters += it;
+  return -it;
+}
+
+template <int D>
+static int imp_bicgstab_t(nlps_engine* e, const double* b, double* x) {
+  ImplicitCtx* c = e->imp;
+  const int* na = e->G.n_active;
+  BiParts P_;
+  P_.rho[0] = c->part2; P_.rho[1] = c->part2 + IMP_NPART; P_.rr = c->part2 + 2 * IMP_NPART;
+  double* big = c->part2 + 3 * IMP_NPART;
+  for (int q = 0; q < 2; q++) { P_.rv[q] = big + (size_t)q * IMP_NSPMV; P_.ts[q] = big + (size_t)(2 + q) * IMP_NSPMV; P_.tt[q] = big + (size_t)(4 + q) * IMP_NSPMV; }
+  k_bi_init<<<IMP_NPART, 256, 0, e->stream>>>(na, D, b, x, c->r, c->brh, P_.rho[0], P_.rr);
+  auto norm_rr = [&]() {
+    cudaMemcpyAsync(c->h_part, P_.rr, sizeof(double) * IMP_NPART, cudaMemcpyDeviceToHost, e->stream);
+    cudaStreamSynchronize(e->stream);
+    double s_ = 0.0;
+    for (int i = 0; i < IMP_NPART; i++) s_ += c->h_part[i];
+    return sqrt(s_);
+  };
+  const double bnorm = norm_rr();
+  if (bnorm == 0.0) return 0;
+  const double target = c->prm.pcg_rtol * bnorm;
+  int it = 0;
+  const int check = 4;
+  while (it < c->prm.pcg_max_iter) {
+    for (int k = 0; k < check; k++, it++) {
+      const int q = it & 1;
+      k_bi_p<<<IMP_NPART, 256, 0, e->stream>>>(na, D, P_, it, c->r, c->bv, c->diag, c->p, c->by);
+      k_bsr_spmv<D><<<IMP_NSPMV, 256, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->by, c->bv, c->brh, P_.rv[q], nullptr);
+      k_bi_s<<<IMP_NPART, 256, 0, e->stream>>>(na, D, P_, it, c->r, c->bv, c->diag, c->bs, c->z);
+      k_bsr_spmv<D><<<IMP_NSPMV, 256, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->z, c->bt, c->bs, P_.ts[q], P_.tt[q]);
+      k_bi_x<<<IMP_NPART, 256, 0, e->stream>>>(na, D, P_, it, c->by, c->z, c->bs, c->bt, c->brh, x, c->r);
+    }
+    e->launches += 5 * check;
+    const double rn = norm_rr();
+    if (!(rn == rn)) return -it;
     if (rn <= target) { c->pcg_iters += it; return it; }
   }
   c->pcg_iters += it;
@@ -715,7 +893,7 @@ static int imp_step_t(nlps_engine* e, int step) {
     tock(c->ms_assemble);
     k_vec_neg<<<IMP_NPART, 256, 0, e->stream>>>(na, D, c->R, c->Rt);  // Rt doubles as the right-hand side
     tick();
-    const int its = imp_pcg_t<D>(e, c->Rt, c->delta);
+    const int its = c->plastic ? imp_bicgstab_t<D>(e, c->Rt, c->delta) : imp_pcg_t<D>(e, c->Rt, c->delta);
     tock(c->ms_pcg);
     if (poll_error(e)) { status = 1; break; }
     if (its < 0 && getenv("NLPS_VERBOSE")) fprintf(stderr, "nlps_b200 (implicit): PCG stopped after %d iterations\n", -its);

@@ -132,10 +132,11 @@ def column_collapse_2d(scale=1.0, nsteps=1000):
                               (0.0, -9.81))
 
 
-def block_2d(cells=16, nsteps=200):
+def block_2d(cells=16, nsteps=200, material=NH_C1):
     """BASELINE configs[0]: elastic block under gravity."""
-    return structured_problem(2, (cells + 4, cells + 4), 1.0 / cells, (cells, cells), (2, 0), NH_C1, nsteps, 0.5,
-                              (1e6 / 1000.0) ** 0.5 * 1.3, (0.0, -9.81))
+    cel = (material[1][1] / material[1][0]) ** 0.5 * 1.3
+    return structured_problem(2, (cells + 4, cells + 4), 1.0 / cells, (cells, cells), (2, 0), material, nsteps, 0.5,
+                              cel, (0.0, -9.81))
 
 
 def cube_3d(cells=24, nsteps=100, material=NH_C1, gamma_lme=6.0):

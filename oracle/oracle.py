@@ -238,3 +238,23 @@ class Oracle:
             ctypes.byref(W), cep.ctypes.data_as(_dp))
         return dict(status=st, stress=stress, b_e_n1=be1, eps_n1=e1.value, kappa_n1=k1.value,
                     W=W.value, C_ep=cep)
+
+
+def stiffness_ep(d, u, v, b_e, stress, c_ep):
+    """Elastoplastic tangent block of one node pair (restates Elastoplastic-Tangent-Matrix.c:42-160);
+    b_e, stress: d x d row-major."""
+    out = np.zeros(d * d)
+    u, v, b_e, stress, c_ep = _d(u), _d(v), _d(b_e), _d(stress), _d(c_ep)
+    lib().orc_stiffness_ep(d, out.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp),
+                           b_e.ctypes.data_as(_dp), stress.ctypes.data_as(_dp), c_ep.ctypes.data_as(_dp))
+    return out
+
+
+def stiffness_nh(d, u, v, un, vn, F_n, J, E, nu):
+    """Neo-Hookean tangent block of one node pair (restates Neo-Hookean.c:89-141)."""
+    out = np.zeros(d * d)
+    u, v, un, vn, F_n = _d(u), _d(v), _d(un), _d(vn), _d(F_n)
+    lib().orc_stiffness_nh(d, out.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp),
+                           un.ctypes.data_as(_dp), vn.ctypes.data_as(_dp), F_n.ctypes.data_as(_dp),
+                           ctypes.c_double(J), ctypes.c_double(E), ctypes.c_double(nu))
+    return out

@@ -584,3 +584,30 @@ int refh_masks(int step, int *nodes2mask, int *dofs2mask) {
   free(D.Nodes2Mask);
   return n;
 }
+
+/* The reference's own tangent blocks (implicit scheme, K5), callable without a deck: pins the restatement in
+ * nlps_oracle.c.  compute_stiffness_elastoplastic__Constitutive__ (Elastoplastic-Tangent-Matrix.c:42-160) and
+ * compute_stiffness_density_Neo_Hookean (Neo-Hookean.c:89-141). */
+#include "Constitutive/Plasticity/Elastoplastic-Tangent-Matrix.h"
+#include "Constitutive/Hyperelastic/Neo-Hookean.h"
+int refh_stiffness_ep(double *out, const double *dN_alpha_n1, const double *dN_beta_n1, double *b_e, double *stress,
+                      double *C_ep) {
+  State_Parameters S;
+  memset(&S, 0, sizeof(S));
+  S.b_e = b_e;
+  S.Stress = stress;
+  S.C_ep = C_ep;
+  return compute_stiffness_elastoplastic__Constitutive__(out, dN_alpha_n1, dN_beta_n1, S);
+}
+int refh_stiffness_nh(double *out, const double *dN_alpha_n1, const double *dN_beta_n1, const double *dN_alpha_n,
+                      const double *dN_beta_n, double *F_n, double J, double E, double nu) {
+  State_Parameters S;
+  Material M;
+  memset(&S, 0, sizeof(S));
+  memset(&M, 0, sizeof(M));
+  S.D_phi_n = F_n;
+  S.J = J;
+  M.E = E;
+  M.nu = nu;
+  return compute_stiffness_density_Neo_Hookean(out, dN_alpha_n1, dN_beta_n1, dN_alpha_n, dN_beta_n, S, M);
+}

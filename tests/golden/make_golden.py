@@ -137,12 +137,47 @@ def gen_points(case):
     print(case, "points:", len(rows_in), "plastic:", nplastic)
 
 
+def gen_tangent_blocks(_case="all"):
+    """Golden vectors of the implicit scheme's tangent blocks (K5) from the reference's own compiled functions:
+    compute_stiffness_elastoplastic__Constitutive__ (Elastoplastic-Tangent-Matrix.c:42-160) on the material-point
+    states of {dp,mn}_points.npz (plastic and elastic, rotated principal axes) and
+    compute_stiffness_density_Neo_Hookean (Neo-Hookean.c:89-141) on random deformed states."""
+    import refharness
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for case in ("dp", "mn"):
+        pts = np.load(os.path.join(HERE, f"{case}_points.npz"))
+        o = pts["outputs"]
+        sel = np.linspace(0, len(o) - 1, 160).astype(int)
+        rows_in, rows_out = [], []
+        for k in sel:
+            stress, be, cep = o[k, 0:5], o[k, 5:10], o[k, 13:17]
+            u, v = rng.standard_normal(2), rng.standard_normal(2)
+            K = refharness.stiffness_ep(u, v, be, stress, cep)
+            rows_in.append(np.concatenate([u, v, be[:4], stress[:4], cep]))
+            rows_out.append(K)
+        out[case + "_in"], out[case + "_out"] = np.array(rows_in), np.array(rows_out)
+    rows_in, rows_out = [], []
+    for k in range(120):
+        F = np.eye(2) + 0.2 * rng.standard_normal((2, 2))
+        J = float(np.linalg.det(np.eye(2) + 0.05 * rng.standard_normal((2, 2)) ) * np.linalg.det(F))
+        E, nu = 10.0 ** rng.uniform(4, 8), rng.uniform(0.0, 0.45)
+        u, v, un, vn = (rng.standard_normal(2) for _ in range(4))
+        K = refharness.stiffness_nh(u, v, un, vn, F.ravel(), J, E, nu)
+        rows_in.append(np.concatenate([u, v, un, vn, F.ravel(), [J, E, nu]]))
+        rows_out.append(K)
+    out["nh_in"], out["nh_out"] = np.array(rows_in), np.array(rows_out)
+    np.savez_compressed(os.path.join(HERE, "tangent_blocks.npz"), **out)
+    print("tangent blocks:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
                            if os.environ.get("QUIET") else None)
         for c in ("dp", "mn"):
             subprocess.run([sys.executable, __file__, "points", c], check=True)
+        subprocess.run([sys.executable, __file__, "tangent", "all"], check=True)

@@ -154,3 +154,31 @@ class RefHarness:
             ctypes.byref(k1), ctypes.byref(W), cep.ctypes.data_as(_dp))
         return dict(status=st, stress=stress, b_e_n1=be1, eps_n1=e1.value, kappa_n1=k1.value,
                     W=W.value, C_ep=cep)
+
+
+# -- the reference's tangent blocks (implicit scheme, K5): pure functions, no deck needed -----------------------
+def _arr(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def stiffness_ep(u, v, b_e, stress, c_ep, so: str = REF_SO):
+    """compute_stiffness_elastoplastic__Constitutive__ (Elastoplastic-Tangent-Matrix.c:42-160), 2D build."""
+    L = ctypes.CDLL(os.path.abspath(so))
+    u, v, b_e, stress, c_ep = _arr(u), _arr(v), _arr(b_e).copy(), _arr(stress).copy(), _arr(c_ep).copy()
+    out = np.zeros(4)
+    rc = L.refh_stiffness_ep(out.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp),
+                             b_e.ctypes.data_as(_dp), stress.ctypes.data_as(_dp), c_ep.ctypes.data_as(_dp))
+    assert rc == 0
+    return out
+
+
+def stiffness_nh(u, v, un, vn, F_n, J, E, nu, so: str = REF_SO):
+    """compute_stiffness_density_Neo_Hookean (Neo-Hookean.c:89-141), 2D build."""
+    L = ctypes.CDLL(os.path.abspath(so))
+    u, v, un, vn, F_n = _arr(u), _arr(v), _arr(un), _arr(vn), _arr(F_n).copy()
+    out = np.zeros(4)
+    rc = L.refh_stiffness_nh(out.ctypes.data_as(_dp), u.ctypes.data_as(_dp), v.ctypes.data_as(_dp),
+                             un.ctypes.data_as(_dp), vn.ctypes.data_as(_dp), F_n.ctypes.data_as(_dp),
+                             ctypes.c_double(J), ctypes.c_double(E), ctypes.c_double(nu))
+    assert rc == 0
+    return out

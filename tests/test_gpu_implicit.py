@@ -7,19 +7,30 @@ import pytest
 
 import oracle
 from nlps_b200 import engine, synthetic
-from util import assert_close, field_scales
+from util import assert_close, field_scales, load_problem
 
 pytestmark = pytest.mark.gpu
+
+def _golden(case):
+    def make(n):
+        P = load_problem(case)       # the 2D fixtures exported from the reference's own parser (tests/golden);
+        assert P.solver["nsteps"] >= n   # their load curves are tabulated for the fixture's own step count: keep it
+        return P
+    return make
+
 
 CASES = {
     "block2d": lambda n: synthetic.block_2d(cells=8, nsteps=n),
     "cube3d": lambda n: synthetic.cube_3d(cells=3, nsteps=n),
+    "dp2d": _golden("dp"),
+    "mn2d": _golden("mn"),
+    "dp3d": lambda n: synthetic.cube_3d(cells=3, nsteps=n, material=synthetic.DP_C2),
 }
 
 
 def _pair(case, nsteps, cfl, tol=1e-12, explicit_trial=False):
     P = CASES[case](nsteps)
-    P.solver["cfl"] = cfl
+    P.solver["cfl"] = cfl if cfl > 0 else -cfl * P.solver["cfl"]     # negative: multiple of the case's own CFL
     o = oracle.Oracle(P)
     assert o.init_lme() == 0
     o.newmark_setup(tol=tol, max_iter=25, explicit_trial=explicit_trial)
@@ -96,8 +107,54 @@ def test_converged_steps_match_the_oracle(case, cfl):
     eng.close()
 
 
-def test_implicit_refuses_what_is_not_built():
-    P = synthetic.column_collapse_2d(scale=0.03, nsteps=2)   # Drucker-Prager: no tangent restated
+@pytest.mark.parametrize("case,cfl,pre", [("dp2d", -4.0, 5), ("mn2d", -2.0, 2), ("dp3d", 2.0, 2)])
+def test_elastoplastic_stages_match_the_oracle(case, cfl, pre):
+    """Drucker-Prager / Matsuoka-Nakai tangent (compute_stiffness_elastoplastic__Constitutive__,
+    Elastoplastic-Tangent-Matrix.c:42-160): every block of the device CSR against the oracle's dense matrix, on a state
+    reached by `pre` converged implicit steps (plastic for dp2d)."""
+    P, o, eng = _pair(case, pre + 2, cfl, tol=1e-10)
+    for k in range(pre):
+        assert o.newmark_step(k) == 0, o.error()
+        assert eng.newmark_step(k) == 0, eng.error()
+    if case == "dp2d":
+        assert (o.field("EPS_n") > 0).sum() > 50
+    assert o.newmark_begin(pre) == 0 and eng.newmark_begin(pre) == 0
+    dU = o.newmark_get("dU")
+    st, Ro = o.newmark_residual(pre, dU)
+    rc, Rg = eng.newmark_residual(pre, dU)
+    assert st == 0 and rc == 0
+    assert np.abs(Rg - Ro).max() <= 1e-7 * np.abs(Ro).max()     # the two histories differ by the Newton tolerance
+    st, Ko = o.newmark_tangent()
+    Kg, rows, rp = dense_from_csr(eng, P, o, 1.0 / (0.25 * P.dt() ** 2))
+    assert st == 0
+    assert np.abs(Kg - Ko).max() <= 1e-6 * np.abs(Ko).max()
+    if case != "mn2d":       # non-associated flow: the operator is not symmetric, hence BiCGStab
+        assert np.abs(Ko - Ko.T).max() > 1e-9 * np.abs(Ko).max()
+    eng.close()
+
+
+@pytest.mark.parametrize("case,cfl,nsteps", [("dp2d", -4.0, 8), ("mn2d", -2.0, 4), ("dp3d", 2.0, 3)])
+def test_elastoplastic_converged_steps_match_the_oracle(case, cfl, nsteps):
+    P, o, eng = _pair(case, nsteps, cfl, tol=1e-11)
+    for k in range(nsteps):
+        assert o.newmark_step(k) == 0, o.error()
+        assert eng.newmark_step(k) == 0, eng.error()
+    f = eng.download()
+    sc = field_scales(P)
+    # linear convergence (the reference's tangent is not exact): both loops stop at 1e-11 |R0|, the states agree to ~1e-7
+    for name in ("x_GC", "dis", "vel", "F_n", "Stress", "J_n", "EPS_n", "b_e_n"):
+        assert_close(f[name], o.field(name), f"{case} {name}", rtol=2e-6, scale=sc.get(name))
+    assert np.array_equal(f["I0"], o.ints("I0"))
+    s = eng.newmark_stats()
+    assert s["pcg_iters_total"] > 0
+    eng.close()
+
+
+def test_implicit_refuses_invalid_parameters():
+    P = synthetic.block_2d(cells=4, nsteps=2)
     eng = engine.Engine(P, device=0)
-    assert eng.newmark_setup() != 0
+    assert eng.initialize_lme() == 0
+    assert eng.newmark_setup(beta=0.0) != 0          # a1 = 1/(beta dt^2)
+    assert eng.newmark_step(0) != 0                  # no scheme was set up
+    assert eng.newmark_setup() == 0 and eng.newmark_step(0) == 0
     eng.close()

@@ -1,7 +1,11 @@
-"""CPU checks of the implicit Newmark-beta restatement in oracle/ (parity unpinned: PETSc is absent, the
-reference scheme cannot run here): the tangent is the derivative of the residual, the trapezoidal
-scheme converges to the explicit oracle as dt -> 0, Newton converges quadratically."""
+"""CPU checks of the implicit Newmark-beta restatement in oracle/.  The scheme as a whole is parity-unpinned
+(PETSc is absent, the reference's U_Newmark_Beta cannot run here), but its per-particle tangent blocks are pinned to
+the reference's own compiled functions (tests/golden/tangent_blocks.npz).  Beyond that: the tangent is the derivative
+of the residual, the trapezoidal scheme converges to the explicit oracle as dt -> 0, Newton converges quadratically."""
+import os
+
 import numpy as np
+import pytest
 
 import oracle
 from nlps_b200 import synthetic
@@ -61,3 +65,60 @@ def test_newton_converges_at_ten_times_the_explicit_step():
         assert o.newmark_iters() <= 6
         R = o.newmark_get("R")
         assert np.linalg.norm(R) <= 1e-7 * P.materials[0][1][1] * P.dx ** 2
+
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tangent_blocks.npz")
+
+
+@pytest.mark.parametrize("case", ["dp", "mn"])
+def test_elastoplastic_tangent_block_matches_reference(case):
+    g = np.load(GOLD)
+    gin, gout = g[case + "_in"], g[case + "_out"]
+    assert len(gin) >= 100
+    worst = 0.0
+    for row, ref in zip(gin, gout):
+        K = oracle.stiffness_ep(2, row[0:2], row[2:4], row[4:8], row[8:12], row[12:16])
+        worst = max(worst, np.abs(K - ref).max() / max(np.abs(ref).max(), 1e-300))
+    assert worst <= 1e-12, worst
+
+
+def test_neo_hookean_tangent_block_matches_reference():
+    g = np.load(GOLD)
+    for row, ref in zip(g["nh_in"], g["nh_out"]):
+        K = oracle.stiffness_nh(2, row[0:2], row[2:4], row[4:6], row[6:8], row[8:12], row[12], row[13], row[14])
+        assert np.array_equal(K, ref) or np.abs(K - ref).max() <= 1e-15 * np.abs(ref).max()
+
+
+def test_tangent_blocks_against_the_compiled_reference_live():
+    """same check against oracle/_ref itself where it exists (this container), on fresh random states"""
+    import refharness
+    if not refharness.available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        A = rng.standard_normal((2, 2))
+        be = np.eye(2) + 0.1 * (A + A.T)
+        B = rng.standard_normal((2, 2))
+        tau = 1e4 * (B + B.T)
+        cep = 1e6 * rng.standard_normal(4)
+        u, v = rng.standard_normal(2), rng.standard_normal(2)
+        ref = refharness.stiffness_ep(u, v, list(be.ravel()) + [1.0], list(tau.ravel()) + [0.0], cep)
+        K = oracle.stiffness_ep(2, u, v, be.ravel(), tau.ravel(), cep)
+        assert np.abs(K - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("case,mult,nsteps", [("dp", 4.0, 6), ("mn", 2.0, 3)])
+def test_elastoplastic_newton_converges(case, mult, nsteps):
+    """Drucker-Prager / Matsuoka-Nakai with the reference's spectral tangent: it is not the exact derivative of the
+    residual (Newton converges linearly, as in the reference), but every step must reach the tolerance"""
+    from util import load_problem
+    P = load_problem(case)
+    P.solver["cfl"] *= mult
+    o = _implicit(P, tol=1e-10)
+    for k in range(nsteps):
+        assert o.newmark_step(k) == 0, o.error()
+        assert o.newmark_iters() < 25
+    if case == "dp":
+        assert (o.field("EPS_n") > 0).sum() > 50      # the tangent was evaluated on plastic states
+    st, K = o.newmark_tangent()
+    assert st == 0 and np.isfinite(K).all()
