@@ -1729,6 +1729,15 @@ struct nlps_engine {
   // staging for AoS <-> SoA
   double* stage = nullptr;
   size_t stage_doubles = 0;
+  // asynchronous results download (scheme call): fields are transposed into `snap` on the compute stream and copied to
+  // the caller's buffers on `dl_stream` while the next steps run
+  double* snap = nullptr;
+  size_t snap_doubles = 0, snap_off = 0;
+  int dl_async = 0, dl_pending = 0;
+  cudaStream_t dl_stream = nullptr;
+  cudaEvent_t dl_ready = nullptr, dl_done = nullptr;
+  struct DlCopy { void* h; const void* d; size_t bytes; };
+  std::vector<DlCopy> dl_copies;
   // profiling
   int profile = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -2100,11 +2109,21 @@ static int get_field(nlps_engine* e, double* h, const double* d, int cols, int a
   if (!h || !d || e->np == 0) return 0;
   const size_t n = (size_t)e->np * aos_stride;
   const int* rowmap = rows == 0 ? e->P.orig : nullptr;
+  double* stage = e->stage;
+  if (e->dl_async && rows != 1) {  // own region of the snapshot, copied later on dl_stream (download_flush)
+    stage = e->snap + e->snap_off;
+    e->snap_off += (n + 1) & ~(size_t)1;
+    if (cols != aos_stride && !d_extra) cudaMemsetAsync(stage, 0, n * sizeof(double), e->stream);
+  }
   if (cols != aos_stride) {
     // partial rows (2D tensors: 4 in-plane + slot 4): assemble the whole row on the device
-    if (d_extra) k_soa_to_aos<<<nblk((size_t)e->np, 256), 256, 0, e->stream>>>(d_extra, e->stage, rowmap, e->np, e->P.ld, 1, aos_stride, cols);
+    if (d_extra) k_soa_to_aos<<<nblk((size_t)e->np, 256), 256, 0, e->stream>>>(d_extra, stage, rowmap, e->np, e->P.ld, 1, aos_stride, cols);
   }
-  k_soa_to_aos<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(d, e->stage, rowmap, e->np, e->P.ld, cols, aos_stride, col0);
+  k_soa_to_aos<<<nblk((size_t)e->np * cols, 256), 256, 0, e->stream>>>(d, stage, rowmap, e->np, e->P.ld, cols, aos_stride, col0);
+  if (stage != e->stage) {
+    e->dl_copies.push_back({h, stage, n * sizeof(double)});
+    return 0;
+  }
   if (rows == 1) {
     e->h_rows.resize(n);
     CUDA_OK(cudaMemcpyAsync(e->h_rows.data(), e->stage, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
@@ -2118,6 +2137,13 @@ static int get_field(nlps_engine* e, double* h, const double* d, int cols, int a
 }
 static int get_ints(nlps_engine* e, int* h, const int* d, int rows) {
   if (!h || e->np == 0) return 0;
+  if (e->dl_async && rows != 1) {
+    int* stage = (int*)(e->snap + e->snap_off);
+    e->snap_off += ((size_t)e->np / 2 + 2) & ~(size_t)1;
+    k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(d, stage, rows == 0 ? e->P.orig : nullptr, e->np);
+    e->dl_copies.push_back({h, stage, sizeof(int) * e->np});
+    return 0;
+  }
   k_unpermute_int<<<nblk(e->np, 256), 256, 0, e->stream>>>(d, (int*)e->stage, rows == 0 ? e->P.orig : nullptr, e->np);
   if (rows == 1) {
     std::vector<int> tmp(e->np);
@@ -2505,6 +2531,9 @@ void nlps_b200_destroy(nlps_engine* e) {
   if (e->h_mig) cudaFreeHost(e->h_mig);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->dl_stream) { cudaStreamSynchronize(e->dl_stream); cudaStreamDestroy(e->dl_stream); }
+  if (e->dl_ready) cudaEventDestroy(e->dl_ready);
+  if (e->dl_done) cudaEventDestroy(e->dl_done);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -3230,6 +3259,39 @@ void nlps_b200_reset_kernel_times(nlps_engine* e) {
 }
 long long nlps_b200_launch_count(nlps_engine* e) { return e->launches; }
 
+// ---- asynchronous results download (scheme call) ----------------------------------------------------------------
+// snapshot: every field is transposed to the caller's AoS layout into its own region of `snap` on the compute stream;
+// flush: the D2H copies run on dl_stream after the snapshot, while the compute stream is already stepping on.
+static int snapshot_prepare(nlps_engine* e) {
+  const int D = e->D, T = e->T, DD = D * D;
+  const size_t per = 6 * (size_t)D + 6 * (size_t)T + DD + 11 + 2;
+  const size_t need = per * (size_t)std::max(e->np, 1) + 2 * 40;
+  if (!e->dl_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&e->dl_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&e->dl_ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&e->dl_done, cudaEventDisableTiming));
+  }
+  if (e->snap_doubles < need) {
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    const size_t want = need + need / 8;  // slab populations grow by migration
+    if (!use_pool() && want * sizeof(double) > fr / 2) return 1;  // not worth half of what is left: synchronous path
+    if (dev_alloc(e, &e->snap, want)) { cudaGetLastError(); e->snap = nullptr; e->snap_doubles = 0; return 1; }
+    e->snap_doubles = want;
+  }
+  e->snap_off = 0;
+  e->dl_copies.clear();
+  return 0;
+}
+static int snapshot_flush(nlps_engine* e) {
+  CUDA_OK(cudaStreamWaitEvent(e->dl_stream, e->dl_ready, 0));
+  for (const auto& c : e->dl_copies) CUDA_OK(cudaMemcpyAsync(c.h, c.d, c.bytes, cudaMemcpyDeviceToHost, e->dl_stream));
+  CUDA_OK(cudaEventRecord(e->dl_done, e->dl_stream));
+  CUDA_OK(cudaEventSynchronize(e->dl_done));
+  e->dl_copies.clear();
+  return 0;
+}
+
 // Page-lock the caller's field buffers for the duration of a scheme call: the D2H copies before every results
 // step then run at PCIe/C2C speed instead of through the driver's pageable bounce buffers.  Best effort.
 static void pin_state(const nlps_particles* st, int D, int T, bool on, std::vector<void*>& pinned) {
@@ -3286,6 +3348,23 @@ static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_b
   int status = 0;
   if (run_initialize) status = nlps_b200_initialize_lme(e);
   int k = solver->initial_step;
+  // Results steps: the fields of step k are snapshotted on the device, the next chunk of steps is enqueued, and only
+  // then are the snapshot's D2H copies issued (on their own stream) and cb(k) called: copies and the caller's output
+  // code overlap the stepping.  The caller's buffers hold step k when cb(k) runs and are not touched again before it
+  // returns.  NLPS_SYNC_IO=1 restores download-then-continue.
+  const bool async_io = !getenv("NLPS_SYNC_IO");
+  bool have_snap = false;
+  int snap_k = -1;
+  auto snapshot = [&]() {  // returns 0 ok (have_snap set), 1 error; falls back to a synchronous fetch
+    if (!async_io || snapshot_prepare(e)) return fetch();
+    e->dl_async = 1;
+    const int rc = fetch();
+    e->dl_async = 0;
+    if (rc) return rc;
+    if (cudaEventRecord(e->dl_ready, e->stream) != cudaSuccess) return 1;
+    have_snap = true;
+    return 0;
+  };
   while (!status && k < solver->num_steps) {
     int chunk = solver->num_steps - k;
     if (results_every > 0) {  // results after every step with TimeStep % ResultsTimeStep == 0 (U-Verlet.c:1097)
@@ -3293,18 +3372,37 @@ static int scheme_call(const nlps_mesh* mesh, const nlps_solver* solver, int n_b
       chunk = std::min(chunk, nxt - k + 1);
     }
     double t0 = now();
-    status = nlps_b200_run(e, k, chunk);
+    for (int q = k; q < k + chunk; q++)
+      for (int s_ = NLPS_STAGE_SEARCH; s_ <= NLPS_STAGE_G2P; s_++) enqueue_stage(e, s_, q);
+    if (have_snap) {
+      double t1 = now();
+      status = snapshot_flush(e);
+      have_snap = false;
+      if (!status && cb) cb(snap_k, user);
+      t_io += now() - t1;
+      t0 += now() - t1;
+    }
+    if (!status) status = poll_error(e);
     t_run += now() - t0;
     k += chunk;
     if (!status && results_every > 0 && ((k - 1) % results_every == 0)) {
       t0 = now();
-      status = fetch();
+      snap_k = k - 1;
+      status = snapshot();
+      if (!status && !have_snap && cb) cb(snap_k, user);  // synchronous fallback: the data is already there
       t_io += now() - t0;
-      if (!status && cb) cb(k - 1, user);
     }
   }
   double t0 = now();
-  if (!status) status = fetch();
+  if (!status && have_snap) {
+    status = snapshot_flush(e);
+    have_snap = false;
+    if (!status && cb) cb(snap_k, user);
+  }
+  if (!status) {
+    status = snapshot();
+    if (!status && have_snap) status = snapshot_flush(e);
+  }
   t_io += now() - t0;
   t0 = now();
   nlps_b200_destroy(e);

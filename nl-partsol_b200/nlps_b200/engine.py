@@ -507,22 +507,27 @@ def make_slab(slab: dict, n_state, keep: list):
                 int(slab.get("node_offset", 0)), comm.h if comm is not None else None)
 
 
+RESULTS_CB = C.CFUNCTYPE(None, C.c_int, C.c_void_p)
+
+
 def u_verlet(prob: Problem, run_initialize=False, results_every=0, device=0, quirk=-1, initial_step=0, slab=None,
-             inplace=False):
+             inplace=False, callback=None):
     """The whole scheme call with HOST buffers (nlps_b200_u_verlet[_slab]).  Returns the final fields
-    (slab engines: rows of other slabs keep their input values; with global_id: compact rows)."""
+    (slab engines: rows of other slabs keep their input values; with global_id: compact rows).
+    callback(step, fields): called for every results step with the host buffers holding that step."""
     L = lib()
     m = _Marshal(prob, quirk, 0, initial_step, copy=not inplace)
+    cb = RESULTS_CB(lambda k, _u: callback(k, m.host)) if callback is not None else None
     args = (C.byref(m.mesh), C.byref(m.solver), len(prob.bounds), m.bounds, len(prob.neumann),
             m.neumann, m.gravity.ctypes.data_as(_dp) if m.gravity is not None else None,
             len(prob.materials), m.materials, C.byref(m.state))
     if slab is None:
-        rc = L.nlps_b200_u_verlet(*args, int(run_initialize), int(results_every), None, None, device)
+        rc = L.nlps_b200_u_verlet(*args, int(run_initialize), int(results_every), cb, None, device)
     else:
         sl = make_slab(slab, prob.np_, m.keep)
         ids = np.zeros(max(prob.np_, 1), np.int32)
         rc = L.nlps_b200_u_verlet_slab(*args, C.byref(sl), ids.ctypes.data_as(_ip), int(run_initialize),
-                                       int(results_every), None, None, device)
+                                       int(results_every), cb, None, device)
     if rc != 0:
         raise RuntimeError("nlps_b200_u_verlet failed")
     n = m.state.n

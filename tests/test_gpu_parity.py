@@ -215,6 +215,37 @@ def test_u_verlet_host_call_matches_engine():
     eng.close()
 
 
+@pytest.mark.parametrize("sync_io", ("", "1"))
+def test_u_verlet_results_callback_sees_its_own_step(sync_io, monkeypatch):
+    """Results steps (TimeStep % ResultsTimeStep == 0, U-Verlet.c:1097): the download of step k overlaps the following
+    steps (snapshot on the device, copies on their own stream); when cb(k) runs the host buffers must hold step k."""
+    if sync_io:
+        monkeypatch.setenv("NLPS_SYNC_IO", "1")
+    P = load_problem("dp")
+    P.solver["nsteps"] = 13
+    for b in P.bounds:
+        b["dir"], b["val"] = b["dir"][:, :13], b["val"][:, :13]
+    P.gravity = P.gravity[:, :13]
+    seen = {}
+
+    def cb(k, host):
+        seen[k] = {n: host[n].copy() for n in ("x_GC", "vel", "Stress", "EPS_n", "I0")}
+
+    f = engine.u_verlet(P, results_every=4, callback=cb)
+    assert sorted(seen) == [0, 4, 8, 12]
+    eng = engine.Engine(P)
+    done = 0
+    for k in sorted(seen):
+        assert eng.run(done, k + 1 - done) == 0
+        done = k + 1
+        g = eng.download()
+        for n, v in seen[k].items():
+            assert np.array_equal(v, g[n]), (k, n)
+    for n in ("x_GC", "vel", "Stress", "EPS_n"):
+        assert np.array_equal(f[n], g[n]), n
+    eng.close()
+
+
 @pytest.mark.parametrize("name", ("column2d_dp", "block2d_nh", "cube3d_nh", "cube3d_dp", "cube3d_mn"))
 def test_synthetic_clouds_against_oracle(name):
     """Synthetic inputs of the bench shapes (2D and 3D) through engine and oracle.  3D has no
