@@ -135,7 +135,7 @@ struct SlabDev { int on, axis; double lo, hi, own_lo, own_hi; };
 // One thread block works on C consecutive OCCUPIED cells (a cell = all particles with the same closest
 // node I0) = one contiguous run of the cell-sorted particle order.  SL = longest 2-ring row, PCAP =
 // particles whose per-particle scratch fits in shared memory at once (longer runs go in chunks).
-struct BlockCfg { int C, SL, PCAP, threads; unsigned magic; int NCA, NCB; };  // NCA / NCB: compact weight cache entries per particle in k_lme_p2g / k_kin_force (0 = none)  // magic = ceil(2^21 / SL): e / SL == (e * magic) >> 21 for e < C*SL (checked at create)
+struct BlockCfg { int C, SL, PCAP, threads; unsigned magic; int NCA, NCB; int cellfast; };  // cellfast: bit 0 / 1 = cell-fastest pair order in the uncached cell phase of k_lme_p2g / k_kin_force  // NCA / NCB: compact weight cache entries per particle in k_lme_p2g / k_kin_force (0 = none)  // magic = ceil(2^21 / SL): e / SL == (e * magic) >> 21 for e < C*SL (checked at create)
 
 struct Carve {
   size_t off = 0;
@@ -144,12 +144,13 @@ struct Carve {
 // shared-memory layouts, evaluated identically on host (size) and device (offsets)
 template <int D, int W, bool CACHE>
 struct LayoutA {  // k_lme_p2g
-  size_t tab, cs, base, len, B, rank, q, X, pa, zinv, mass, ddis, mask, px, plam, pbeta, cw, pre, ovf, total;
+  size_t tab, cs, base, len, B, cs2, base2, len2, B2, rank, q, X, pa, zinv, mass, ddis, mask, px, plam, pbeta, cw, pre, ovf, total;
   __host__ __device__ LayoutA(const BlockCfg& c) {
     Carve k;
     const size_t pairs = (size_t)c.C * c.SL, pc = c.PCAP;
     tab = k.take(8 * 32);
     cs = k.take(4 * (c.C + 1)); base = k.take(4 * c.C); len = k.take(4 * c.C); B = k.take(4 * c.C);
+    cs2 = k.take(4 * (c.C + 1)); base2 = k.take(4 * c.C); len2 = k.take(4 * c.C); B2 = k.take(4 * c.C);  // next group (pipeline)
     rank = k.take(4 * pairs); q = k.take(pairs); X = k.take(8 * D * pairs);
     pa = CACHE ? k.take(8 * pc * c.SL) : 0;
     zinv = k.take(8 * pc); mass = k.take(8 * pc); ddis = k.take(8 * D * pc); mask = k.take(4 * W * pc);
@@ -165,12 +166,13 @@ struct LayoutA {  // k_lme_p2g
 };
 template <int D, int W, bool CACHE>
 struct LayoutB {  // k_kin_force
-  size_t tab, cs, base, len, B, rank, q, X, U, pa, zinv, G, px, trac, mask, plam, pbeta, total;
+  size_t tab, cs, base, len, B, cs2, base2, len2, B2, rank, q, X, U, pa, zinv, G, px, trac, mask, plam, pbeta, total;
   __host__ __device__ LayoutB(const BlockCfg& c) {
     Carve k;
     const size_t pairs = (size_t)c.C * c.SL, pc = c.PCAP;
     tab = k.take(8 * 32);
     cs = k.take(4 * (c.C + 1)); base = k.take(4 * c.C); len = k.take(4 * c.C); B = k.take(4 * c.C);
+    cs2 = k.take(4 * (c.C + 1)); base2 = k.take(4 * c.C); len2 = k.take(4 * c.C); B2 = k.take(4 * c.C);  // next group (pipeline)
     rank = k.take(4 * pairs); q = k.take(pairs); X = k.take(8 * D * pairs); U = k.take(8 * D * pairs);
     pa = CACHE ? k.take(8 * pc * c.SL) : 0;
     zinv = k.take(8 * pc); G = k.take(8 * D * D * pc); px = k.take(8 * D * pc); trac = k.take(8 * D * pc);
@@ -182,12 +184,13 @@ struct LayoutB {  // k_kin_force
 };
 template <int D>
 struct LayoutC {  // k_g2p
-  size_t tab, cs, base, len, B, rank, X, U, A, total;
+  size_t tab, cs, base, len, B, cs2, base2, len2, B2, rank, X, U, A, total;
   __host__ __device__ LayoutC(const BlockCfg& c) {
     Carve k;
     const size_t pairs = (size_t)c.C * c.SL;
     tab = k.take(8 * 32);
     cs = k.take(4 * (c.C + 1)); base = k.take(4 * c.C); len = k.take(4 * c.C); B = k.take(4 * c.C);
+    cs2 = k.take(4 * (c.C + 1)); base2 = k.take(4 * c.C); len2 = k.take(4 * c.C); B2 = k.take(4 * c.C);  // next group (pipeline)
     rank = k.take(4 * pairs); X = k.take(8 * D * pairs); U = k.take(8 * D * pairs); A = k.take(8 * D * pairs);
     total = k.off;
   }
@@ -631,6 +634,138 @@ __device__ __forceinline__ void stage_nodes(const MeshDev& m, const GridDev& G, 
     }
   }
 }
+// ---- cell-group pipeline -----------------------------------------------------------------------------------------
+// A persistent block walks over the groups g, g + grid, g + 2 grid, ...  While it works on group g, the metadata of
+// group g + 2 grid and the ring node ids of group g + grid are already in flight (registers), so that the staging of
+// the next group starts with its ids at hand: one dependent global round trip (node data) instead of three
+// (metadata -> ring ids -> node data).
+constexpr int NLPS_NID = 8;  // ring ids a thread holds for the next group: C * SL <= NLPS_NID * threads (checked at create)
+struct MetaPtrs { int *cs, *base, *len, *B; };
+// thread i <-> cell c0 + i of group g (i <= C): the record travels through a register
+__device__ __forceinline__ int4 meta_fetch(const GridDev& G, const BlockCfg& cfg, int nocc, int g) {
+  int4 mt = make_int4(0, 0, 0, 0);
+  const int i = threadIdx.x, c0 = g * cfg.C;
+  if (i <= cfg.C && c0 + i < nocc) mt = G.occ_meta[c0 + i];
+  return mt;
+}
+__device__ __forceinline__ void meta_put(const BlockCfg& cfg, int nocc, int np, int g, const int4& mt, const MetaPtrs& s) {
+  const int i = threadIdx.x, c0 = g * cfg.C, ncell = min(cfg.C, nocc - c0);
+  if (i <= ncell) {
+    if (c0 + i < nocc) {
+      s.cs[i] = mt.y;
+      if (i < ncell) { s.B[i] = mt.x; s.base[i] = mt.z; s.len[i] = mt.w; }
+    } else {
+      s.cs[i] = np;  // the last occupied cell ends at the last particle
+    }
+  }
+}
+__device__ __forceinline__ void ids_fetch(const MeshDev& m, const BlockCfg& cfg, int ncell, const MetaPtrs& s, int (&ids)[NLPS_NID]) {
+  const int npairs = ncell * cfg.SL;
+#pragma unroll
+  for (int u = 0; u < NLPS_NID; u++) {
+    const int e = threadIdx.x + u * blockDim.x;
+    ids[u] = -1;
+    if (e < npairs) {
+      const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * cfg.SL;
+      if (k < s.len[c]) ids[u] = m.r2i[s.base[c] + k];
+    }
+  }
+}
+// stage_nodes with the ring ids already in registers (pair e = threadIdx.x + u * blockDim.x <-> ids[u])
+template <int D, bool WANT_Q, int NF>
+__device__ __forceinline__ void stage_nodes_ids(const MeshDev& m, const GridDev& G, const BlockCfg& cfg, int ncell,
+                                                const MetaPtrs& s, const int (&ids)[NLPS_NID], int* s_rank,
+                                                unsigned char* s_q, double* s_X, double* s_U, double* s_A) {
+  constexpr int U = 4;
+  static_assert(NLPS_NID % U == 0, "batches");
+  const int npairs = ncell * cfg.SL, SL = cfg.SL;
+#pragma unroll
+  for (int b0 = 0; b0 < NLPS_NID; b0 += U) {
+    if ((int)(b0 * blockDim.x) >= npairs) break;
+    int rank[U];
+    unsigned char qv[U];
+    double2 x0[U], x1[U], u0[U], u1[U], a0[U], a1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int nd = max(ids[b0 + u], 0);  // invalid pairs load node 0 (harmless): unconditional independent loads
+      const double* px = &m.X[(size_t)nd * NS<D>::X];
+      const double* pu = &G.UA[(size_t)nd * 2 * NS<D>::X];
+      rank[u] = G.arank[nd];
+      x0[u] = *reinterpret_cast<const double2*>(px);
+      if (D == 3) x1[u] = *reinterpret_cast<const double2*>(px + 2);
+      if (WANT_Q) {
+        const int e = threadIdx.x + (b0 + u) * blockDim.x;
+        qv[u] = 0;
+        if (ids[b0 + u] >= 0) {
+          const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
+          qv[u] = m.r2q[s.base[c] + k];
+        }
+      }
+      if (NF >= 1) {
+        u0[u] = *reinterpret_cast<const double2*>(pu);
+        if (D == 3) u1[u] = *reinterpret_cast<const double2*>(pu + 2);
+      }
+      if (NF >= 2) {
+        a0[u] = *reinterpret_cast<const double2*>(pu + NS<D>::X);
+        if (D == 3) a1[u] = *reinterpret_cast<const double2*>(pu + NS<D>::X + 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int e = threadIdx.x + (b0 + u) * blockDim.x;
+      if (e < npairs) {
+        s_rank[e] = (ids[b0 + u] >= 0) ? rank[u] : -1;
+        if (WANT_Q) s_q[e] = qv[u];
+        double* dx = s_X + (size_t)e * D;
+        dx[0] = x0[u].x; dx[1] = x0[u].y;
+        if (D == 3) dx[2] = x1[u].x;
+        if (NF >= 1) {
+          double* du = s_U + (size_t)e * D;
+          du[0] = u0[u].x; du[1] = u0[u].y;
+          if (D == 3) du[2] = u1[u].x;
+        }
+        if (NF >= 2) {
+          double* da = s_A + (size_t)e * D;
+          da[0] = a0[u].x; da[1] = a0[u].y;
+          if (D == 3) da[2] = a1[u].x;
+        }
+      }
+    }
+  }
+}
+// loop head / tail of the pipelined walk (used by the three cell-block kernels)
+#define NLPS_PIPE_BEGIN(WANT_Q, NF, SQ, SU, SA)                                                                        \
+  MetaPtrs mc{(int*)(smem + L.cs), (int*)(smem + L.base), (int*)(smem + L.len), (int*)(smem + L.B)};                    \
+  MetaPtrs mn{(int*)(smem + L.cs2), (int*)(smem + L.base2), (int*)(smem + L.len2), (int*)(smem + L.B2)};                \
+  int ids[NLPS_NID];                                                                                                   \
+  {                                                                                                                    \
+    const int g0 = blockIdx.x, g1 = blockIdx.x + gridDim.x;                                                            \
+    if (g0 < ngroups) meta_put(cfg, nocc, P.np, g0, meta_fetch(G, cfg, nocc, g0), mc);                                  \
+    if (g1 < ngroups) meta_put(cfg, nocc, P.np, g1, meta_fetch(G, cfg, nocc, g1), mn);                                  \
+    __syncthreads();                                                                                                   \
+    if (g0 < ngroups) ids_fetch(m, cfg, min(cfg.C, nocc - g0 * cfg.C), mc, ids);                                        \
+  }                                                                                                                    \
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {                                                        \
+    int* const s_cs = mc.cs; int* const s_base = mc.base; int* const s_len = mc.len; int* const s_B = mc.B;             \
+    (void)s_base; (void)s_B;                                                                                           \
+    Blk b;                                                                                                             \
+    b.ncell = min(cfg.C, nocc - grp * cfg.C);                                                                          \
+    b.t0 = s_cs[0];                                                                                                    \
+    b.t1 = s_cs[b.ncell];                                                                                              \
+    stage_nodes_ids<D, WANT_Q, NF>(m, G, cfg, b.ncell, mc, ids, s_rank, SQ, s_X, SU, SA);                               \
+    __syncthreads();                                                                                                   \
+    const int g_n = grp + gridDim.x, g_nn = g_n + gridDim.x;                                                           \
+    int ids_n[NLPS_NID];                                                                                               \
+    int4 mt_nn = make_int4(0, 0, 0, 0);                                                                                \
+    if (g_n < ngroups) ids_fetch(m, cfg, min(cfg.C, nocc - g_n * cfg.C), mn, ids_n);                                    \
+    if (g_nn < ngroups) mt_nn = meta_fetch(G, cfg, nocc, g_nn);
+// (the body must end with a __syncthreads(): nobody reads the metadata of this group any more)
+#define NLPS_PIPE_END()                                                                                                \
+    if (g_nn < ngroups) meta_put(cfg, nocc, P.np, g_nn, mt_nn, mc);                                                     \
+    _Pragma("unroll") for (int u = 0; u < NLPS_NID; u++) ids[u] = ids_n[u];                                            \
+    { const MetaPtrs t_ = mc; mc = mn; mn = t_; }                                                                      \
+  }
+
 __device__ __forceinline__ int cell_of(const int* s_cs, int ncell, int t) {
   int lo = 0, hi = ncell;
   while (hi - lo > 1) {
@@ -650,37 +785,49 @@ __device__ __forceinline__ int cell_of(const int* s_cs, int ncell, int t) {
 //   cell phase (warp / cell, lane / 2-ring node): ... so that M_A, sum m_p N_A DU_p (U-Verlet.c:166-225,
 //     301-367) over the cell's particles need no second evaluation and no atomics; the partials go to
 //     part[(slot of the cell in A's transposed ring, rank(A))], summed per node in a fixed order by k_grid_disp.
+// 3D: the neighbour loops of a particle are split over LP = 2 adjacent lanes (mask words w with w % LP == lane % LP),
+// the Newton sums are combined by shuffles: a 2-cell-by-8-particle group fills the 128 threads, and the dependent
+// chain per thread halves.  Both lanes of a pair compute bit-identical sums (a + b == b + a) and take the same branches.
+template <int D, int W>
+struct LanesPerParticle { static constexpr int value = (D == 3 && W % 2 == 0) ? 2 : 1; };
+template <int LP>
+__device__ __forceinline__ double pair_sum(double v, unsigned pm) {
+#pragma unroll
+  for (int o = 1; o < LP; o <<= 1) v += __shfl_xor_sync(pm, v, o);
+  return v;
+}
 template <int D, int W, bool CACHE>
 __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg, int* err,
                                                  int do_predictor) {
   extern __shared__ __align__(16) unsigned char smem[];
   const LayoutA<D, W, CACHE> L(cfg);
-  int* s_cs = (int*)(smem + L.cs); int* s_base = (int*)(smem + L.base); int* s_len = (int*)(smem + L.len);
   int* s_rank = (int*)(smem + L.rank); unsigned char* s_q = smem + L.q; double* s_X = (double*)(smem + L.X);
   double* s_pa = (double*)(smem + L.pa); double* s_zinv = (double*)(smem + L.zinv);
   double* s_mass = (double*)(smem + L.mass); double* s_ddis = (double*)(smem + L.ddis);
   uint32_t* s_mask = (uint32_t*)(smem + L.mask);
   double* s_px = (double*)(smem + L.px); double* s_plam = (double*)(smem + L.plam); double* s_pbeta = (double*)(smem + L.pbeta);
   double* s_cw = (double*)(smem + L.cw); unsigned char* s_pre = smem + L.pre;
-  const int NC = CACHE ? 0 : cfg.NCA;
+#ifndef NLPS_LME_LP
+#define NLPS_LME_LP 2
+#endif
+  constexpr int LP = (CACHE || NLPS_LME_LP < 2) ? 1 : LanesPerParticle<D, W>::value;
+  const int NC = (CACHE || LP > 1) ? 0 : cfg.NCA;
   int& s_ovf = *(int*)(smem + L.ovf);  // a particle of the chunk has more neighbours than the compact cache holds: recompute
   double* s_tab = (double*)(smem + L.tab);
-  int* s_B = (int*)(smem + L.B);
   if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
   const int nocc = *G.n_occ, ngroups = (nocc + cfg.C - 1) / cfg.C;
-  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ...
-  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-  Blk b;
-  blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
-  stage_nodes<D, true, 0>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, s_q, s_X, nullptr, nullptr);
-  __syncthreads();
+  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ... (pipelined)
+  NLPS_PIPE_BEGIN(true, 0, s_q, nullptr, nullptr)
   const int SL = cfg.SL, np = P.ld;  // np: SoA stride
   for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
     const int nb = min(cfg.PCAP, b.t1 - tb);
     if (threadIdx.x == 0) s_ovf = 0;
     __syncthreads();
     // ---- particle phase
-    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    for (int jt = threadIdx.x; jt < nb * LP; jt += blockDim.x) {
+      const int j = jt / LP, sub = jt % LP;
+      const unsigned pm = (LP == 1) ? 0u : (((1u << LP) - 1u) << ((threadIdx.x & 31) & ~(LP - 1)));
+      (void)pm;
       const int t = tb + j, p = G.plist[t];
       const int ci = cell_of(s_cs, b.ncell, t);
       const int len = s_len[ci];
@@ -705,17 +852,38 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
       int n = 0;
       if (sp.reuse_lists) {
 #pragma unroll
-        for (int w = 0; w < W; w++) { mk[w] = P.mask[(size_t)w * np + p]; n += __popc(mk[w]); }
+        for (int w = 0; w < W; w++) {
+          mk[w] = P.mask[(size_t)w * np + p];
+          n += __popc(mk[w]);
+          if (LP > 1 && (w % LP) != sub) mk[w] = 0u;  // this lane walks its own words only
+        }
       } else {
-        for (int k = 0; k < len; k++) {
-          if (rk[k] < 0) continue;  // inactive node
-          double l[D];
-          const double s = dist2_exact<D>(xp, Xc + k * D, l);
-          if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
+        if (LP == 1) {
+          for (int k = 0; k < len; k++) {
+            if (rk[k] < 0) continue;  // inactive node
+            double l[D];
+            const double s = dist2_exact<D>(xp, Xc + k * D, l);
+            if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
+          }
+        } else {
+#pragma unroll
+          for (int w = 0; w < W; w++) {
+            if ((w % LP) != sub) continue;
+            const int k1 = min(len, 32 * w + 32);
+            for (int k = 32 * w; k < k1; k++) {
+              if (rk[k] < 0) continue;
+              double l[D];
+              const double s = dist2_exact<D>(xp, Xc + k * D, l);
+              if (s <= sstar) { mk[w] |= 1u << (k & 31); n++; }
+            }
+          }
+#pragma unroll
+          for (int o = 1; o < LP; o <<= 1) n += __shfl_xor_sync(pm, n, o);
         }
 #pragma unroll
-        for (int w = 0; w < W; w++) P.mask[(size_t)w * np + p] = mk[w];
-        P.nnodes[p] = n;
+        for (int w = 0; w < W; w++)
+          if (LP == 1 || (w % LP) == sub) P.mask[(size_t)w * np + p] = mk[w];
+        if (sub == 0) P.nnodes[p] = n;
       }
       if (CACHE && !DenseSlots<D, W>::value) {  // slots that are not neighbours carry weight 0: the cell phase needs no mask test
 #pragma unroll
@@ -726,10 +894,10 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
         }
       }
       bool ok = true;
-      if (n < D + 1) { latch_error(err, NLPS_ERR_FEW_NEIGHBOURS, P.orig[p]); ok = false; }
+      if (n < D + 1) { if (sub == 0) latch_error(err, NLPS_ERR_FEW_NEIGHBOURS, P.orig[p]); ok = false; }
       const double h = m.h_avg[s_B[ci]];
       const double beta = sp.reuse_lists ? beta_old : __ddiv_rn(sp.gamma_lme, __dmul_rn(h, h));
-      if (!sp.reuse_lists) P.beta[p] = beta;
+      if (!sp.reuse_lists && sub == 0) P.beta[p] = beta;
       // Newton on lambda
       int NumIter = 0;
       double Z = 1.0;
@@ -741,7 +909,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
 #pragma unroll
         for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
         int ord = 0;  // ordinal of the neighbour in ascending slot order (compact cache)
-        const bool keep = !CACHE && NC > 0 && n <= NC;
+        const bool keep = LP == 1 && !CACHE && NC > 0 && n <= NC;
         for_slots<D, W>(mk, len, [&](int k0, int k1, double w0, double w1) {
           double l0[D], l1[D], X0[D], X1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
           ldsvec<D>(Xc + k0 * D, X0);
@@ -781,6 +949,15 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
             for (int jj = i; jj < D; jj++) JJ[i * D + jj] += e1 * l1[i] * l1[jj];
           }
         });
+        if (LP > 1) {  // the two halves of the neighbour sums
+          Z = pair_sum<LP>(Z, pm);
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            r[i] = pair_sum<LP>(r[i], pm);
+#pragma unroll
+            for (int jj = i; jj < D; jj++) JJ[i * D + jj] = pair_sum<LP>(JJ[i * D + jj], pm);
+          }
+        }
         const double Zi = 1.0 / Z;
         double nr = 0.0;
 #pragma unroll
@@ -794,7 +971,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
               JJ[i * D + jj] = JJ[i * D + jj] * Zi - r[i] * r[jj];
               JJ[jj * D + i] = JJ[i * D + jj];
             }
-          if (rcond_as_reference<D>(JJ) < 1E-8) { ok = false; latch_error(err, NLPS_ERR_SINGULAR_HESSIAN, P.orig[p]); break; }
+          if (rcond_as_reference<D>(JJ) < 1E-8) { ok = false; if (sub == 0) latch_error(err, NLPS_ERR_SINGULAR_HESSIAN, P.orig[p]); break; }
           double Ji[D * D];
           inverse<D>(JJ, Ji);
 #pragma unroll
@@ -809,7 +986,11 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
           break;
         }
       }
-      if (ok && NumIter >= sp.max_iter_lme) latch_error(err, NLPS_ERR_NEWTON_LME, P.orig[p]);
+      if (ok && NumIter >= sp.max_iter_lme && sub == 0) latch_error(err, NLPS_ERR_NEWTON_LME, P.orig[p]);
+#pragma unroll
+      for (int w = 0; w < W; w++)
+        if (LP == 1 || (w % LP) == sub) s_mask[j * W + w] = ok ? mk[w] : 0u;
+      if (sub != 0) continue;  // the first lane of the pair writes the particle's results
 #pragma unroll
       for (int i = 0; i < D; i++) P.lam[i * np + p] = lam[i];
       // predictor (gamma = 0.5, U-Verlet.c:76,248)
@@ -836,8 +1017,6 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
       }
       s_zinv[j] = ok ? 1.0 / Z : 0.0;
       s_mass[j] = mp;
-#pragma unroll
-      for (int w = 0; w < W; w++) s_mask[j * W + w] = ok ? mk[w] : 0u;
       if (CACHE) {
         // the cell phase sums weight * (m/Z) and weight * (m/Z) * DU_p
         const double wgt = ok ? mp / Z : 0.0;
@@ -850,10 +1029,15 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
     }
     __syncthreads();
     // ---- cell phase: one thread per (cell, 2-ring node) pair sums over the cell's particles
-    for (int e = threadIdx.x; e < b.ncell * SL; e += blockDim.x) {
+    for (int q = threadIdx.x; q < b.ncell * SL; q += blockDim.x) {
+      // weights cached (2D): slot fastest.  Recomputed weights (3D): cell fastest, so that the lanes of a warp ask for the
+      // same slot of different cells -- on regular clouds the same neighbour pattern, i.e. no divergence at the mask test
+      int c, k;
+      if (CACHE || !(cfg.cellfast & 1)) { c = (int)(((unsigned)q * cfg.magic) >> 21); k = q - c * SL; }
+      else { k = q / b.ncell; c = q - k * b.ncell; }
+      const int e = c * SL + k;
       const int rank = s_rank[e];
       if (rank < 0) continue;
-      const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
       const int ja = max(s_cs[c], tb) - tb, jb = min(s_cs[c + 1], tb + nb) - tb;
       if (ja >= jb) continue;
       const bool first = s_cs[c] >= tb;
@@ -906,7 +1090,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
     }
     __syncthreads();
   }
-  }  // cell groups
+  NLPS_PIPE_END()  // cell groups
 }
 
 // Stage 2 + G1 (node kernel): M_A = sum_p N_A m_p (U-Verlet.c:166-225); DU_A = sum_p m_p N_A DU_p / M_A
@@ -989,22 +1173,16 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
                                                                                 int has_traction) {
   extern __shared__ __align__(16) unsigned char smem[];
   const LayoutB<D, W, CACHE> L(cfg);
-  int* s_cs = (int*)(smem + L.cs); int* s_base = (int*)(smem + L.base); int* s_len = (int*)(smem + L.len);
   int* s_rank = (int*)(smem + L.rank); unsigned char* s_q = smem + L.q; double* s_X = (double*)(smem + L.X);
   double* s_U = (double*)(smem + L.U); double* s_pa = (double*)(smem + L.pa); double* s_zinv = (double*)(smem + L.zinv);
   double* s_G = (double*)(smem + L.G); double* s_px = (double*)(smem + L.px); double* s_trac = (double*)(smem + L.trac);
   uint32_t* s_mask = (uint32_t*)(smem + L.mask);
   double* s_plam = (double*)(smem + L.plam); double* s_pbeta = (double*)(smem + L.pbeta);
   double* s_tab = (double*)(smem + L.tab);
-  int* s_B = (int*)(smem + L.B);
   if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
   const int nocc = *G.n_occ, ngroups = (nocc + cfg.C - 1) / cfg.C;
-  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ...
-  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-  Blk b;
-  blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
-  stage_nodes<D, true, 1>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, s_q, s_X, s_U, nullptr);
-  __syncthreads();
+  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ... (pipelined)
+  NLPS_PIPE_BEGIN(true, 1, s_q, s_U, nullptr)
   const int SL = cfg.SL, np = P.ld;  // np: SoA stride
   constexpr int T = (D == 2) ? 5 : 9;
   for (int tb = b.t0; tb < b.t1; tb += cfg.PCAP) {
@@ -1206,10 +1384,15 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
     }
     __syncthreads();
     // ---- cell phase: f_A partials, one thread per (cell, 2-ring node) pair
-    for (int e = threadIdx.x; e < b.ncell * SL; e += blockDim.x) {
+    for (int q = threadIdx.x; q < b.ncell * SL; q += blockDim.x) {
+      // weights cached (2D): slot fastest.  Recomputed weights (3D): cell fastest, so that the lanes of a warp ask for the
+      // same slot of different cells -- on regular clouds the same neighbour pattern, i.e. no divergence at the mask test
+      int c, k;
+      if (CACHE || !(cfg.cellfast & 2)) { c = (int)(((unsigned)q * cfg.magic) >> 21); k = q - c * SL; }
+      else { k = q / b.ncell; c = q - k * b.ncell; }
+      const int e = c * SL + k;
       const int rank = s_rank[e];
       if (rank < 0) continue;
-      const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
       const int ja = max(s_cs[c], tb) - tb, jb = min(s_cs[c + 1], tb + nb) - tb;
       if (ja >= jb) continue;
       const bool first = s_cs[c] >= tb;
@@ -1250,7 +1433,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
     }
     __syncthreads();
   }
-  }  // cell groups
+  NLPS_PIPE_END()  // cell groups
 }
 
 // Neumann tractions: per loaded particle t_p = sum_loads T(step) * A0_p, A0 = Vol_0 / thickness
@@ -1316,24 +1499,25 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
 // K4: G2P + corrector (U-Verlet.c:963-1084).  The n+1 -> n roll of F, J, b_e, kappa, EPS is a
 // pointer swap on the host side of the engine.
 template <int D, int W>
-__global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg) {
+__global__ void __launch_bounds__(128, D == 2 ? 5 : 3) k_g2p(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg) {
   extern __shared__ __align__(16) unsigned char smem[];
   const LayoutC<D> L(cfg);
-  int* s_cs = (int*)(smem + L.cs); int* s_base = (int*)(smem + L.base); int* s_len = (int*)(smem + L.len);
   int* s_rank = (int*)(smem + L.rank); double* s_X = (double*)(smem + L.X);
   double* s_U = (double*)(smem + L.U); double* s_A = (double*)(smem + L.A);
   double* s_tab = (double*)(smem + L.tab);
-  int* s_B = (int*)(smem + L.B);
   if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
   const int nocc = *G.n_occ, ngroups = (nocc + cfg.C - 1) / cfg.C;
-  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ...
-  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
-  Blk b;
-  blk_prologue(G, cfg, nocc, P.np, grp, s_cs, s_base, s_len, s_B, b);
-  stage_nodes<D, false, 2>(m, G, cfg.SL, cfg.magic, b.ncell, s_base, s_len, s_rank, nullptr, s_X, s_U, s_A);
-  __syncthreads();
+  // persistent blocks: each walks over cell groups blockIdx.x, blockIdx.x + gridDim.x, ... (pipelined)
+  NLPS_PIPE_BEGIN(false, 2, nullptr, s_U, s_A)
   const int SL = cfg.SL, np = P.ld;  // np: SoA stride
-  for (int t = b.t0 + threadIdx.x; t < b.t1; t += blockDim.x) {
+#ifndef NLPS_G2P_LP
+#define NLPS_G2P_LP 1  // measured on the 64^3 cube: two lanes per particle cost 14 % here (1.26 vs 1.11 ms), gain 9 % in k_lme_p2g
+#endif
+  constexpr int LP = NLPS_G2P_LP > 1 ? LanesPerParticle<D, W>::value : 1;
+  for (int jt = threadIdx.x; jt < (b.t1 - b.t0) * LP; jt += blockDim.x) {
+    const int t = b.t0 + jt / LP, sub = jt % LP;
+    const unsigned pm = (LP == 1) ? 0u : (((1u << LP) - 1u) << ((threadIdx.x & 31) & ~(LP - 1)));
+    (void)pm;
     const int p = G.plist[t];
     const int ci = cell_of(s_cs, b.ncell, t);
     const double* Xc = s_X + (size_t)ci * SL * D;
@@ -1349,7 +1533,7 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
     double Z = 0.0;
     uint32_t mk[W];
 #pragma unroll
-    for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
+    for (int w = 0; w < W; w++) mk[w] = (LP == 1 || (w % LP) == sub) ? P.mask[(size_t)w * np + p] : 0u;
     for_slots<D, W>(mk, s_len[ci], [&](int k0, int k1, double w0, double w1) {
       double X0[D], X1[D], U0[D], U1[D], A0[D], A1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
       ldsvec<D>(Xc + k0 * D, X0);
@@ -1381,6 +1565,12 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
         du[i] += e1 * U1[i];
       }
     });
+    if (LP > 1) {
+      Z = pair_sum<LP>(Z, pm);
+#pragma unroll
+      for (int i = 0; i < D; i++) { a[i] = pair_sum<LP>(a[i], pm); du[i] = pair_sum<LP>(du[i], pm); }
+      if (sub != 0) continue;
+    }
     const double Zi = 1.0 / Z;
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -1393,7 +1583,7 @@ __global__ void __launch_bounds__(128) k_g2p(MeshDev m, PartDev P, GridDev G, St
     }
   }
   __syncthreads();
-  }  // cell groups
+  NLPS_PIPE_END()  // cell groups
 }
 
 
@@ -2687,6 +2877,8 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     // a particle with more neighbours recompute).  OFF by default: measured on the 64^3 cube it saves the exp of the
     // cell phase but its 25-33 KB of shared memory cost more in resident warps (4.31 -> 4.68 ms at 48, 5.63 at 64).
     c.NCA = c.NCB = 0;
+    c.cellfast = 1;
+    if (const char* s_ = getenv("NLPS_CELLFAST")) c.cellfast = atoi(s_);
     if (const char* s_ = getenv("NLPS_NCA")) c.NCA = (D == 3) ? std::max(0, atoi(s_)) : 0;
     auto sizes = [&](const BlockCfg& k, size_t& a, size_t& b, size_t& g) {
       if (D == 2) {
@@ -2702,6 +2894,12 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
         g = LayoutC<3>(k).total;
       }
     };
+    // the group pipeline keeps the ring ids of the next group in NLPS_NID registers per thread and moves one metadata
+    // record per thread
+    c.threads = std::min(c.threads, 128);  // __launch_bounds__ of the cell-block kernels
+    while (c.C > 1 && ((size_t)c.C * c.SL > (size_t)NLPS_NID * c.threads || c.C + 1 > c.threads)) c.C /= 2;
+    if ((size_t)c.C * c.SL > (size_t)NLPS_NID * c.threads)
+      return set_err(err, err_len, "2-ring too large for the cell-group pipeline");
     // keep at least two blocks per SM resident: halve the cells per block until the largest layout fits
     const size_t budget = std::min<size_t>((size_t)e->max_smem_optin, 100 * 1024);
     for (;;) {
