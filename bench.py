@@ -43,13 +43,13 @@ STAGE_GROUPS = {"K0+K1 lme+p2g_mass_disp+grid_disp": (("lme_p2g_mass_disp", "gri
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload at
-# scale 1.0 (profiles/r01_ncu_full_c2_v5.txt); None for other sizes
-NCU_DRAM_BYTES_PER_LAUNCH = {"lme_p2g_mass_disp": 129.36e6 + 161.36e6, "kin_stress_p2g_force": 206.33e6 + 234.36e6,
-                             "g2p_update": 122.87e6 + 35.49e6}
+# scale 1.0 (profiles/r01_ncu_full_c2_v7.txt); None for other sizes
+NCU_DRAM_BYTES_PER_LAUNCH = {"lme_p2g_mass_disp": 129.31e6 + 160.93e6, "kin_stress_p2g_force": 206.51e6 + 238.15e6,
+                             "g2p_update": 122.94e6 + 34.43e6}
 # fp64 FMA roof of the B200 (profiles/fp64_peak.cu: 58.8 DFMA / clk / SM at 1965 MHz = 17.1e12 DFMA/s) and the fp64
 # pipe utilisation of the three kernels in the same capture: the second roof SURVEY 8(d) asks for
-FP64_ROOF = {"dfma_per_s": 1.711e13, "pipe_util_ncu": {"lme_p2g_mass_disp": 0.162, "kin_stress_p2g_force": 0.242,
-                                                      "g2p_update": 0.252}, "source": "profiles/r01_ncu_full_c2_v5.txt"}
+FP64_ROOF = {"dfma_per_s": 1.711e13, "pipe_util_ncu": {"lme_p2g_mass_disp": 0.196, "kin_stress_p2g_force": 0.267,
+                                                      "g2p_update": 0.338}, "source": "profiles/r01_ncu_full_c2_v7.txt"}
 
 
 # --workload c3: BASELINE configs[2], 3D Neo-Hookean cube, 126^3 particle cells x 8 = 16,003,008 particles, gamma 6,
@@ -338,7 +338,7 @@ def run_ours(args):
         traffic = round(NCU_DRAM_BYTES_PER_LAUNCH[dom] / (per_kernel[dom]["ms"] * 1e-3) / 1e9, 1)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["alg_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": per_kernel[dom]["frac"], "traffic": traffic,
-                "traffic_note": "ncu dram bytes per launch (profiles/r01_ncu_full_c2_v5.txt) / live launch duration",
+                "traffic_note": "ncu dram bytes per launch (profiles/r01_ncu_full_c2_v7.txt) / live launch duration",
                 "fp64_roof": FP64_ROOF, "peak_source": peak_src,
                 "step_achieved_gbs": round(step_bytes * K / (ms_max * 1e-3) / 1e9, 1),
                 "step_frac": round(step_bytes * K / (ms_max * 1e-3) / 1e9 / (peak * world), 4),
@@ -401,11 +401,24 @@ def run_ours(args):
         mesh_bytes = sum(a.nbytes for a in (P2.coords, P2.r1p, P2.r1i, P2.r2p, P2.r2i, P2.h_avg))
         state_bytes = sum(v.nbytes for v in P2.fields.values()) + P2.I0.nbytes + P2.MatIdx.nbytes
         every = 50 if not c3 else 20
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        engine.u_verlet(P2, run_initialize=False, results_every=every, device=local, slab=slab2, inplace=True)
-        e2e_s = time.perf_counter() - t0
+        # the scheme call works in place on the caller's buffers: keep the initial state to repeat the measurement
+        # (3 calls at N=1 on the 2D workload, the median is reported; each call is a complete create..destroy)
+        reps = 3 if (world == 1 and not c3) else 1
+        init = {k: v.copy() for k, v in P2.fields.items()} if reps > 1 else None
+        init_I0 = P2.I0.copy()
+        samples = []
+        for rep in range(reps):
+            if rep > 0:
+                for k, v in init.items():
+                    P2.fields[k][...] = v
+                P2.I0[...] = init_I0
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            engine.u_verlet(P2, run_initialize=False, results_every=every, device=local, slab=slab2, inplace=True)
+            samples.append(time.perf_counter() - t0)
+        e2e_s = sorted(samples)[len(samples) // 2]
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -415,6 +428,7 @@ def run_ours(args):
                "h2d_bytes_per_step": int(world * (mesh_bytes + state_bytes) / e2e_steps),
                "d2h_bytes_per_step": int(world * state_bytes * n_dl / e2e_steps),
                "steps": e2e_steps, "results_every": every, "seconds": round(e2e_s, 4),
+               "seconds_all_calls": [round(x, 4) for x in samples],
                "host_memory": "pageable" if os.environ.get("NLPS_BENCH_PAGEABLE") else "pinned",
                "call": "nlps_b200_u_verlet[_slab] (create + H2D of mesh and state, steps, D2H of all fields every 50 steps overlapped with the following steps, destroy), host wall clock"}
 

@@ -159,6 +159,21 @@ int nlps_b200_stage(nlps_engine *e, int stage, int time_step);
 int nlps_b200_download(nlps_engine *e, nlps_particles *out);
 int nlps_b200_upload(nlps_engine *e, const nlps_particles *in);
 
+/* Output overlapped with stepping (the reference stops the time loop for every
+ * particle_results_vtk__InOutFun__, U-Verlet.c:1088-1227 / InOutFun/Outputs/WriteVtk.c:95-268):
+ *   nlps_b200_run_async      enqueue `count` steps and return at once;
+ *   nlps_b200_sync           wait for everything enqueued, poll the error flag (what nlps_b200_run ends with);
+ *   nlps_b200_download_begin snapshot the fields of the current step on the device (stream-ordered: steps enqueued
+ *                            afterwards do not disturb it);
+ *   nlps_b200_download_end   copy the snapshot into `out` of the matching begin and wait for the copy only.
+ * Typical loop: run_async(to the output step) ... sync; download_begin; run_async(next chunk); download_end;
+ * write the files while the GPU steps on; sync.  `out` must stay valid between begin and end.  When the snapshot
+ * buffer cannot be had, begin downloads synchronously and end is a no-op. */
+int nlps_b200_run_async(nlps_engine *e, int first_step, int count);
+int nlps_b200_sync(nlps_engine *e);
+int nlps_b200_download_begin(nlps_engine *e, nlps_particles *out);
+int nlps_b200_download_end(nlps_engine *e);
+
 /* Nodal arrays of the last step in full-grid indexing, n_nodes x ndim, zero on
  * inactive nodes.  which: 0 lumped mass (per DOF, d identical copies as
  * U-Verlet.c:216), 1 D_Displacement, 2 Forces, 3 Acceleration, 4 Reactions. */

@@ -785,9 +785,12 @@ __device__ __forceinline__ int cell_of(const int* s_cs, int ncell, int t) {
 //   cell phase (warp / cell, lane / 2-ring node): ... so that M_A, sum m_p N_A DU_p (U-Verlet.c:166-225,
 //     301-367) over the cell's particles need no second evaluation and no atomics; the partials go to
 //     part[(slot of the cell in A's transposed ring, rank(A))], summed per node in a fixed order by k_grid_disp.
-// 3D: the neighbour loops of a particle are split over LP = 2 adjacent lanes (mask words w with w % LP == lane % LP),
-// the Newton sums are combined by shuffles: a 2-cell-by-8-particle group fills the 128 threads, and the dependent
-// chain per thread halves.  Both lanes of a pair compute bit-identical sums (a + b == b + a) and take the same branches.
+// Optional (-DNLPS_LME_LP=2 / -DNLPS_G2P_LP=2, 3D only): the neighbour loops of a particle are split over LP = 2 adjacent
+// lanes (mask words w with w % LP == lane % LP), the Newton sums are combined by shuffles, so that an 8-cell group of
+// 64 particles fills the 128 threads and the dependent chain per thread halves.  Both lanes of a pair compute
+// bit-identical sums (a + b == b + a) and take the same branches.  OFF by default: the 3D kernels are bound by
+// shared-memory wavefronts and issue slots, not by the length of the per-thread chain -- measured 5 % (k_lme_p2g) and
+// 14 % (k_g2p) SLOWER on the 64^3 cube (gpurun_out/ab_3d2.log, ab_3d3.log).
 template <int D, int W>
 struct LanesPerParticle { static constexpr int value = (D == 3 && W % 2 == 0) ? 2 : 1; };
 template <int LP>
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
   double* s_px = (double*)(smem + L.px); double* s_plam = (double*)(smem + L.plam); double* s_pbeta = (double*)(smem + L.pbeta);
   double* s_cw = (double*)(smem + L.cw); unsigned char* s_pre = smem + L.pre;
 #ifndef NLPS_LME_LP
-#define NLPS_LME_LP 2
+#define NLPS_LME_LP 1  // measured on the 64^3 cube: 3.54 ms with one lane per particle, 3.72 ms with two
 #endif
   constexpr int LP = (CACHE || NLPS_LME_LP < 2) ? 1 : LanesPerParticle<D, W>::value;
   const int NC = (CACHE || LP > 1) ? 0 : cfg.NCA;
@@ -1511,7 +1514,7 @@ __global__ void __launch_bounds__(128, D == 2 ? 5 : 3) k_g2p(MeshDev m, PartDev 
   NLPS_PIPE_BEGIN(false, 2, nullptr, s_U, s_A)
   const int SL = cfg.SL, np = P.ld;  // np: SoA stride
 #ifndef NLPS_G2P_LP
-#define NLPS_G2P_LP 1  // measured on the 64^3 cube: two lanes per particle cost 14 % here (1.26 vs 1.11 ms), gain 9 % in k_lme_p2g
+#define NLPS_G2P_LP 1  // measured on the 64^3 cube: 1.11 ms with one lane per particle, 1.26 ms with two
 #endif
   constexpr int LP = NLPS_G2P_LP > 1 ? LanesPerParticle<D, W>::value : 1;
   for (int jt = threadIdx.x; jt < (b.t1 - b.t0) * LP; jt += blockDim.x) {
@@ -3488,6 +3491,35 @@ static int snapshot_flush(nlps_engine* e) {
   CUDA_OK(cudaEventSynchronize(e->dl_done));
   e->dl_copies.clear();
   return 0;
+}
+
+int nlps_b200_run_async(nlps_engine* e, int first_step, int count) {
+  cudaSetDevice(e->device);
+  for (int k = first_step; k < first_step + count; k++)
+    for (int s_ = NLPS_STAGE_SEARCH; s_ <= NLPS_STAGE_G2P; s_++) enqueue_stage(e, s_, k);
+  return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+int nlps_b200_sync(nlps_engine* e) {
+  cudaSetDevice(e->device);
+  return poll_error(e);
+}
+int nlps_b200_download_begin(nlps_engine* e, nlps_particles* out) {
+  cudaSetDevice(e->device);
+  if (e->dl_pending) return 1;  // one snapshot at a time
+  if (e->slab_on || snapshot_prepare(e)) return nlps_b200_download(e, out);  // rows by global id need the host scatter
+  e->dl_async = 1;
+  const int rc = download_impl(e, out, 0);
+  e->dl_async = 0;
+  if (rc) return rc;
+  CUDA_OK(cudaEventRecord(e->dl_ready, e->stream));
+  e->dl_pending = 1;
+  return 0;
+}
+int nlps_b200_download_end(nlps_engine* e) {
+  cudaSetDevice(e->device);
+  if (!e->dl_pending) return 0;
+  e->dl_pending = 0;
+  return snapshot_flush(e);
 }
 
 // Page-lock the caller's field buffers for the duration of a scheme call: the D2H copies before every results

@@ -15,7 +15,8 @@
  *      include/nlps_b200.h -- the engine never frees or reallocates them (driver ownership,
  *      driver-nl-partsol.c:575-660);
  *   3. run the steps on the B200, copying fields back into those buffers before each
- *      particle_results_vtk__InOutFun__ call (every ResultsTimeStep steps, U-Verlet.c:1088-1227).
+ *      particle_results_vtk__InOutFun__ call (every ResultsTimeStep steps, U-Verlet.c:1088-1227); the copy and the
+ *      writer of output step k overlap the steps after k.
  *
  * Error convention as the reference: EXIT_SUCCESS / EXIT_FAILURE, RED message on stderr.
  */
@@ -45,10 +46,12 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
   }
   DeltaTimeStep = nlps_b200_dt(eng);
 
-  const int cap = nlps_b200_list_capacity(eng);
-  int *counts = (int *)malloc(sizeof(int) * Np);
-  int *lists = (int *)malloc(sizeof(int) * (size_t)Np * cap);
-
+  /* Output overlapped with stepping: at an output step the fields are snapshotted on the device
+   * (nlps_b200_download_begin), the next chunk of steps is enqueued, and only then is the snapshot copied into the
+   * reference's buffers and particle_results_vtk__InOutFun__ run -- the (slow, ASCII) writer of step k works while
+   * the B200 computes the steps after k.  The writer reads Phi and I0 / MatIdx only (WriteVtk.c:95-268), not the
+   * neighbour chains, which are rebuilt once at the end (b200_finish). */
+  int pending_out = -1;
   for (int TimeStep = Parameters_Solver.InitialTimeStep; TimeStep < NumTimeStep && STATUS == EXIT_SUCCESS;) {
     /* run up to (and including) the next output step in one go */
     int next_out = TimeStep;
@@ -56,7 +59,17 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
     int count = (ResultsTimeStep > 0) ? next_out - TimeStep + 1 : NumTimeStep - TimeStep;
     if (TimeStep + count > NumTimeStep) count = NumTimeStep - TimeStep;
     print_step(TimeStep, NumTimeStep, DeltaTimeStep);
-    if (nlps_b200_run(eng, TimeStep, count) != EXIT_SUCCESS) {
+    if (nlps_b200_run_async(eng, TimeStep, count) != EXIT_SUCCESS) {
+      fprintf(stderr, "" RED "Error in nlps_b200_run_async() at steps [%i,%i)" RESET " \n", TimeStep, TimeStep + count);
+      STATUS = EXIT_FAILURE;
+      break;
+    }
+    if (pending_out >= 0) {
+      if (nlps_b200_download_end(eng) != EXIT_SUCCESS) { STATUS = EXIT_FAILURE; break; }
+      particle_results_vtk__InOutFun__(MPM_Mesh, pending_out, ResultsTimeStep);
+      pending_out = -1;
+    }
+    if (nlps_b200_sync(eng) != EXIT_SUCCESS) {
       fprintf(stderr, "" RED "Error in nlps_b200_run() at steps [%i,%i)" RESET " \n", TimeStep, TimeStep + count);
       STATUS = EXIT_FAILURE;
       break;
@@ -64,21 +77,19 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
     TimeStep += count;
     if (ResultsTimeStep > 0 && (TimeStep - 1) % ResultsTimeStep == 0) {
       /* output_selector (U-Verlet.c:1088-1227): vtk results read the host Fields */
-      if (nlps_b200_download(eng, &in.st) != EXIT_SUCCESS ||
-          nlps_b200_get_lists(eng, counts, lists, cap) != EXIT_SUCCESS) {
-        STATUS = EXIT_FAILURE;
-        break;
-      }
-      lists_to_chains(MPM_Mesh, counts, lists, cap);
-      particle_results_vtk__InOutFun__(MPM_Mesh, TimeStep - 1, ResultsTimeStep);
+      if (nlps_b200_download_begin(eng, &in.st) != EXIT_SUCCESS) { STATUS = EXIT_FAILURE; break; }
+      pending_out = TimeStep - 1;
     }
     print_Status("DONE !!!", TimeStep - 1);
+  }
+  if (STATUS == EXIT_SUCCESS && pending_out >= 0) {
+    if (nlps_b200_download_end(eng) != EXIT_SUCCESS) STATUS = EXIT_FAILURE;
+    else particle_results_vtk__InOutFun__(MPM_Mesh, pending_out, ResultsTimeStep);
   }
 
   if (STATUS == EXIT_SUCCESS) STATUS = b200_finish(eng, &in, FEM_Mesh, MPM_Mesh);
 
   nlps_b200_destroy(eng);
-  free(counts); free(lists);
   b200_release(&in);
   return STATUS;
 }

@@ -406,6 +406,23 @@ class Engine:
         prm = Newmark(beta, gamma, tol, int(max_iter), int(explicit_trial), pcg_rtol, int(pcg_max_iter))
         return self.L.nlps_b200_newmark_setup(self.h, C.byref(prm))
 
+    def run_async(self, first, count):
+        return self.L.nlps_b200_run_async(self.h, int(first), int(count))
+
+    def sync(self):
+        return self.L.nlps_b200_sync(self.h)
+
+    def download_begin(self):
+        """Snapshot of the current step; returns the host dict that download_end() completes."""
+        if self.L.nlps_b200_download_begin(self.h, C.byref(self.m.state)) != 0:
+            raise RuntimeError("nlps_b200_download_begin failed")
+        return self.m.host
+
+    def download_end(self):
+        if self.L.nlps_b200_download_end(self.h) != 0:
+            raise RuntimeError("nlps_b200_download_end failed")
+        return {k: v.copy() for k, v in self.m.host.items()}
+
     def newmark_step(self, k):
         return self.L.nlps_b200_newmark_step(self.h, int(k))
 
