@@ -241,7 +241,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+            os.environ["NCCL_DEBUG"] = "NONE"  # VERSION and WARN both print "NCCL version ..." to stdout: keep it to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     K, Wm = args.steps, max(args.warmup, 3)

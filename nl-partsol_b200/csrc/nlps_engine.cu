@@ -26,6 +26,8 @@
 #include <omp.h>
 #endif
 #include <string>
+#include <mutex>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/nlps_b200.h"
@@ -1970,6 +1972,9 @@ struct nlps_engine {
   struct ImplicitCtx* imp = nullptr;
   std::vector<int> h_ids;           // host copy of P.orig (slab I/O)
   std::vector<double> h_rows;       // host staging of compact rows (slab I/O)
+  void* p2p_ce[2] = {nullptr, nullptr};  // P2PCacheEntry of each side while this engine uses it
+  int* d_rows = nullptr;            // create: state-row index of every held particle (device-side row gather)
+  int up_rows = 0;                  // create: rows of the caller's state buffers
 };
 
 // ---------------------------------------------------------------------------
@@ -2282,8 +2287,12 @@ static int refresh_ids(nlps_engine* e) {
 // device), 1: by global id, gathered on the host (slab engines hold a subset), 2: compact, row = slot.
 static int put_field(nlps_engine* e, const double* h, double* d, int cols, int aos_stride, int col0, int rows = 0) {
   if (!h || !d || e->np == 0) return 0;
-  const size_t n = (size_t)e->np * aos_stride;
+  size_t n = (size_t)e->np * aos_stride;
   const int* rowmap = e->P.orig;
+  if (rows == 3) {  // the caller's whole buffer goes up as it is (pinned buffers: full link speed), rows picked on the device
+    n = (size_t)e->up_rows * aos_stride;
+    rowmap = e->d_rows;
+  } else
   if (rows == 1) {
     e->h_rows.resize(n);
     for (int p = 0; p < e->np; p++) memcpy(&e->h_rows[(size_t)p * aos_stride], h + (size_t)e->h_ids[p] * aos_stride, sizeof(double) * aos_stride);
@@ -2706,6 +2715,38 @@ int nlps_b200_trim(int device) {
 
 const char* nlps_b200_version(void) { return "nlps_b200 0.1 (sm_100a, fp64, explicit NPC-FS)"; }
 
+// Process-wide cache of the peer-memory halo buffers (cudaMalloc + CUDA IPC export on my side, the opened mapping of
+// the neighbour's buffer on the other): creating and tearing them down costs 0.15-0.45 s per engine (cudaMalloc,
+// cudaIpcOpenMemHandle, cudaIpcCloseMemHandle, cudaFree all synchronise the device), far more than the halo traffic of a
+// short run.  Entries live until the process exits (like the stream-ordered memory pool).  Every engine still does the
+// handshake: a side reuses ITS buffer when it is large enough and says so through the generation number it sends; the
+// neighbour keeps its mapping when the generation (and the exporter's pid) is the one it already opened.
+struct P2PCacheEntry {
+  int device, rank, peer, side;
+  size_t bytes = 0;                      // of my receive buffer
+  double* rbuf = nullptr;                // mine
+  unsigned long long* flag = nullptr;
+  cudaIpcMemHandle_t h_buf, h_flag;
+  unsigned long long gen = 0;
+  unsigned long long peer_gen = 0;       // generation of the neighbour's buffer that is mapped below (0 = none)
+  long long peer_pid = 0;
+  double* peer_rbuf = nullptr;
+  unsigned long long* peer_flag = nullptr;
+  bool in_use = false;                   // by a live engine (a second engine of the same slab side falls back to NCCL)
+};
+static std::vector<P2PCacheEntry*> g_p2p_cache;
+static unsigned long long g_p2p_gen = 0;
+static std::mutex g_p2p_mutex;
+static P2PCacheEntry* p2p_cache_get(int device, int rank, int peer, int side) {
+  std::lock_guard<std::mutex> lk(g_p2p_mutex);
+  for (auto* c : g_p2p_cache)
+    if (c->device == device && c->rank == rank && c->peer == peer && c->side == side) return c;
+  auto* c = new P2PCacheEntry();
+  c->device = device; c->rank = rank; c->peer = peer; c->side = side;
+  g_p2p_cache.push_back(c);
+  return c;
+}
+
 void nlps_b200_destroy(nlps_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
@@ -2713,10 +2754,13 @@ void nlps_b200_destroy(nlps_engine* e) {
   implicit_free(e);
   for (int s_ = 0; s_ < 2; s_++) {
     auto& h = e->side[s_];
-    if (h.peer_rbuf) cudaIpcCloseMemHandle(h.peer_rbuf);
-    if (h.peer_flag) cudaIpcCloseMemHandle(h.peer_flag);
-    if (h.p2p_rbuf) cudaFree(h.p2p_rbuf);
-    if (h.p2p_flag) cudaFree(h.p2p_flag);
+    // peer-memory halo buffers and mappings belong to the process-wide cache (P2PCacheEntry): nothing to release here
+    h.peer_rbuf = nullptr; h.peer_flag = nullptr; h.p2p_rbuf = nullptr; h.p2p_flag = nullptr;
+    if (e->p2p_ce[s_]) {
+      std::lock_guard<std::mutex> lk(g_p2p_mutex);
+      ((P2PCacheEntry*)e->p2p_ce[s_])->in_use = false;
+      e->p2p_ce[s_] = nullptr;
+    }
   }
   for (void* p : e->allocs) pool_free(p, e->stream);
   if (e->stream) cudaStreamSynchronize(e->stream);
@@ -3058,7 +3102,20 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   // ---- slab engine: gather the held rows on the host, ids = global ids
   {
     e->h_ids = rows;  // state-row indices: upload_impl(rows = 1) gathers by them
-    if (upload_impl(e, st, 1)) return 1;
+    // a caller that passes exactly its own particles (sub-mesh slabs: every row is held) needs no host gather:
+    // the buffers go to the device as they are (pinned buffers then move at full link speed)
+    bool all_rows = (int)rows.size() == st->n;
+    for (int p = 0; all_rows && p < np; p++) all_rows = rows[p] == p;
+    mark("slab particle arrays");
+    // most rows held (a slab's own particles plus a margin): upload whole buffers, gather the held rows on the device
+    int mode = all_rows ? 2 : 1;
+    if (!all_rows && (size_t)st->n * std::max(e->T, D * D) <= e->stage_doubles) {
+      if (dev_upload(e, &e->d_rows, rows.data(), rows.size())) return 1;
+      e->up_rows = st->n;
+      mode = 3;
+    }
+    if (upload_impl(e, st, mode)) return 1;
+    mark(mode == 2 ? "slab field upload (direct)" : mode == 3 ? "slab field upload (device gather)" : "slab field upload (host gather)");
     std::vector<int> i0(std::max(np, 1)), mi(std::max(np, 1)), gid(std::max(np, 1));
     for (int p = 0; p < np; p++) {
       i0[p] = st->I0[rows[p]];
@@ -3074,6 +3131,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     e->h_ids = gid;
     e->h_ids.resize(np);
   }
+  mark("slab particle upload");
   // ---- halo node lists (identical on both sides of a cut) and exchange buffers
   for (int s_ = 0; s_ < 2; s_++) {
     const int peer = s_ == 0 ? e->rank - 1 : e->rank + 1;
@@ -3102,24 +3160,48 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     CUDA_OK(cudaMallocHost(&e->h_mig, 16 * sizeof(int)));
     CUDA_OK(cudaStreamSynchronize(e->stream));
   }
+  mark("halo + migration buffers");
   // ---- peer-memory halo path (NVLink stores through CUDA IPC mappings): needs the NCCL transport (the handles
   // travel over it) and one process per GPU; any failure leaves the NCCL path in place
   if (e->comm && e->comm->is_nccl && e->world > 1 && !(getenv("NLPS_P2P") && atoi(getenv("NLPS_P2P")) == 0)) {
-    struct Blob { cudaIpcMemHandle_t buf, flag; int ok; int pad; };
+    struct Blob { cudaIpcMemHandle_t buf, flag; int ok; int pad; unsigned long long gen; long long pid; };
     Blob mine[2], theirs[2];
     memset(mine, 0, sizeof(mine));
     memset(theirs, 0, sizeof(theirs));
+    P2PCacheEntry* ce[2] = {nullptr, nullptr};
     bool ok = true;
     for (int s_ = 0; s_ < 2 && ok; s_++) {
       auto& h = e->side[s_];
       if (h.peer < 0) continue;
       const size_t nb = sizeof(double) * 3 * (size_t)std::max(h.n, 1) * (1 + D);
-      ok = cudaMalloc(&h.p2p_rbuf, nb) == cudaSuccess && cudaMalloc(&h.p2p_flag, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-           cudaMemset(h.p2p_rbuf, 0, nb) == cudaSuccess && cudaMemset(h.p2p_flag, 0, 4 * sizeof(unsigned long long)) == cudaSuccess &&
-           cudaIpcGetMemHandle(&mine[s_].buf, h.p2p_rbuf) == cudaSuccess &&
-           cudaIpcGetMemHandle(&mine[s_].flag, h.p2p_flag) == cudaSuccess;
+      P2PCacheEntry* c = ce[s_] = p2p_cache_get(e->device, e->rank, h.peer, s_);
+      {
+        std::lock_guard<std::mutex> lk(g_p2p_mutex);
+        if (c->in_use) { ok = false; ce[s_] = nullptr; mine[s_].ok = 0; break; }
+        c->in_use = true;
+        e->p2p_ce[s_] = c;
+      }
+      if (!c->rbuf || c->bytes < nb) {
+        // (a smaller buffer of an earlier engine stays allocated: the neighbour may still have it mapped)
+        double* rb = nullptr;
+        unsigned long long* fl = nullptr;
+        ok = cudaMalloc(&rb, nb) == cudaSuccess && cudaMalloc(&fl, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+             cudaIpcGetMemHandle(&c->h_buf, rb) == cudaSuccess && cudaIpcGetMemHandle(&c->h_flag, fl) == cudaSuccess;
+        if (ok) {
+          std::lock_guard<std::mutex> lk(g_p2p_mutex);
+          c->rbuf = rb; c->flag = fl; c->bytes = nb; c->gen = ++g_p2p_gen;
+        }
+      }
+      if (ok) {
+        // the neighbour's previous engine has pushed everything my previous engine waited for: safe to reset
+        ok = cudaMemsetAsync(c->rbuf, 0, nb, e->stream) == cudaSuccess &&
+             cudaMemsetAsync(c->flag, 0, 4 * sizeof(unsigned long long), e->stream) == cudaSuccess;
+        h.p2p_rbuf = c->rbuf; h.p2p_flag = c->flag;
+        mine[s_].buf = c->h_buf; mine[s_].flag = c->h_flag; mine[s_].gen = c->gen; mine[s_].pid = (long long)getpid();
+      }
       mine[s_].ok = ok ? 1 : 0;
     }
+    CUDA_OK(cudaStreamSynchronize(e->stream));  // buffers are zero before anybody learns (again) where they are
     // exchange the handles with the two neighbours over the transport (device bounce buffers)
     Blob *d_mine = nullptr, *d_theirs = nullptr;
     if (dev_alloc(e, &d_mine, 2) || dev_alloc(e, &d_theirs, 2)) return 1;
@@ -3134,11 +3216,25 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     for (int s_ = 0; s_ < 2; s_++) {
       auto& h = e->side[s_];
       if (h.peer < 0) continue;
-      if (!mine[s_].ok || !theirs[s_].ok) { ok = false; continue; }
+      if (!mine[s_].ok || !theirs[s_].ok || !ce[s_]) { ok = false; continue; }
+      P2PCacheEntry* c = ce[s_];
+      if (c->peer_rbuf && c->peer_gen == theirs[s_].gen && c->peer_pid == theirs[s_].pid) {
+        h.peer_rbuf = c->peer_rbuf;  // the mapping opened by an earlier engine
+        h.peer_flag = c->peer_flag;
+        continue;
+      }
+      if (c->peer_rbuf) {  // the neighbour moved to a new buffer
+        cudaIpcCloseMemHandle(c->peer_rbuf);
+        cudaIpcCloseMemHandle(c->peer_flag);
+        c->peer_rbuf = nullptr; c->peer_flag = nullptr; c->peer_gen = 0;
+      }
       if (cudaIpcOpenMemHandle((void**)&h.peer_rbuf, theirs[s_].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
           cudaIpcOpenMemHandle((void**)&h.peer_flag, theirs[s_].flag, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         cudaGetLastError();
+        h.peer_rbuf = nullptr; h.peer_flag = nullptr;
         ok = false;
+      } else {
+        c->peer_rbuf = h.peer_rbuf; c->peer_flag = h.peer_flag; c->peer_gen = theirs[s_].gen; c->peer_pid = theirs[s_].pid;
       }
     }
     // everybody must take the same path: the verdict travels along the chain of slabs (world - 1 rounds of
@@ -3164,6 +3260,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     }
     if (dev_alloc(e, &e->p2p_done, 4)) return 1;
     e->p2p_on = 1;
+    mark("peer-memory halo setup");
   }
   return 0;
 }
