@@ -321,6 +321,9 @@ typedef struct nlps_newmark {
   int use_explicit_trial;  /* Use_explicit_trial (:879-957) */
   double pcg_rtol;         /* |r| <= pcg_rtol |b|   (0 = 1e-8; PETSc's default would be 1e-5) */
   int pcg_max_iter;        /* 0 = 10000 (PETSc default) */
+  int quasi_static;        /* 1: U_Static (Formulations/Displacements/U-Static.c:83-322) -- the same loop without inertia:
+                            * residual f_int - f_trac - M b, tangent K only, particles updated in position and history,
+                            * velocities and accelerations untouched; beta / gamma are ignored */
 } nlps_newmark;
 typedef struct nlps_newmark_stats {
   int newton_iters;        /* of the last step */

@@ -640,7 +640,7 @@ static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
     fprintf(stderr, "nlps_b200_newmark_setup: the implicit scheme runs on a single slab\n");
     return 1;
   }
-  if (!(prm->beta > 0.0) || !(prm->gamma > 0.0)) {  // a1 = 1/(beta dt^2): explicit central differences are U_Verlet's job
+  if (!prm->quasi_static && (!(prm->beta > 0.0) || !(prm->gamma > 0.0))) {  // a1 = 1/(beta dt^2): explicit central differences are U_Verlet's job
     fprintf(stderr, "nlps_b200_newmark_setup: beta and gamma must be positive (beta=%g gamma=%g)\n", prm->beta, prm->gamma);
     return 1;
   }
@@ -658,6 +658,11 @@ static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
   c->a4 = g / (b * dt);
   c->a5 = 1 - g / b;
   c->a6 = (1 - g / (2 * b)) * dt;
+  if (prm->quasi_static) {  // U_Static (U-Static.c): no inertia; v_n = a_n = 0 below make every other term vanish
+    c->a1 = c->a2 = c->a4 = c->a6 = 0.0;
+    c->a3 = -1.0;  // G2P: dA = -(a3 + 1) a_n
+    c->a5 = 1.0;   // G2P: dV = (a5 - 1) v_n
+  }
   const int nn = e->nn, D = e->D, xs = (D == 2) ? 2 : 4;
   // ---- static coupling adjacency on the host: B couples with A when one cell's 2-ring holds both and they are
   // closer than two support radii (a particle can have both in its list); sorted by node id
@@ -748,6 +753,10 @@ static int imp_begin_t(nlps_engine* e, int step) {
   stage_search_t<D>(e, step, 1, 0, e->P.acc, 1);
   { auto kf = k_grid_disp<D, 1>; LAUNCH(e, K_GRID_DISP, kf, nb128, 128, e->mesh, G, e->bc, step); }
   k_imp_nodal<D><<<nb128, 128, 0, e->stream>>>(G, e->bc, step, 0, c->An, c->fx);
+  if (c->prm.quasi_static) {  // the projections above are kept for the lumped mass and the restricted-DOF flags
+    cudaMemsetAsync(c->Vn, 0, sizeof(double) * (size_t)e->max_act * D, e->stream);
+    cudaMemsetAsync(c->An, 0, sizeof(double) * (size_t)e->max_act * D, e->stream);
+  }
   // pattern
   const int items = e->max_act + 1, nb = nblk(items, SCAN_ITEMS);
   k_csr_count<<<nblk(items, 256), 256, 0, e->stream>>>(G, c->cpl_ptr, c->cpl_idx, c->packed, items);
@@ -947,7 +956,7 @@ extern "C" {
 
 int nlps_b200_newmark_setup(nlps_engine* e, const nlps_newmark* prm) {
   cudaSetDevice(e->device);
-  if (!prm || !(prm->beta > 0.0)) return 1;
+  if (!prm || (!prm->quasi_static && !(prm->beta > 0.0))) return 1;
   return imp_setup(e, prm);
 }
 

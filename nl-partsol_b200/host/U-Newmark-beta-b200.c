@@ -14,12 +14,13 @@
 
 extern double DeltaTimeStep; /* U-Verlet-b200.c */
 
-int U_Newmark_Beta(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver) {
+static int b200_implicit_scheme(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver, int quasi_static) {
   const int NumTimeStep = Parameters_Solver.NumTimeStep;
   int STATUS = EXIT_SUCCESS;
 
   if (strcmp(ShapeFunctionGP, "LME") != 0) {
-    fprintf(stderr, "" RED "Error in U_Newmark_Beta() [B200]: only GramsShapeFun (Type=LME) is supported" RESET " \n");
+    fprintf(stderr, "" RED "Error in %s() [B200]: only GramsShapeFun (Type=LME) is supported" RESET " \n",
+            quasi_static ? "U_Static" : "U_Newmark_Beta");
     return EXIT_FAILURE;
   }
   b200_inputs in;
@@ -41,7 +42,8 @@ int U_Newmark_Beta(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_
   prm.gamma = Parameters_Solver.gamma_Newmark_beta;
   prm.tol = Parameters_Solver.TOL_Newmark_beta;     /* :171-172: rtol, atol = 100 tol */
   prm.max_iter = Parameters_Solver.MaxIter;
-  prm.use_explicit_trial = Parameters_Solver.Use_explicit_trial;
+  prm.use_explicit_trial = quasi_static ? 0 : Parameters_Solver.Use_explicit_trial;
+  prm.quasi_static = quasi_static; /* U_Static: the same loop without inertia (U-Static.c:83-322) */
   if (nlps_b200_newmark_setup(eng, &prm) != EXIT_SUCCESS) {
     fprintf(stderr, "" RED "Error in nlps_b200_newmark_setup()" RESET " \n");
     STATUS = EXIT_FAILURE;
@@ -77,4 +79,15 @@ int U_Newmark_Beta(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_
   free(counts); free(lists);
   b200_release(&in);
   return STATUS;
+}
+
+int U_Newmark_Beta(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver) {
+  return b200_implicit_scheme(FEM_Mesh, MPM_Mesh, Parameters_Solver, 0);
+}
+
+/* PetscErrorCode U_Static(Mesh, Particle, Time_Int_Params) (Formulations/Displacements/U-Static.c:83, dispatched from
+ * driver-nl-partsol.c:373-375 for `NLPS-Solver (Type=Static)`): residual f_int - f_trac - M b, tangent K, particles
+ * updated in position and history only.  Linked INSTEAD OF U-Static.c. */
+int U_Static(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver) {
+  return b200_implicit_scheme(FEM_Mesh, MPM_Mesh, Parameters_Solver, 1);
 }

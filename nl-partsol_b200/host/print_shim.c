@@ -11,11 +11,3 @@ void print_convergence_stats(int Time, int NumTimeStep, int Iter, int MaxIter, d
   printf("Step [%i/%i] iter %i/%i err0 %e err %e rel %e\n", Time, NumTimeStep, Iter, MaxIter, Error0, Error_total,
          Error_relative);
 }
-
-/* U_Static needs PETSc (Formulations/Displacements/U-Static.c); the reference driver references it
- * unconditionally (driver-nl-partsol.c:374-377), so a PETSc-free build needs this stub. */
-struct Mesh; struct Particle;
-int U_Static() {
-  fprintf(stderr, "U_Static: this build has no PETSc\n");
-  return 1;
-}

@@ -65,7 +65,8 @@ class Slab(C.Structure):
 
 class Newmark(C.Structure):
     _fields_ = [("beta", C.c_double), ("gamma", C.c_double), ("tol", C.c_double), ("max_iter", C.c_int),
-                ("use_explicit_trial", C.c_int), ("pcg_rtol", C.c_double), ("pcg_max_iter", C.c_int)]
+                ("use_explicit_trial", C.c_int), ("pcg_rtol", C.c_double), ("pcg_max_iter", C.c_int),
+                ("quasi_static", C.c_int)]
 
 
 class NewmarkStats(C.Structure):
@@ -402,8 +403,9 @@ class Engine:
 
     # ---- implicit Newmark-beta (nlps_b200_newmark_*)
     def newmark_setup(self, beta=0.25, gamma=0.5, tol=1e-10, max_iter=10, explicit_trial=False, pcg_rtol=0.0,
-                      pcg_max_iter=0):
-        prm = Newmark(beta, gamma, tol, int(max_iter), int(explicit_trial), pcg_rtol, int(pcg_max_iter))
+                      pcg_max_iter=0, quasi_static=False):
+        prm = Newmark(beta, gamma, tol, int(max_iter), int(explicit_trial), pcg_rtol, int(pcg_max_iter),
+                      int(quasi_static))
         return self.L.nlps_b200_newmark_setup(self.h, C.byref(prm))
 
     def run_async(self, first, count):

@@ -170,6 +170,10 @@ class Oracle:
         self.L.orc_newmark_setup(self.h, ctypes.c_double(beta), ctypes.c_double(gamma), ctypes.c_double(tol),
                                  int(max_iter), int(explicit_trial))
 
+    def static_setup(self, tol=1e-10, max_iter=10):
+        """U_Static: the implicit loop without inertia (U-Static.c)."""
+        self.L.orc_static_setup(self.h, ctypes.c_double(tol), int(max_iter))
+
     def newmark_begin(self, step):
         return self.L.orc_newmark_begin(self.h, int(step))
 

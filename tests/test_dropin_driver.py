@@ -81,3 +81,40 @@ def test_reference_driver_with_b200_implicit_scheme(tmp_path):
         x = _points(files[0])
         assert np.abs(x - o.field("x_GC")).max() <= 1e-8 * np.abs(o.field("x_GC")).max(), k
     assert np.abs(o.field("dis")).max() > 1e-6
+
+
+@pytest.mark.gpu
+def test_reference_driver_with_b200_static_scheme(tmp_path):
+    """`NLPS-Solver (Type=Static)`: driver-nl-partsol.c:373-375 dispatches to U_Static, here the B200 shim (the implicit
+    engine without inertia).  VTK positions against the CPU restatement."""
+    if not os.path.exists(BIN):
+        pytest.skip("drop-in binary not built (needs /root/reference at build time)")
+    import deckgen
+    import make_golden
+    import oracle
+    from util import load_problem
+    nsteps, tol = 3, 1e-11
+    spec = make_golden.spec_for("nh")
+    spec.scheme = "Static"
+    spec.nsteps, spec.out_every = nsteps, 1
+    spec.solver_extra = {"TOL-Newmark-beta": tol, "Max-Iter": 25, "Epsilon": 0.0}
+    deckgen.write_deck(spec, str(tmp_path))
+    r = subprocess.run([BIN, "--FORMULATION-U", "-f", "deck.nlp"], cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "abnormally" not in r.stdout + r.stderr
+    P = load_problem("nh")
+    P.solver["nsteps"] = nsteps
+    for b in P.bounds:
+        b["dir"], b["val"] = b["dir"][:, :nsteps], b["val"][:, :nsteps]
+    P.gravity = P.gravity[:, :nsteps]
+    o = oracle.Oracle(P)
+    assert o.init_lme() == 0
+    o.static_setup(tol=tol, max_iter=25)
+    for k in range(nsteps):
+        assert o.newmark_step(k) == 0, o.error()
+        files = glob.glob(os.path.join(str(tmp_path), "Results", f"*_{k}.vtk"))
+        assert files, f"no VTK for step {k}"
+        x = _points(files[0])
+        assert np.abs(x - o.field("x_GC")).max() <= 1e-8 * np.abs(o.field("x_GC")).max(), k
+    assert np.abs(o.field("dis")).max() > 1e-6

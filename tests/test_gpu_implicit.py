@@ -150,6 +150,34 @@ def test_elastoplastic_converged_steps_match_the_oracle(case, cfl, nsteps):
     eng.close()
 
 
+@pytest.mark.parametrize("case", ["block2d", "cube3d", "dp2d"])
+def test_static_scheme_matches_the_oracle(case):
+    """U_Static (Formulations/Displacements/U-Static.c:83-322): the implicit loop without inertia -- residual
+    f_int - f_trac - M b, tangent K only, positions / history updated, velocities untouched."""
+    nsteps = 3 if case != "dp2d" else 1    # the plastic deck: one converged step (the reference's inexact elastoplastic
+    P = CASES[case](nsteps)                # tangent stagnates on the next ones, in the oracle as on the device)
+    if case == "dp2d":
+        P.gravity = P.gravity * 0.01       # a load the column carries (a static limit load has no solution); still yields
+    o = oracle.Oracle(P)
+    assert o.init_lme() == 0
+    o.static_setup(tol=1e-11, max_iter=30)
+    eng = engine.Engine(P, device=0)
+    assert eng.initialize_lme() == 0
+    assert eng.newmark_setup(tol=1e-11, max_iter=30, pcg_rtol=1e-13, quasi_static=True) == 0
+    v0 = np.array(P.fields["vel"], copy=True)
+    for k in range(nsteps):
+        assert o.newmark_step(k) == 0, o.error()
+        assert eng.newmark_step(k) == 0, eng.error()
+    f = eng.download()
+    sc = field_scales(P)
+    for name in ("x_GC", "dis", "F_n", "Stress", "rho", "J_n"):
+        assert_close(f[name], o.field(name), f"static {case} {name}", rtol=2e-6 if case == "dp2d" else 1e-8, scale=sc.get(name))
+    assert np.array_equal(f["vel"], v0) and np.abs(f["acc"]).max() == 0.0
+    assert np.abs(f["dis"]).max() > 0.0
+    assert np.array_equal(f["I0"], o.ints("I0"))
+    eng.close()
+
+
 def test_implicit_refuses_invalid_parameters():
     P = synthetic.block_2d(cells=4, nsteps=2)
     eng = engine.Engine(P, device=0)

@@ -122,3 +122,25 @@ def test_elastoplastic_newton_converges(case, mult, nsteps):
         assert (o.field("EPS_n") > 0).sum() > 50      # the tangent was evaluated on plastic states
     st, K = o.newmark_tangent()
     assert st == 0 and np.isfinite(K).all()
+
+
+def test_static_scheme_balances_gravity():
+    """U_Static (U-Static.c): Newton on f_int - f_trac - M b = 0.  After a converged step the internal forces carry the
+    weight (the vertical reactions on the fixed nodes sum to m g), velocities and accelerations stay untouched."""
+    P = synthetic.block_2d(cells=6, nsteps=3)
+    o = oracle.Oracle(P)
+    assert o.init_lme() == 0
+    o.static_setup(tol=1e-11, max_iter=25)
+    v0 = o.field("vel").copy()
+    for k in range(2):
+        assert o.newmark_step(k) == 0, o.error()
+        assert o.newmark_iters() <= 8
+    assert np.array_equal(o.field("vel"), v0) and np.abs(o.field("acc")).max() == 0.0
+    # residual at the converged increment: zero on the free dofs
+    assert o.newmark_begin(2) == 0
+    dU = o.newmark_get("dU")
+    st, R = o.newmark_residual(2, dU)
+    free = (o.active()[:, None] > 0) & (o.fixed() == 0)
+    weight = 9.81 * float(P.fields["mass"].sum())
+    assert st == 0 and np.abs(R[free]).max() <= 1e-6 * weight    # one more step is already (nearly) in equilibrium
+    assert np.abs(o.field("dis")[:, 1]).max() > 1e-4               # the block did settle
