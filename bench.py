@@ -56,6 +56,13 @@ FP64_ROOF = {"dfma_per_s": 1.711e13, "pipe_util_ncu": {"lme_p2g_mass_disp": 0.19
 # STRONG scaling over z slabs (the global problem is fixed).  SURVEY 8(d) 3D NH: K0 100+4n, K1 160, K2 380, K3 208, K4 248.
 ALG_BYTES_3D_NH = {"lme_p2g_mass_disp": lambda n: 100 + 4 * n + 160.0, "kin_stress_p2g_force": lambda n: 380.0 + 208.0,
                    "g2p_update": lambda n: 248.0}
+# --workload c4: BASELINE configs[3], 3D 45-degree slope, Matsuoka-Nakai, 8,037,120 particles, gamma 6, slabs along the
+# slope with particle migration every 10 steps, STRONG scaling.  SURVEY 8(d) 3D plastic: K2 556 instead of 380.
+ALG_BYTES_3D_PLASTIC = {"lme_p2g_mass_disp": lambda n: 100 + 4 * n + 160.0, "kin_stress_p2g_force": lambda n: 556.0 + 208.0,
+                        "g2p_update": lambda n: 248.0}
+STAGE_GROUPS_3D_PLASTIC = {"K0+K1 lme+p2g_mass_disp+grid_disp": (("lme_p2g_mass_disp", "grid_disp_bc"), lambda n: 260 + 4 * n),
+                           "K2+K3 kin_stress+p2g_force+grid_acc": (("traction", "kin_stress_p2g_force", "grid_acc"), lambda n: 764.0),
+                           "K4 g2p_update": (("g2p_update",), lambda n: 248.0)}
 STAGE_GROUPS_3D = {"K0+K1 lme+p2g_mass_disp+grid_disp": (("lme_p2g_mass_disp", "grid_disp_bc"), lambda n: 260 + 4 * n),
                    "K2+K3 kin_stress+p2g_force+grid_acc": (("traction", "kin_stress_p2g_force", "grid_acc"), lambda n: 588.0),
                    "K4 g2p_update": (("g2p_update",), lambda n: 248.0)}
@@ -248,11 +255,23 @@ def run_ours(args):
     nsteps_total = Wm + K + 2
     t_setup = time.perf_counter()
     comm = slab = None
-    c3 = args.workload == "c3"
-    alg_k = ALG_BYTES_3D_NH if c3 else ALG_BYTES_2D_PLASTIC
-    groups_k = STAGE_GROUPS_3D if c3 else STAGE_GROUPS
-    step_alg = (lambda n: 1096 + 4 * n) if c3 else (lambda n: 832 + 4 * n)
-    if c3:
+    c4 = args.workload == "c4"
+    c3 = args.workload == "c3" or c4       # "c3" below: the 3D strong-scaling code path (c4 differs in the generator only)
+    alg_k = ALG_BYTES_3D_PLASTIC if c4 else ALG_BYTES_3D_NH if c3 else ALG_BYTES_2D_PLASTIC
+    groups_k = STAGE_GROUPS_3D_PLASTIC if c4 else STAGE_GROUPS_3D if c3 else STAGE_GROUPS
+    step_alg = (lambda n: 1272 + 4 * n) if c4 else (lambda n: 1096 + 4 * n) if c3 else (lambda n: 832 + 4 * n)
+    if c4:
+        cells, width = max(16 * world, int(round(160 * args.scale))), max(8, int(round(78 * args.scale)))
+        P, slab = synthetic.slope_slab_3d(rank, world, cells=cells, width=width, nsteps=nsteps_total)
+        if world == 1:
+            eng = engine.Engine(P, device=local)
+            total_particles = P.np_
+        else:
+            comm = engine.NcclComm(rank, world, local)
+            total_particles = slab["n_particles"]
+            slab = dict({k: v for k, v in slab.items() if k != "n_particles"}, comm=comm, migrate_every=10)
+            eng = engine.Engine(P, device=local, slab=slab)
+    elif c3:
         cells = max(8 * world, int(round(126 * args.scale)))
         if world == 1:
             P = synthetic.cube_3d(cells=cells, nsteps=nsteps_total)
@@ -346,7 +365,7 @@ def run_ours(args):
     eng.close()
 
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not c4:
         # end to end through the scheme call with HOST buffers (create + H2D, steps, D2H of the results)
         e2e_steps = max(K, 200) if not c3 else max(K, 40)   # the scheme call amortises its set-up over the run
         if c3:
@@ -445,12 +464,13 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong" if c3 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": ("BASELINE configs[2]: 3D Neo-Hookean cube, explicit NPC-FS, LME gamma=6, GPxElement 8"
+                "config": {"workload": ("BASELINE configs[3]: 3D 45-degree slope, Matsuoka-Nakai (cohesion 1e3), explicit NPC-FS, LME gamma=6, GPxElement 8, gravity ramp"
+                                        if c4 else "BASELINE configs[2]: 3D Neo-Hookean cube, explicit NPC-FS, LME gamma=6, GPxElement 8"
                                         if c3 else "BASELINE configs[1]: 2D granular column collapse, Drucker-Prager, "
                                         "explicit NPC-FS, LME gamma=3, GPxElement 4"),
                            "particles_per_gpu": npart, "background_nodes": P.nn, "scale": args.scale,
                            "l2": "inputs larger than L2 (particle state + records ~0.7 GB per GPU)",
-                           "multi_gpu": (f"strong scaling over {world} spatial slabs along z of the fixed cube: halo sums + migration"
+                           "multi_gpu": (f"strong scaling over {world} spatial slabs along z of the fixed problem (c4: cuts at particle-count quantiles): halo sums + migration every 10 steps"
                                          if c3 and world > 1 else
                                          f"weak scaling over {world} spatial slabs along y (column {world}x taller): "
                                          "NCCL halo sums of occupancy / mass+momentum / forces every step, "
@@ -474,8 +494,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="linear scale of the C2 workload (1.0 = 10^6 particles)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer scheme call (large --workload c3 runs)")
-    ap.add_argument("--workload", default="c2", choices=("c2", "c3"),
-                    help="c2 (default, the driver's bench line): BASELINE configs[1]; c3: configs[2], 3D cube, strong scaling")
+    ap.add_argument("--workload", default="c2", choices=("c2", "c3", "c4"),
+                    help="c2 (default, the driver's bench line): BASELINE configs[1]; c3: configs[2], 3D cube, strong scaling; "
+                         "c4: configs[3], 3D Matsuoka-Nakai slope, slabs + migration, strong scaling (no e2e leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -42,7 +42,8 @@ def _grid(nx, ny, nz, h, origin, cell_offset=(0, 0, 0)):
 
 def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, material, nsteps, cfl, cel,
                        gravity, gamma_lme=3.0, fixed=("bottom",), rollers=("left", "right"), jitter=0.0,
-                       seed=20261018, tol_radial=None, maxiter_radial=None, bc_scale=None, cell_offset=(0, 0, 0)):
+                       seed=20261018, tol_radial=None, maxiter_radial=None, bc_scale=None, cell_offset=(0, 0, 0),
+                       keep_cell=None):
     """Block of block_cells particle cells (one particle cell = one background cell, GPxElement 4 / 8)
     placed at block_origin_cell inside a grid of grid_cells cells of size h.  cell_offset places the
     grid inside a larger global one (sub-mesh of one slab); block_origin_cell stays LOCAL."""
@@ -78,7 +79,11 @@ def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, mate
         P.bounds.append(dict(nodes=idx[sel[name]].astype(np.int32), dir=np.ones((d, nsteps), np.int32), val=zeros.copy()))
     for name in rollers:
         dr = np.zeros((d, nsteps), np.int32)
-        dr[1 if name in ("front", "back") else 0, :] = 1
+        if isinstance(name, tuple):     # (face, constrained direction)
+            name, axis_ = name
+            dr[axis_, :] = 1
+        else:
+            dr[1 if name in ("front", "back") else 0, :] = 1
         P.bounds.append(dict(nodes=idx[sel[name]].astype(np.int32), dir=dr, val=zeros.copy()))
     # ---- particles
     bx, by = block_cells[0], block_cells[1]
@@ -87,6 +92,10 @@ def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, mate
     oz = block_origin_cell[2] if d == 3 else 0
     e = np.arange(bx * by * bz)
     ei, ej, ek = e % bx + ox, (e // bx) % by + oy, e // (bx * by) + oz
+    if keep_cell is not None:   # carve the block: keep_cell(global cell indices i, j, k) -> bool mask
+        m_ = keep_cell(ei + cell_offset[0], ej + cell_offset[1], ek + (cell_offset[2] if d == 3 else 0))
+        ei, ej, ek = ei[m_], ej[m_], ek[m_]
+        P.kept_cells = np.nonzero(m_)[0]
     if d == 2:
         xi = np.array([[_G, _G], [_G, -_G], [-_G, _G], [-_G, -_G]])          # Q4.c:358-366
     else:
@@ -176,6 +185,54 @@ def column_slab_2d(rank, world, scale=1.0, nsteps=1000, band_cells=6):
     cuts = np.array([(r * by + 0.5) * h for r in range(1, world)])
     slab = dict(rank=rank, world=world, axis=1, cuts=cuts, band_cells=band_cells, global_id=gid,
                 n_global=4 * bx * tot_rows, node_offset=j0 * (nx + 1))
+    return P, slab
+
+
+def slope_slab_3d(rank, world, cells=160, width=78, nsteps=100, gamma_lme=6.0, band_cells=6, material=MN_C4,
+                  ramp_steps=100):
+    """BASELINE configs[3]: a 45-degree slope of Matsuoka-Nakai soil, GPxElement 8, gravity ramped over
+    `ramp_steps` steps, fixed base, rollers on the four sides, LME gamma 6; cells=160, width=78: 1,004,640 particle cells
+    = 8,037,120 particles.  Axes: the VERTICAL is the grid's x axis (ground plane i = 0, gravity (-g, 0, 0)), the slope
+    runs along z, the slab axis (node ids of a z sub-mesh are the global ids minus a constant, which is what the
+    migration of closest-node ids needs): the particle cells (i, j, k) with i + k < cells of a cells x width x cells block.
+    Cuts at particle-count quantiles (the wedge is taller at small z, so the slabs there are thinner); every rank builds
+    only the sub-mesh within band_cells + 2 layers of its cuts and the particles of its layers (+1 layer each side; the
+    engine keeps what the slab owns).  world == 1: (Problem, None).  Strong scaling of a fixed global problem."""
+    c, w = cells, width
+    h = 1.0 / c
+    col = np.arange(c, 0, -1, dtype=np.int64)                 # particle cells in the z layer k: (c - k) * w
+    cum = np.concatenate([[0], np.cumsum(col)])
+    lay = [0] + [int(np.searchsorted(cum, cum[-1] * r / world)) for r in range(1, world)] + [c]
+    for r in range(1, world):                                 # slabs must be wider than two halo bands
+        lay[r] = max(lay[r], lay[r - 1] + 2 * band_cells + 2)
+    nx, ny, nz_glob = c + 4, w + 4, c + 4
+    pad = band_cells + 2
+    k0 = max(0, lay[rank] + 2 - pad) if rank > 0 else 0                     # sub-mesh cell layers (global indices)
+    k1 = min(nz_glob, lay[rank + 1] + 2 + pad) if rank < world - 1 else nz_glob
+    c0 = max(0, lay[rank] - 1) if rank > 0 else 0                           # particle-cell layers generated here
+    c1 = min(c, lay[rank + 1] + 1) if rank < world - 1 else c
+    cel = (material[1][1] / material[1][0]) ** 0.5 * 1.3
+    # the particle block starts at grid cell (0, 2, 2): global particle-cell layer of grid layer gk is gk - 2
+    keep = lambda gi, gj, gk: gi + (gk - 2) < c
+    rollers = [("front", 1), ("back", 1)]
+    if k0 == 0:
+        rollers.append(("bottom", 2))
+    if k1 == nz_glob:
+        rollers.append(("top", 2))
+    P = structured_problem(3, (nx, ny, k1 - k0), h, (c, w, c1 - c0), (0, 2, c0 + 2 - k0), material, nsteps, 0.5, cel,
+                           (-9.81, 0.0, 0.0), gamma_lme=gamma_lme, fixed=("left",), rollers=tuple(rollers),
+                           cell_offset=(0, 0, k0), keep_cell=keep)
+    ramp = np.minimum(1.0, (np.arange(nsteps) + 1.0) / max(1, ramp_steps))
+    P.gravity = P.gravity * ramp[None, :]
+    if world == 1:
+        return P, None
+    # global ids: (global particle-cell index, x fastest, z slowest) * 8 + Gauss point; carved-away cells leave gaps
+    e = P.kept_cells.astype(np.int64)
+    gcell = e + c0 * c * w
+    gid = (gcell[:, None] * 8 + np.arange(8)[None, :]).ravel().astype(np.int32)
+    cuts = np.array([(lay[r] + 2 + 0.5) * h for r in range(1, world)])
+    slab = dict(rank=rank, world=world, axis=2, cuts=cuts, band_cells=band_cells, global_id=gid, n_global=8 * c * w * c,
+                node_offset=k0 * (nx + 1) * (ny + 1), n_particles=int(8 * cum[-1] * w))
     return P, slab
 
 

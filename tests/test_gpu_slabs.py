@@ -186,6 +186,40 @@ def test_submesh_slabs_3d_match_global_engine():
     compare(G, single, res, check_active=False)
 
 
+def test_slope_slabs_match_global_engine():
+    """bench.py --workload c4 (BASELINE configs[3]): the Matsuoka-Nakai slope, slabs along the slope with cuts at
+    particle-count quantiles, each slab on its own sub-mesh, global particle ids with gaps (carved cells), migration every
+    3 steps -- against one engine holding the whole slope."""
+    from nlps_b200 import synthetic
+    world, cells, width, nsteps = 2, 40, 5, 24
+    G, _ = synthetic.slope_slab_3d(0, 1, cells=cells, width=width, nsteps=nsteps, ramp_steps=10)
+    G.fields["vel"][:, 2] = 0.15 * G.solver["cel"]           # drift along the slab axis: particles cross the cut
+    gid_G = (G.kept_cells.astype(np.int64)[:, None] * 8 + np.arange(8)[None, :]).ravel()
+    per_rank = []
+    for r in range(world):
+        Pr, sl = synthetic.slope_slab_3d(r, world, cells=cells, width=width, nsteps=nsteps, ramp_steps=10)
+        Pr.fields["vel"][:, 2] = 0.15 * Pr.solver["cel"]
+        per_rank.append((Pr, {k: v for k, v in sl.items() if k != "n_particles"}))
+    assert per_rank[0][1]["n_global"] > G.np_                 # the id space has gaps
+    single = run_single(G, nsteps)
+
+    class _Ids:                                               # run_slabs_threads sizes its list arrays by the id space
+        np_ = per_rank[0][1]["n_global"]
+    res, axis, cuts = run_slabs_threads(_Ids, nsteps, world, migrate_every=3, per_rank=per_rank)
+    assert axis == 2 and sum(r[5] for r in res) > 0           # particles did migrate
+    compact = []
+    for (f, ids, counts, lists, *rest), (Pr, sl) in zip(res, per_rank):
+        rows = np.searchsorted(gid_G, ids)
+        assert np.array_equal(gid_G[rows], ids)
+        f["I0"] = f["I0"] + sl["node_offset"]
+        cc = np.zeros(G.np_, np.int32)
+        ll = np.full((G.np_, lists.shape[1]), -7, np.int32)
+        cc[rows], ll[rows] = counts[ids], lists[ids]
+        compact.append((f, rows, cc, ll, *rest))
+    compare(G, single, compact, check_active=False)
+    assert np.abs(single[0]["Stress"]).max() > 0.0
+
+
 def test_excursion_is_latched():
     """Without migration a particle eventually leaves the band its slab may roam in: error 9."""
     nsteps = 60
