@@ -215,6 +215,32 @@ def test_u_verlet_host_call_matches_engine():
     eng.close()
 
 
+def test_async_download_snapshot_is_stream_ordered():
+    """nlps_b200_run_async / _download_begin / _download_end / _sync: the snapshot taken after step k
+    is what arrives on the host, although further steps were enqueued before the copy was issued."""
+    P = load_problem("dp")
+    eng = engine.Engine(P)
+    assert eng.run(0, 5) == 0
+    ref5 = eng.download()
+    eng.close()
+    eng = engine.Engine(P)
+    assert eng.run_async(0, 5) == 0 and eng.sync() == 0
+    eng.download_begin()
+    assert eng.run_async(5, 20) == 0          # the GPU steps on while the snapshot waits for its copy
+    got = eng.download_end()
+    assert eng.sync() == 0
+    for n in ("x_GC", "vel", "Stress", "F_n", "EPS_n", "I0", "NumberNodes"):
+        assert np.array_equal(got[n], ref5[n]), n
+    after = eng.download()
+    assert not np.array_equal(after["x_GC"], ref5["x_GC"])
+    ref = engine.Engine(P)
+    assert ref.run(0, 25) == 0
+    f25 = ref.download()
+    assert np.array_equal(after["x_GC"], f25["x_GC"]) and np.array_equal(after["Stress"], f25["Stress"])
+    ref.close()
+    eng.close()
+
+
 @pytest.mark.parametrize("sync_io", ("", "1"))
 def test_u_verlet_results_callback_sees_its_own_step(sync_io, monkeypatch):
     """Results steps (TimeStep % ResultsTimeStep == 0, U-Verlet.c:1097): the download of step k overlaps the following
