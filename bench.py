@@ -262,7 +262,10 @@ def run_ours(args):
     step_alg = (lambda n: 1272 + 4 * n) if c4 else (lambda n: 1096 + 4 * n) if c3 else (lambda n: 832 + 4 * n)
     if c4:
         cells, width = max(16 * world, int(round(160 * args.scale))), max(8, int(round(78 * args.scale)))
-        P, slab = synthetic.slope_slab_3d(rank, world, cells=cells, width=width, nsteps=nsteps_total)
+        # band of 4 cells: a slab must be wider than two bands, and the quantile cuts make the slabs at the tall end of
+        # the wedge ~10 layers thin at N=8 (with the default 6 they were clamped to 14 layers: 38 % more particles on rank 0);
+        # particles may roam 0.5 cell between two migrations, the gravity-driven velocities stay far below that
+        P, slab = synthetic.slope_slab_3d(rank, world, cells=cells, width=width, nsteps=nsteps_total, band_cells=4)
         if world == 1:
             eng = engine.Engine(P, device=local)
             total_particles = P.np_
@@ -298,6 +301,11 @@ def run_ours(args):
     assert eng.initialize_lme() == 0, eng.error()
     setup_s = time.perf_counter() - t_setup
     npart = eng.local_count() if world > 1 else P.np_
+    npart_max = npart
+    if world > 1:
+        tn = torch.tensor([npart], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+        npart_max = int(tn.item())
     # warm-up
     assert eng.run(0, Wm) == 0, eng.error()
     sampler, sampler2 = NvmlSampler(local), ClockSampler(local)
@@ -468,7 +476,7 @@ def run_ours(args):
                                         if c4 else "BASELINE configs[2]: 3D Neo-Hookean cube, explicit NPC-FS, LME gamma=6, GPxElement 8"
                                         if c3 else "BASELINE configs[1]: 2D granular column collapse, Drucker-Prager, "
                                         "explicit NPC-FS, LME gamma=3, GPxElement 4"),
-                           "particles_per_gpu": npart, "background_nodes": P.nn, "scale": args.scale,
+                           "particles_per_gpu": npart, "particles_max_rank": npart_max, "background_nodes": P.nn, "scale": args.scale,
                            "l2": "inputs larger than L2 (particle state + records ~0.7 GB per GPU)",
                            "multi_gpu": (f"strong scaling over {world} spatial slabs along z of the fixed problem (c4: cuts at particle-count quantiles): halo sums + migration every 10 steps"
                                          if c3 and world > 1 else

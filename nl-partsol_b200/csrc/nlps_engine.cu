@@ -350,9 +350,12 @@ __global__ void __launch_bounds__(256) k_mark(MeshDev m, GridDev G) {
   if (A >= m.nn) return;
   if (G.cnt[A] > 0 || G.rocc[A]) {
     // test before set: thousands of threads mark the same few bytes (the stale read is a benign race)
-    for (int q = m.r2p[A]; q < m.r2p[A + 1]; q++) { const int b = m.r2i[q] >> 8; if (!G.dirty_cur[b]) G.dirty_cur[b] = 1; }
-    for (int q = m.r1p[A]; q < m.r1p[A + 1]; q++) { const int b = m.r1i[q] >> 8; if (!G.dirty_cur[b]) G.dirty_cur[b] = 1; }
-    if (!G.dirty_cur[A >> 8]) G.dirty_cur[A >> 8] = 1;
+    // (consecutive ring entries mostly fall into the same 256-node block: one flag access per run; the 1-ring is a
+    // subset of the 2-ring wherever both exist, but nothing here relies on it)
+    int last = -1;
+    for (int q = m.r2p[A]; q < m.r2p[A + 1]; q++) { const int b = m.r2i[q] >> 8; if (b != last) { last = b; if (!G.dirty_cur[b]) G.dirty_cur[b] = 1; } }
+    for (int q = m.r1p[A]; q < m.r1p[A + 1]; q++) { const int b = m.r1i[q] >> 8; if (b != last) { last = b; if (!G.dirty_cur[b]) G.dirty_cur[b] = 1; } }
+    if ((A >> 8) != last && !G.dirty_cur[A >> 8]) G.dirty_cur[A >> 8] = 1;
   }
 }
 __global__ void __launch_bounds__(256) k_live(GridDev G, int nblocks) {
