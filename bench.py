@@ -262,10 +262,11 @@ def run_ours(args):
     step_alg = (lambda n: 1272 + 4 * n) if c4 else (lambda n: 1096 + 4 * n) if c3 else (lambda n: 832 + 4 * n)
     if c4:
         cells, width = max(16 * world, int(round(160 * args.scale))), max(8, int(round(78 * args.scale)))
-        # band of 4 cells: a slab must be wider than two bands, and the quantile cuts make the slabs at the tall end of
-        # the wedge ~10 layers thin at N=8 (with the default 6 they were clamped to 14 layers: 38 % more particles on rank 0);
-        # particles may roam 0.5 cell between two migrations, the gravity-driven velocities stay far below that
-        P, slab = synthetic.slope_slab_3d(rank, world, cells=cells, width=width, nsteps=nsteps_total, band_cells=4)
+        # band of 5 cells: a slab must be wider than two bands, and the quantile cuts make the slabs at the tall end of
+        # the wedge ~11 layers thin at N=8 (with the default 6 they were clamped to 14 layers: 33 % more particles on rank 0,
+        # 15 % with 5).  A particle's closest node may then sit one node layer beyond the cut between two migrations
+        # (band - 3.5 cells; a band of 4 leaves no room at all: the first crossing would be an excursion).
+        P, slab = synthetic.slope_slab_3d(rank, world, cells=cells, width=width, nsteps=nsteps_total, band_cells=5)
         if world == 1:
             eng = engine.Engine(P, device=local)
             total_particles = P.np_

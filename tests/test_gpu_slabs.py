@@ -199,7 +199,7 @@ def test_slope_slabs_match_global_engine(law):
 
     def make(r, w):
         P_, sl_ = synthetic.slope_slab_3d(r, w, cells=cells, width=width, nsteps=nsteps, ramp_steps=10, material=mat,
-                                          band_cells=4)      # as bench.py --workload c4
+                                          band_cells=5)      # as bench.py --workload c4
         if law == "nh_drift":
             P_.fields["vel"][:, 2] = -0.15 * P_.solver["cel"] * np.clip((P_.fields["x_GC"][:, 2] - 0.2) / 0.4, 0.0, 1.0)
         return P_, sl_
