@@ -11,6 +11,7 @@
  * switch its dispatch on.  Host glue only, as U-Verlet-b200.c.
  */
 #include "b200_flatten.h"
+#include "b200_vtk_binary.h" /* NLPS_B200_VTK_BINARY=1: binary twin of the reference's VTK writer */
 
 extern double DeltaTimeStep; /* U-Verlet-b200.c */
 
@@ -71,7 +72,7 @@ static int b200_implicit_scheme(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Param
         break;
       }
       lists_to_chains(MPM_Mesh, counts, lists, cap);
-      particle_results_vtk__InOutFun__(MPM_Mesh, TimeStep, ResultsTimeStep);
+      b200_write_particle_results(MPM_Mesh, TimeStep, ResultsTimeStep);
     }
   }
   if (STATUS == EXIT_SUCCESS) STATUS = b200_finish(eng, &in, FEM_Mesh, MPM_Mesh);

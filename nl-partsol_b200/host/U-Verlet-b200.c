@@ -21,6 +21,7 @@
  * Error convention as the reference: EXIT_SUCCESS / EXIT_FAILURE, RED message on stderr.
  */
 #include "b200_flatten.h"
+#include "b200_vtk_binary.h" /* NLPS_B200_VTK_BINARY=1: binary twin of the reference's VTK writer */
 
 double DeltaTimeStep; /* defined by U-Verlet.c:3 in the reference; other TUs reference it */
 
@@ -66,7 +67,7 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
     }
     if (pending_out >= 0) {
       if (nlps_b200_download_end(eng) != EXIT_SUCCESS) { STATUS = EXIT_FAILURE; break; }
-      particle_results_vtk__InOutFun__(MPM_Mesh, pending_out, ResultsTimeStep);
+      b200_write_particle_results(MPM_Mesh, pending_out, ResultsTimeStep);
       pending_out = -1;
     }
     if (nlps_b200_sync(eng) != EXIT_SUCCESS) {
@@ -84,7 +85,7 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
   }
   if (STATUS == EXIT_SUCCESS && pending_out >= 0) {
     if (nlps_b200_download_end(eng) != EXIT_SUCCESS) STATUS = EXIT_FAILURE;
-    else particle_results_vtk__InOutFun__(MPM_Mesh, pending_out, ResultsTimeStep);
+    else b200_write_particle_results(MPM_Mesh, pending_out, ResultsTimeStep);
   }
 
   if (STATUS == EXIT_SUCCESS) STATUS = b200_finish(eng, &in, FEM_Mesh, MPM_Mesh);

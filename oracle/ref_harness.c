@@ -611,3 +611,18 @@ int refh_stiffness_nh(double *out, const double *dN_alpha_n1, const double *dN_b
   M.nu = nu;
   return compute_stiffness_density_Neo_Hookean(out, dN_alpha_n1, dN_beta_n1, dN_alpha_n, dN_beta_n, S, M);
 }
+
+/* The particle VTK writers on the harness' current state: the reference's own ASCII writer (binary == 0) or its binary
+ * twin of nl-partsol_b200/host/b200_vtk_binary.h (binary == 1; returns 1 when it declines).  Files go to OutputDir. */
+#include "b200_vtk_binary.h"
+int refh_write_vtk(int step, int results_every, int binary, const char *dir, const char *stem) {
+  strcpy(OutputDir, dir);
+  strcpy(OutputParticlesFile, stem);
+  if (binary) return b200_particle_results_vtk_binary(MPM_Mesh, step, results_every);
+  particle_results_vtk__InOutFun__(MPM_Mesh, step, results_every);
+  return 0;
+}
+void refh_set_outputs(int all) {
+  Out_global_coordinates = Out_mass = Out_density = Out_nodal_idx = Out_material_idx = Out_velocity = Out_acceleration =
+      Out_displacement = Out_stress = Out_volumetric_stress = Out_deformation_gradient = Out_energy = Out_EPS = all != 0;
+}

@@ -45,6 +45,37 @@ def test_reference_driver_with_b200_scheme(tmp_path):
 
 
 @pytest.mark.gpu
+def test_reference_driver_binary_vtk_output(tmp_path):
+    """NLPS_B200_VTK_BINARY=1: the shim writes the results steps with the binary twin of the reference's writer
+    (host/b200_vtk_binary.h), overlapped with the following steps; positions and stresses of the plastic
+    deck against the golden trace."""
+    if not os.path.exists(BIN):
+        pytest.skip("drop-in binary not built (needs /root/reference at build time)")
+    import deckgen
+    import make_golden
+    import vtkio
+    from util import load_trace
+    spec = make_golden.spec_for("dp")
+    spec.out_every = 1
+    deckgen.write_deck(spec, str(tmp_path))
+    r = subprocess.run([BIN, "--FORMULATION-U", "-f", "deck.nlp"], cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, NLPS_B200_VTK_BINARY="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    tr = load_trace("dp")
+    for cp in (1, 5, 60, 120):
+        files = glob.glob(os.path.join(str(tmp_path), "Results", f"*_{cp - 1}.vtk"))
+        assert files, f"no VTK for step {cp - 1}"
+        assert b"BINARY" in open(files[0], "rb").read(200)
+        v = vtkio.read_binary(files[0])
+        x, ref = v["POINTS"][:, :2], tr[f"s{cp}_x_GC"]
+        assert np.abs(x - ref).max() <= 1e-10 * np.abs(ref).max()
+        if "STRESS" in v:
+            s_ref = tr[f"s{cp}_Stress"]
+            got = v["STRESS"][:, [0, 1, 3, 4, 8]]
+            assert np.abs(got - s_ref).max() <= 1e-9 * max(np.abs(s_ref).max(), 1.0)
+
+
+@pytest.mark.gpu
 def test_reference_driver_with_b200_implicit_scheme(tmp_path):
     """`NLPS-Solver (Type=Newmark-beta-Finite-Strains)`: the reference driver (compiled with -DUSE_PETSC against
     stand-in headers, no PETSc library) dispatches to U_Newmark_Beta, which here is the B200 shim.  The VTK
