@@ -585,34 +585,39 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(GridDev G, const int* row_ptr,
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int nact = *G.n_active;
   double dot = 0.0, dyy = 0.0;
+  // lane <-> (block of the row, row i of the block): D contiguous doubles of K and the D values of x per lane and
+  // block (a third of the instructions of a lane-per-scalar-entry mapping: the kernel is bound by issue slots before HBM)
+  constexpr int BPW = 32 / D;               // blocks per warp sweep (10 in 3D: lanes 30, 31 idle)
+  const int sub = lane % D, lb = lane / D;
   for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < nact; t += gridDim.x * wpb) {
-    const int q0 = row_ptr[t], nent = (row_ptr[t + 1] - q0) * DD;
-    const double* v = vals + (size_t)q0 * DD;
-    double acc[D];
+    const int q0 = row_ptr[t], nb = row_ptr[t + 1] - q0;
+    const double* v = vals + (size_t)q0 * DD + sub * D;
+    double acc = 0.0;
+    if (lb < BPW) {
+      for (int blk = lb; blk < nb; blk += BPW) {
+        const int c = cols[q0 + blk];
+        const unsigned fxc = fxr[c];
+        const double* kv = v + (size_t)blk * DD;
+        const double* xv = x + (size_t)c * D;
 #pragma unroll
-    for (int i = 0; i < D; i++) acc[i] = 0.0;
-    for (int e = lane; e < nent; e += 32) {
-      const int blk = e / DD, ij = e - blk * DD, i = ij / D, j = ij - i * D;
-      const int c = cols[q0 + blk];
-      const double xv = ((fxr[c] >> j) & 1u) ? 0.0 : x[(size_t)c * D + j];
-      const double cv = v[e] * xv;
-#pragma unroll
-      for (int k = 0; k < D; k++) acc[k] += (k == i) ? cv : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < D; i++)
-      for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
-    if (lane == 0) {
-      const double M = G.M[G.act_list[t]];
-      const unsigned fx = fxr[t];
-#pragma unroll
-      for (int i = 0; i < D; i++) {
-        const double xi = x[(size_t)t * D + i];
-        const double yi = ((fx >> i) & 1u) ? xi : acc[i] + a1 * M * xi;
-        y[(size_t)t * D + i] = yi;
-        dot += w[(size_t)t * D + i] * yi;
-        dyy += yi * yi;
+        for (int j = 0; j < D; j++) acc += kv[j] * (((fxc >> j) & 1u) ? 0.0 : xv[j]);
       }
+    }
+    // sum over the lanes of the same block row (lane stride D); BPW need not be a power of two
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (o >= BPW) continue;
+      const double other = __shfl_down_sync(0xffffffffu, acc, o * D);
+      if (lb < o && lb + o < ((2 * o < BPW) ? 2 * o : BPW)) acc += other;
+    }
+    if (lane < D) {
+      const int i = lane;
+      const double M = G.M[G.act_list[t]];
+      const double xi = x[(size_t)t * D + i];
+      const double yi = ((fxr[t] >> i) & 1u) ? xi : acc + a1 * M * xi;
+      y[(size_t)t * D + i] = yi;
+      dot += w[(size_t)t * D + i] * yi;
+      dyy += yi * yi;
     }
   }
   const double s = block_sum(dot, sh);
