@@ -49,3 +49,41 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CUDA device"):
         engine.Engine(synthetic.block_2d(cells=4, nsteps=2))
+
+
+def test_slope_slabs_partition_the_global_slope():
+    """bench.py --workload c4 host logic (no GPU): the per-rank slope problems of synthetic.slope_slab_3d tile the
+    single-domain slope -- every particle of the global problem is owned by exactly one slab (by its closest node and the
+    cuts), global ids match positions bit for bit, the quantile cuts balance the particle counts."""
+    import numpy as np
+    from nlps_b200 import synthetic
+    cells, width, world = 48, 4, 4
+    G, none = synthetic.slope_slab_3d(0, 1, cells=cells, width=width, nsteps=2, band_cells=5)
+    assert none is None
+    assert G.np_ == 8 * width * cells * (cells + 1) // 2
+    gid_G = (G.kept_cells.astype(np.int64)[:, None] * 8 + np.arange(8)[None, :]).ravel()
+    xg = G.fields["x_GC"]
+    owned = np.zeros(G.np_, np.int32)
+    counts = []
+    for r in range(world):
+        P, sl = synthetic.slope_slab_3d(r, world, cells=cells, width=width, nsteps=2, band_cells=5)
+        assert sl["n_particles"] == G.np_ and sl["axis"] == 2 and len(sl["cuts"]) == world - 1
+        rows = np.searchsorted(gid_G, sl["global_id"])
+        assert np.array_equal(gid_G[rows], sl["global_id"])
+        assert np.array_equal(P.fields["x_GC"], xg[rows])              # same bits as the global problem
+        assert np.array_equal(P.coords[P.I0], G.coords[G.I0[rows]])    # same closest node, in sub-mesh numbering
+        z = P.coords[P.I0][:, 2]                                       # the owner is decided by the closest node layer
+        lo = sl["cuts"][r - 1] if r > 0 else -np.inf
+        hi = sl["cuts"][r] if r < world - 1 else np.inf
+        mine = (z > lo) & (z < hi)
+        owned[rows[mine]] += 1
+        counts.append(int(mine.sum()))
+        assert (P.I0 + sl["node_offset"] == G.I0[rows]).all()          # z sub-mesh: node ids differ by a constant
+    assert np.all(owned == 1)
+    # quantile cuts: balanced wherever the slabs may be thinner than the clamp (two halo bands + 2 layers)
+    c2 = []
+    for r in range(2):
+        P, sl = synthetic.slope_slab_3d(r, 2, cells=cells, width=width, nsteps=2, band_cells=5)
+        z = P.coords[P.I0][:, 2]
+        c2.append(int(((z > sl["cuts"][0]) if r else (z < sl["cuts"][0])).sum()))
+    assert sum(c2) == G.np_ and max(c2) <= 1.1 * G.np_ / 2, c2
