@@ -58,12 +58,14 @@ def test_more_slabs_than_layers_is_refused():
         engine.slab_cuts(P, 64)
 
 
-def test_slab_protocol_world2_gloo():
+@pytest.mark.parametrize("case,port", [("column2d", "29731"), ("slope3d", "29733")])
+def test_slab_protocol_world2_gloo(case, port):
     """Two gloo ranks, each stepping its slab with the oracle and exchanging exactly what the engine
-    exchanges; particle fields match the single-domain oracle to 1e-10, lists bit-exact."""
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    exchanges; particle fields match the single-domain oracle to 1e-10, lists bit-exact.  column2d: the
+    Drucker-Prager column of the bench line; slope3d: the Matsuoka-Nakai slope of bench.py --workload c4."""
+    env = dict(os.environ, OMP_NUM_THREADS="2", SLAB_CASE=case)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tests", "workers", "slab_gloo_worker.py")]
+           "127.0.0.1", "--master-port", port, os.path.join(ROOT, "tests", "workers", "slab_gloo_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("steps OK") == 2
