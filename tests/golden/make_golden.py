@@ -171,9 +171,62 @@ def gen_tangent_blocks(_case="all"):
     print("tangent blocks:", {k: v.shape for k, v in out.items()})
 
 
+def gen_points3d(case):
+    """3D material points through the reference's OWN compiled 3D laws (oracle/_ref/libnlps3d_laws_ref.so = Drucker-Prager.c /
+    Matsuoka-Nakai.c / Elastoplastic-Tangent-Matrix.c built with NumberDimensions == 3 + oracle/ref_harness3d.c; `make -C oracle
+    ref3d`): sheared strain paths that rotate the principal axes, so that the row-indexed eigenvectors of the plastic branches
+     are exercised in 3D, plus tangent blocks on the resulting states."""
+    import ctypes
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "nl-partsol_b200"))
+    from nlps_b200 import synthetic
+    L = ctypes.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libnlps3d_laws_ref.so"))
+    dp_ = ctypes.POINTER(ctypes.c_double)
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    law, mpar = {"dp": synthetic.DP_C2, "mn": synthetic.MN_C4}[case]
+    mpar = arr(mpar)
+    tol, mi = {"dp": (1e-14, 10), "mn": (1e-10, 20)}[case]
+    rng = np.random.default_rng(20261020 + (case == "mn"))
+    rows_in, rows_out, tang_in, tang_out = [], [], [], []
+    for path in range(16):
+        be, eps, kap, F = np.eye(3).ravel(), 0.0, float(mpar[4]), np.eye(3)
+        amp = 10.0 ** rng.uniform(-3.6, -2.2)
+        drift = rng.standard_normal((3, 3))
+        for step in range(40):
+            D = np.eye(3) + amp * (-np.abs(drift) * np.eye(3) * (1.0 if case == "mn" else 2.0) + 0.5 * drift +
+                                   0.2 * rng.standard_normal((3, 3)))
+            if path == 0:
+                D = np.diag([1.0, 0.999, 1.0])      # the reference's stand-alone test path, in 3D
+            F = D @ F
+            st, be1, cep = np.zeros(9), np.zeros(9), np.zeros(9)
+            e1, k1, W = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+            Dc, Fc, bec = arr(D.ravel()), arr(F.ravel()), arr(be)
+            rc = L.refh3_stress_point(law.encode(), mpar.ctypes.data_as(dp_), ctypes.c_double(tol), mi, Dc.ctypes.data_as(dp_),
+                                      Fc.ctypes.data_as(dp_), bec.ctypes.data_as(dp_), ctypes.c_double(eps),
+                                      ctypes.c_double(kap), st.ctypes.data_as(dp_), be1.ctypes.data_as(dp_), ctypes.byref(e1),
+                                      ctypes.byref(k1), ctypes.byref(W), cep.ctypes.data_as(dp_))
+            if rc != 0 or not np.all(np.isfinite(st)) or not np.all(np.isfinite(cep)):
+                break
+            rows_in.append(np.concatenate([D.ravel(), F.ravel(), [float(np.linalg.det(F))], be, [eps, kap]]))
+            rows_out.append(np.concatenate([st, be1, [e1.value, k1.value, W.value], cep]))
+            if step % 5 == 4:
+                u, v = rng.standard_normal(3), rng.standard_normal(3)
+                K = np.zeros(9)
+                b2, s2, c2 = be1.copy(), st.copy(), cep.copy()
+                assert L.refh3_stiffness_ep(K.ctypes.data_as(dp_), arr(u).ctypes.data_as(dp_), arr(v).ctypes.data_as(dp_),
+                                            b2.ctypes.data_as(dp_), s2.ctypes.data_as(dp_), c2.ctypes.data_as(dp_)) == 0
+                tang_in.append(np.concatenate([u, v, be1, st, cep]))
+                tang_out.append(K)
+            be, eps, kap = be1, e1.value, k1.value
+    rows_in, rows_out = np.array(rows_in), np.array(rows_out)
+    np.savez_compressed(os.path.join(HERE, f"{case}_points3d.npz"), inputs=rows_in, outputs=rows_out, mat_type=np.array(law),
+                        mat_params=mpar, tol_radial=tol, maxiter_radial=mi, tang_in=np.array(tang_in),
+                        tang_out=np.array(tang_out))
+    print(case, "3D points:", len(rows_in), "plastic:", int((rows_out[:, 18] != rows_in[:, 28]).sum()), "tangents:", len(tang_in))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
@@ -181,3 +234,5 @@ if __name__ == "__main__":
         for c in ("dp", "mn"):
             subprocess.run([sys.executable, __file__, "points", c], check=True)
         subprocess.run([sys.executable, __file__, "tangent", "all"], check=True)
+        for c in ("dp", "mn"):
+            subprocess.run([sys.executable, __file__, "points3d", c], check=True)

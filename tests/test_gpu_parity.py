@@ -186,6 +186,38 @@ def test_material_points_match_reference(case):
         assert bad.sum() <= (3 if nm in loose else 0), (nm, int(bad.sum()), float(e[bad].max()))
 
 
+@pytest.mark.parametrize("case", ["dp", "mn"])
+def test_3d_material_points_against_the_compiled_reference(case):
+    """The device's 3D Drucker-Prager / Matsuoka-Nakai updates on the strain paths frozen from the reference's OWN compiled
+    3D laws (tests/golden/*_points3d.npz, oracle/ref_harness3d.c).  With quirk_transposed_eigvec = 1 (row-indexed
+    eigenvectors in the plastic branches, SURVEY F10-i, which the compiled 3D laws do have) the kernel reproduces the
+    reference; the engine's 3D default (0, the intended column form) agrees on the elastic steps only."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"{case}_points3d.npz"))
+    X, Y = z["inputs"], z["outputs"]
+    plastic = (Y[:, 18] != X[:, 28]) | (Y[:, 19] != X[:, 29])
+    s = np.abs(Y[:, :9]).max(axis=1) + 1.0
+
+    def run(quirk):
+        r = engine.stress_points(3, str(z["mat_type"]), z["mat_params"], float(z["tol_radial"]), int(z["maxiter_radial"]),
+                                 X[:, 0:9], X[:, 9:18], X[:, 18], X[:, 19:28], X[:, 28], X[:, 29], quirk=quirk)
+        assert np.all(r["status"] == 0)
+        return r
+    r1 = run(1)
+    d = np.abs(r1["stress"] - Y[:, :9]).max(axis=1) / s
+    tol = 1e-10 if case == "dp" else 1e-7      # MN: 5x5 Newton stopped at 1e-10 on badly conditioned systems (DESIGN 6.6)
+    # a rotated plastic state whose trial eigenvalues nearly coincide has no stable eigenvector signs: allow a few
+    assert (d > tol).sum() <= (0 if case == "dp" else 6), (int((d > tol).sum()), float(d.max()))
+    de = np.abs(r1["eps_n1"] - Y[:, 18])
+    if case == "dp":
+        assert de.max() <= 1e-12
+    else:   # MN's internal variables are defined to solver tolerance x conditioning only (see the 2D test above)
+        assert (de > 1e-6).mean() <= 0.05, (int((de > 1e-6).sum()), float(de.max()))     # measured: 16 of 608, max 5e-4
+    r0 = run(0)
+    d0 = np.abs(r0["stress"] - Y[:, :9]).max(axis=1) / s
+    assert d0[~plastic].max() <= 1e-9 and d0[plastic].max() > 1e-2
+
+
 def test_error_latch_negative_jacobian():
     """Device-side failure is surfaced through the reference's EXIT_FAILURE convention."""
     P = load_problem("nh")
