@@ -94,7 +94,11 @@ typedef struct nlps_solver {
   double tol_radial_returning;
   int max_iter_radial_returning;
   double thickness;
-  int quirk_transposed_eigvec; /* -1 = default (1 in 2D, 0 in 3D); SURVEY F10-i */
+  int quirk_transposed_eigvec; /* the reference's plastic branches index the eigenvector matrix by row
+                                * (Drucker-Prager.c:957-958).  -1 = default: 1 in 2D (bit-compatible with the reference),
+                                * 0 in 3D (the intended column form; the compiled 3D laws do have the row form and 1
+                                * reproduces them, but its result depends on the arbitrary eigenvectors of degenerate
+                                * trial states -- DESIGN.md section 6, deviation 3) */
   int compute_c_ep;            /* write Phi.C_ep (needed by the implicit tangent only) */
 } nlps_solver;
 
