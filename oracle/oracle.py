@@ -170,6 +170,15 @@ class Oracle:
         self.L.orc_newmark_setup(self.h, ctypes.c_double(beta), ctypes.c_double(gamma), ctypes.c_double(tol),
                                  int(max_iter), int(explicit_trial))
 
+    def lme_point(self, l, lam, beta):
+        """Newton for lambda from `lam`, then N and grad N, for one particle given l = x_p - x_a (n x d)."""
+        l, lam = _d(l), _d(lam).copy()
+        n = l.shape[0]
+        N, dN = np.zeros(n), np.zeros((n, self.d))
+        st = self.L.orc_lme_point(self.h, n, l.ctypes.data_as(_dp), lam.ctypes.data_as(_dp), ctypes.c_double(beta),
+                                  N.ctypes.data_as(_dp), dN.ctypes.data_as(_dp))
+        return st, lam, N, dN
+
     def static_setup(self, tol=1e-10, max_iter=10):
         """U_Static: the implicit loop without inertia (U-Static.c)."""
         self.L.orc_static_setup(self.h, ctypes.c_double(tol), int(max_iter))

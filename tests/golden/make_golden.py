@@ -224,9 +224,53 @@ def gen_points3d(case):
     print(case, "3D points:", len(rows_in), "plastic:", int((rows_out[:, 18] != rows_in[:, 28]).sum()), "tangents:", len(tang_in))
 
 
+def gen_lme3d(_case="all"):
+    """3D LME evaluations through the reference's OWN compiled LME.c (oracle/_ref/libnlps3d_lme_ref.so = Nodes/LME.c +
+    its Matlib helpers built with NumberDimensions == 3 behind oracle/ref_harness3d_lme.c): for particles of a jittered 3D
+    cloud (neighbour sets of 20-110 nodes, gamma 3 and 6) the converged lambda of __lambda_Newton_Rapson from two start
+    values (the cloud's own lambda and zero), N = p__LME__ and grad N = dp__LME__."""
+    import ctypes
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "nl-partsol_b200"))
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+    import oracle
+    from nlps_b200 import synthetic
+    L = ctypes.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libnlps3d_lme_ref.so"))
+    dp_ = ctypes.POINTER(ctypes.c_double)
+    rows = []
+    for gamma in (6.0, 3.0):
+        P = synthetic.structured_problem(3, (8, 8, 8), 0.125, (4, 4, 4), (2, 2, 0), synthetic.NH_C1, 4, 0.5, 40.0,
+                                         (0.0, 0.0, -9.81), gamma_lme=gamma, jitter=0.2,
+                                         rollers=("left", "right", "front", "back"))
+        o = oracle.Oracle(P)
+        assert o.init_lme() == 0
+        for k in range(2):
+            assert o.step(k) == 0
+        x, lam, beta, lists, nn = o.field("x_GC"), o.field("lambda"), o.field("Beta"), o.lists(), o.ints("NumberNodes")
+        for p in range(0, P.np_, 3):
+            n = int(nn[p])
+            l = np.ascontiguousarray(x[p][None, :] - P.coords[lists[p, :n]])
+            for start in (lam[p].copy(), np.zeros(3)):
+                lm = np.ascontiguousarray(start, dtype=np.float64).copy()
+                N, dN = np.zeros(n), np.zeros((n, 3))
+                st = L.refh3_lme_point(n, l.ctypes.data_as(dp_), lm.ctypes.data_as(dp_), ctypes.c_double(float(beta[p])),
+                                       ctypes.c_double(P.solver["tol_wrapper"]), int(P.solver["max_iter_lme"]),
+                                       N.ctypes.data_as(dp_), dN.ctypes.data_as(dp_))
+                assert st == 0
+                rows.append(dict(l=l, start=np.array(start, float), beta=float(beta[p]), lam=lm, N=N, dN=dN))
+    cap = max(len(r["N"]) for r in rows)
+    pad = lambda a, shape: np.pad(a, [(0, s - t) for s, t in zip(shape, a.shape)])
+    np.savez_compressed(os.path.join(HERE, "lme_points3d.npz"),
+                        n=np.array([len(r["N"]) for r in rows]), l=np.array([pad(r["l"], (cap, 3)) for r in rows]),
+                        start=np.array([r["start"] for r in rows]), beta=np.array([r["beta"] for r in rows]),
+                        lam=np.array([r["lam"] for r in rows]), N=np.array([pad(r["N"], (cap,)) for r in rows]),
+                        dN=np.array([pad(r["dN"], (cap, 3)) for r in rows]), tol_wrapper=1e-10, max_iter=10)
+    ns = [len(r["N"]) for r in rows]
+    print("3D LME points:", len(rows), "neighbours", min(ns), "-", max(ns))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
@@ -236,3 +280,4 @@ if __name__ == "__main__":
         subprocess.run([sys.executable, __file__, "tangent", "all"], check=True)
         for c in ("dp", "mn"):
             subprocess.run([sys.executable, __file__, "points3d", c], check=True)
+        subprocess.run([sys.executable, __file__, "lme3d", "all"], check=True)

@@ -79,3 +79,23 @@ def test_3d_elastoplastic_tangent_block_matches_the_compiled_reference(case):
             continue
         worst = max(worst, np.abs(K - ref).max() / max(np.abs(ref).max(), 1e-300))
     assert worst <= 1e-9, worst
+
+
+def test_3d_lme_matches_the_compiled_reference():
+    """K0 in 3D: the Newton solve for lambda (LME.c:272-353, from the cloud's own lambda and from zero), N = p__LME__ and
+    grad N = dp__LME__ (:700-891) of the oracle against the reference's own LME.c compiled with NumberDimensions == 3
+    (oracle/ref_harness3d_lme.c, tests/golden/lme_points3d.npz: 684 evaluations, 24-111 neighbours, gamma 3 and 6)."""
+    g = np.load(os.path.join(GOLD, "lme_points3d.npz"))
+    P = synthetic.cube_3d(cells=2, nsteps=2)
+    P.solver["tol_wrapper"], P.solver["max_iter_lme"] = float(g["tol_wrapper"]), int(g["max_iter"])
+    o = oracle.Oracle(P)
+    worst = dict(lam=0.0, N=0.0, dN=0.0)
+    for k in range(len(g["n"])):
+        n = int(g["n"][k])
+        st, lam, N, dN = o.lme_point(g["l"][k, :n], g["start"][k], float(g["beta"][k]))
+        assert st == 0
+        assert abs(N.sum() - 1.0) < 1e-13
+        worst["lam"] = max(worst["lam"], np.abs(lam - g["lam"][k]).max() / max(np.abs(g["lam"][k]).max(), 1.0))
+        worst["N"] = max(worst["N"], np.abs(N - g["N"][k, :n]).max())
+        worst["dN"] = max(worst["dN"], np.abs(dN - g["dN"][k, :n]).max() / np.abs(g["dN"][k, :n]).max())
+    assert worst["lam"] <= 1e-12 and worst["N"] <= 1e-13 and worst["dN"] <= 1e-11, worst
