@@ -6,8 +6,9 @@
  *     Constitutive/Plasticity/Drucker-Prager.c, Matsuoka-Nakai.c, Elastoplastic-Tangent-Matrix.c
  * compiled from where they lie WITHOUT -DUSE_PLAINSTRAIN (NumberDimensions == 3, Macros.h:34-36) by `make ref3d`.  This
  * file gives them the two driver globals they read and flat entry points, so that the 3D branches of the oracle port
- * (oracle/nlps_oracle.c) are pinned to compiled reference code for the laws of BASELINE configs[3] (tests/golden/
- * points3d_*.npz, tests/test_oracle_3d_laws.py).  LME, kinematics and Neo-Hookean in 3D stay restated (they need TensorLib).
+ * (oracle/nlps_oracle.c) are pinned to compiled reference code for the laws of BASELINE configs[2]-[4] (tests/golden/
+ * {dp,mn,nh}_points3d.npz, tests/test_oracle_3d_laws.py).  Neo-Hookean.c and Particles/compute-Strains.c join them further
+ * down; the 3D LME has its own harness (ref_harness3d_lme.c).
  */
 #include <stdbool.h>
 #include <stdio.h>
@@ -19,6 +20,7 @@
 #include "Constitutive/Plasticity/Drucker-Prager.h"
 #include "Constitutive/Plasticity/Matsuoka-Nakai.h"
 #include "Constitutive/Plasticity/Elastoplastic-Tangent-Matrix.h"
+#include "Constitutive/Hyperelastic/Neo-Hookean.h"
 
 #if NumberDimensions != 3
 #error "ref_harness3d.c is the 3D build: compile without -DUSE_PLAINSTRAIN"
@@ -85,4 +87,46 @@ int refh3_stiffness_ep(double *out, const double *dN_alpha_n1, const double *dN_
   S.Stress = stress;
   S.C_ep = C_ep;
   return compute_stiffness_elastoplastic__Constitutive__(out, dN_alpha_n1, dN_beta_n1, S);
+}
+
+/* ---- Neo-Hookean in 3D (BASELINE configs[2] and [4]): Constitutive/Hyperelastic/Neo-Hookean.c and Particles/compute-Strains.c
+ * compile in 3D; the Kirchhoff stress, its energy and the tangent block only reach left_Cauchy_Green__Particles__ (plain
+ * arithmetic).  The TensorLib symbols other functions of those two TUs reference are unreachable from here and abort. */
+static void unreachable3d(const char *what) { fprintf(stderr, "ref_harness3d: %s reached\n", what); abort(); }
+#define STUB_TENSOR(name, args) Tensor name args { unreachable3d(#name); Tensor t_; memset(&t_, 0, sizeof(t_)); return t_; }
+STUB_TENSOR(alloc__TensorLib__, (int o))
+STUB_TENSOR(Identity__TensorLib__, (void))
+STUB_TENSOR(Inverse__TensorLib__, (Tensor a))
+STUB_TENSOR(dyadic_Product__TensorLib__, (Tensor a, Tensor b))
+STUB_TENSOR(vector_linear_mapping__TensorLib__, (Tensor a, Tensor b))
+STUB_TENSOR(matrix_product_old__TensorLib__, (Tensor a, Tensor b))
+void free__TensorLib__(Tensor a) { (void)a; unreachable3d("free__TensorLib__"); }
+/* the strain energy of Neo-Hookean.c calls I1__TensorLib__, whose 3D branch is the line that stops TensorLib.c from compiling
+ * (TensorLib.c:120 assigns the trace to an undeclared `I3`): restated as the trace it evidently means */
+double I1__TensorLib__(const double *a) { return a[0] + a[4] + a[8]; }
+double I3__TensorLib__(const double *a) { (void)a; unreachable3d("I3__TensorLib__"); return 0.0; }
+double inner_product__TensorLib__(Tensor a, Tensor b) { (void)a; (void)b; unreachable3d("inner_product__TensorLib__"); return 0.0; }
+int compute_inverse__TensorLib__(double *o, const double *a) { (void)o; (void)a; unreachable3d("compute_inverse__TensorLib__"); return 1; }
+int compute_adjunt__TensorLib__(double *o, const double *a) { (void)o; (void)a; unreachable3d("compute_adjunt__TensorLib__"); return 1; }
+void matrix_product__TensorLib__(double *o, const double *a, const double *b) { (void)o; (void)a; (void)b; unreachable3d("matrix_product__TensorLib__"); }
+
+int refh3_stress_nh(double E, double nu, const double *F_n1, double J, double *stress, double *W) {
+  Material M;
+  State_Parameters S;
+  memset(&M, 0, sizeof(M));
+  memset(&S, 0, sizeof(S));
+  double Dphi[9];
+  memcpy(Dphi, F_n1, sizeof(Dphi));
+  M.E = E; M.nu = nu;
+  S.Stress = stress; S.D_phi_n1 = Dphi; S.J = J; S.W = W;
+  return compute_Kirchhoff_Stress_Neo_Hookean__Constitutive__(S, M);
+}
+int refh3_stiffness_nh(double *out, const double *dN_alpha_n1, const double *dN_beta_n1, const double *dN_alpha_n,
+                       const double *dN_beta_n, double *F_n, double J, double E, double nu) {
+  State_Parameters S;
+  Material M;
+  memset(&S, 0, sizeof(S));
+  memset(&M, 0, sizeof(M));
+  S.D_phi_n = F_n; S.J = J; M.E = E; M.nu = nu;
+  return compute_stiffness_density_Neo_Hookean(out, dN_alpha_n1, dN_beta_n1, dN_alpha_n, dN_beta_n, S, M);
 }

@@ -268,9 +268,41 @@ def gen_lme3d(_case="all"):
     print("3D LME points:", len(rows), "neighbours", min(ns), "-", max(ns))
 
 
+def gen_nh3d(_case="all"):
+    """Neo-Hookean in 3D through the reference's compiled Neo-Hookean.c (oracle/_ref/libnlps3d_laws_ref.so): Kirchhoff stress
+    and strain energy (Neo-Hookean.c:38-85) on random deformation gradients, tangent blocks (:89-141) on random states."""
+    import ctypes
+    L = ctypes.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libnlps3d_laws_ref.so"))
+    dp_ = ctypes.POINTER(ctypes.c_double)
+    arr = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    rng = np.random.default_rng(20261021)
+    s_in, s_out, t_in, t_out = [], [], [], []
+    for k in range(200):
+        F = np.eye(3) + 10.0 ** rng.uniform(-3, -0.7) * rng.standard_normal((3, 3))
+        if np.linalg.det(F) <= 0.1:
+            continue
+        J, E, nu = float(np.linalg.det(F)), 10.0 ** rng.uniform(4, 8), rng.uniform(0.0, 0.45)
+        T, W, Fc = np.zeros(9), ctypes.c_double(), arr(F.ravel())
+        assert L.refh3_stress_nh(ctypes.c_double(E), ctypes.c_double(nu), Fc.ctypes.data_as(dp_), ctypes.c_double(J),
+                                 T.ctypes.data_as(dp_), ctypes.byref(W)) == 0
+        s_in.append(np.concatenate([F.ravel(), [J, E, nu]]))
+        s_out.append(np.concatenate([T, [W.value]]))
+        u, v, un, vn = (arr(rng.standard_normal(3)) for _ in range(4))
+        K, Fn = np.zeros(9), arr(F.ravel())
+        Jt = float(J * (1 + 0.05 * rng.standard_normal()))
+        assert L.refh3_stiffness_nh(K.ctypes.data_as(dp_), u.ctypes.data_as(dp_), v.ctypes.data_as(dp_), un.ctypes.data_as(dp_),
+                                    vn.ctypes.data_as(dp_), Fn.ctypes.data_as(dp_), ctypes.c_double(Jt), ctypes.c_double(E),
+                                    ctypes.c_double(nu)) == 0
+        t_in.append(np.concatenate([u, v, un, vn, F.ravel(), [Jt, E, nu]]))
+        t_out.append(K)
+    np.savez_compressed(os.path.join(HERE, "nh_points3d.npz"), s_in=np.array(s_in), s_out=np.array(s_out), t_in=np.array(t_in),
+                        t_out=np.array(t_out))
+    print("3D NH points:", len(s_in), "tangent blocks:", len(t_in))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
@@ -281,3 +313,4 @@ if __name__ == "__main__":
         for c in ("dp", "mn"):
             subprocess.run([sys.executable, __file__, "points3d", c], check=True)
         subprocess.run([sys.executable, __file__, "lme3d", "all"], check=True)
+        subprocess.run([sys.executable, __file__, "nh3d", "all"], check=True)

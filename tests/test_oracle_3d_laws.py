@@ -99,3 +99,22 @@ def test_3d_lme_matches_the_compiled_reference():
         worst["N"] = max(worst["N"], np.abs(N - g["N"][k, :n]).max())
         worst["dN"] = max(worst["dN"], np.abs(dN - g["dN"][k, :n]).max() / np.abs(g["dN"][k, :n]).max())
     assert worst["lam"] <= 1e-12 and worst["N"] <= 1e-13 and worst["dN"] <= 1e-11, worst
+
+
+def test_3d_neo_hookean_matches_the_compiled_reference():
+    """BASELINE configs[2] / [4]: Kirchhoff stress + strain energy (Neo-Hookean.c:38-85) and the tangent block (:89-141) of
+    the oracle in 3D against the reference's compiled Neo-Hookean.c (tests/golden/nh_points3d.npz)."""
+    g = np.load(os.path.join(GOLD, "nh_points3d.npz"))
+    for row, ref in zip(g["t_in"], g["t_out"]):
+        K = oracle.stiffness_nh(3, row[0:3], row[3:6], row[6:9], row[9:12], row[12:21], row[21], row[22], row[23])
+        assert np.abs(K - ref).max() <= 1e-14 * max(np.abs(ref).max(), 1e-300)
+    worst_s = worst_w = 0.0
+    for row, ref in zip(g["s_in"], g["s_out"]):
+        F, J, E, nu = row[0:9], float(row[9]), float(row[10]), float(row[11])
+        P = synthetic.cube_3d(cells=2, nsteps=2, material=("Neo-Hookean-Wriggers", [1000.0, E, nu] + [0.0] * 13))
+        o = oracle.Oracle(P)
+        a = o.stress_point(0, np.eye(3).ravel(), F, J, np.eye(3).ravel(), 0.0, 0.0)
+        assert a["status"] == 0
+        worst_s = max(worst_s, np.abs(a["stress"] - ref[:9]).max() / max(np.abs(ref[:9]).max(), 1e-300))
+        worst_w = max(worst_w, abs(a["W"] - ref[9]) / max(abs(ref[9]), 1e-300))
+    assert worst_s <= 1e-13 and worst_w <= 1e-10, (worst_s, worst_w)
