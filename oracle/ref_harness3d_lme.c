@@ -62,3 +62,55 @@ int refh3_lme_point(int n, const double *l, double *lambda, double beta, double 
   return status;
 }
 double refh3_beta(double gamma, double h_avg) { return beta__LME__(gamma, h_avg); }
+
+/* tributary__LME__ (LME.c:1019-1099, static: reachable because this TU includes LME.c) on one particle: the candidate nodes
+ * are the 2-ring of its closest node in chain order, with their coordinates and ActiveNode flags; out = the accepted
+ * nodes as LOCAL candidate indices in the order of the returned chain (reverse acceptance order); returns their number. */
+int refh3_tributary(int n_cand, const double *coords, const unsigned char *active, const double *xp, double beta,
+                    double tol_zero, int *out) {
+  TOL_zero_LME = tol_zero;
+  Mesh M;
+  memset(&M, 0, sizeof(M));
+  double *cc = (double *)malloc(sizeof(double) * 3 * (size_t)n_cand);
+  memcpy(cc, coords, sizeof(double) * 3 * (size_t)n_cand);
+  M.NumNodesMesh = n_cand;
+  M.Coordinates = memory_to_matrix__MatrixLib__(n_cand, 3, cc);
+  M.ActiveNode = (bool *)malloc(sizeof(bool) * (size_t)n_cand);
+  for (int i = 0; i < n_cand; i++) M.ActiveNode[i] = active[i] != 0;
+  ChainPtr ring = NULL;
+  for (int i = n_cand - 1; i >= 0; i--) push__SetLib__(&ring, i); /* push adds at the head: traversal = 0 .. n_cand-1 */
+  ChainPtr locality[1] = {ring};
+  int size[1] = {n_cand};
+  M.NodalLocality = locality;
+  M.SizeNodalLocality = size;
+  double x[3] = {xp[0], xp[1], xp[2]};
+  Matrix X_p = memory_to_matrix__MatrixLib__(3, 1, x);
+  ChainPtr lst = tributary__LME__(0, X_p, beta, 0, M);
+  const int n = lenght__SetLib__(lst);
+  int *arr = set_to_memory__SetLib__(lst, n);
+  memcpy(out, arr, sizeof(int) * (size_t)n);
+  free(arr);
+  free__SetLib__(&lst);
+  free__SetLib__(&ring);
+  free(M.Coordinates.nM);
+  free(M.ActiveNode);
+  free(cc);
+  return n;
+}
+
+/* get_closest_node__MeshTools__ (Nodes/Nodes-Tools.c:476-538) among the given candidates (the 1-ring of the previous
+ * closest node in chain order): returns the LOCAL index of the winner. */
+int refh3_closest(int n_cand, const double *coords, const double *xp) {
+  double *cc = (double *)malloc(sizeof(double) * 3 * (size_t)n_cand);
+  memcpy(cc, coords, sizeof(double) * 3 * (size_t)n_cand);
+  Matrix C = memory_to_matrix__MatrixLib__(n_cand, 3, cc);
+  ChainPtr ring = NULL;
+  for (int i = n_cand - 1; i >= 0; i--) push__SetLib__(&ring, i);
+  double x[3] = {xp[0], xp[1], xp[2]};
+  Matrix X_p = memory_to_matrix__MatrixLib__(3, 1, x);
+  const int best = get_closest_node__MeshTools__(X_p, ring, C);
+  free__SetLib__(&ring);
+  free(C.nM);
+  free(cc);
+  return best;
+}

@@ -300,9 +300,71 @@ def gen_nh3d(_case="all"):
     print("3D NH points:", len(s_in), "tangent blocks:", len(t_in))
 
 
+LISTS3D = dict(grid=(8, 8, 8), h=0.125, block=(4, 4, 4), origin=(2, 2, 0), jitter=0.2, steps=3)
+
+
+def lists3d_state(gamma):
+    """the 3D oracle state whose neighbour lists are frozen in lists3d.npz (also replayed by the test)"""
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "nl-partsol_b200"))
+    sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
+    import oracle
+    from nlps_b200 import synthetic
+    c = LISTS3D
+    P = synthetic.structured_problem(3, c["grid"], c["h"], c["block"], c["origin"], synthetic.NH_C1, 6, 0.5, 40.0,
+                                     (0.0, 0.0, -9.81), gamma_lme=gamma, jitter=c["jitter"],
+                                     rollers=("left", "right", "front", "back"))
+    P.fields["vel"][:, 2] = -0.2 * P.solver["cel"]          # particles change cells, lists change
+    o = oracle.Oracle(P)
+    assert o.init_lme() == 0
+    for k in range(c["steps"]):
+        assert o.step(k) == 0
+    x, beta_old, I0_old = o.field("x_GC").copy(), o.field("Beta").copy(), o.ints("I0").copy()
+    assert o.search_closest() == 0
+    I0, active = o.ints("I0").copy(), o.active().copy()
+    assert o.search_lists() == 0
+    o.I0_before_search = I0_old
+    return P, o, x, beta_old, I0, active
+
+
+def gen_lists3d(_case="all"):
+    """3D neighbour lists through the reference's OWN tributary__LME__ (LME.c:1019-1099, compiled in 3D inside
+    oracle/_ref/libnlps3d_lme_ref.so): for every particle of a moving jittered cloud, the 2-ring of its closest node in
+    chain order + ActiveNode flags + the previous beta go in, the ordered list comes out."""
+    import ctypes
+    L = ctypes.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libnlps3d_lme_ref.so"))
+    dp_, ip_ = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+    out = {}
+    for gamma in (6.0, 3.0):
+        P, o, x, beta_old, I0, active = lists3d_state(gamma)
+        I0_ref = np.zeros(P.np_, np.int32)      # get_closest_node__MeshTools__ over the 1-ring of the previous closest node
+        for p in range(P.np_):
+            cand = P.r1i[P.r1p[o.I0_before_search[p]]:P.r1p[o.I0_before_search[p] + 1]]
+            cc, xp = np.ascontiguousarray(P.coords[cand]), np.ascontiguousarray(x[p])
+            I0_ref[p] = cand[L.refh3_closest(len(cand), cc.ctypes.data_as(dp_), xp.ctypes.data_as(dp_))]
+        out[f"g{int(gamma)}_I0"] = I0_ref
+        assert (I0_ref != o.I0_before_search).sum() > 20          # the cloud did move
+        cap = int((P.r2p[1:] - P.r2p[:-1]).max())
+        lists = np.full((P.np_, cap), -1, np.int32)
+        counts = np.zeros(P.np_, np.int32)
+        for p in range(P.np_):
+            cand = P.r2i[P.r2p[I0[p]]:P.r2p[I0[p] + 1]]
+            cc = np.ascontiguousarray(P.coords[cand])
+            act = np.ascontiguousarray(active[cand].astype(np.uint8))
+            res = np.zeros(len(cand), np.int32)
+            xp = np.ascontiguousarray(x[p])
+            n = L.refh3_tributary(len(cand), cc.ctypes.data_as(dp_), act.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                                  xp.ctypes.data_as(dp_), ctypes.c_double(float(beta_old[p])),
+                                  ctypes.c_double(P.solver["tol_zero"]), res.ctypes.data_as(ip_))
+            counts[p] = n
+            lists[p, :n] = cand[res[:n]]
+        out[f"g{int(gamma)}_lists"], out[f"g{int(gamma)}_counts"] = lists, counts
+        print("gamma", gamma, "particles", P.np_, "neighbours", counts.min(), "-", counts.max())
+    np.savez_compressed(os.path.join(HERE, "lists3d.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
@@ -314,3 +376,4 @@ if __name__ == "__main__":
             subprocess.run([sys.executable, __file__, "points3d", c], check=True)
         subprocess.run([sys.executable, __file__, "lme3d", "all"], check=True)
         subprocess.run([sys.executable, __file__, "nh3d", "all"], check=True)
+        subprocess.run([sys.executable, __file__, "lists3d", "all"], check=True)

@@ -118,3 +118,21 @@ def test_3d_neo_hookean_matches_the_compiled_reference():
         worst_s = max(worst_s, np.abs(a["stress"] - ref[:9]).max() / max(np.abs(ref[:9]).max(), 1e-300))
         worst_w = max(worst_w, abs(a["W"] - ref[9]) / max(abs(ref[9]), 1e-300))
     assert worst_s <= 1e-13 and worst_w <= 1e-10, (worst_s, worst_w)
+
+
+@pytest.mark.parametrize("gamma", [6.0, 3.0])
+def test_3d_neighbour_lists_match_the_compiled_reference(gamma):
+    """K0 in 3D, the search: the ordered neighbour lists of a moving jittered cloud (closest node after the move, 2-ring
+    in chain order, ActiveNode flags, radius from the previous beta) against the reference's own tributary__LME__
+    (LME.c:1019-1099) compiled in 3D -- bit-exact, order included (tests/golden/lists3d.npz)."""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden
+    P, o, x, beta_old, I0, active = make_golden.lists3d_state(gamma)
+    g = np.load(os.path.join(GOLD, "lists3d.npz"))
+    ref_l, ref_c = g[f"g{int(gamma)}_lists"], g[f"g{int(gamma)}_counts"]
+    assert np.array_equal(I0, g[f"g{int(gamma)}_I0"])          # get_closest_node__MeshTools__ (Nodes-Tools.c:476-538)
+    assert np.array_equal(o.ints("NumberNodes"), ref_c)
+    got = o.lists()
+    assert np.array_equal(got[:, :ref_l.shape[1]], ref_l)
+    assert ref_c.min() >= 4 and (ref_c != ref_c[0]).any()
