@@ -21,6 +21,7 @@
 #include "Constitutive/Plasticity/Matsuoka-Nakai.h"
 #include "Constitutive/Plasticity/Elastoplastic-Tangent-Matrix.h"
 #include "Constitutive/Hyperelastic/Neo-Hookean.h"
+#include "Particles.h" /* prototypes of Particles/compute-Strains.c */
 
 #if NumberDimensions != 3
 #error "ref_harness3d.c is the 3D build: compile without -DUSE_PLAINSTRAIN"
@@ -129,4 +130,11 @@ int refh3_stiffness_nh(double *out, const double *dN_alpha_n1, const double *dN_
   memset(&M, 0, sizeof(M));
   S.D_phi_n = F_n; S.J = J; M.E = E; M.nu = nu;
   return compute_stiffness_density_Neo_Hookean(out, dN_alpha_n1, dN_beta_n1, dN_alpha_n, dN_beta_n, S, M);
+}
+
+/* kinematics of one particle (Particles/compute-Strains.c:20-44, 76-105, compiled in 3D): DF = I + sum_A dU_A (x) grad N_A,
+ * F_n1 = DF F_n */
+void refh3_kinematics(int n, const double *dU, const double *grad, const double *F_n, double *DF, double *F_n1) {
+  update_increment_Deformation_Gradient__Particles__(DF, dU, grad, (unsigned)n);
+  update_Deformation_Gradient_n1__Particles__(F_n1, F_n, DF);
 }

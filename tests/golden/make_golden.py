@@ -362,9 +362,37 @@ def gen_lists3d(_case="all"):
     np.savez_compressed(os.path.join(HERE, "lists3d.npz"), **out)
 
 
+def kin3d_state():
+    """3D oracle state stopped between the nodal increments and the kinematics of a step (replayed by the test)"""
+    P, o, x, beta_old, I0, active = lists3d_state(6.0)
+    k = LISTS3D["steps"]
+    assert o.stage("p2g_mass_disp", k) == 0 and o.stage("grid_disp", k) == 0
+    return P, o, k
+
+
+def gen_kin3d(_case="all"):
+    """3D kinematics through the reference's compiled Particles/compute-Strains.c (:20-44, :76-105 inside
+    oracle/_ref/libnlps3d_laws_ref.so): DF = I + sum_A dU_A (x) grad N_A and F_n1 = DF F_n for every particle of the moving
+    jittered cloud, from the oracle's nodal increments, neighbour lists and gradients."""
+    import ctypes
+    L = ctypes.CDLL(os.path.join(HERE, "..", "..", "oracle", "_ref", "libnlps3d_laws_ref.so"))
+    dp_ = ctypes.POINTER(ctypes.c_double)
+    P, o, k = kin3d_state()
+    dU, lists, nn, Fn = o.nodal(1), o.lists(), o.ints("NumberNodes"), o.field("F_n")
+    DF, F1 = np.zeros((P.np_, 9)), np.zeros((P.np_, 9))
+    for p in range(P.np_):
+        n = int(nn[p])
+        N, dN = o.shape(p)
+        du, gr, fn = (np.ascontiguousarray(a, dtype=np.float64) for a in (dU[lists[p, :n]], dN, Fn[p]))
+        L.refh3_kinematics(n, du.ctypes.data_as(dp_), gr.ctypes.data_as(dp_), fn.ctypes.data_as(dp_),
+                           DF[p].ctypes.data_as(dp_), F1[p].ctypes.data_as(dp_))
+    np.savez_compressed(os.path.join(HERE, "kin3d.npz"), DF=DF, F_n1=F1)
+    print("3D kinematics:", P.np_, "particles, max |DF - I|", float(np.abs(DF - np.eye(3).ravel()).max()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
@@ -377,3 +405,4 @@ if __name__ == "__main__":
         subprocess.run([sys.executable, __file__, "lme3d", "all"], check=True)
         subprocess.run([sys.executable, __file__, "nh3d", "all"], check=True)
         subprocess.run([sys.executable, __file__, "lists3d", "all"], check=True)
+        subprocess.run([sys.executable, __file__, "kin3d", "all"], check=True)

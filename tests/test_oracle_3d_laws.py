@@ -136,3 +136,17 @@ def test_3d_neighbour_lists_match_the_compiled_reference(gamma):
     got = o.lists()
     assert np.array_equal(got[:, :ref_l.shape[1]], ref_l)
     assert ref_c.min() >= 4 and (ref_c != ref_c[0]).any()
+
+
+def test_3d_kinematics_match_the_compiled_reference():
+    """K2a in 3D: DF = I + sum_A dU_A (x) grad N_A and F_n1 = DF F_n (compute-Strains.c:20-44, 76-105, compiled in 3D) for
+    every particle of the moving jittered cloud -- the oracle's kinematics stage against tests/golden/kin3d.npz."""
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden
+    P, o, k = make_golden.kin3d_state()
+    assert o.stage("kin_stress", k) == 0
+    g = np.load(os.path.join(GOLD, "kin3d.npz"))
+    assert np.abs(g["DF"] - np.eye(3).ravel()).max() > 1e-4
+    assert np.abs(o.field("DF") - g["DF"]).max() <= 1e-15
+    assert np.abs(o.field("F_n1") - g["F_n1"]).max() <= 1e-15
