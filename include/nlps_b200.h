@@ -116,6 +116,9 @@ typedef struct nlps_particles {
   double *lambda; /* n x d  (Particle.lambda) */
   double *Beta;   /* n      (Particle.Beta)   */
   int *I0, *NumberNodes, *MatIdx;                         /* n */
+  double *Area_0; /* n: Particle.Phi.Area_0, the area a 3D Neumann load acts on (U-Verlet.c:847-849,
+                   * U-Newmark-beta.c:1442, U-Static.c:930); 2D uses Vol_0 / Thickness_Plain_Stress and ignores it.
+                   * nlps_b200_create fails for a 3D deck with Neumann loads and Area_0 == NULL. */
 } nlps_particles;
 
 typedef struct nlps_engine nlps_engine;

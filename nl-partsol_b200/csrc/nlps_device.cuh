@@ -13,7 +13,31 @@
 struct MatParams {
   int type;
   double rho, E, nu, p_ref, kappa_0, H, eps_0, phi, psi, m_exp, cohesion, alpha_borja, a1, a2, a3;
+  // constants of the material, computed ONCE on the host with the C library the reference itself uses (mat_hoist):
+  // no tan / sin / cos / sqrt per particle per step, and the values are bit-identical to the reference's
+  double K, G, lame;                               // bulk, shear and Lame moduli
+  double dp_alpha_F, dp_alpha_Q, dp_beta, dp_ads;  // Drucker-Prager cone constants (plane strain or 3D) and sqrt(1 + 3 alpha_Q^2)
+  double mn_c;                                     // Matsuoka-Nakai: cohesion / tan(phi)
 };
+// Drucker-Prager.c:361-375 (cone constants), Neo-Hookean.c:17-35, Matsuoka-Nakai.c:320-340 (elastic constants)
+static inline void mat_hoist(MatParams& m, int ndim) {
+  m.K = m.E / (3.0 * (1.0 - 2.0 * m.nu));
+  m.G = m.E / (2.0 * (1.0 + m.nu));
+  m.lame = m.E * m.nu / ((1.0 + m.nu) * (1.0 - 2.0 * m.nu));
+  const double rphi = (NLPS_PI / 180.0) * m.phi, rpsi = (NLPS_PI / 180.0) * m.psi;
+  if (ndim == 2) {  // plane-strain cone constants :361-368
+    const double tp = tan(rphi), tq = tan(rpsi);
+    m.dp_alpha_F = sqrt(2. / 3.) * tp / sqrt(3. + 4. * (tp * tp));
+    m.dp_alpha_Q = sqrt(2. / 3.) * tq / sqrt(3. + 4. * (tq * tq));
+    m.dp_beta = sqrt(2. / 3.) * 3. / sqrt(3. + 4. * (tp * tp));
+  } else {  // :370-375
+    m.dp_alpha_F = sqrt(2 / 3.) * 2 * sin(rphi) / (3 - sin(rphi));
+    m.dp_alpha_Q = sqrt(2 / 3.) * 2 * sin(rpsi) / (3 - sin(rpsi));
+    m.dp_beta = sqrt(2 / 3.) * 6 * cos(rphi) / (3 - sin(rphi));
+  }
+  m.dp_ads = sqrt(1.0 + 3.0 * m.dp_alpha_Q * m.dp_alpha_Q);
+  m.mn_c = rphi > 0.0 ? m.cohesion / tan(rphi) : 0.0;
+}
 
 struct ReturnMapParams {
   double tol;
@@ -230,8 +254,7 @@ __device__ inline void jacobi3_dev(const double* a_in, double* w, double* z) {
 template <int D>
 __device__ inline void stress_neo_hookean(const MatParams& m, const double* F, double J, double* tau,
                                           double& W) {
-  double G = m.E / (2 * (1 + m.nu));
-  double lam = m.nu * m.E / ((1 - m.nu * 2) * (1 + m.nu));
+  const double G = m.G, lam = m.lame;
   double c0 = lam * 0.5 * (J * J - 1.0);
   double I1 = 0.0;
 #pragma unroll
@@ -309,26 +332,16 @@ __device__ inline int stress_drucker_prager(const MatParams& m, const ReturnMapP
   trial_be<D>(be, dphi, eval, evec);
 #pragma unroll
   for (int i = 0; i < 3; i++) Eh[i] = 0.5 * log(eval[i]);
-  const double K = m.E / (3.0 * (1.0 - 2.0 * m.nu)), G = m.E / (2.0 * (1.0 + m.nu));
-  const double rphi = (NLPS_PI / 180.0) * m.phi, rpsi = (NLPS_PI / 180.0) * m.psi;
-  double alpha_F, alpha_Q, beta;
-  if (D == 2) {  // plane-strain cone constants :361-368
-    double tp = tan(rphi), tq = tan(rpsi);
-    alpha_F = sqrt(2. / 3.) * tp / sqrt(3. + 4. * (tp * tp));
-    alpha_Q = sqrt(2. / 3.) * tq / sqrt(3. + 4. * (tq * tq));
-    beta = sqrt(2. / 3.) * 3. / sqrt(3. + 4. * (tp * tp));
-  } else {  // :370-375
-    alpha_F = sqrt(2 / 3.) * 2 * sin(rphi) / (3 - sin(rphi));
-    alpha_Q = sqrt(2 / 3.) * 2 * sin(rpsi) / (3 - sin(rpsi));
-    beta = sqrt(2 / 3.) * 6 * cos(rphi) / (3 - sin(rphi));
-  }
+  // cone constants (:361-375) and elastic moduli come from the host (mat_hoist)
+  const double K = m.K, G = m.G;
+  const double alpha_F = m.dp_alpha_F, alpha_Q = m.dp_alpha_Q, beta = m.dp_beta;
   double n[3] = {0, 0, 0}, dEp[3] = {0, 0, 0};
   double PHI, PHI_0, d_PHI, J2, pressure, dg = 0;
   const double eps_n = eps;
   double eps_k = eps_n, kappa_k = kappa, dkappa = 0.0;
   const double TOL = rp.tol;
   int Iter = 0;
-  const double ads = sqrt(1.0 + 3.0 * alpha_Q * alpha_Q);
+  const double ads = m.dp_ads;
   const double trE = Eh[0] + Eh[1] + Eh[2];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -370,7 +383,7 @@ __device__ inline int stress_drucker_prager(const MatParams& m, const ReturnMapP
         if (fabs(d_PHI) < TOL) return 6;
         dg += -PHI / d_PHI;
         if (dg < 0.0) return 6;
-        eps_k = eps_n + dg * sqrt(3.0 * alpha_Q * alpha_Q + 1.0);
+        eps_k = eps_n + dg * ads;
         if (eps_k < 0.0) return 6;
         base = 1.0 + eps_k / m.eps_0;
         if (base < 0.0) return 6;
@@ -414,7 +427,7 @@ __device__ inline int stress_drucker_prager(const MatParams& m, const ReturnMapP
                    (kappa_k + dkappa * sqrt((dg1 * dg1) + 3.0 * (alpha_Q * alpha_Q) * (dg * dg))) -
                pressure + 3.0 * K * alpha_Q * dg);
       }
-      eps_k = eps_n + dg * sqrt(3.0 * alpha_Q * alpha_Q + 1.0);
+      eps_k = eps_n + dg * ads;
       if (eps_k < 0.0) return 6;
 #pragma unroll
       for (int i = 0; i < 3; i++) {
@@ -518,10 +531,9 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
   for (int i = 0; i < 3; i++) Etr[i] = 0.5 * log(eval[i]);
   MNPar q;
   q.E = m.E; q.nu = m.nu;
-  q.Lame = m.E * m.nu / ((1.0 + m.nu) * (1.0 - 2.0 * m.nu));
-  q.G = m.E / (2.0 * (1.0 + m.nu));
-  double rphi = (NLPS_PI / 180.0) * m.phi;
-  q.c = rphi > 0.0 ? m.cohesion / tan(rphi) : 0.0;
+  q.Lame = m.lame;
+  q.G = m.G;
+  q.c = m.mn_c;
   q.alpha = m.alpha_borja; q.a0 = m.a1; q.a1 = m.a2; q.a2 = m.a3;
   const double AAd = q.Lame + 2 * q.G, AAo = q.Lame;
   const double CCd = 1.0 / q.E, CCo = -q.nu / q.E;

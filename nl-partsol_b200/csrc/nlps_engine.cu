@@ -32,6 +32,8 @@
 
 #include "../../include/nlps_b200.h"
 #include "nlps_device.cuh"
+#include "nlps_types.cuh"
+#include "nlps_cellwarp.h"
 
 #define CUDA_OK(call)                                                                       \
   do {                                                                                      \
@@ -42,102 +44,15 @@
     }                                                                                       \
   } while (0)
 
-static const int MAX_MATERIALS = 8;
-static const int MAX_MASK_WORDS = 8;  // 2-ring up to 256 nodes
-__constant__ MatParams c_mat[MAX_MATERIALS];
 
 enum KernelId {
   K_SEARCH = 0, K_MARK, K_NODE_FLAGS, K_SCAN1, K_SCAN2, K_SCAN3, K_FILL, K_NODE_FINISH, K_REORDER, K_LME_P2G,
-  K_GRID_DISP, K_TRACTION, K_KIN_FORCE, K_GRID_ACC, K_G2P, K_HALO, K_COUNT
+  K_GRID_DISP, K_TRACTION, K_KIN_FORCE, K_GRID_ACC, K_G2P, K_HALO, K_KIN_GATHER, K_STRESS, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {
     "search_closest_node", "mark_live_blocks", "node_flags", "scan_reduce", "scan_tops", "scan_apply", "cell_fill",
     "node_finish", "reorder", "lme_p2g_mass_disp", "grid_disp_bc", "traction", "kin_stress_p2g_force",
-    "grid_acc", "g2p_update", "halo_exchange"};
-
-// ---------------------------------------------------------------------------
-// Device views
-// node records are padded so that one node is one or two 16-byte vector loads
-template <int D> struct NS { static constexpr int X = (D == 2) ? 2 : 4; };   // coordinates stride (doubles)
-template <int D>
-__device__ __forceinline__ void ldvec(const double* p, double* out) {
-  double2 a = *reinterpret_cast<const double2*>(p);
-  out[0] = a.x; out[1] = a.y;
-  if (D == 3) { double2 b = *reinterpret_cast<const double2*>(p + 2); out[2] = b.x; }
-}
-// D doubles from shared memory: one 16-byte load in 2D (the staged node arrays are 16-byte aligned, stride 2)
-template <int D>
-__device__ __forceinline__ void ldsvec(const double* p, double* out) {
-  if constexpr (D == 2) {
-    const double2 a = *reinterpret_cast<const double2*>(p);
-    out[0] = a.x; out[1] = a.y;
-  } else {
-#pragma unroll
-    for (int i = 0; i < D; i++) out[i] = p[i];
-  }
-}
-struct MeshDev {
-  int nn;
-  const double* X;  // nn x NS<D>::X (row-major, padded)
-  const int *r1p, *r1i, *r2p, *r2i;
-  const int *r1tp, *r1ti, *r2tp, *r2ti;  // transposed adjacency (who lists me)
-  const unsigned char* r2q;              // r2q[r2p[B]+s] = position of B inside the r2t row of node r2i[r2p[B]+s]
-  const double* h_avg;
-};
-
-struct PartDev {
-  int np;  // particles held by this engine (changes when particles migrate between slabs)
-  int ld;  // leading dimension of the SoA arrays = capacity (np <= ld)
-  // SoA, component-major: f[c*ld + p]; p is the PHYSICAL slot (cell-sorted every few steps),
-  // orig[p] the caller's (global) particle id and inv[] its inverse (-1: not held by this slab).
-  double *x, *dis, *ddis, *vel, *acc, *lam;
-  double *beta, *mass, *vol0, *rho, *W;
-  double *J_n, *J_n1, *eps_n, *eps_n1, *kap_n, *kap_n1;
-  double *F_n, *F_n1, *DF, *be_n, *be_n1, *stress, *cep;
-  double *Fs4, *DFs4;  // 2D slot 4 of F / DF (never touched by the kinematics, Appendix B)
-  double* trac;        // D x np: Neumann traction * A0 of the current step (allocated only with loads)
-  int *I0, *nnodes, *matidx, *orig, *inv;
-  uint32_t* mask;  // W words, word-major: mask[w*np + p]
-};
-
-struct GridDev {
-  double *M, *F;  // M: nn ; F: nn x D (row-major)
-  double* MOM;    // nn x D: sum m N DU_p before the division by M (kept for the slab halo sums)
-  unsigned char* rocc;  // cell occupied by particles of a NEIGHBOUR slab (multi-GPU), zero otherwise
-  double* UA;     // per node [dU (NS) | A (NS)]: the two nodal fields the G2P gathers read, one record
-  unsigned char *active, *fixed;
-  int *cnt, *cursor, *cell_start, *plist, *act_list, *n_active;
-  int *occ_list, *n_occ, *act_pos, *occ_pos;
-  int4* occ_meta;   // per occupied cell (in node order): {node B, first particle slot, 2-ring base, 2-ring length}
-  int* arank;       // rank of a node among the active nodes, -1 when inactive
-  uint32_t* occm;   // per active rank: transposed-2-ring slots whose cell is occupied (w2t words, word-major)
-  ulonglong2 *packed, *scan_blk;
-  // per block of 256 node ids: holds an occupied cell (set by the search) / lies in the 2-ring of one (this step,
-  // previous step) / must be processed by the node kernels this step (= dirty now or last step: leaving blocks are
-  // visited once more so that their flags return to zero)
-  unsigned char *occ_blk, *dirty_cur, *dirty_prev, *live;
-  double* part;     // slot-major cell partial sums: part[(q * max_act + rank) * NV + v]
-  int cap, max_act, w2t;
-};
-
-struct StepParams {
-  double dt, gamma_lme, neg_log_tol, tol_wrapper, thickness;
-  int max_iter_lme, nsteps, step, update_I0, W;
-  ReturnMapParams rp;
-  // implicit scheme (U-Newmark-beta.c): project `proj` (D x ld SoA) instead of D_dis, keep the neighbour lists and
-  // beta of the search already done this step, leave the density alone in the kinematics
-  const double* proj;
-  int reuse_lists, implicit;
-};
-
-// slab view of the kernels: ownership interval [own_lo, own_hi) of closest-node coordinates along `axis`
-// and the wider interval [lo, hi] a particle may roam between two migrations (halo band minus 3.5 cells)
-struct SlabDev { int on, axis; double lo, hi, own_lo, own_hi; };
-
-// One thread block works on C consecutive OCCUPIED cells (a cell = all particles with the same closest
-// node I0) = one contiguous run of the cell-sorted particle order.  SL = longest 2-ring row, PCAP =
-// particles whose per-particle scratch fits in shared memory at once (longer runs go in chunks).
-struct BlockCfg { int C, SL, PCAP, threads; unsigned magic; int NCA, NCB; int cellfast; };  // cellfast: bit 0 / 1 = cell-fastest pair order in the uncached cell phase of k_lme_p2g / k_kin_force  // NCA / NCB: compact weight cache entries per particle in k_lme_p2g / k_kin_force (0 = none)  // magic = ceil(2^21 / SL): e / SL == (e * magic) >> 21 for e < C*SL (checked at create)
+    "grid_acc", "g2p_update", "halo_exchange", "kin_gather", "stress_update"};
 
 struct Carve {
   size_t off = 0;
@@ -198,112 +113,21 @@ struct LayoutC {  // k_g2p
   }
 };
 
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void latch_error(int* err, int code, int p) {
-  if (atomicCAS(&err[0], 0, code) == 0) err[1] = p;
-}
 
-// squared distance with the reference's rounding sequence: sum_i (x_i - X_i)*(x_i - X_i),
-// products and sums rounded separately (no FMA contraction), Nodes-Tools.c:400-420 and
-// MatrixOp.c:895-920.  Needed for bit-exact closest node / neighbour lists.
-template <int D>
-__device__ __forceinline__ double dist2_exact(const double* xp, const double* XA, double* l) {
-  double s = 0.0;
-#pragma unroll
-  for (int i = 0; i < D; i++) {
-    l[i] = __dsub_rn(xp[i], XA[i]);
-    s = __dadd_rn(s, __dmul_rn(l[i], l[i]));
-  }
-  return s;
+// s* of a search radius (see sstar_from_Ra): per node for beta = gamma / h_avg^2 (beta__LME__, LME.c:177-185), and
+// per particle for the beta it carries (the PREVIOUS step's, LME.c:973,983-984; 0 after allocation => infinite radius)
+__global__ void __launch_bounds__(256) k_sstar_nodes(const double* h_avg, int nn, double gamma_lme, double neg_log_tol, double* sst) {
+  const int A = blockIdx.x * blockDim.x + threadIdx.x;
+  if (A >= nn) return;
+  const double h = h_avg[A];
+  const double beta = __ddiv_rn(gamma_lme, __dmul_rn(h, h));
+  sst[A] = sstar_from_Ra(__dsqrt_rn(__ddiv_rn(neg_log_tol, beta)));
 }
-
-// largest s with sqrt_rn(s) <= Ra, so that "s <= sstar" is EXACTLY the reference's
-// "sqrt(s) <= Ra" (LME.c:1074) without a square root per candidate.
-__device__ inline double sstar_from_Ra(double Ra) {
-  if (!(Ra < 1.0e150)) return (Ra != Ra) ? -1.0 : 1.0e300;
-  double t = __dmul_rn(Ra, Ra);
-  for (int it = 0; it < 4 && __dsqrt_rn(t) > Ra; it++) t = __longlong_as_double(__double_as_longlong(t) - 1);
-  for (int it = 0; it < 4; it++) {
-    double u = __longlong_as_double(__double_as_longlong(t) + 1);
-    if (__dsqrt_rn(u) <= Ra) t = u; else break;
-  }
-  return t;
+__global__ void __launch_bounds__(256) k_sstar_particles(const double* beta, int np, double neg_log_tol, double* sstar) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  sstar[p] = sstar_from_Ra(__dsqrt_rn(__ddiv_rn(neg_log_tol, beta[p])));
 }
-
-// exp() for the LME weights: exp(x) = 2^(k/32) * exp(r), k = rint(32 x / ln 2), |r| <= ln2/64, table of
-// 2^(j/32) (shared memory) times a degree-6 Taylor polynomial: 11 fp64 operations instead of libdevice's 17
-// plus constant moves, max relative error 1.94e-16 (0.9 ulp; checked against mpmath over [-700, 700]).
-// The kernels issue two of these chains per loop iteration (for_neighbour_pairs): the fp64 pipe, not the
-// latency of one dependent chain, then bounds the shape-function loops.
-__device__ const double g_exp2tab[32] = {
-    1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,
-    1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,
-    1.2690509571917332, 1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
-    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228, 1.5422108254079407,
-    1.5759808451078865, 1.6104903319492543, 1.645755478153965, 1.681792830507429, 1.718619298122478,
-    1.7562521603732995, 1.7947090750031072, 1.8340080864093424, 1.8741676341103, 1.9152065613971474,
-    1.9571441241754002};
-// constants in the constant bank: a DFMA takes them as a direct operand (an immediate would cost two moves each)
-__constant__ double c_fexp[8] = {46.16624130844683,        // 32 / ln 2
-                                 -0.02166084938653512,     // -ln2/32, high part (21 trailing zero bits: exact product)
-                                 -5.9631716539705866e-12,  // -ln2/32, low part
-                                 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.0};
-__device__ __forceinline__ double fexp(double x, const double* tab) {
-  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*c + MAGIC is rint(x*c)
-  const double kd = __fma_rn(x, c_fexp[0], MAGIC);
-  const int k = __double2loint(kd);
-  const double kf = kd - MAGIC;
-  double r = __fma_rn(kf, c_fexp[1], x);
-  r = __fma_rn(kf, c_fexp[2], r);
-  double q = __fma_rn(r, c_fexp[3], c_fexp[4]);
-  q = __fma_rn(r, q, c_fexp[5]);
-  q = __fma_rn(r, q, c_fexp[6]);
-  q = __fma_rn(r, q, 0.5);
-  q = __fma_rn(r, q, 1.0);
-  // 2^(k/32) = table entry with the exponent shifted (clamped: |x| > 708 saturates instead of wrapping;
-  // a NaN argument still gives NaN through r)
-  const int m = max(-1021, min(1022, k >> 5));
-  const double T = tab[k & 31];
-  const double Ts = __hiloint2double(__double2hiint(T) + (m << 20), __double2loint(T));
-  return __fma_rn(Ts, r * q, Ts);
-}
-// visit the set bits of a neighbour mask two at a time; `two` is false for the odd one out (k1 == k0)
-template <int W, class F>
-__device__ __forceinline__ void for_neighbour_pairs(const uint32_t* mk, F&& f) {
-#pragma unroll
-  for (int w = 0; w < W; w++) {
-    uint32_t mm = mk[w];
-    while (mm) {
-      const int b0 = __ffs(mm) - 1;
-      mm &= mm - 1;
-      const bool two = mm != 0u;
-      const int b1 = two ? __ffs(mm) - 1 : b0;
-      mm &= mm - 1;
-      f(w * 32 + b0, w * 32 + b1, two);
-    }
-  }
-}
-
-// 2D: walk ALL slots of the cell's 2-ring in order, two at a time, with weight 0 for the slots that are not
-// neighbours: the lanes of a warp that sit in the same cell then read the same shared-memory words in the same
-// instruction (broadcast: one wavefront instead of one per lane -- the LSU data pipe is the busiest unit of these
-// kernels, profiles/r01_ncu_full_c2_v5.txt) and the bit scanning disappears; the price is 25 instead of ~22 exp
-// evaluations, which the fp64 pipe (16-25 % busy) absorbs.  3D (125 slots, ~40 neighbours) keeps the bit iteration.
-template <int D, int W, class F>
-__device__ __forceinline__ void for_slots(const uint32_t* mk, int len, F&& f) {
-  if constexpr (D == 2 && W == 1) {
-    const uint32_t m = mk[0];
-    for (int k = 0; k < len; k += 2) {
-      const bool has1 = k + 1 < len;
-      const double w0 = ((m >> k) & 1u) ? 1.0 : 0.0;
-      const double w1 = (has1 && ((m >> (k + 1)) & 1u)) ? 1.0 : 0.0;
-      f(k, has1 ? k + 1 : k, w0, w1);
-    }
-  } else {
-    for_neighbour_pairs<W>(mk, [&](int k0, int k1, bool two) { f(k0, k1, 1.0, two ? 1.0 : 0.0); });
-  }
-}
-template <int D, int W> struct DenseSlots { static constexpr bool value = (D == 2 && W == 1); };
 
 // ---------------------------------------------------------------------------
 // K0a: closest node + cell histogram.   local_search__LME__ first loop (LME.c:917-944),
@@ -1178,7 +1002,8 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
 template <int D, int W, int MAT, bool CACHE>
 __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_force(MeshDev m, PartDev P, GridDev G,
                                                                                 StepParams sp, BlockCfg cfg, int* err,
-                                                                                int has_traction) {
+                                                                                int has_traction,
+                                                                                const __grid_constant__ MatTable mt) {
   extern __shared__ __align__(16) unsigned char smem[];
   const LayoutB<D, W, CACHE> L(cfg);
   int* s_rank = (int*)(smem + L.rank); unsigned char* s_q = smem + L.q; double* s_X = (double*)(smem + L.X);
@@ -1323,7 +1148,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
         const double dJ = det<D>(DF);
         if (!sp.implicit) P.rho[p] = rho_p / dJ;  // the implicit scheme updates rho once, after convergence
         // constitutive update
-        const MatParams& mat = c_mat[mid];
+        const MatParams& mat = mt.m[mid];
         double tau[T], Wp = 0.0;
         const int mtype = (MAT >= 0) ? MAT : mat.type;
         int st = 0;
@@ -1445,7 +1270,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
 }
 
 // Neumann tractions: per loaded particle t_p = sum_loads T(step) * A0_p, A0 = Vol_0 / thickness
-// in 2D (U-Verlet.c:826-869), into P.trac (zero for unloaded particles).
+// in 2D, Phi.Area_0 in 3D (U-Verlet.c:826-869), into P.trac (zero for unloaded particles).
 struct NeuDev {
   int n_entries;        // flattened (load, particle) pairs, load-major; particle = the caller's id
   const int* part;
@@ -1462,7 +1287,8 @@ __global__ void k_traction(PartDev P, NeuDev nu, double thickness, int step) {
   if (e >= nu.n_entries) return;
   int p = P.inv[nu.part[e]], b = nu.load[e];
   if (p < 0) return;  // the particle lives in another slab
-  double A0 = P.vol0[p] / thickness;
+  // 2D: Vol_0 / Thickness_Plain_Stress; 3D: Phi.Area_0 (U-Verlet.c:844-849)
+  const double A0 = (D == 3) ? P.area0[p] : P.vol0[p] / thickness;
   for (int k = 0; k < nu.load_dim[b] && k < D; k++) {
     size_t o = ((size_t)b * nu.maxdim + k) * nu.nsteps + step;
     if (nu.dir[o] == 1) atomicAdd(&P.trac[(size_t)k * P.ld + p], nu.val[o] * A0);
@@ -1600,10 +1426,10 @@ __global__ void __launch_bounds__(128, D == 2 ? 5 : 3) k_g2p(MeshDev m, PartDev 
 // first step both copies hold the initial n1 value.  With the pointer-swap roll that is reproduced by
 // copying n1 -> n once, before the first swap.
 template <int D>
-__global__ void k_sync_inert(PartDev P) {
+__global__ void k_sync_inert(PartDev P, const __grid_constant__ MatTable mt) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.np) return;
-  if (c_mat[P.matidx[p]].type != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) return;
+  if (mt.m[P.matidx[p]].type != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) return;
   constexpr int TB = (D == 2) ? 5 : 9;
 #pragma unroll
   for (int i = 0; i < TB; i++) P.be_n[(size_t)i * P.ld + p] = P.be_n1[(size_t)i * P.ld + p];
@@ -1865,13 +1691,13 @@ __global__ void k_export_nodal(GridDev G, int nn, int D, int which, double* out)
 // Stress_integration__Constitutive__ (Constitutive.c:18-258) on arrays of material points
 // (AoS host layout), the GPU twin used by the point-wise parity tests.
 template <int D>
-__global__ void k_stress_points(int n, int mat, ReturnMapParams rp, const double* DF, const double* F1, const double* J1,
+__global__ void k_stress_points(int n, const __grid_constant__ MatTable mt, ReturnMapParams rp, const double* DF, const double* F1, const double* J1,
                                 const double* be_n, const double* eps_n, const double* kap_n, double* stress,
                                 double* be_n1, double* eps_n1, double* kap_n1, double* W, double* cep, int* status) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   constexpr int T = (D == 2) ? 5 : 9;
-  const MatParams& m = c_mat[mat];
+  const MatParams& m = mt.m[0];
   double df[D * D], f1[D * D], be[T], tau[T], c[D * D], Wp = 0.0;
 #pragma unroll
   for (int i = 0; i < D * D; i++) { df[i] = DF[(size_t)p * T + i]; f1[i] = F1[(size_t)p * T + i]; c[i] = 0.0; }
@@ -1912,6 +1738,12 @@ struct nlps_engine {
   int max_occ = 0, max_act = 0;
   int cap_r2 = 0;  // largest 2-ring row
   int uniform_mat = -1;  // material type shared by all materials, or -1
+  MatTable mat{};        // this engine's material table (kernel parameter of the stress kernels)
+  // kernel generation of the three hot stages: 2 = warp-per-cell kernels (nlps_cellwarp.cu), 1 = block-per-cell-group
+  // kernels (below).  NLPS_KERNELS overrides; NLPS_SPLIT_NH=1 runs Neo-Hookean clouds through gather / stress / force too
+  int kver = 2, split_nh = 0;
+  CwCfg cw{};
+  CwState cws{};
   int inert_synced = 0;
   BlockCfg cfg{};          // cells per block / 2-ring row length / particle chunk of the cell-block kernels
   size_t smemA = 0, smemB = 0, smemC = 0;
@@ -1943,6 +1775,7 @@ struct nlps_engine {
   int k_n[K_COUNT] = {0};
   long long launches = 0;
   int last_code = 0, last_particle = -1;
+  int host_fail = 0;  // a host-side failure (migration, halo transport): sticky, reported by every later poll
   // ---- spatial slab (multi-GPU); slab_on == 0: the engine owns every particle
   int slab_on = 0, rank = 0, world = 1, axis = 0, band_cells = 6, migrate_every = 10, n_global = 0;
   int steps_since_migration = 0;
@@ -1993,6 +1826,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi* nccl_api() {
@@ -2009,10 +1843,10 @@ static NcclApi* nccl_api() {
     if (api.h) {
 #define SYM_(f) *(void**)(&api.f) = dlsym(api.h, "nccl" #f)
       SYM_(GetUniqueId); SYM_(CommInitRank); SYM_(CommDestroy); SYM_(GroupStart); SYM_(GroupEnd); SYM_(Send); SYM_(Recv);
-      SYM_(GetErrorString);
+      SYM_(AllReduce); SYM_(GetErrorString);
 #undef SYM_
       if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.GroupStart || !api.GroupEnd || !api.Send ||
-          !api.Recv || !api.GetErrorString)
+          !api.Recv || !api.AllReduce || !api.GetErrorString)
         api.h = nullptr;
     }
     if (!api.h) fprintf(stderr, "nlps_b200: libnccl.so.2 not found (set NLPS_NCCL_LIB)\n");
@@ -2042,6 +1876,41 @@ static int comm_exchange(nlps_comm* c, int n, const nlps_msg* msgs, cudaStream_t
     fprintf(stderr, "nlps_b200: NCCL exchange failed: %s\n", N->GetErrorString(r != ncclSuccess ? r : r2));
     return 1;
   }
+  return 0;
+}
+
+// Collective "did everybody succeed": minimum of `ok` (0 / 1) over all slabs.  NCCL: one ncclAllReduce on the engine's
+// stream.  Custom transports only know neighbour exchanges: the minimum travels along the chain of slabs in world - 1
+// rounds.  d_buf: device int[4] (value | to neighbours | from lower | from upper).  Every slab must call it.
+static int comm_all_ok(nlps_comm* c, int rank, int world, int ok, int* d_buf, cudaStream_t stream, int* verdict) {
+  *verdict = ok;
+  if (!c || world <= 1) return 0;
+  int v = ok ? 1 : 0;
+  if (c->is_nccl) {
+    NcclApi* N = nccl_api();
+    if (cudaMemcpyAsync(d_buf, &v, sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
+    if (N->AllReduce(d_buf, d_buf, 1, ncclInt, ncclMin, c->nccl, stream) != ncclSuccess) return 1;
+    if (cudaMemcpyAsync(&v, d_buf, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess)
+      return 1;
+    *verdict = v;
+    return 0;
+  }
+  for (int round = 0; round < world - 1; round++) {
+    int got[2] = {1, 1};
+    if (cudaMemcpyAsync(d_buf, &v, sizeof(int), cudaMemcpyHostToDevice, stream) != cudaSuccess) return 1;
+    nlps_msg msgs[2];
+    int nm = 0;
+    if (rank > 0) msgs[nm++] = nlps_msg{rank - 1, d_buf, sizeof(int), d_buf + 2, sizeof(int)};
+    if (rank < world - 1) msgs[nm++] = nlps_msg{rank + 1, d_buf, sizeof(int), d_buf + 3, sizeof(int)};
+    if (comm_exchange(c, nm, msgs, stream)) return 1;
+    if (cudaMemcpyAsync(got, d_buf + 2, sizeof(got), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess)
+      return 1;
+    if (rank > 0) v = std::min(v, got[0]);
+    if (rank < world - 1) v = std::min(v, got[1]);
+  }
+  *verdict = v;
   return 0;
 }
 
@@ -2376,6 +2245,7 @@ static int poll_error(nlps_engine* e) {
     e->last_code = NLPS_ERR_CUDA;
     return 1;
   }
+  if (e->host_fail && e->h_err[0] == 0) return 1;  // last_code was set where the failure happened
   if (e->h_err[0] != 0) {
     e->last_code = e->h_err[0];
     e->last_particle = e->h_err[1];
@@ -2414,7 +2284,7 @@ static void reorder_particles(nlps_engine* e) {
   gd(P.beta, 1); gd(P.mass, 1); gd(P.vol0, 1); gd(P.rho, 1); gd(P.W, 1);
   gd(P.J_n, 1); gd(P.J_n1, 1); gd(P.eps_n, 1); gd(P.eps_n1, 1); gd(P.kap_n, 1); gd(P.kap_n1, 1);
   gd(P.F_n, DD); gd(P.F_n1, DD); gd(P.DF, DD); gd(P.be_n, T); gd(P.be_n1, T); gd(P.stress, T); gd(P.cep, DD);
-  gd(P.Fs4, 1); gd(P.DFs4, 1);
+  gd(P.Fs4, 1); gd(P.DFs4, 1); gd(P.area0, 1); gd(P.sstar, 1);
   gi(P.I0, 1); gi(P.nnodes, 1); gi(P.matidx, 1); gi(P.orig, 1); gi((int*)P.mask, e->W);
   k_after_sort<<<nblk(np, 256), 256, 0, e->stream>>>(P, e->G);
   e->launches++;
@@ -2503,7 +2373,7 @@ static int halo_exchange(nlps_engine* e, int which) {
     e->k_ms[K_HALO] += ms;
     e->k_n[K_HALO]++;
   }
-  if (rc) e->last_code = NLPS_ERR_CUDA;
+  if (rc) { e->last_code = NLPS_ERR_CUDA; e->host_fail = 1; }
   return rc;
 }
 
@@ -2522,20 +2392,33 @@ static int migrate_t(nlps_engine* e) {
   int nm = 0;
   for (int s_ = 0; s_ < 2; s_++)
     if (e->side[s_].peer >= 0) msgs[nm++] = nlps_msg{e->side[s_].peer, e->mig_cnt + 6 + s_, sizeof(int), e->mig_cnt + 8 + s_, sizeof(int)};
-  if (comm_exchange(e->comm, nm, msgs, e->stream)) return 1;
+  if (comm_exchange(e->comm, nm, msgs, e->stream)) { e->last_code = NLPS_ERR_CUDA; return 1; }
   CUDA_OK(cudaMemcpyAsync(e->h_mig, e->mig_cnt, sizeof(int) * 16, cudaMemcpyDeviceToHost, e->stream));
   CUDA_OK(cudaStreamSynchronize(e->stream));
   const int n_stay = e->h_mig[0], n_out[2] = {e->h_mig[1], e->h_mig[2]}, n_in[2] = {e->h_mig[8], e->h_mig[9]};
   e->steps_since_migration = 0;
+  // The decision to go on is taken by ALL slabs together: a slab that bailed out on its own would leave its
+  // neighbours waiting in the row exchange below (or pairing that receive with a later halo message).
+  int my_code = 0;
   if ((n_out[0] && e->side[0].peer < 0) || (n_out[1] && e->side[1].peer < 0)) {
     fprintf(stderr, "nlps_b200: slab %d: particles left the outer end of the slab range\n", e->rank);
-    e->last_code = NLPS_ERR_SLAB_EXCURSION;
-    return 1;
+    my_code = NLPS_ERR_SLAB_EXCURSION;
   }
   const int np_new = n_stay + n_in[0] + n_in[1];
-  if (np_new > ld || std::max(std::max(n_out[0], n_out[1]), std::max(n_in[0], n_in[1])) > e->mig_cap) {
+  if (!my_code && (np_new > ld || std::max(std::max(n_out[0], n_out[1]), std::max(n_in[0], n_in[1])) > e->mig_cap)) {
     fprintf(stderr, "nlps_b200: slab %d: migration exceeds the capacity (%d rows, %d per message)\n", e->rank, ld, e->mig_cap);
-    e->last_code = NLPS_ERR_SLAB_CAPACITY;
+    my_code = NLPS_ERR_SLAB_CAPACITY;
+  }
+  int all_ok = 1;
+  if (comm_all_ok(e->comm, e->rank, e->world, my_code == 0, e->mig_cnt + 12, e->stream, &all_ok)) {
+    e->last_code = NLPS_ERR_CUDA;
+    e->host_fail = 1;
+    return 1;
+  }
+  if (!all_ok) {  // every slab returns here, none enters the row exchange
+    e->last_code = my_code ? my_code : NLPS_ERR_SLAB_CAPACITY;
+    e->host_fail = 1;
+    if (!my_code) fprintf(stderr, "nlps_b200: slab %d: another slab could not migrate its particles\n", e->rank);
     return 1;
   }
   const bool any = n_out[0] + n_out[1] + n_in[0] + n_in[1] > 0;
@@ -2554,6 +2437,8 @@ static int migrate_t(nlps_engine* e) {
   addd(P.J_n, 1); addd(P.J_n1, 1); addd(P.eps_n, 1); addd(P.eps_n1, 1); addd(P.kap_n, 1); addd(P.kap_n1, 1);
   addd(P.F_n, DD); addd(P.F_n1, DD); addd(P.DF, DD); addd(P.be_n, T); addd(P.be_n1, T); addd(P.stress, T); addd(P.cep, DD);
   addd(P.Fs4, 1); addd(P.DFs4, 1);
+  if (P.area0) addd(P.area0, 1);
+  addd(P.sstar, 1);
   addi(P.I0, 1); tab.back().is_int = 2;
   addi(P.nnodes, 1); addi(P.matidx, 1); addi(P.orig, 1); addi((int*)P.mask, e->W);
   const unsigned long long row_bytes = off;
@@ -2571,7 +2456,7 @@ static int migrate_t(nlps_engine* e) {
     if (n_out[s_] || n_in[s_])
       msgs[nm++] = nlps_msg{e->side[s_].peer, e->mig_sbuf[s_], row_bytes * n_out[s_], e->mig_rbuf[s_], row_bytes * n_in[s_]};
   }
-  if (comm_exchange(e->comm, nm, msgs, e->stream)) return 1;
+  if (comm_exchange(e->comm, nm, msgs, e->stream)) { e->last_code = NLPS_ERR_CUDA; return 1; }
   if (!any) return 0;
   row0 = n_stay;
   for (int s_ = 0; s_ < 2; s_++) {
@@ -2589,6 +2474,29 @@ static int migrate_t(nlps_engine* e) {
   return 0;
 }
 
+// launch record of the warp-per-cell kernels (nlps_cellwarp.cu)
+static CwLaunch cw_launch_record(nlps_engine* e, const StepParams& sp) {
+  CwLaunch L;
+  L.m = e->mesh; L.P = e->P; L.G = e->G; L.sp = sp; L.cfg = e->cw; L.err = e->err; L.stream = e->stream;
+  const int units = std::max(1, nblk((size_t)e->max_occ, e->cw.CPW));
+  L.max_blocks = std::max(1, nblk((size_t)units, e->cw.warps));
+  return L;
+}
+#define CW_TIMED(e, id, call)                                    \
+  do {                                                           \
+    if ((e)->profile) cudaEventRecord((e)->ev0, (e)->stream);    \
+    if (call) (e)->last_code = NLPS_ERR_CUDA;                    \
+    (e)->launches++;                                             \
+    if ((e)->profile) {                                          \
+      cudaEventRecord((e)->ev1, (e)->stream);                    \
+      cudaEventSynchronize((e)->ev1);                            \
+      float _ms = 0;                                             \
+      cudaEventElapsedTime(&_ms, (e)->ev0, (e)->ev1);            \
+      (e)->k_ms[id] += _ms;                                      \
+      (e)->k_n[id]++;                                            \
+    }                                                            \
+  } while (0)
+
 // proj != nullptr: implicit scheme, project that field instead of D_dis; lists_only_reuse: skip the whole search
 // (second projection of the same step) and reuse lists, beta and lambda
 template <int D>
@@ -2598,6 +2506,11 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
     StepParams sp = make_params(e, step, update_I0);
     sp.proj = proj;
     sp.reuse_lists = 1;
+    if (e->kver == 2) {
+      const CwLaunch L = cw_launch_record(e, sp);
+      CW_TIMED(e, K_LME_P2G, cw_launch_lme_p2g(D, e->W, L, e->cws, e->sm_count, e->max_smem_optin, 0));
+      return;
+    }
     const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, 0); }
 #define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
@@ -2608,7 +2521,9 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
 #undef CASE_WC
     return;
   }
-  if (e->slab_on && update_I0 && e->migrate_every > 0 && e->steps_since_migration >= e->migrate_every) migrate_t<D>(e);
+  if (e->slab_on && update_I0 && e->migrate_every > 0 && e->steps_since_migration >= e->migrate_every && !e->host_fail &&
+      migrate_t<D>(e))
+    e->host_fail = 1;
   e->steps_since_migration++;
   const int np = e->np, nn = e->nn;
   cudaMemsetAsync(e->G.cnt, 0, sizeof(int) * nn, e->stream);
@@ -2628,6 +2543,11 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
   e->steps_since_sort++;
   StepParams sp = make_params(e, step, update_I0);
   sp.proj = proj;
+  if (e->kver == 2) {
+    const CwLaunch L = cw_launch_record(e, sp);
+    CW_TIMED(e, K_LME_P2G, cw_launch_lme_p2g(D, e->W, L, e->cws, e->sm_count, e->max_smem_optin, do_predictor));
+    return;
+  }
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, do_predictor); }
 #define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
@@ -2656,8 +2576,19 @@ static void stage_kin_stress_t(nlps_engine* e, int step) {
   }
   StepParams sp = make_params(e, step, 1);
   sp.implicit = e->implicit_on;
+  if (e->kver == 2) {
+    const CwLaunch L = cw_launch_record(e, sp);
+    if (e->uniform_mat == NLPS_MAT_NEO_HOOKEAN_WRIGGERS && !e->split_nh) {
+      CW_TIMED(e, K_KIN_FORCE, cw_launch_kin(D, e->W, CW_KIN_FUSED, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
+    } else {  // gather (DF) -> stress (thread per particle) -> force sums
+      CW_TIMED(e, K_KIN_GATHER, cw_launch_kin(D, e->W, CW_KIN_GATHER, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
+      CW_TIMED(e, K_STRESS, cw_launch_stress(D, L, e->mat, e->uniform_mat, e->has_traction));
+      CW_TIMED(e, K_KIN_FORCE, cw_launch_kin(D, e->W, CW_FORCE, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
+    }
+    return;
+  }
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
-#define CASE_WMC(w, mt, c) { auto kfn = k_kin_force<D, w, mt, c>; LAUNCH_SMEM(e, K_KIN_FORCE, kfn, grid, e->cfg.threads, e->smemB, e->mesh, e->P, e->G, sp, e->cfg, e->err, e->has_traction); }
+#define CASE_WMC(w, mt, c) { auto kfn = k_kin_force<D, w, mt, c>; LAUNCH_SMEM(e, K_KIN_FORCE, kfn, grid, e->cfg.threads, e->smemB, e->mesh, e->P, e->G, sp, e->cfg, e->err, e->has_traction, e->mat); }
 #define CASE_WM(w, mt) if (D == 2 && e->cache_pa) CASE_WMC(w, mt, (D == 2)) else CASE_WMC(w, mt, false)
 #define CASE_W(w) case w: switch (e->uniform_mat) { case 0: CASE_WM(w, 0) break; case 1: CASE_WM(w, 1) break; case 2: CASE_WM(w, 2) break; default: CASE_WM(w, -1) break; } break;
   if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_W(4) CASE_W(8) } }
@@ -2678,12 +2609,17 @@ static void stage_force_t(nlps_engine* e, int step) {
 template <int D>
 static void stage_g2p_t(nlps_engine* e, int step) {
   StepParams sp = make_params(e, step, 1);
+  if (e->kver == 2) {
+    const CwLaunch L = cw_launch_record(e, sp);
+    CW_TIMED(e, K_G2P, cw_launch_g2p(D, e->W, L, e->cws, e->sm_count, e->max_smem_optin));
+  } else {
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH_SMEM(e, K_G2P, kfn, grid, e->cfg.threads, e->smemC, e->mesh, e->P, e->G, sp, e->cfg); } break;
   if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_W(4) CASE_W(8) } }
 #undef CASE_W
+  }
   if (!e->inert_synced) {
-    if (e->np) k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P);
+    if (e->np) k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P, e->mat);
     e->inert_synced = 1;
   }
   // roll n+1 -> n (U-Verlet.c:1043-1081) as pointer swaps
@@ -2889,7 +2825,10 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   }
   if (maxr2t > 255) return set_err(err, err_len, "transposed 2-ring larger than 255 nodes is not supported");
   mark("transposed adjacency");
-  e->mesh = MeshDev{nn, dX, r1p, r1i, r2p, r2i, t1p, t1i, t2p, t2i, dq, dh};
+  double* dsst = nullptr;
+  if (dev_alloc(e, &dsst, (size_t)nn)) return 1;
+  if (nn) k_sstar_nodes<<<nblk(nn, 256), 256, 0, e->stream>>>(dh, nn, solver->gamma_lme, e->neg_log_tol, dsst);
+  e->mesh = MeshDev{nn, dX, r1p, r1i, r2p, r2i, t1p, t1i, t2p, t2i, dq, dh, dsst};
   mark("transposed adjacency upload");
   e->max_occ = (int)std::min<long long>(nn, std::max(ld, 1));
   e->max_act = (int)std::min<long long>(nn, (long long)std::max(ld, 1) * maxr1);
@@ -2965,6 +2904,27 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     c.magic = ((1u << 21) + c.SL - 1) / c.SL;
     for (unsigned q = 0; q < (unsigned)(c.C * c.SL); q++)
       if (((q * c.magic) >> 21) != q / c.SL) return set_err(err, err_len, "internal: pair-index division constant");
+    // ---- warp-per-cell kernels (nlps_cellwarp.cu)
+    {
+      CwCfg& w = e->cw;
+      w.SL = maxr2;
+      w.warps = 4;
+      w.CPW = (D == 2) ? 4 : 1;
+      w.NC = (D == 2) ? ((maxr2 + 3) & ~3) : 48;  // 3D gamma = 6: 33-48 neighbours; longer lists take two particle slots
+      if (const char* s_ = getenv("NLPS_CW_CPW")) w.CPW = std::min(31, std::max(1, atoi(s_)));
+      if (const char* s_ = getenv("NLPS_CW_NC")) w.NC = std::max(4, atoi(s_) & ~3);
+      if (const char* s_ = getenv("NLPS_CW_WARPS")) w.warps = std::min(4, std::max(1, atoi(s_)));
+      w.NC = std::max(w.NC, (((maxr2 + 3) & ~3) + 7) / 8);  // the longest possible list must fit the 8 slots of a chunk
+      w.NC = (w.NC + 3) & ~3;
+      w.CL = (maxr2 + 3) & ~3;
+      w.magic = ((1u << 21) + w.SL - 1) / w.SL;
+      for (unsigned q = 0; q < (unsigned)(w.CPW * w.SL); q++)
+        if (((q * w.magic) >> 21) != q / w.SL) return set_err(err, err_len, "internal: pair-index division constant (warp tiles)");
+      e->kver = 2;
+      if (const char* s_ = getenv("NLPS_KERNELS")) e->kver = atoi(s_) == 1 ? 1 : 2;
+      if (const char* s_ = getenv("NLPS_SPLIT_NH")) e->split_nh = atoi(s_) != 0;
+      if (maxr2 > 256) e->kver = 1;  // slot ids of the compact lists are bytes
+    }
     if (const char* s_ = getenv("NLPS_REORDER_EVERY")) e->reorder_every = atoi(s_);
     CUDA_OK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
     if (const char* s_ = getenv("NLPS_GRID")) e->grid_override = std::max(1, atoi(s_));
@@ -3051,8 +3011,9 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
                         s.plastic_strain_0, s.phi_frictional, s.psi_frictional, s.exponent_hardening_ortiz,
                         s.cohesion, s.alpha_hardening_borja, s.a_hardening_borja[0], s.a_hardening_borja[1],
                         s.a_hardening_borja[2]};
+      mat_hoist(hm[i], D);
+      e->mat.m[i] = hm[i];
     }
-    CUDA_OK(cudaMemcpyToSymbol(c_mat, hm, sizeof(hm)));
     e->uniform_mat = hm[0].type;
     for (int i = 1; i < n_materials; i++)
       if (hm[i].type != hm[0].type) e->uniform_mat = -1;
@@ -3069,9 +3030,17 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   A_(J_n, 1) A_(J_n1, 1) A_(eps_n, 1) A_(eps_n1, 1) A_(kap_n, 1) A_(kap_n1, 1)
   A_(F_n, DD) A_(F_n1, DD) A_(DF, DD) A_(be_n, TBv) A_(be_n1, TBv) A_(stress, T) A_(cep, DD)
   A_(Fs4, 1) A_(DFs4, 1)
+  A_(zi, 1) A_(ji, D * (D + 1) / 2) A_(gop, DD) A_(sstar, 1)
 #undef A_
+  if (dev_alloc(e, &P.clist, (size_t)ld * e->cw.CL)) return 1;
   P.trac = nullptr;
+  P.area0 = nullptr;
   if (e->has_traction && dev_alloc(e, &P.trac, (size_t)ld * D)) return 1;
+  if (e->has_traction && D == 3) {
+    if (!st->Area_0)
+      return set_err(err, err_len, "3D Neumann loads act on Particle.Phi.Area_0 (U-Verlet.c:847-849): state->Area_0 is NULL");
+    if (dev_alloc(e, &P.area0, (size_t)ld)) return 1;
+  }
   if (dev_alloc(e, &P.I0, ld) || dev_alloc(e, &P.nnodes, ld) || dev_alloc(e, &P.matidx, ld) ||
       dev_alloc(e, &P.orig, ld) || dev_alloc(e, &P.inv, std::max(e->n_global, 1)) || dev_alloc(e, &P.mask, (size_t)ld * e->W))
     return 1;
@@ -3153,7 +3122,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   }
   // ---- migration buffers
   {
-    const size_t row_bytes = 8 * (size_t)(6 * D + 11 + 4 * DD + 3 * T + 2) + 4 * (size_t)(4 + e->W);
+    const size_t row_bytes = 8 * (size_t)(6 * D + 11 + 4 * DD + 3 * T + 2 + 1 + (P.area0 ? 1 : 0)) + 4 * (size_t)(4 + e->W);
     e->mig_cap = std::max(4096, ld / 8);
     if (dev_alloc(e, &e->mig_dest, ld) || dev_alloc(e, &e->mig_cnt, 16) || dev_alloc(e, &e->mig_tab, 256)) return 1;
     for (int s_ = 0; s_ < 2; s_++)
@@ -3334,8 +3303,9 @@ static int upload_impl(nlps_engine* e, const nlps_particles* in, int rows) {
       put_field(e, in->Vol_0, P.vol0, 1, 1, 0, rows) || put_field(e, in->W, P.W, 1, 1, 0, rows) ||
       put_field(e, in->EPS_n, P.eps_n, 1, 1, 0, rows) || put_field(e, in->EPS_n1, P.eps_n1, 1, 1, 0, rows) ||
       put_field(e, in->Kappa_n, P.kap_n, 1, 1, 0, rows) || put_field(e, in->Kappa_n1, P.kap_n1, 1, 1, 0, rows) ||
-      put_field(e, in->Beta, P.beta, 1, 1, 0, rows))
+      put_field(e, in->Beta, P.beta, 1, 1, 0, rows) || put_field(e, in->Area_0, P.area0, 1, 1, 0, rows))
     return 1;
+  if (e->np) k_sstar_particles<<<nblk(e->np, 256), 256, 0, e->stream>>>(P.beta, e->np, e->neg_log_tol, P.sstar);
   return 0;
 }
 
@@ -3405,6 +3375,7 @@ int nlps_b200_download_local(nlps_engine* e, nlps_particles* out, int* ids) {
 int nlps_b200_migrate(nlps_engine* e) {
   cudaSetDevice(e->device);
   int rc = (e->D == 2) ? migrate_t<2>(e) : migrate_t<3>(e);
+  if (rc) e->host_fail = 1;
   return rc ? 1 : poll_error(e);
 }
 long long nlps_b200_migrated_count(nlps_engine* e) { return e->n_migrated_in; }
@@ -3773,13 +3744,14 @@ int nlps_b200_stress_points(int ndim, const nlps_material* material, double tol_
   CUDA_OK(cudaSetDevice(device));
   const int T = ndim == 2 ? 5 : 9, DD = ndim * ndim;
   const nlps_material& sm = *material;
-  MatParams hm[MAX_MATERIALS];
-  memset(hm, 0, sizeof(hm));
+  MatTable pt;  // the call's own table: no engine of the process is touched
+  memset(&pt, 0, sizeof(pt));
+  MatParams* hm = pt.m;
   hm[0] = MatParams{sm.type, sm.rho, sm.E, sm.nu, sm.reference_pressure, sm.kappa_0, sm.hardening_modulus,
                     sm.plastic_strain_0, sm.phi_frictional, sm.psi_frictional, sm.exponent_hardening_ortiz,
                     sm.cohesion, sm.alpha_hardening_borja, sm.a_hardening_borja[0], sm.a_hardening_borja[1],
                     sm.a_hardening_borja[2]};
-  CUDA_OK(cudaMemcpyToSymbol(c_mat, hm, sizeof(hm)));
+  mat_hoist(hm[0], ndim);
   ReturnMapParams rp{tol_radial, max_iter_radial, quirk_transposed_eigvec < 0 ? (ndim == 2) : quirk_transposed_eigvec, 1};
   size_t nT = (size_t)n * T;
   double* d = nullptr;
@@ -3795,8 +3767,8 @@ int nlps_b200_stress_points(int ndim, const nlps_material* material, double tol_
   cudaMemcpy(dJ, J_n1, n * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(deps, eps_n, n * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(dkap, kappa_n, n * 8, cudaMemcpyHostToDevice);
-  if (ndim == 2) k_stress_points<2><<<nblk(n, 64), 64>>>(n, 0, rp, dDF, dF1, dJ, dbe, deps, dkap, dS, dbe1, deps1, dkap1, dW, dC, dst);
-  else k_stress_points<3><<<nblk(n, 64), 64>>>(n, 0, rp, dDF, dF1, dJ, dbe, deps, dkap, dS, dbe1, deps1, dkap1, dW, dC, dst);
+  if (ndim == 2) k_stress_points<2><<<nblk(n, 64), 64>>>(n, pt, rp, dDF, dF1, dJ, dbe, deps, dkap, dS, dbe1, deps1, dkap1, dW, dC, dst);
+  else k_stress_points<3><<<nblk(n, 64), 64>>>(n, pt, rp, dDF, dF1, dJ, dbe, deps, dkap, dS, dbe1, deps1, dkap1, dW, dC, dst);
   cudaError_t st = cudaDeviceSynchronize();
   if (st == cudaSuccess) {
     cudaMemcpy(stress, dS, nT * 8, cudaMemcpyDeviceToHost);

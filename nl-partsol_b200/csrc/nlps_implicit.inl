@@ -207,7 +207,7 @@ __device__ __forceinline__ int csr_find(const int* cols, int lo, int hi, int key
 // flow rule is not associated, hence BiCGStab below.  The law is read per particle (mixed clouds work).
 template <int D, int W, bool EP>
 __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridDev G, const int* row_ptr, const int* cols, double* vals,
-                                                     int* err) {
+                                                     int* err, const __grid_constant__ MatTable mt) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NMAX = 32 * W, DD = D * D;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridD
       }
     }
     __syncwarp();
-    const MatParams& mat = c_mat[P.matidx[p]];
+    const MatParams& mat = mt.m[P.matidx[p]];
     const double Gm = mat.E / (2 * (1 + mat.nu)), lm = mat.nu * mat.E / ((1 - mat.nu * 2) * (1 + mat.nu));
     const double J = P.J_n1[p], V0 = P.vol0[p];
     const double c0 = V0 * lm * J * J, c1 = V0 * (Gm - 0.5 * lm * (J * J - 1.0)), cg = V0 * Gm;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridD
 // particle (3D, 8 particles per cell: 2.8x fewer RED.E.ADD.F64, the unit that bounds the assembly).
 template <int D, int W>
 __global__ void __launch_bounds__(128) k_assemble_cell_nh(MeshDev m, PartDev P, GridDev G, const int* row_ptr, const int* cols,
-                                                          double* vals, int* err) {
+                                                          double* vals, int* err, const __grid_constant__ MatTable mats) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int SL = 32 * W, DD = D * D, MP = 8, V = 3 * D;
   double* s_g = (double*)smem;                        // [MP][SL][V]: g | g1 | b_n g
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(128) k_assemble_cell_nh(MeshDev m, PartDev P, 
           }
         }
         if (lane == 0) {
-          const MatParams& mat = c_mat[P.matidx[p]];
+          const MatParams& mat = mats.m[P.matidx[p]];
           const double Gm = mat.E / (2 * (1 + mat.nu)), lm = mat.nu * mat.E / ((1 - mat.nu * 2) * (1 + mat.nu));
           const double J = P.J_n1[p], V0 = P.vol0[p];
           s_coef[j * 4 + 0] = V0 * lm * J * J;
@@ -969,7 +969,7 @@ static int imp_assemble_t(nlps_engine* e) {
     const size_t smem = (size_t)wpb * 32 * W * (3 * D * sizeof(double) + sizeof(int));
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = std::max(1, std::min(nblk(e->np, wpb), e->sm_count * 8));
-    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err);
+    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err, e->mat);
   };
   auto launch_cell = [&](auto kfn, int W) {
     const int SL = 32 * W, MP = 8;
@@ -977,7 +977,7 @@ static int imp_assemble_t(nlps_engine* e) {
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int per_sm = std::max(1, std::min(8, (int)((size_t)e->max_smem_optin / (smem + 1024))));
     const int grid = std::max(1, std::min(std::max(e->max_occ, 1), e->sm_count * per_sm));
-    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err);
+    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err, e->mat);
   };
   static const bool cell_asm = !(getenv("NLPS_ASM_CELL") && atoi(getenv("NLPS_ASM_CELL")) == 0);
   if (!c->plastic && cell_asm) {
@@ -1129,7 +1129,7 @@ static int imp_step_t(nlps_engine* e, int step) {
   else { if (e->W == 4) g2p(k_g2p_implicit<3, 4>); else g2p(k_g2p_implicit<3, 8>); }
   e->launches++;
   if (!e->inert_synced) {
-    if (e->np) k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P);
+    if (e->np) k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P, e->mat);
     e->inert_synced = 1;
   }
   std::swap(e->P.F_n, e->P.F_n1);

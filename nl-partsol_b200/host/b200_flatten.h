@@ -184,6 +184,13 @@ static int b200_flatten(b200_inputs *in, Mesh FEM_Mesh, Particle MPM_Mesh, Time_
   st.EPS_n = Phi->EPS_n; st.EPS_n1 = Phi->EPS_n1; st.Kappa_n = Phi->Kappa_n; st.Kappa_n1 = Phi->Kappa_n1;
   st.lambda = MPM_Mesh.lambda.nV; st.Beta = MPM_Mesh.Beta.nV;
   st.I0 = MPM_Mesh.I0; st.NumberNodes = MPM_Mesh.NumberNodes; st.MatIdx = MPM_Mesh.MatIdx;
+  /* 3D Neumann loads act on Phi.Area_0 (U-Verlet.c:847-849); the reference declares the field (Types.h:196) and never
+   * allocates it, so a 3D deck with loads fails loudly in nlps_b200_create instead of reading a volume as an area */
+#if NumberDimensions == 3
+  st.Area_0 = Phi->Area_0.nV;
+#else
+  st.Area_0 = NULL;
+#endif
 
   in->mesh = mesh; in->solver = solver; in->bounds = bounds; in->neumann = neumann; in->gravity = gravity;
   in->mats = mats; in->st = st; in->r1p = r1p; in->r1i = r1i; in->r2p = r2p; in->r2i = r2i;

@@ -49,7 +49,7 @@ _PFIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "F_n1", "DF", "b_e_n", 
 
 class Particles(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, _dp) for k in _PFIELDS] + [("I0", _ip), ("NumberNodes", _ip),
-                                                                  ("MatIdx", _ip)]
+                                                                  ("MatIdx", _ip), ("Area_0", _dp)]
 
 
 class Msg(C.Structure):
@@ -311,6 +311,9 @@ class _Marshal:
             setattr(st, kname, host[kname].ctypes.data_as(_dp) if kname in host else None)
         for kname in ("I0", "MatIdx", "NumberNodes"):
             setattr(st, kname, host[kname].ctypes.data_as(_ip))
+        if "Area_0" in prob.fields:  # 3D Neumann loads (Phi.Area_0); constant, never downloaded
+            host["Area_0"] = cp(_d(prob.fields["Area_0"]))
+            st.Area_0 = host["Area_0"].ctypes.data_as(_dp)
         return st, host
 
 
@@ -384,7 +387,7 @@ class Engine:
     def download_local(self):
         """Compact rows of the particles this slab holds + their global ids."""
         n = self.local_count()
-        host = {k: np.zeros((max(n, 1),) + v.shape[1:], v.dtype) for k, v in self.m.host.items()}
+        host = {k: np.zeros((max(n, 1),) + v.shape[1:], v.dtype) for k, v in self.m.host.items() if k != "Area_0"}
         st = Particles()
         st.n = max(n, 1)
         for k in _PFIELDS:

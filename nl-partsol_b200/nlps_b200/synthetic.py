@@ -253,6 +253,8 @@ def beam_3d(cells_per_unit=8, nsteps=20, gamma_lme=6.0, E=1e7, cfl=10.0, tractio
     val = np.zeros((3, nsteps))
     val[2, :] = traction * np.minimum(1.0, (np.arange(nsteps) + 1) / max(nsteps, 1))
     P.neumann.append(dict(nodes=tip, dir=dr, val=val))
+    # Phi.Area_0 of a 3D Neumann load (U-Verlet.c:847-849): the 8 particles of a tip cell share its face, V0 / h each
+    P.fields["Area_0"] = P.fields["Vol_0"] * c
     return P
 
 
