@@ -298,6 +298,8 @@ nlps_engine *nlps_b200_create_slab(const nlps_mesh *mesh, const nlps_solver *sol
                                    const nlps_particles *state, const nlps_slab *slab,
                                    int device, char *err, int err_len);
 int nlps_b200_local_count(nlps_engine *e);
+/* which data plane carries the per-step halo sums of this slab engine (a static string) */
+const char *nlps_b200_transport(nlps_engine *e);
 /* compact download: rows 0..local_count-1 of `out` (out->n >= local_count) and their global ids */
 int nlps_b200_download_local(nlps_engine *e, nlps_particles *out, int *ids);
 /* move particles that crossed a cut now (also runs every migrate_every steps inside run) */

@@ -1,23 +1,32 @@
-// nlps_cellwarp.cu -- warp-per-cell kernels of the explicit NPC-FS step (sm_100a, fp64).
+// nlps_cellwarp.cu -- warp-per-cell kernels of the explicit NPC-FS step in three dimensions (sm_100a, fp64).
+// (2D decks run the block-per-cell-group kernels of nlps_engine.cu: 25 ring slots and 4 particles per cell leave
+// nothing to split over the lanes of a warp.)
 //
-// One WARP owns a run of CPW consecutive occupied cells (a cell = all particles with the same closest node I0, i.e.
-// one contiguous run of the cell-sorted particle order) and nothing is shared between the warps of a block: no block
-// barrier anywhere, every warp is at its own point of its own cell.  The warp stages the 2-ring node data of its
-// cells in its slice of shared memory and walks the particles in chunks of 8; the neighbour loop of a particle is
-// split over 4 lanes (8 .. 32 for lists longer than the compact cache), partial sums meet in xor-shuffles.  A
-// particle's neighbour list is COMPACTED by the LME kernel from its bitmask into ascending slot ids (P.clist, one byte
-// per neighbour), so that every lane of every kernel of the step runs over neighbours only (3D: ~40 of 125 ring slots)
-// and the lanes of a particle stay balanced.
+// One WARP owns one occupied cell at a time (a cell = all particles with the same closest node I0 = one contiguous run
+// of the cell-sorted particle order) and walks a contiguous range of cells; nothing is shared between the warps of a
+// block: no block barrier anywhere.  The warp stages the 2-ring node data of its cell in its slice of shared memory and
+// takes the particles in chunks of 8; the neighbour loop of a particle is split over 4 lanes (8 .. 32 when the weights
+// of a long list must wait in the compact cache), partial sums meet in xor-shuffles.
 //
-// Particle-to-grid without atomics: the particles of a chunk are taken one after the other, the lanes of the warp
-// run over THAT particle's neighbours (distinct slots: no conflict) and add into the warp's (cell, slot) accumulators
-// in shared memory; a cell's accumulators go to part[(slot of the cell in the node's transposed ring, node rank)] and
-// are summed per node in a fixed order by k_grid_disp / k_grid_acc (nlps_engine.cu).  Deterministic.
+// Pipeline: the ring node ids of the NEXT cell and the cell record after it arrive by cp.async (LDGSTS) while the
+// current cell computes, so that a cell starts with one dependent global round trip (node data) instead of three
+// (record -> ring ids -> node data); the particle rows of the next cell are prefetched to L2.
+//
+// Neighbour lists: the LME kernel tests the 2-ring slots with the lanes interleaved (no bank conflicts), stores the
+// reference's list as a bitmask and ALSO as ascending slot ids, one byte per neighbour (P.clist): every kernel of the
+// step then runs over neighbours only (~40 of 125 ring slots at gamma = 6) with balanced lanes.
+//
+// Particle-to-grid without atomics.  Mass / momentum: the weights of the converged LME evaluation sit in a dense
+// [particle][slot] table in shared memory (zero for non-neighbours); lane k sums column k over the particles of the
+// chunk and writes part[(slot of the cell in the node's transposed ring, node rank)] straight from registers.  Forces:
+// the particles of a chunk are taken one after the other, the lanes run over THAT particle's neighbours (distinct
+// slots: no conflict) and add into the cell's accumulators in shared memory.  Either way the cell's sums are added per
+// node in a fixed order by k_grid_disp / k_grid_acc (nlps_engine.cu): deterministic.
 //
 // The LME kernel leaves 1/Z and the inverse Hessian J^-1 of the converged evaluation per particle (P.zi, P.ji): the
-// kinematics, force and G2P kernels of the same step evaluate the weights exp(-beta |l|^2 + lambda.l) once and need
-// no second pass for Z, r, J.  Plastic laws run in a kernel of their own with a thread per particle (the return
-// mapping would leave 3 of the 4 lanes of a particle idle): gather (DF) -> stress -> force sums.
+// kinematics, force and G2P kernels evaluate the weights exp(-beta |l|^2 + lambda.l) once and need no second pass
+// for Z, r, J.  Plastic laws run in a kernel of their own with a thread per particle (the return mapping would leave
+// 3 of the 4 lanes of a particle idle): gather (DF) -> stress -> force sums.
 //
 // Reference citations are relative to nl-partsol/src of migmolper/NL-PartSol.
 #include <stdio.h>
@@ -29,11 +38,12 @@
 
 namespace {
 
+constexpr int D = 3;            // every kernel of this file
 constexpr int LPP0 = 4;         // lanes per particle of the base mapping
 constexpr int PPW = 32 / LPP0;  // particles per chunk
+constexpr int NJ = D * (D + 1) / 2;
+constexpr int PVN = 2 * D + 2 + D * D + D;  // per-particle record of the force sums
 constexpr unsigned FULL = 0xffffffffu;
-
-template <int D> struct PV { static constexpr int N = 2 * D + 2 + D * D + D; };  // per-particle record of the force sums
 
 struct Carve {
   size_t off = 0;
@@ -41,129 +51,185 @@ struct Carve {
 };
 // shared-memory slice of ONE warp, evaluated identically on host (size) and device (offsets)
 struct CwLayout {
-  size_t meta, rank, q, X, U, A, acc, list, wts, pv, total;
-  __host__ __device__ CwLayout(const CwCfg& c, int D, int kernel) {
+  size_t mrec, um, ids, rank, q, X, U, A, acc, wd, list, wts, pv, total;
+  __host__ __device__ CwLayout(const CwCfg& c, int kernel) {
     Carve k;
-    const size_t pairs = (size_t)c.CPW * c.SL;
-    const bool wantQ = kernel == CW_LME_P2G || kernel == CW_KIN_FUSED || kernel == CW_FORCE;
-    const bool wantU = kernel == CW_KIN_FUSED || kernel == CW_KIN_GATHER || kernel == CW_G2P;
-    const int nacc = kernel == CW_LME_P2G ? 1 + D : ((kernel == CW_KIN_FUSED || kernel == CW_FORCE) ? D : 0);
-    const bool wantW = kernel == CW_LME_P2G || kernel == CW_KIN_FUSED;
-    const bool wantPV = kernel == CW_KIN_FUSED || kernel == CW_FORCE;
-    // LME kernel: x (D) | lambda (D) | DU_p (D) | beta | mass per particle, then p, cell, n (or -1) and the mask words
-    const size_t pvk = kernel == CW_LME_P2G ? 8 * (size_t)PPW * (3 * D + 2) + 4 * (size_t)PPW * (3 + MAX_MASK_WORDS) : 0;
-    meta = k.take(4 * (size_t)(4 * c.CPW + 1));
-    rank = k.take(4 * pairs);
-    q = wantQ ? k.take(pairs) : 0;
-    X = k.take(8 * D * pairs);
-    U = wantU ? k.take(8 * D * pairs) : 0;
-    A = kernel == CW_G2P ? k.take(8 * D * pairs) : 0;
-    acc = nacc ? k.take(8 * (size_t)nacc * pairs) : 0;
-    list = kernel == CW_LME_P2G ? k.take((size_t)PPW * c.NC) : 0;
-    wts = wantW ? k.take(8 * (size_t)PPW * c.NC) : 0;
-    pv = wantPV ? k.take(8 * (size_t)PPW * (2 * D + 2 + D * D + D)) : (pvk ? k.take(pvk) : 0);
+    const size_t SL = c.SL;
+    const bool lme = kernel == CW_LME_P2G, fused = kernel == CW_KIN_FUSED, force = kernel == CW_FORCE;
+    const bool wantQ = lme || fused || force;
+    const bool wantU = fused || kernel == CW_KIN_GATHER || kernel == CW_G2P;
+    mrec = k.take(16 * 4);                    // ring of 4 cell records (int4)
+    um = k.take(4 * MAX_MASK_WORDS);          // union of the neighbour masks of the cell's particles
+    ids = k.take(4 * (size_t)c.CL);           // ring node ids of the next cell (cp.async)
+    rank = wantQ ? k.take(4 * SL) : 0;
+    q = wantQ ? k.take(SL) : 0;
+    X = k.take(8 * D * SL);
+    U = wantU ? k.take(8 * D * SL) : 0;
+    A = kernel == CW_G2P ? k.take(8 * D * SL) : 0;
+    acc = (fused || force) ? k.take(8 * D * SL) : 0;
+    wd = lme ? k.take(8 * (size_t)PPW * (c.CL + 1)) : 0;   // dense weights [particle][slot], row stride CL + 1
+    list = k.take((size_t)PPW * c.CL);
+    wts = fused ? k.take(8 * (size_t)PPW * c.NC) : 0;
+    pv = (fused || force) ? k.take(8 * (size_t)PPW * PVN) : (lme ? k.take(8 * (size_t)PPW * 4) : 0);
     total = k.off;
   }
 };
 struct WarpTile {
-  int *cs, *base, *len, *B, *rank;
+  int4* mrec;
+  uint32_t* um;
+  int *ids, *rank;
   unsigned char *q, *list;
-  double *X, *U, *A, *acc, *wts, *pv;
+  double *X, *U, *A, *acc, *wd, *wts, *pv;
 };
-__device__ __forceinline__ WarpTile carve_tile(unsigned char* w, const CwLayout& L, const CwCfg& c) {
+__device__ __forceinline__ WarpTile carve_tile(unsigned char* w, const CwLayout& L) {
   WarpTile T;
-  T.cs = (int*)(w + L.meta); T.base = T.cs + (c.CPW + 1); T.len = T.base + c.CPW; T.B = T.len + c.CPW;
-  T.rank = (int*)(w + L.rank); T.q = w + L.q; T.list = w + L.list;
+  T.mrec = (int4*)(w + L.mrec); T.um = (uint32_t*)(w + L.um); T.ids = (int*)(w + L.ids); T.rank = (int*)(w + L.rank);
+  T.q = w + L.q; T.list = w + L.list;
   T.X = (double*)(w + L.X); T.U = (double*)(w + L.U); T.A = (double*)(w + L.A);
-  T.acc = (double*)(w + L.acc); T.wts = (double*)(w + L.wts); T.pv = (double*)(w + L.pv);
+  T.acc = (double*)(w + L.acc); T.wd = (double*)(w + L.wd); T.wts = (double*)(w + L.wts); T.pv = (double*)(w + L.pv);
   return T;
 }
 
-// metadata of the warp's cells: one record per lane (first particle slot, node, 2-ring base and length)
-__device__ __forceinline__ void cw_meta(const GridDev& G, int nocc, int np, int c0, int ncell, const WarpTile& T, int lane) {
-  if (lane <= ncell) {
-    if (c0 + lane < nocc) {
-      const int4 mt = G.occ_meta[c0 + lane];
-      T.cs[lane] = mt.y;
-      if (lane < ncell) { T.B[lane] = mt.x; T.base[lane] = mt.z; T.len[lane] = mt.w; }
-    } else {
-      T.cs[lane] = np;  // the last occupied cell ends at the last particle
+// ---- cp.async (LDGSTS): global -> shared without a register in between
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// hint: the particle rows [t, t + 8) of `ncomp` SoA components (next cell of this warp) -> L2
+__device__ __forceinline__ void cw_prefetch_rows(const double* f, int ld, int ncomp, int t, int np, int lane) {
+  if (lane < 2 * ncomp) {
+    const int tt = min(t + ((lane & 1) ? 7 : 0), np - 1);
+    if (tt >= 0) prefetch_l2(f + (size_t)(lane >> 1) * ld + tt);
+  }
+}
+
+// ---- cell pipeline.  Warp gw takes the cells gw, gw + nw, gw + 2 nw, ... (nw = warps of the grid): at any moment the
+// warps of an SM -- and of the whole chip -- work on NEIGHBOURING cells, whose ring nodes they share in L1 / L2 (a
+// contiguous range per warp scatters the active cells over the whole mesh: measured 20 % slower).  Cell records live in
+// a ring of 4 (index i & 3 for the warp's i-th cell): at cell i the records of i and i + 1 are there, i + 2 is on its way;
+// the ring node ids of cell i are in T.ids, those of i + 1 are requested as soon as the staging of i has read them.
+struct Cell { int B, t0, t1, base, len; };
+__device__ __forceinline__ void cw_pipe_init(const MeshDev& m, const GridDev& G, const WarpTile& T, int gw, int nw, int nocc,
+                                             int lane) {
+  if (gw >= nocc) return;
+  if (lane < 2 && gw + lane * nw < nocc) T.mrec[lane] = G.occ_meta[gw + lane * nw];
+  __syncwarp();
+  const int4 r = T.mrec[0];
+  for (int k = lane; k < (r.w & 511); k += 32) T.ids[k] = m.r2i[r.z + k];
+  __syncwarp();
+}
+__device__ __forceinline__ Cell cw_cell(const WarpTile& T, int i) {
+  const int4 r = T.mrec[i & 3];
+  Cell c;
+  c.B = r.x; c.t0 = r.y; c.base = r.z; c.len = r.w & 511;
+  c.t1 = r.y + (r.w >> 9);
+  return c;
+}
+// first particle slot of the warp's next cell (for the L2 prefetch of its rows), -1 when there is none
+__device__ __forceinline__ int cw_next_t0(const WarpTile& T, int i, int u, int nw, int nocc) {
+  return (u + nw < nocc) ? T.mrec[(i + 1) & 3].y : -1;
+}
+// call after the staging of cell i (= global cell u) has consumed T.ids (and a __syncwarp)
+__device__ __forceinline__ void cw_pipe_next(const MeshDev& m, const GridDev& G, const WarpTile& T, int i, int u, int nw, int nocc,
+                                             int lane) {
+  if (u + nw < nocc) {
+    const int4 r1 = T.mrec[(i + 1) & 3];
+    for (int k = lane; k < (r1.w & 511); k += 32) cp_async4(&T.ids[k], &m.r2i[r1.z + k]);
+  }
+  if (lane == 0 && u + 2 * nw < nocc) cp_async16(&T.mrec[(i + 2) & 3], &G.occ_meta[u + 2 * nw]);
+}
+// end of a cell: everything requested for the next one has landed
+__device__ __forceinline__ void cw_pipe_wait() {
+  cp_async_wait_all();
+  __syncwarp();
+}
+
+// 2-ring node data of the cell -> the warp's shared-memory slice (ring ids from T.ids).  A node record (32 bytes of
+// coordinates, 32 + 32 bytes of nodal dU | a) is fetched by a PAIR of lanes, 16 bytes each: a warp instruction touches 16
+// sectors and uses all of each (a lane per record would touch 32 sectors per instruction and half of each, and the L1
+// data pipe is the busiest unit of these kernels); four records per lane pair in flight.
+// UNION: only the slots that are a neighbour of some particle of the cell are fetched (T.um), ~70 of 125 at gamma = 6.
+// SENT: inactive nodes and the padding of short rings get coordinates at 1e300, so that the neighbour test of the LME
+// kernel rejects them without looking at the rank (x - 1e300 squared overflows to +inf, never <= s*)
+template <bool WANT_Q, int NF, bool SENT, bool UNION>
+__device__ __forceinline__ void cw_stage(const MeshDev& m, const GridDev& G, int SL, const Cell& c, const WarpTile& T, int lane) {
+  constexpr int U = 4;
+  const int half = lane & 1, row0 = lane >> 1;
+  for (int k0 = 0; k0 < SL; k0 += 16 * U) {
+    int node[U];
+    bool need[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int k = k0 + 16 * u + row0;
+      node[u] = (k < c.len) ? T.ids[k] : -1;
+      need[u] = node[u] >= 0 && (!UNION || ((T.um[k >> 5] >> (k & 31)) & 1u));
+    }
+    int rank[U];
+    unsigned char qv[U];
+    double2 x[U], uu[U], aa[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int k = k0 + 16 * u + row0;
+      rank[u] = -1;
+      qv[u] = 0;
+      if ((WANT_Q || SENT) && node[u] >= 0 && half == 0) rank[u] = G.arank[node[u]];
+      if (WANT_Q && node[u] >= 0 && half == 0) qv[u] = m.r2q[c.base + k];
+      if (need[u]) {
+        x[u] = *reinterpret_cast<const double2*>(&m.X[(size_t)node[u] * NS<D>::X + 2 * half]);
+        if (NF >= 1) uu[u] = *reinterpret_cast<const double2*>(&G.UA[(size_t)node[u] * 2 * NS<D>::X + 2 * half]);
+        if (NF >= 2) aa[u] = *reinterpret_cast<const double2*>(&G.UA[(size_t)node[u] * 2 * NS<D>::X + NS<D>::X + 2 * half]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int k = k0 + 16 * u + row0;
+      if (k < SL) {
+        if (WANT_Q && half == 0) { T.rank[k] = rank[u]; T.q[k] = qv[u]; }
+        double* dx = T.X + (size_t)k * D;
+        if (SENT) {
+          const int rk = __shfl_sync(__activemask(), rank[u], lane & ~1);
+          const bool far = node[u] < 0 || rk < 0;
+          if (half == 0) { dx[0] = far ? 1.0e300 : x[u].x; dx[1] = far ? 1.0e300 : x[u].y; }
+          else dx[2] = far ? 1.0e300 : x[u].x;
+        } else if (need[u]) {
+          if (half == 0) { dx[0] = x[u].x; dx[1] = x[u].y; } else dx[2] = x[u].x;
+        }
+        if (NF >= 1 && need[u]) {
+          double* du = T.U + (size_t)k * D;
+          if (half == 0) { du[0] = uu[u].x; du[1] = uu[u].y; } else du[2] = uu[u].x;
+        }
+        if (NF >= 2 && need[u]) {
+          double* da = T.A + (size_t)k * D;
+          if (half == 0) { da[0] = aa[u].x; da[1] = aa[u].y; } else da[2] = aa[u].x;
+        }
+      }
+    }
+  }
+}
+// union of the neighbour masks of the cell's particles -> T.um
+__device__ __forceinline__ void cw_union(const PartDev& P, const GridDev& G, const Cell& c, int W, const WarpTile& T, int lane) {
+  if (lane < MAX_MASK_WORDS) T.um[lane] = 0u;
+  __syncwarp();
+  for (int tt = c.t0; tt < c.t1; tt += 32) {
+    const int t = tt + lane;
+    const int p = t < c.t1 ? G.plist[t] : -1;
+    for (int w = 0; w < W; w++) {
+      uint32_t v = p >= 0 ? P.mask[(size_t)w * P.ld + p] : 0u;
+      v = __reduce_or_sync(FULL, v);
+      if (lane == 0) T.um[w] |= v;
     }
   }
   __syncwarp();
 }
-// 2-ring node data of the warp's cells -> its shared-memory slice; four (cell, slot) pairs per lane in flight
-// SENT: inactive nodes and the padding of short rings get coordinates at 1e300, so that the neighbour test of the LME
-// kernel rejects them without looking at the rank (x - 1e300 squared overflows to +inf, never <= s*)
-template <int D, bool WANT_Q, int NF, bool SENT = false>
-__device__ __forceinline__ void cw_stage(const MeshDev& m, const GridDev& G, const CwCfg& cfg, int ncell, const WarpTile& T,
-                                         int lane) {
-  constexpr int U = 4;
-  const int SL = cfg.SL, npairs = ncell * SL;
-  for (int e0 = lane; e0 < npairs; e0 += U * 32) {
-    int node[U], idx[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int e = e0 + u * 32;
-      node[u] = -1;
-      idx[u] = 0;
-      if (e < npairs) {
-        const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
-        if (k < T.len[c]) { idx[u] = T.base[c] + k; node[u] = m.r2i[idx[u]]; }
-      }
-    }
-    int rank[U];
-    unsigned char qv[U];
-    double2 x0[U], x1[U], u0[U], u1[U], a0[U], a1[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int nd = max(node[u], 0);  // invalid pairs load node 0 (harmless): unconditional independent loads
-      const double* px = &m.X[(size_t)nd * NS<D>::X];
-      const double* pu = &G.UA[(size_t)nd * 2 * NS<D>::X];
-      rank[u] = G.arank[nd];
-      x0[u] = *reinterpret_cast<const double2*>(px);
-      if (D == 3) x1[u] = *reinterpret_cast<const double2*>(px + 2);
-      if (WANT_Q) qv[u] = m.r2q[idx[u]];
-      if (NF >= 1) {
-        u0[u] = *reinterpret_cast<const double2*>(pu);
-        if (D == 3) u1[u] = *reinterpret_cast<const double2*>(pu + 2);
-      }
-      if (NF >= 2) {
-        a0[u] = *reinterpret_cast<const double2*>(pu + NS<D>::X);
-        if (D == 3) a1[u] = *reinterpret_cast<const double2*>(pu + NS<D>::X + 2);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const int e = e0 + u * 32;
-      if (e < npairs) {
-        T.rank[e] = (node[u] >= 0) ? rank[u] : -1;
-        if (WANT_Q) T.q[e] = qv[u];
-        double* dx = T.X + (size_t)e * D;
-        const bool far = SENT && (node[u] < 0 || rank[u] < 0);
-        dx[0] = far ? 1.0e300 : x0[u].x; dx[1] = far ? 1.0e300 : x0[u].y;
-        if (D == 3) dx[2] = far ? 1.0e300 : x1[u].x;
-        if (NF >= 1) {
-          double* du = T.U + (size_t)e * D;
-          du[0] = u0[u].x; du[1] = u0[u].y;
-          if (D == 3) du[2] = u1[u].x;
-        }
-        if (NF >= 2) {
-          double* da = T.A + (size_t)e * D;
-          da[0] = a0[u].x; da[1] = a0[u].y;
-          if (D == 3) da[2] = a1[u].x;
-        }
-      }
-    }
-  }
-}
-__device__ __forceinline__ int cw_cell_of(const int* cs, int ncell, int t) {
-  int c = 0;
-  for (int i = 1; i < ncell; i++) c += (cs[i] <= t) ? 1 : 0;  // cs ascending; empty cells do not occur in the occupied list
-  return c;
-}
-// shape of a pass: the 8 particles of a chunk share 8 * NC compact-cache entries; lists longer than NC take the
-// entries of 2, 4 or 8 particle slots and the chunk is then worked off in 2, 4 or 8 passes with 8, 16 or 32 lanes per particle
+// shape of a pass (fused kinematics kernel): the 8 particles of a chunk share 8 * NC compact-cache entries; lists
+// longer than NC take the entries of 2, 4 or 8 particle slots and the chunk is then worked off in 2, 4 or 8 passes with
+// 8, 16 or 32 lanes per particle
 __device__ __forceinline__ void cw_pass_shape(int n_mine, int NC, int& stride, int& nper, int& lshift) {
   int nmax = n_mine;
 #pragma unroll
@@ -173,13 +239,12 @@ __device__ __forceinline__ void cw_pass_shape(int n_mine, int NC, int& stride, i
   lshift = 2;  // log2(lanes per particle)
   while (nper > 1 && nper * stride > PPW * NC) { nper >>= 1; lshift++; }
 }
-// neighbour bitmask -> ascending slot ids.  Lane `subp` of the particle's LPP lanes writes the bits b with b % LPP ==
-// subp of every mask word (neighbours cluster in a few words of the chain-ordered ring: equal RANGES of bits would leave
-// most lanes idle), at the position the bit has in ascending slot order.
+// neighbour bitmask -> ascending slot ids.  Lane `sub` of the particle's 4 lanes writes the bits b with b % 4 == sub of
+// every mask word (neighbours cluster in a few words of the chain-ordered ring: equal RANGES of bits would leave most
+// lanes idle), at the position the bit has in ascending slot order.
 template <int W>
-__device__ __forceinline__ void cw_compact(const uint32_t (&mk)[W], int lshift, int subp, unsigned char* lst) {
-  // bits b = subp (mod LPP): LPP = 4 -> 0x11111111 << subp, 8 -> 0x01010101 << subp, 16 -> 0x00010001 << subp, 32 -> 1 << subp
-  const uint32_t pat = (lshift == 2 ? 0x11111111u : (lshift == 3 ? 0x01010101u : (lshift == 4 ? 0x00010001u : 1u))) << subp;
+__device__ __forceinline__ void cw_compact(const uint32_t (&mk)[W], int sub, unsigned char* lst) {
+  const uint32_t pat = 0x11111111u << sub;
   int pre = 0;
 #pragma unroll
   for (int w = 0; w < W; w++) {
@@ -201,22 +266,20 @@ __device__ __forceinline__ uint32_t spread8(uint32_t x) {
   x = (x | (x << 3)) & 0x11111111u;
   return x;
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-// hint: the particle rows [t, t + 8) of `ncomp` SoA components (next unit of this warp) -> L2
-__device__ __forceinline__ void cw_prefetch_rows(const double* f, int ld, int ncomp, int t, int np, int lane) {
-  if (lane < 2 * ncomp) {
-    const int tt = min(t + ((lane & 1) ? 7 : 0), np - 1);
-    if (tt >= 0) prefetch_l2(f + (size_t)(lane >> 1) * ld + tt);
-  }
+// the particle's compact list P.clist -> the warp's slice (4-byte words, the particle's lanes share the copy)
+__device__ __forceinline__ void cw_fetch_list(const unsigned char* gl, unsigned char* sl, int n, int subp, int lpp) {
+  const uint32_t* g = reinterpret_cast<const uint32_t*>(gl);
+  uint32_t* s_ = reinterpret_cast<uint32_t*>(sl);
+  for (int i = subp; i < (n + 3) >> 2; i += lpp) s_[i] = g[i];
 }
-template <int D>
+template <int Dd>
 __device__ __forceinline__ void sym_to_full(const double* s, double* A) {
-  if (D == 2) { A[0] = s[0]; A[1] = s[1]; A[2] = s[1]; A[3] = s[2]; }
+  if (Dd == 2) { A[0] = s[0]; A[1] = s[1]; A[2] = s[1]; A[3] = s[2]; }
   else { A[0] = s[0]; A[1] = s[1]; A[2] = s[2]; A[3] = s[1]; A[4] = s[3]; A[5] = s[4]; A[6] = s[2]; A[7] = s[4]; A[8] = s[5]; }
 }
-template <int D>
+template <int Dd>
 __device__ __forceinline__ void full_to_sym(const double* A, double* s) {
-  if (D == 2) { s[0] = A[0]; s[1] = A[1]; s[2] = A[3]; }
+  if (Dd == 2) { s[0] = A[0]; s[1] = A[1]; s[2] = A[3]; }
   else { s[0] = A[0]; s[1] = A[1]; s[2] = A[2]; s[3] = A[4]; s[4] = A[5]; s[5] = A[8]; }
 }
 
@@ -224,55 +287,56 @@ __device__ __forceinline__ void full_to_sym(const double* A, double* s) {
 // K0 + K1: tributary__LME__ (LME.c:1019-1099) with the PREVIOUS beta, beta__LME__ (LME.c:177-185),
 // __lambda_Newton_Rapson (LME.c:272-353, warm start), __predictor_PARTICLES (U-Verlet.c:229-253) and the cell sums
 // of the lumped mass and of the mass-weighted displacement increment (U-Verlet.c:166-225, 301-367).
-template <int D, int W>
+template <int W>
 __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const PartDev P, const GridDev G, const StepParams sp,
                                                      const CwCfg cfg, int* err, int do_predictor) {
   extern __shared__ __align__(16) unsigned char smem[];
+  // exp() with the 2^(j/32) table: the Newton loop of this kernel sits at the register limit of 4 blocks per SM and
+  // the table version needs 8 registers less than the polynomial one of the other kernels
   __shared__ double s_tab[32];
   if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
   __syncthreads();  // the only block-wide barrier of the kernel
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const CwLayout L(cfg, D, CW_LME_P2G);
-  const WarpTile T = carve_tile(smem + (size_t)wib * L.total, L, cfg);
-  constexpr int NV = 1 + D, NJ = D * (D + 1) / 2;
-  const int SL = cfg.SL, ld = P.ld;
-  const int nocc = *G.n_occ, nunits = (nocc + cfg.CPW - 1) / cfg.CPW;
-  // every warp walks a CONTIGUOUS range of units: its next cell is the neighbour of this one (shared ring nodes are
-  // still in L1 / L2) and the particle rows it will need next follow the current ones
+  const CwLayout L(cfg, CW_LME_P2G);
+  const WarpTile T = carve_tile(smem + (size_t)wib * L.total, L);
+  constexpr int NV = 1 + D;
+  const int SL = cfg.SL, ld = P.ld, CL = cfg.CL, WS = cfg.CL + 1;  // WS: row stride of the dense weight table
+  const int nocc = *G.n_occ;
   const int nwarps = gridDim.x * wpb, gw = blockIdx.x * wpb + wib;
-  const int u_lo = (int)((long long)gw * nunits / nwarps), u_hi = (int)((long long)(gw + 1) * nunits / nwarps);
-  for (int u = u_lo; u < u_hi; u++) {
-    const int c0 = u * cfg.CPW, ncell = min(cfg.CPW, nocc - c0);
-    cw_meta(G, nocc, P.np, c0, ncell, T, lane);
-    const int t0 = T.cs[0], t1 = T.cs[ncell];
-    if (u + 1 < u_hi) {  // the first rows of the next unit -> L2 while this unit computes
-      cw_prefetch_rows(P.x, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.lam, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(do_predictor ? P.vel : P.ddis, ld, D, t1, P.np, lane);
-      if (do_predictor) cw_prefetch_rows(P.acc, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.beta, ld, 1, t1, P.np, lane);
-      cw_prefetch_rows(P.mass, ld, 1, t1, P.np, lane);
-      cw_prefetch_rows(P.sstar, ld, 1, t1, P.np, lane);
+  for (int e = lane; e < PPW * WS; e += 32) T.wd[e] = 0.0;  // invariant: the table is all zero between chunks
+  cw_pipe_init(m, G, T, gw, nwarps, nocc, lane);
+  const int j = lane >> 2, sub = lane & (LPP0 - 1);  // particle of the chunk, lane of the particle
+  unsigned char* const lst = T.list + j * CL;
+  double* const wd = T.wd + (size_t)j * WS;
+  double* const pw = T.pv + j * 4;  // per particle: m / Z and m / Z * DU_p
+  for (int u = gw, ic = 0; u < nocc; u += nwarps, ic++) {
+    const Cell c = cw_cell(T, ic);
+    const int tn = cw_next_t0(T, ic, u, nwarps, nocc);
+    if (tn >= 0) {  // the first rows of the next cell -> L2 while this cell computes
+      cw_prefetch_rows(P.x, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.lam, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(do_predictor ? P.vel : P.ddis, ld, D, tn, P.np, lane);
+      if (do_predictor) cw_prefetch_rows(P.acc, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.beta, ld, 1, tn, P.np, lane);
+      cw_prefetch_rows(P.mass, ld, 1, tn, P.np, lane);
+      cw_prefetch_rows(P.sstar, ld, 1, tn, P.np, lane);
     }
-    cw_stage<D, true, 0, true>(m, G, cfg, ncell, T, lane);
-    for (int e = lane; e < ncell * SL * NV; e += 32) T.acc[e] = 0.0;
+    cw_stage<true, 0, true, false>(m, G, SL, c, T, lane);
     __syncwarp();
-    for (int tb = t0; tb < t1; tb += PPW) {
-      // ---- base mapping: 4 lanes per particle; neighbour list and beta
-      const int sub = lane & (LPP0 - 1);
-      const int t = tb + (lane >> 2);
-      const bool valid = t < t1;
-      int p = 0, ci = 0, len = 0;
-      double xp[D], lam[D], dd[D], beta_old = 1.0, mp = 0.0, sstar = -1.0;
+    cw_pipe_next(m, G, T, ic, u, nwarps, nocc, lane);
+    for (int tb = c.t0; tb < c.t1; tb += PPW) {
+      const int t = tb + j;
+      const bool valid = t < c.t1;
+      int p = 0;
+      double xp[D], lam[D], beta_old = 1.0, sstar = -1.0;
 #pragma unroll
-      for (int i = 0; i < D; i++) { xp[i] = 0.0; lam[i] = 0.0; dd[i] = 0.0; }
+      for (int i = 0; i < D; i++) { xp[i] = 0.0; lam[i] = 0.0; }
       if (valid) {
         p = G.plist[t];
-        ci = cw_cell_of(T.cs, ncell, t);
-        len = T.len[ci];
         beta_old = P.beta[p];
         sstar = P.sstar[p];
-        mp = P.mass[p];
+        const double mp = P.mass[p];
+        double dd[D];
 #pragma unroll
         for (int i = 0; i < D; i++) {
           xp[i] = P.x[i * ld + p];
@@ -289,6 +353,7 @@ __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const Part
             dd[i] = v;
           }
         }
+        if (sub == 0) { pw[0] = mp; pw[1] = mp * dd[0]; pw[2] = mp * dd[1]; pw[3] = mp * dd[2]; }  // times 1 / Z below
       }
       uint32_t mk[W];
       if (sp.reuse_lists) {
@@ -302,13 +367,14 @@ __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const Part
         uint32_t part[WL];
 #pragma unroll
         for (int w = 0; w < WL; w++) part[w] = 0u;
-        const double* Xc = T.X + (size_t)ci * SL * D;
-        for (int k = sub; k < len; k += LPP0) {
-          double l[D];
-          const double s = dist2_exact<D>(xp, Xc + k * D, l);
-          if (s <= sstar) {
-            if constexpr (WL == 1) part[0] |= 1u << (k >> 2);
-            else part[k >> 7] |= 1u << ((k >> 2) & 31);
+        if (valid) {
+          for (int k = sub; k < c.len; k += LPP0) {
+            double l[D];
+            const double s = dist2_exact<D>(xp, T.X + k * D, l);
+            if (s <= sstar) {
+              if constexpr (WL == 1) part[0] |= 1u << (k >> 2);
+              else part[k >> 7] |= 1u << ((k >> 2) & 31);
+            }
           }
         }
         // mask word w = slots [32 w, 32 w + 32) = bits [8 w, 8 w + 8) of the four lanes, interleaved
@@ -333,205 +399,161 @@ __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const Part
       if (valid && n < D + 1) { if (sub == 0) latch_error(err, NLPS_ERR_FEW_NEIGHBOURS, P.orig[p]); ok = false; }
       double beta = beta_old;
       if (valid && !sp.reuse_lists) {
-        const int B = T.B[ci];
-        const double h = m.h_avg[B];
+        const double h = m.h_avg[c.B];
         beta = __ddiv_rn(sp.gamma_lme, __dmul_rn(h, h));
-        if (sub == 0) { P.beta[p] = beta; P.sstar[p] = m.sst[B]; }
+        if (sub == 0) { P.beta[p] = beta; P.sstar[p] = m.sst[c.B]; }
       }
-      int stride, nper, lshift;
-      cw_pass_shape(ok ? n : 0, cfg.NC, stride, nper, lshift);
-      const int LPP = 1 << lshift;
-      // the particle's variables travel through shared memory: the base-mapping registers die here
-      constexpr int PVK = 3 * D + 2;
-      int* const pvi = (int*)(T.pv + PPW * PVK);
-      if (sub == 0) {
-        double* pj = T.pv + (lane >> 2) * PVK;
-#pragma unroll
-        for (int i = 0; i < D; i++) { pj[i] = xp[i]; pj[D + i] = lam[i]; pj[2 * D + i] = dd[i]; }
-        pj[3 * D] = beta;
-        pj[3 * D + 1] = mp;
-        int* ij = pvi + (lane >> 2) * (3 + W);
-        ij[0] = p; ij[1] = ci; ij[2] = valid ? (ok ? n : -1 - n) : -(1 << 20);  // n | too few neighbours | no particle
-#pragma unroll
-        for (int w = 0; w < W; w++) ij[3 + w] = (int)mk[w];
-      }
+      // the list as ascending slot ids: shared memory for this kernel, P.clist for the other kernels of the step
+      if (valid) cw_compact<W>(mk, sub, lst);
       __syncwarp();
-      for (int h = 0; h < PPW / nper; h++) {
-        // ---- pass mapping: LPP lanes per particle
-        const int jp = lane >> lshift, subp = lane & (LPP - 1);
-        const int js = h * nper + jp;
-        const double* pj = T.pv + js * PVK;
-        const int* ij = pvi + js * (3 + W);
-        double x_[D], lam_[D];
+      if (valid) {
+        const uint32_t* sl = reinterpret_cast<const uint32_t*>(lst);
+        uint32_t* gl = reinterpret_cast<uint32_t*>(P.clist + (size_t)p * CL);
+        for (int i = sub; i < (n + 3) >> 2; i += LPP0) gl[i] = sl[i];
+      }
+      // ---- Newton on lambda: lane `sub` takes the neighbour pairs (2 sub, 2 sub + 1), + 8, ...
+      const int n_ = ok ? n : 0;
+      int NumIter = 0;
+      bool act = ok;
+      double Zi = 0.0;
+      while (__any_sync(FULL, act)) {
+        double Z = 0.0, r[D], JJ[D * D];
 #pragma unroll
-        for (int i = 0; i < D; i++) { x_[i] = pj[i]; lam_[i] = pj[D + i]; }
-        const double beta_ = pj[3 * D];
-        const int p_ = ij[0], ci_ = ij[1], n_raw = ij[2];
-        const bool here = n_raw > -(1 << 20);
-        bool ok_ = n_raw >= 0;
-        const int n_ = ok_ ? n_raw : 0;
-        const int n_list = here ? (ok_ ? n_raw : -1 - n_raw) : 0;  // the list is written for every particle (its consumers read P.nnodes entries)
-        unsigned char* lst = T.list + jp * stride;
-        double* wt = T.wts + jp * stride;
-        {
-          uint32_t mk_[W];
+        for (int i = 0; i < D; i++) r[i] = 0.0;
 #pragma unroll
-          for (int w = 0; w < W; w++) mk_[w] = (uint32_t)ij[3 + w];
-          if (here) cw_compact<W>(mk_, lshift, subp, lst);
-        }
-        __syncwarp();
-        // the compact list of the step -> P.clist (read by the kinematics, force and G2P kernels)
-        if (here) {
-          const uint32_t* sl = reinterpret_cast<const uint32_t*>(lst);
-          uint32_t* gl = reinterpret_cast<uint32_t*>(P.clist + (size_t)p_ * cfg.CL);
-          for (int i = subp; i < (n_list + 3) >> 2; i += LPP) gl[i] = sl[i];
-        }
-        // ---- Newton on lambda: lane subp takes the neighbour pairs (2 subp, 2 subp + 1), + 2 LPP, ...
-        const double* Xc_ = T.X + (size_t)ci_ * SL * D;
-        int NumIter = 0;
-        bool act = ok_;
-        double Zi = 0.0;
-        while (__any_sync(FULL, act)) {
-          double Z = 0.0, r[D], JJ[D * D];
-#pragma unroll
-          for (int i = 0; i < D; i++) r[i] = 0.0;
-#pragma unroll
-          for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
-          if (act) {
-            for (int i0 = 2 * subp; i0 < n_; i0 += 2 * LPP) {
-              const bool two = i0 + 1 < n_;
-              const unsigned kk = *reinterpret_cast<const unsigned short*>(lst + i0);
-              const int k0 = kk & 0xffu, k1 = two ? (int)(kk >> 8) : k0;
-              double l0[D], l1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
-#pragma unroll
-              for (int i = 0; i < D; i++) {
-                l0[i] = x_[i] - Xc_[k0 * D + i];
-                l1[i] = x_[i] - Xc_[k1 * D + i];
-                ll0 += l0[i] * l0[i];
-                ll1 += l1[i] * l1[i];
-                lx0 += l0[i] * lam_[i];
-                lx1 += l1[i] * lam_[i];
-              }
-              const double e0 = fexp(-beta_ * ll0 + lx0, s_tab);
-              const double e1 = two ? fexp(-beta_ * ll1 + lx1, s_tab) : 0.0;
-              wt[i0] = e0;
-              if (two) wt[i0 + 1] = e1;
-              Z += e0;
-#pragma unroll
-              for (int i = 0; i < D; i++) {
-                const double el = e0 * l0[i];
-                r[i] += el;
-#pragma unroll
-                for (int jj = i; jj < D; jj++) JJ[i * D + jj] += el * l0[jj];
-              }
-              Z += e1;
-#pragma unroll
-              for (int i = 0; i < D; i++) {
-                const double el = e1 * l1[i];
-                r[i] += el;
-#pragma unroll
-                for (int jj = i; jj < D; jj++) JJ[i * D + jj] += el * l1[jj];
-              }
-            }
-          }
-          for (int o = 1; o < LPP; o <<= 1) {
-            Z += __shfl_xor_sync(FULL, Z, o);
+        for (int i = 0; i < D * D; i++) JJ[i] = 0.0;
+        if (act) {
+          for (int i0 = 2 * sub; i0 < n_; i0 += 2 * LPP0) {
+            const bool two = i0 + 1 < n_;
+            const unsigned kk = *reinterpret_cast<const unsigned short*>(lst + i0);
+            const int k0 = kk & 0xffu, k1 = two ? (int)(kk >> 8) : k0;
+            double l0[D], l1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
 #pragma unroll
             for (int i = 0; i < D; i++) {
-              r[i] += __shfl_xor_sync(FULL, r[i], o);
+              l0[i] = xp[i] - T.X[k0 * D + i];
+              l1[i] = xp[i] - T.X[k1 * D + i];
+              ll0 += l0[i] * l0[i];
+              ll1 += l1[i] * l1[i];
+              lx0 += l0[i] * lam[i];
+              lx1 += l1[i] * lam[i];
+            }
+            const double e0 = fexp(-beta * ll0 + lx0, s_tab);
+            const double e1 = two ? fexp(-beta * ll1 + lx1, s_tab) : 0.0;
+            wd[k0] = e0;  // the weights of the LAST evaluation are the ones the cell sums use
+            if (two) wd[k1] = e1;
+            Z += e0;
 #pragma unroll
-              for (int jj = i; jj < D; jj++) JJ[i * D + jj] += __shfl_xor_sync(FULL, JJ[i * D + jj], o);
+            for (int i = 0; i < D; i++) {
+              const double el = e0 * l0[i];
+              r[i] += el;
+#pragma unroll
+              for (int jj = i; jj < D; jj++) JJ[i * D + jj] += el * l0[jj];
+            }
+            Z += e1;
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+              const double el = e1 * l1[i];
+              r[i] += el;
+#pragma unroll
+              for (int jj = i; jj < D; jj++) JJ[i * D + jj] += el * l1[jj];
             }
           }
-          if (act) {
-            Zi = 1.0 / Z;
-            double nr = 0.0;
+        }
 #pragma unroll
-            for (int i = 0; i < D; i++) { r[i] *= Zi; nr += r[i] * r[i]; }
-            nr = sqrt(nr);
+        for (int o = 1; o < LPP0; o <<= 1) {
+          Z += __shfl_xor_sync(FULL, Z, o);
 #pragma unroll
-            for (int i = 0; i < D; i++)
+          for (int i = 0; i < D; i++) {
+            r[i] += __shfl_xor_sync(FULL, r[i], o);
 #pragma unroll
-              for (int jj = i; jj < D; jj++) {
-                JJ[i * D + jj] = JJ[i * D + jj] * Zi - r[i] * r[jj];
-                JJ[jj * D + i] = JJ[i * D + jj];
-              }
-            double Ji[D * D];
-            if (nr > sp.tol_wrapper) {
-              if (rcond_as_reference<D>(JJ) < 1E-8) {
-                ok_ = false;
-                act = false;
-                if (subp == 0) latch_error(err, NLPS_ERR_SINGULAR_HESSIAN, P.orig[p_]);
-              } else {
-                inverse<D>(JJ, Ji);
+            for (int jj = i; jj < D; jj++) JJ[i * D + jj] += __shfl_xor_sync(FULL, JJ[i * D + jj], o);
+          }
+        }
+        if (act) {
+          Zi = 1.0 / Z;
+          double nr = 0.0;
 #pragma unroll
-                for (int i = 0; i < D; i++) {
-                  double dl = 0.0;
+          for (int i = 0; i < D; i++) { r[i] *= Zi; nr += r[i] * r[i]; }
+          nr = sqrt(nr);
 #pragma unroll
-                  for (int jj = 0; jj < D; jj++) dl += Ji[i * D + jj] * r[jj];
-                  lam_[i] -= dl;
-                }
-                NumIter++;
-                act = NumIter <= sp.max_iter_lme;
-              }
-            } else {  // converged: this evaluation's Z and Hessian are the step's shape-function data
-              inverse<D>(JJ, Ji);
-              if (subp == 0) {
-                double Jis[NJ];
-                full_to_sym<D>(Ji, Jis);
+          for (int i = 0; i < D; i++)
 #pragma unroll
-                for (int i = 0; i < NJ; i++) P.ji[(size_t)i * ld + p_] = Jis[i];
-              }
+            for (int jj = i; jj < D; jj++) {
+              JJ[i * D + jj] = JJ[i * D + jj] * Zi - r[i] * r[jj];
+              JJ[jj * D + i] = JJ[i * D + jj];
+            }
+          double Ji[D * D];
+          if (nr > sp.tol_wrapper) {
+            if (rcond_as_reference<D>(JJ) < 1E-8) {
+              ok = false;
               act = false;
+              if (sub == 0) latch_error(err, NLPS_ERR_SINGULAR_HESSIAN, P.orig[p]);
+            } else {
+              inverse<D>(JJ, Ji);
+#pragma unroll
+              for (int i = 0; i < D; i++) {
+                double dl = 0.0;
+#pragma unroll
+                for (int jj = 0; jj < D; jj++) dl += Ji[i * D + jj] * r[jj];
+                lam[i] -= dl;
+              }
+              NumIter++;
+              act = NumIter <= sp.max_iter_lme;
             }
+          } else {  // converged: this evaluation's Z and Hessian are the step's shape-function data
+            inverse<D>(JJ, Ji);
+            if (sub == 0) {
+              double Jis[NJ];
+              full_to_sym<D>(Ji, Jis);
+#pragma unroll
+              for (int i = 0; i < NJ; i++) P.ji[(size_t)i * ld + p] = Jis[i];
+            }
+            act = false;
           }
         }
-        if (ok_ && NumIter >= sp.max_iter_lme && subp == 0) latch_error(err, NLPS_ERR_NEWTON_LME, P.orig[p_]);
-        if (here && subp == 0) {
+      }
+      if (ok && NumIter >= sp.max_iter_lme && sub == 0) latch_error(err, NLPS_ERR_NEWTON_LME, P.orig[p]);
+      if (valid && sub == 0) {
 #pragma unroll
-          for (int i = 0; i < D; i++) P.lam[i * ld + p_] = lam_[i];
-          P.zi[p_] = ok_ ? Zi : 0.0;
+        for (int i = 0; i < D; i++) P.lam[i * ld + p] = lam[i];
+        const double z = ok ? Zi : 0.0;
+        P.zi[p] = z;
+#pragma unroll
+        for (int i = 0; i < 4; i++) pw[i] *= z;
+      }
+      __syncwarp();
+      // ---- cell sums: lane k sums column k of the weight table over the particles of the chunk
+      const int cnt = min(PPW, c.t1 - tb);
+      const bool first = tb == c.t0;
+      for (int k = lane; k < SL; k += 32) {
+        const int rank = T.rank[k];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int jq = 0; jq < cnt; jq++) {
+          const double w = T.wd[(size_t)jq * WS + k];
+          const double2 q01 = *reinterpret_cast<const double2*>(T.pv + jq * 4);
+          const double2 q23 = *reinterpret_cast<const double2*>(T.pv + jq * 4 + 2);
+          a0 += w * q01.x; a1 += w * q01.y; a2 += w * q23.x; a3 += w * q23.y;
         }
-        // ---- cell sums: the particles of the pass one after the other, lanes over that particle's neighbours
-        const double wgt = ok_ ? pj[3 * D + 1] * Zi : 0.0;
-        for (int jq = 0; jq < nper; jq++) {
-          const int sl = jq << lshift;
-          const int nq = __shfl_sync(FULL, ok_ ? n_ : 0, sl);
-          const double wq = __shfl_sync(FULL, wgt, sl);
-          double dq[D];
-#pragma unroll
-          for (int i = 0; i < D; i++) dq[i] = T.pv[(h * nper + jq) * PVK + 2 * D + i] * wq;
-          const int cq = __shfl_sync(FULL, ci_, sl);
-          const unsigned char* lq = T.list + jq * stride;
-          const double* wtq = T.wts + jq * stride;
-          double* accq = T.acc + (size_t)cq * NV * SL;
-          for (int i = lane; i < nq; i += 32) {
-            const int k = lq[i];
-            const double e = wtq[i];
-            accq[k] += e * wq;
-#pragma unroll
-            for (int d = 0; d < D; d++) accq[(1 + d) * SL + k] += e * dq[d];
+        if (rank >= 0) {
+          double* dst = G.part + ((size_t)T.q[k] * G.max_act + rank) * NV;
+          if (!first) {  // cells with more than 8 particles: add to what the earlier chunks wrote
+            const double2 o01 = *reinterpret_cast<const double2*>(dst), o23 = *reinterpret_cast<const double2*>(dst + 2);
+            a0 += o01.x; a1 += o01.y; a2 += o23.x; a3 += o23.y;
           }
-          __syncwarp();
+          *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
+          *reinterpret_cast<double2*>(dst + 2) = make_double2(a2, a3);
         }
       }
-    }
-    // ---- the cells' sums -> part[(slot of the cell in the node's transposed ring, node rank)]
-    for (int e = lane; e < ncell * SL; e += 32) {
-      const int rank = T.rank[e];
-      if (rank < 0) continue;
-      const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
-      double* dst = G.part + ((size_t)T.q[e] * G.max_act + rank) * NV;
-      const double* a = T.acc + (size_t)c * NV * SL + k;
-      if constexpr (D == 3) {
-        *reinterpret_cast<double2*>(dst) = make_double2(a[0], a[SL]);
-        *reinterpret_cast<double2*>(dst + 2) = make_double2(a[2 * SL], a[3 * SL]);
-      } else {
-#pragma unroll
-        for (int v = 0; v < NV; v++) dst[v] = a[v * SL];
+      __syncwarp();
+      // the table returns to zero: every lane clears the entries it wrote
+      for (int i0 = 2 * sub; i0 < n_; i0 += 2 * LPP0) {
+        const unsigned kk = *reinterpret_cast<const unsigned short*>(lst + i0);
+        wd[kk & 0xffu] = 0.0;
+        if (i0 + 1 < n_) wd[kk >> 8] = 0.0;
       }
+      __syncwarp();
     }
-    __syncwarp();
+    cw_pipe_wait();
   }
 }
 
@@ -644,54 +666,50 @@ __global__ void __launch_bounds__(128) cw_stress(const PartDev P, const StepPara
 // (compute-Strains.c:20-44, LME.c:836-891), the particle part above, and the cell sums of the nodal forces with the
 // weights of the gather still in shared memory.  CW_KIN_GATHER: DF only.  CW_FORCE: force sums from P.gop.
 // Neighbours come from the compact lists of the LME kernel (P.clist, P.nnodes), 1 / Z and J^-1 from P.zi, P.ji.
-template <int D, int W, int MODE>
-__global__ void __launch_bounds__(128, 4) cw_kin(const MeshDev m, const PartDev P, const GridDev G, const StepParams sp,
+template <int MODE>
+__global__ void __launch_bounds__(128, MODE == CW_KIN_FUSED ? 3 : 4) cw_kin(const MeshDev m, const PartDev P, const GridDev G, const StepParams sp,
                                                  const CwCfg cfg, const __grid_constant__ MatTable mt, int* err,
                                                  int has_traction) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double s_tab[32];
-  if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
-  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const CwLayout L(cfg, D, MODE);
-  const WarpTile T = carve_tile(smem + (size_t)wib * L.total, L, cfg);
-  constexpr int NJ = D * (D + 1) / 2, PVN = PV<D>::N;
+  const CwLayout L(cfg, MODE);
+  const WarpTile T = carve_tile(smem + (size_t)wib * L.total, L);
   constexpr bool GATHER = MODE != CW_FORCE, SCATTER = MODE != CW_KIN_GATHER, FUSED = MODE == CW_KIN_FUSED;
   // per-particle record of the force sums: x (D) | lambda (D) | beta | 1/Z | G (D*D) | t (D)
   constexpr int PX = 0, PL = D, PB = 2 * D, PZ = 2 * D + 1, PG = 2 * D + 2, PT = 2 * D + 2 + D * D;
   const int SL = cfg.SL, ld = P.ld, CL = cfg.CL;
-  const int nocc = *G.n_occ, nunits = (nocc + cfg.CPW - 1) / cfg.CPW;
+  const int nocc = *G.n_occ;
   const int nwarps = gridDim.x * wpb, gw = blockIdx.x * wpb + wib;
-  const int u_lo = (int)((long long)gw * nunits / nwarps), u_hi = (int)((long long)(gw + 1) * nunits / nwarps);
-  for (int u = u_lo; u < u_hi; u++) {
-    const int c0 = u * cfg.CPW, ncell = min(cfg.CPW, nocc - c0);
-    cw_meta(G, nocc, P.np, c0, ncell, T, lane);
-    const int t0 = T.cs[0], t1 = T.cs[ncell];
-    if (u + 1 < u_hi) {  // the first rows of the next unit -> L2 while this unit computes
-      cw_prefetch_rows(P.x, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.lam, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.beta, ld, 1, t1, P.np, lane);
-      cw_prefetch_rows(P.zi, ld, 1, t1, P.np, lane);
-      if (GATHER) cw_prefetch_rows(P.ji, ld, NJ, t1, P.np, lane);
+  cw_pipe_init(m, G, T, gw, nwarps, nocc, lane);
+  for (int u = gw, ic = 0; u < nocc; u += nwarps, ic++) {
+    const Cell c = cw_cell(T, ic);
+    const int tn = cw_next_t0(T, ic, u, nwarps, nocc);
+    if (tn >= 0) {  // the first rows of the next cell -> L2 while this cell computes
+      cw_prefetch_rows(P.x, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.lam, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.beta, ld, 1, tn, P.np, lane);
+      cw_prefetch_rows(P.zi, ld, 1, tn, P.np, lane);
+      if (GATHER) cw_prefetch_rows(P.ji, ld, NJ, tn, P.np, lane);
       if (FUSED) {
-        cw_prefetch_rows(P.F_n, ld, D * D, t1, P.np, lane);
-        cw_prefetch_rows(P.rho, ld, 1, t1, P.np, lane);
-        cw_prefetch_rows(P.vol0, ld, 1, t1, P.np, lane);
+        cw_prefetch_rows(P.F_n, ld, D * D, tn, P.np, lane);
+        cw_prefetch_rows(P.rho, ld, 1, tn, P.np, lane);
+        cw_prefetch_rows(P.vol0, ld, 1, tn, P.np, lane);
       }
-      if (MODE == CW_FORCE) cw_prefetch_rows(P.gop, ld, D * D, t1, P.np, lane);
-      if (lane < PPW && t1 + lane < P.np) prefetch_l2(P.clist + (size_t)(t1 + lane) * CL);
+      if (MODE == CW_FORCE) cw_prefetch_rows(P.gop, ld, D * D, tn, P.np, lane);
+      if (lane < PPW && tn + lane < P.np) prefetch_l2(P.clist + (size_t)(tn + lane) * CL);
     }
-    cw_stage<D, SCATTER, GATHER ? 1 : 0>(m, G, cfg, ncell, T, lane);
+    cw_union(P, G, c, cfg.W, T, lane);
+    cw_stage<SCATTER, GATHER ? 1 : 0, false, true>(m, G, SL, c, T, lane);
     if (SCATTER)
-      for (int e = lane; e < ncell * SL * D; e += 32) T.acc[e] = 0.0;
+      for (int e = lane; e < SL * D; e += 32) T.acc[e] = 0.0;
     __syncwarp();
-    for (int tb = t0; tb < t1; tb += PPW) {
+    cw_pipe_next(m, G, T, ic, u, nwarps, nocc, lane);
+    for (int tb = c.t0; tb < c.t1; tb += PPW) {
       const int t = tb + (lane >> 2);
-      const bool valid = t < t1;
-      int p = 0, ci = 0, n = 0;
+      const bool valid = t < c.t1;
+      int p = 0, n = 0;
       if (valid) {
         p = G.plist[t];
-        ci = cw_cell_of(T.cs, ncell, t);
         n = P.nnodes[p];
       }
       int stride = 0, nper = PPW, lshift = 2;
@@ -700,49 +718,49 @@ __global__ void __launch_bounds__(128, 4) cw_kin(const MeshDev m, const PartDev 
       for (int h = 0; h < PPW / nper; h++) {
         const int jp = lane >> lshift, subp = lane & (LPP - 1);
         const int src = (h * nper + jp) * LPP0;
-        const int p_ = __shfl_sync(FULL, p, src), ci_ = __shfl_sync(FULL, ci, src), n_ = __shfl_sync(FULL, n, src);
+        const int p_ = __shfl_sync(FULL, p, src), n_ = __shfl_sync(FULL, n, src);
         const bool here = __shfl_sync(FULL, (int)valid, src) != 0;
-        const unsigned char* cl = P.clist + (size_t)p_ * CL;
+        unsigned char* lst = T.list + jp * CL;
         double* wt = T.wts + jp * stride;
         double* pvj = T.pv + jp * PVN;
         double x_[D], lam_[D], beta_ = 0.0, Zi = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) { x_[i] = 0.0; lam_[i] = 0.0; }
         if (here) {
+          cw_fetch_list(P.clist + (size_t)p_ * CL, lst, n_, subp, LPP);
 #pragma unroll
           for (int i = 0; i < D; i++) { x_[i] = P.x[i * ld + p_]; lam_[i] = P.lam[i * ld + p_]; }
           beta_ = P.beta[p_];
           Zi = P.zi[p_];
         }
-        const double* Xc_ = T.X + (size_t)ci_ * SL * D;
+        __syncwarp();
         if (GATHER) {
-          const double* Uc_ = T.U + (size_t)ci_ * SL * D;
           double Bm[D * D];
 #pragma unroll
           for (int i = 0; i < D * D; i++) Bm[i] = 0.0;
           for (int i0 = 2 * subp; i0 < n_; i0 += 2 * LPP) {
             const bool two = i0 + 1 < n_;
-            const unsigned kk = *reinterpret_cast<const unsigned short*>(cl + i0);
+            const unsigned kk = *reinterpret_cast<const unsigned short*>(lst + i0);
             const int k0 = kk & 0xffu, k1 = two ? (int)(kk >> 8) : k0;
             double l0[D], l1[D], ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
 #pragma unroll
             for (int i = 0; i < D; i++) {
-              l0[i] = x_[i] - Xc_[k0 * D + i];
-              l1[i] = x_[i] - Xc_[k1 * D + i];
+              l0[i] = x_[i] - T.X[k0 * D + i];
+              l1[i] = x_[i] - T.X[k1 * D + i];
               ll0 += l0[i] * l0[i];
               ll1 += l1[i] * l1[i];
               lx0 += l0[i] * lam_[i];
               lx1 += l1[i] * lam_[i];
             }
-            const double e0 = fexp(-beta_ * ll0 + lx0, s_tab);
-            const double e1 = two ? fexp(-beta_ * ll1 + lx1, s_tab) : 0.0;
+            const double e0 = fexp_poly(-beta_ * ll0 + lx0);
+            const double e1 = two ? fexp_poly(-beta_ * ll1 + lx1) : 0.0;
             if (FUSED) {
               wt[i0] = e0;
               if (two) wt[i0 + 1] = e1;
             }
 #pragma unroll
             for (int i = 0; i < D; i++) {
-              const double eu0 = e0 * Uc_[k0 * D + i], eu1 = e1 * Uc_[k1 * D + i];
+              const double eu0 = e0 * T.U[k0 * D + i], eu1 = e1 * T.U[k1 * D + i];
 #pragma unroll
               for (int jj = 0; jj < D; jj++) Bm[i * D + jj] += eu0 * l0[jj];
 #pragma unroll
@@ -797,11 +815,9 @@ __global__ void __launch_bounds__(128, 4) cw_kin(const MeshDev m, const PartDev 
         }
         if (SCATTER) {
           __syncwarp();
+          // the particles of the pass one after the other, lanes over that particle's neighbours
           for (int jq = 0; jq < nper; jq++) {
-            const int sl = jq << lshift;
-            const int nq = __shfl_sync(FULL, here ? n_ : 0, sl);
-            const int cq = __shfl_sync(FULL, ci_, sl);
-            const int pq_ = __shfl_sync(FULL, p_, sl);
+            const int nq = __shfl_sync(FULL, here ? n_ : 0, jq << lshift);
             if (nq == 0) continue;  // uniform
             const double* pq = T.pv + jq * PVN;
             double xq[D], Gq[D * D], tq[D], lq_[D], bq = 0.0;
@@ -815,26 +831,24 @@ __global__ void __launch_bounds__(128, 4) cw_kin(const MeshDev m, const PartDev 
 #pragma unroll
               for (int i = 0; i < D; i++) lq_[i] = pq[PL + i];
             }
-            const unsigned char* clq = P.clist + (size_t)pq_ * CL;
+            const unsigned char* lq = T.list + jq * CL;
             const double* wtq = T.wts + jq * stride;
-            const double* Xq = T.X + (size_t)cq * SL * D;
-            double* accq = T.acc + (size_t)cq * D * SL;
             for (int i = lane; i < nq; i += 32) {
-              const int k = clq[i];
+              const int k = lq[i];
               double l[D], ll = 0.0, lx = 0.0;
 #pragma unroll
               for (int d = 0; d < D; d++) {
-                l[d] = xq[d] - Xq[k * D + d];
+                l[d] = xq[d] - T.X[k * D + d];
                 if (MODE == CW_FORCE) { ll += l[d] * l[d]; lx += l[d] * lq_[d]; }
               }
-              const double e = (MODE == CW_FORCE) ? fexp(-bq * ll + lx, s_tab) : wtq[i];
+              const double e = (MODE == CW_FORCE) ? fexp_poly(-bq * ll + lx) : wtq[i];
               const double N = e * zq;
 #pragma unroll
               for (int d = 0; d < D; d++) {
                 double gl = tq[d];
 #pragma unroll
                 for (int kk = 0; kk < D; kk++) gl += Gq[d * D + kk] * l[kk];
-                accq[d * SL + k] += N * gl;
+                T.acc[d * SL + k] += N * gl;
               }
             }
             __syncwarp();
@@ -844,65 +858,61 @@ __global__ void __launch_bounds__(128, 4) cw_kin(const MeshDev m, const PartDev 
       }
     }
     if (SCATTER) {
-      for (int e = lane; e < ncell * SL; e += 32) {
-        const int rank = T.rank[e];
+      for (int k = lane; k < SL; k += 32) {
+        const int rank = T.rank[k];
         if (rank < 0) continue;
-        const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
-        double* dst = G.part + ((size_t)T.q[e] * G.max_act + rank) * D;
-        const double* a = T.acc + (size_t)c * D * SL + k;
+        double* dst = G.part + ((size_t)T.q[k] * G.max_act + rank) * D;
 #pragma unroll
-        for (int v = 0; v < D; v++) dst[v] = a[v * SL];
+        for (int v = 0; v < D; v++) dst[v] = T.acc[v * SL + k];
       }
     }
-    __syncwarp();
+    cw_pipe_wait();
   }
 }
 
 // ---------------------------------------------------------------------------
 // K4: G2P + corrector (U-Verlet.c:963-1084): a_p = sum N_A a_A, DU_p = sum N_A DU_A, v += gamma dt a, x += DU,
 // dis += DU.  The n+1 -> n roll of F, J, b_e, kappa, EPS is a pointer swap on the host side of the engine.
-template <int D, int W>
 __global__ void __launch_bounds__(128, 4) cw_g2p(const MeshDev m, const PartDev P, const GridDev G, const StepParams sp,
                                                  const CwCfg cfg) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ double s_tab[32];
-  if (threadIdx.x < 32) s_tab[threadIdx.x] = g_exp2tab[threadIdx.x];
-  __syncthreads();
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  const CwLayout L(cfg, D, CW_G2P);
-  const WarpTile T = carve_tile(smem + (size_t)wib * L.total, L, cfg);
+  const CwLayout L(cfg, CW_G2P);
+  const WarpTile T = carve_tile(smem + (size_t)wib * L.total, L);
   const int SL = cfg.SL, ld = P.ld, CL = cfg.CL;
-  const int nocc = *G.n_occ, nunits = (nocc + cfg.CPW - 1) / cfg.CPW;
+  const int nocc = *G.n_occ;
   const int nwarps = gridDim.x * wpb, gw = blockIdx.x * wpb + wib;
-  const int u_lo = (int)((long long)gw * nunits / nwarps), u_hi = (int)((long long)(gw + 1) * nunits / nwarps);
-  for (int u = u_lo; u < u_hi; u++) {
-    const int c0 = u * cfg.CPW, ncell = min(cfg.CPW, nocc - c0);
-    cw_meta(G, nocc, P.np, c0, ncell, T, lane);
-    const int t0 = T.cs[0], t1 = T.cs[ncell];
-    if (u + 1 < u_hi) {
-      cw_prefetch_rows(P.x, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.lam, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.vel, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.dis, ld, D, t1, P.np, lane);
-      cw_prefetch_rows(P.beta, ld, 1, t1, P.np, lane);
-      cw_prefetch_rows(P.zi, ld, 1, t1, P.np, lane);
-      if (lane < PPW && t1 + lane < P.np) prefetch_l2(P.clist + (size_t)(t1 + lane) * CL);
+  cw_pipe_init(m, G, T, gw, nwarps, nocc, lane);
+  // 4 lanes per particle, lane `sub` takes the neighbour pairs (2 sub, 2 sub + 1), + 8, ...
+  const int j = lane >> 2, sub = lane & (LPP0 - 1);
+  unsigned char* const lst = T.list + j * CL;
+  for (int u = gw, ic = 0; u < nocc; u += nwarps, ic++) {
+    const Cell c = cw_cell(T, ic);
+    const int tn = cw_next_t0(T, ic, u, nwarps, nocc);
+    if (tn >= 0) {
+      cw_prefetch_rows(P.x, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.lam, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.vel, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.dis, ld, D, tn, P.np, lane);
+      cw_prefetch_rows(P.beta, ld, 1, tn, P.np, lane);
+      cw_prefetch_rows(P.zi, ld, 1, tn, P.np, lane);
+      if (lane < PPW && tn + lane < P.np) prefetch_l2(P.clist + (size_t)(tn + lane) * CL);
     }
-    cw_stage<D, false, 2>(m, G, cfg, ncell, T, lane);
+    cw_union(P, G, c, cfg.W, T, lane);
+    cw_stage<false, 2, false, true>(m, G, SL, c, T, lane);
     __syncwarp();
-    for (int tb = t0; tb < t1; tb += PPW) {
-      // 4 lanes per particle, lane `sub` takes the neighbour pairs (2 sub, 2 sub + 1), + 8, ...
-      const int sub = lane & (LPP0 - 1);
-      const int t = tb + (lane >> 2);
-      const bool valid = t < t1;
-      int p = 0, ci = 0, n = 0;
+    cw_pipe_next(m, G, T, ic, u, nwarps, nocc, lane);
+    for (int tb = c.t0; tb < c.t1; tb += PPW) {
+      const int t = tb + j;
+      const bool valid = t < c.t1;
+      int p = 0, n = 0;
       double x_[D], lam_[D], a[D], du[D], beta_ = 0.0, Zi = 0.0, vel_s = 0.0, dis_s = 0.0;
 #pragma unroll
       for (int i = 0; i < D; i++) { x_[i] = 0.0; lam_[i] = 0.0; a[i] = 0.0; du[i] = 0.0; }
       if (valid) {
         p = G.plist[t];
-        ci = cw_cell_of(T.cs, ncell, t);
         n = P.nnodes[p];
+        cw_fetch_list(P.clist + (size_t)p * CL, lst, n, sub, LPP0);
 #pragma unroll
         for (int i = 0; i < D; i++) { x_[i] = P.x[i * ld + p]; lam_[i] = P.lam[i * ld + p]; }
         beta_ = P.beta[p];
@@ -910,31 +920,28 @@ __global__ void __launch_bounds__(128, 4) cw_g2p(const MeshDev m, const PartDev 
         // component `sub` of the particle is updated by lane `sub`: its old values are requested now, used after the loop
         if (sub < D) { vel_s = P.vel[sub * ld + p]; dis_s = P.dis[sub * ld + p]; }
       }
-      const unsigned char* cl = P.clist + (size_t)p * CL;
-      const double* Xc_ = T.X + (size_t)ci * SL * D;
-      const double* Uc_ = T.U + (size_t)ci * SL * D;
-      const double* Ac_ = T.A + (size_t)ci * SL * D;
+      __syncwarp();
       for (int i0 = 2 * sub; i0 < n; i0 += 2 * LPP0) {
         const bool two = i0 + 1 < n;
-        const unsigned kk = *reinterpret_cast<const unsigned short*>(cl + i0);
+        const unsigned kk = *reinterpret_cast<const unsigned short*>(lst + i0);
         const int k0 = kk & 0xffu, k1 = two ? (int)(kk >> 8) : k0;
         double ll0 = 0.0, lx0 = 0.0, ll1 = 0.0, lx1 = 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) {
-          const double l0 = x_[i] - Xc_[k0 * D + i], l1 = x_[i] - Xc_[k1 * D + i];
+          const double l0 = x_[i] - T.X[k0 * D + i], l1 = x_[i] - T.X[k1 * D + i];
           ll0 += l0 * l0;
           ll1 += l1 * l1;
           lx0 += l0 * lam_[i];
           lx1 += l1 * lam_[i];
         }
-        const double e0 = fexp(-beta_ * ll0 + lx0, s_tab);
-        const double e1 = two ? fexp(-beta_ * ll1 + lx1, s_tab) : 0.0;
+        const double e0 = fexp_poly(-beta_ * ll0 + lx0);
+        const double e1 = two ? fexp_poly(-beta_ * ll1 + lx1) : 0.0;
 #pragma unroll
         for (int i = 0; i < D; i++) {
-          a[i] += e0 * Ac_[k0 * D + i];
-          du[i] += e0 * Uc_[k0 * D + i];
-          a[i] += e1 * Ac_[k1 * D + i];
-          du[i] += e1 * Uc_[k1 * D + i];
+          a[i] += e0 * T.A[k0 * D + i];
+          du[i] += e0 * T.U[k0 * D + i];
+          a[i] += e1 * T.A[k1 * D + i];
+          du[i] += e1 * T.U[k1 * D + i];
         }
       }
 #pragma unroll
@@ -957,21 +964,18 @@ __global__ void __launch_bounds__(128, 4) cw_g2p(const MeshDev m, const PartDev 
         P.x[sub * ld + p] = xs + di;
         P.dis[sub * ld + p] = dis_s + di;
       }
+      __syncwarp();
     }
-    __syncwarp();
+    cw_pipe_wait();
   }
 }
 
 // ---------------------------------------------------------------------------
 template <class K>
-int cw_prepare(K kernel, int id, const CwLaunch& L, CwState& st, int D, int sm_count, int max_smem_optin) {
+int cw_prepare(K kernel, int id, const CwLaunch& L, CwState& st, int sm_count, int max_smem_optin) {
   if (st.ready[id]) return 0;
-  const size_t per_warp = CwLayout(L.cfg, D, id).total;
+  const size_t per_warp = CwLayout(L.cfg, id).total;
   st.smem[id] = per_warp * L.cfg.warps;
-  if (st.smem[id] > (size_t)max_smem_optin) {
-    fprintf(stderr, "nlps_b200: 2-ring too large for the warp tiles (%zu bytes of shared memory per block)\n", st.smem[id]);
-    return 1;
-  }
   // (the kernels also hold 256 bytes of static shared memory: ask for what the slices need, not for the device limit)
   if (st.smem[id] + 1024 > (size_t)max_smem_optin ||
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st.smem[id]) != cudaSuccess) {
@@ -989,70 +993,57 @@ int cw_prepare(K kernel, int id, const CwLaunch& L, CwState& st, int D, int sm_c
 
 }  // namespace
 
-size_t cw_smem_bytes(int D, int kernel, const CwCfg& cfg) { return CwLayout(cfg, D, kernel).total * cfg.warps; }
+size_t cw_smem_bytes(int kernel, const CwCfg& cfg) { return CwLayout(cfg, kernel).total * cfg.warps; }
 
-int cw_launch_lme_p2g(int D, int W, const CwLaunch& L, CwState& st, int sm_count, int max_smem_optin, int do_predictor) {
-#define GO_(d, w)                                                                                                     \
+int cw_launch_lme_p2g(int ndim, int W, const CwLaunch& L, CwState& st, int sm_count, int max_smem_optin, int do_predictor) {
+  if (ndim != 3) return 1;
+#define GO_(w)                                                                                                        \
   {                                                                                                                   \
-    auto kf = cw_lme_p2g<d, w>;                                                                                       \
-    if (cw_prepare(kf, CW_LME_P2G, L, st, d, sm_count, max_smem_optin)) return 1;                                      \
+    auto kf = cw_lme_p2g<w>;                                                                                          \
+    if (cw_prepare(kf, CW_LME_P2G, L, st, sm_count, max_smem_optin)) return 1;                                         \
     kf<<<std::min(L.max_blocks, st.grid[CW_LME_P2G]), L.cfg.warps * 32, st.smem[CW_LME_P2G], L.stream>>>(              \
         L.m, L.P, L.G, L.sp, L.cfg, L.err, do_predictor);                                                             \
     return 0;                                                                                                         \
   }
-  if (D == 2) { if (W == 1) GO_(2, 1) if (W == 2) GO_(2, 2) }
-  else { if (W == 4) GO_(3, 4) if (W == 8) GO_(3, 8) }
+  if (W == 4) GO_(4)
+  if (W == 8) GO_(8)
 #undef GO_
   return 1;
 }
 
-int cw_launch_kin(int D, int W, int mode, const CwLaunch& L, CwState& st, int sm_count, int max_smem_optin,
-                  const MatTable& mt, int has_traction) {
-#define GO_(d, w, md)                                                                                                 \
+int cw_launch_kin(int ndim, int mode, const CwLaunch& L, CwState& st, int sm_count, int max_smem_optin, const MatTable& mt,
+                  int has_traction) {
+  if (ndim != 3) return 1;
+#define GO_(md)                                                                                                       \
   {                                                                                                                   \
-    auto kf = cw_kin<d, w, md>;                                                                                       \
-    if (cw_prepare(kf, md, L, st, d, sm_count, max_smem_optin)) return 1;                                              \
+    auto kf = cw_kin<md>;                                                                                             \
+    if (cw_prepare(kf, md, L, st, sm_count, max_smem_optin)) return 1;                                                 \
     kf<<<std::min(L.max_blocks, st.grid[md]), L.cfg.warps * 32, st.smem[md], L.stream>>>(L.m, L.P, L.G, L.sp, L.cfg,   \
                                                                                          mt, L.err, has_traction);    \
     return 0;                                                                                                         \
   }
-#define MODE_(d, w)                                                                                                   \
-  {                                                                                                                   \
-    if (mode == CW_KIN_FUSED) GO_(d, w, CW_KIN_FUSED)                                                                  \
-    if (mode == CW_KIN_GATHER) GO_(d, w, CW_KIN_GATHER)                                                                \
-    if (mode == CW_FORCE) GO_(d, w, CW_FORCE)                                                                          \
-  }
-  if (D == 2) { if (W == 1) MODE_(2, 1) if (W == 2) MODE_(2, 2) }
-  else { if (W == 4) MODE_(3, 4) if (W == 8) MODE_(3, 8) }
-#undef MODE_
+  if (mode == CW_KIN_FUSED) GO_(CW_KIN_FUSED)
+  if (mode == CW_KIN_GATHER) GO_(CW_KIN_GATHER)
+  if (mode == CW_FORCE) GO_(CW_FORCE)
 #undef GO_
   return 1;
 }
 
-int cw_launch_stress(int D, const CwLaunch& L, const MatTable& mt, int uniform_mat, int has_traction) {
-  (void)has_traction;
+int cw_launch_stress(int ndim, const CwLaunch& L, const MatTable& mt, int uniform_mat) {
+  if (ndim != 3) return 1;
   const int np = L.P.np;
   if (np <= 0) return 0;
   const int grid = (np + 127) / 128;
-#define GO_(d, mat) { cw_stress<d, mat><<<grid, 128, 0, L.stream>>>(L.P, L.sp, mt, L.err); return 0; }
-#define MAT_(d) switch (uniform_mat) { case 0: GO_(d, 0) case 1: GO_(d, 1) case 2: GO_(d, 2) default: GO_(d, -1) }
-  if (D == 2) MAT_(2) else MAT_(3)
-#undef MAT_
+#define GO_(mat) { cw_stress<D, mat><<<grid, 128, 0, L.stream>>>(L.P, L.sp, mt, L.err); return 0; }
+  switch (uniform_mat) { case 0: GO_(0) case 1: GO_(1) case 2: GO_(2) default: GO_(-1) }
 #undef GO_
   return 1;
 }
 
-int cw_launch_g2p(int D, int W, const CwLaunch& L, CwState& st, int sm_count, int max_smem_optin) {
-#define GO_(d, w)                                                                                                     \
-  {                                                                                                                   \
-    auto kf = cw_g2p<d, w>;                                                                                           \
-    if (cw_prepare(kf, CW_G2P, L, st, d, sm_count, max_smem_optin)) return 1;                                          \
-    kf<<<std::min(L.max_blocks, st.grid[CW_G2P]), L.cfg.warps * 32, st.smem[CW_G2P], L.stream>>>(L.m, L.P, L.G, L.sp,  \
-                                                                                                 L.cfg);              \
-    return 0;                                                                                                         \
-  }
-  if (D == 2) { if (W == 1) GO_(2, 1) if (W == 2) GO_(2, 2) }
-  else { if (W == 4) GO_(3, 4) if (W == 8) GO_(3, 8) }
-#undef GO_
-  return 1;
+int cw_launch_g2p(int ndim, const CwLaunch& L, CwState& st, int sm_count, int max_smem_optin) {
+  if (ndim != 3) return 1;
+  auto kf = cw_g2p;
+  if (cw_prepare(kf, CW_G2P, L, st, sm_count, max_smem_optin)) return 1;
+  kf<<<std::min(L.max_blocks, st.grid[CW_G2P]), L.cfg.warps * 32, st.smem[CW_G2P], L.stream>>>(L.m, L.P, L.G, L.sp, L.cfg);
+  return 0;
 }

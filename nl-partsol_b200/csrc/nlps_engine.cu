@@ -333,7 +333,8 @@ __global__ void __launch_bounds__(256) k_node_finish(MeshDev m, PartDev P, GridD
   if (n > 0) {
     G.occ_list[G.occ_pos[A]] = A;
     const int bs = m.r2p[A];
-    G.occ_meta[G.occ_pos[A]] = make_int4(A, G.cell_start[A], bs, m.r2p[A + 1] - bs);
+    // .w = 2-ring length (9 bits) | particles of the cell << 9
+    G.occ_meta[G.occ_pos[A]] = make_int4(A, G.cell_start[A], bs, (m.r2p[A + 1] - bs) | (n << 9));
   }
   int rank = -1;
   if (G.active[A]) {
@@ -385,7 +386,7 @@ __device__ __forceinline__ void blk_prologue(const GridDev& G, const BlockCfg& c
     if (c0 + i < nocc) {
       const int4 mt = G.occ_meta[c0 + i];
       s_cs[i] = mt.y;
-      if (i < b.ncell) { s_B[i] = mt.x; s_base[i] = mt.z; s_len[i] = mt.w; }
+      if (i < b.ncell) { s_B[i] = mt.x; s_base[i] = mt.z; s_len[i] = mt.w & 511; }
     } else {
       s_cs[i] = np;  // the last occupied cell ends at the last particle
     }
@@ -482,7 +483,7 @@ __device__ __forceinline__ void meta_put(const BlockCfg& cfg, int nocc, int np, 
   if (i <= ncell) {
     if (c0 + i < nocc) {
       s.cs[i] = mt.y;
-      if (i < ncell) { s.B[i] = mt.x; s.base[i] = mt.z; s.len[i] = mt.w; }
+      if (i < ncell) { s.B[i] = mt.x; s.base[i] = mt.z; s.len[i] = mt.w & 511; }
     } else {
       s.cs[i] = np;  // the last occupied cell ends at the last particle
     }
@@ -2478,8 +2479,7 @@ static int migrate_t(nlps_engine* e) {
 static CwLaunch cw_launch_record(nlps_engine* e, const StepParams& sp) {
   CwLaunch L;
   L.m = e->mesh; L.P = e->P; L.G = e->G; L.sp = sp; L.cfg = e->cw; L.err = e->err; L.stream = e->stream;
-  const int units = std::max(1, nblk((size_t)e->max_occ, e->cw.CPW));
-  L.max_blocks = std::max(1, nblk((size_t)units, e->cw.warps));
+  L.max_blocks = std::max(1, nblk((size_t)std::max(e->max_occ, 1), e->cw.warps));
   return L;
 }
 #define CW_TIMED(e, id, call)                                    \
@@ -2579,11 +2579,11 @@ static void stage_kin_stress_t(nlps_engine* e, int step) {
   if (e->kver == 2) {
     const CwLaunch L = cw_launch_record(e, sp);
     if (e->uniform_mat == NLPS_MAT_NEO_HOOKEAN_WRIGGERS && !e->split_nh) {
-      CW_TIMED(e, K_KIN_FORCE, cw_launch_kin(D, e->W, CW_KIN_FUSED, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
+      CW_TIMED(e, K_KIN_FORCE, cw_launch_kin(D, CW_KIN_FUSED, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
     } else {  // gather (DF) -> stress (thread per particle) -> force sums
-      CW_TIMED(e, K_KIN_GATHER, cw_launch_kin(D, e->W, CW_KIN_GATHER, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
-      CW_TIMED(e, K_STRESS, cw_launch_stress(D, L, e->mat, e->uniform_mat, e->has_traction));
-      CW_TIMED(e, K_KIN_FORCE, cw_launch_kin(D, e->W, CW_FORCE, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
+      CW_TIMED(e, K_KIN_GATHER, cw_launch_kin(D, CW_KIN_GATHER, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
+      CW_TIMED(e, K_STRESS, cw_launch_stress(D, L, e->mat, e->uniform_mat));
+      CW_TIMED(e, K_KIN_FORCE, cw_launch_kin(D, CW_FORCE, L, e->cws, e->sm_count, e->max_smem_optin, e->mat, e->has_traction));
     }
     return;
   }
@@ -2611,7 +2611,7 @@ static void stage_g2p_t(nlps_engine* e, int step) {
   StepParams sp = make_params(e, step, 1);
   if (e->kver == 2) {
     const CwLaunch L = cw_launch_record(e, sp);
-    CW_TIMED(e, K_G2P, cw_launch_g2p(D, e->W, L, e->cws, e->sm_count, e->max_smem_optin));
+    CW_TIMED(e, K_G2P, cw_launch_g2p(D, L, e->cws, e->sm_count, e->max_smem_optin));
   } else {
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
 #define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH_SMEM(e, K_G2P, kfn, grid, e->cfg.threads, e->smemC, e->mesh, e->P, e->G, sp, e->cfg); } break;
@@ -2765,7 +2765,8 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     }
     np = (int)rows.size();
     const double capf = slab->capacity_factor > 1.0 ? slab->capacity_factor : 1.3;
-    ld = (int)(capf * std::max<double>(np, (double)e->n_global / slab->world)) + 1024;
+    // (an explicit capacity_factor is taken literally; the default leaves 1024 rows of slack for tiny clouds)
+    ld = (int)(capf * std::max<double>(np, (double)e->n_global / slab->world)) + (slab->capacity_factor > 1.0 ? 1 : 1024);
   }
   e->D = D; e->T = (D == 2) ? 5 : 9; e->TB = e->T; e->nn = nn; e->np = np;
   e->solver = *solver;
@@ -2904,24 +2905,20 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     c.magic = ((1u << 21) + c.SL - 1) / c.SL;
     for (unsigned q = 0; q < (unsigned)(c.C * c.SL); q++)
       if (((q * c.magic) >> 21) != q / c.SL) return set_err(err, err_len, "internal: pair-index division constant");
-    // ---- warp-per-cell kernels (nlps_cellwarp.cu)
+    // ---- warp-per-cell kernels (nlps_cellwarp.cu): three-dimensional decks
     {
       CwCfg& w = e->cw;
       w.SL = maxr2;
       w.warps = 4;
-      w.CPW = (D == 2) ? 4 : 1;
-      w.NC = (D == 2) ? ((maxr2 + 3) & ~3) : 48;  // 3D gamma = 6: 33-48 neighbours; longer lists take two particle slots
-      if (const char* s_ = getenv("NLPS_CW_CPW")) w.CPW = std::min(31, std::max(1, atoi(s_)));
+      w.NC = 48;  // gamma = 6: 33-48 neighbours; longer lists take two particle slots of the weight cache
       if (const char* s_ = getenv("NLPS_CW_NC")) w.NC = std::max(4, atoi(s_) & ~3);
       if (const char* s_ = getenv("NLPS_CW_WARPS")) w.warps = std::min(4, std::max(1, atoi(s_)));
       w.NC = std::max(w.NC, (((maxr2 + 3) & ~3) + 7) / 8);  // the longest possible list must fit the 8 slots of a chunk
       w.NC = (w.NC + 3) & ~3;
       w.CL = (maxr2 + 3) & ~3;
-      w.magic = ((1u << 21) + w.SL - 1) / w.SL;
-      for (unsigned q = 0; q < (unsigned)(w.CPW * w.SL); q++)
-        if (((q * w.magic) >> 21) != q / w.SL) return set_err(err, err_len, "internal: pair-index division constant (warp tiles)");
-      e->kver = 2;
-      if (const char* s_ = getenv("NLPS_KERNELS")) e->kver = atoi(s_) == 1 ? 1 : 2;
+      w.W = e->W;
+      e->kver = (D == 3) ? 2 : 1;
+      if (const char* s_ = getenv("NLPS_KERNELS")) e->kver = (atoi(s_) == 1 || D != 3) ? 1 : 2;
       if (const char* s_ = getenv("NLPS_SPLIT_NH")) e->split_nh = atoi(s_) != 0;
       if (maxr2 > 256) e->kver = 1;  // slot ids of the compact lists are bytes
     }
@@ -3358,6 +3355,13 @@ int nlps_b200_download(nlps_engine* e, nlps_particles* out) {
 }
 
 int nlps_b200_local_count(nlps_engine* e) { return e->np; }
+
+const char* nlps_b200_transport(nlps_engine* e) {
+  if (!e->slab_on || e->world <= 1) return "none (single slab)";
+  if (e->p2p_on) return "peer-memory stores over NVLink (CUDA IPC mappings of the neighbours' halo buffers; NCCL for set-up and migration)";
+  if (e->comm && e->comm->is_nccl) return "ncclSend/ncclRecv (grouped, on the engine's stream)";
+  return "caller-supplied exchange function";
+}
 
 int nlps_b200_download_local(nlps_engine* e, nlps_particles* out, int* ids) {
   cudaSetDevice(e->device);

@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(128) k_assemble_cell_nh(MeshDev m, PartDev P, 
   for (int cell = blockIdx.x; cell < nocc; cell += gridDim.x) {
     const int4 mt = G.occ_meta[cell];
     const int t0 = mt.y, t1 = (cell + 1 < nocc) ? G.occ_meta[cell + 1].y : P.np;
-    const int base = mt.z, len = mt.w;
+    const int base = mt.z, len = mt.w & 511;
     __syncthreads();  // the previous cell's pairs are done with s_rank
     for (int k = threadIdx.x; k < SL; k += blockDim.x) s_rank[k] = (k < len) ? G.arank[m.r2i[base + k]] : -1;
     for (int tb = t0; tb < t1; tb += MP) {

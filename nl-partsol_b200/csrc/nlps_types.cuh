@@ -74,7 +74,7 @@ struct GridDev {
   unsigned char *active, *fixed;
   int *cnt, *cursor, *cell_start, *plist, *act_list, *n_active;
   int *occ_list, *n_occ, *act_pos, *occ_pos;
-  int4* occ_meta;   // per occupied cell (in node order): {node B, first particle slot, 2-ring base, 2-ring length}
+  int4* occ_meta;   // per occupied cell (in node order): {node B, first particle slot, 2-ring base, 2-ring length | particles << 9}
   int* arank;       // rank of a node among the active nodes, -1 when inactive
   uint32_t* occm;   // per active rank: transposed-2-ring slots whose cell is occupied (w2t words, word-major)
   ulonglong2 *packed, *scan_blk;
@@ -174,6 +174,40 @@ __device__ __forceinline__ double fexp(double x, const double* tab) {
   const double T = tab[k & 31];
   const double Ts = __hiloint2double(__double2hiint(T) + (m << 20), __double2loint(T));
   return __fma_rn(Ts, r * q, Ts);
+}
+// exp() without a table (warp-per-cell kernels, whose busiest unit is the shared-memory / L1 data pipe: the table
+// look-up of fexp() was a fifth of their shared-memory wavefronts): exp(x) = 2^k exp(r), k = rint(x / ln 2),
+// |r| <= ln2 / 2, degree-13 Taylor polynomial in Horner form: 17 fp64 operations, max relative error 1.4e-16 (checked
+// against mpmath over [-700, 700]).
+__constant__ static double c_fexp2[16] = {1.4426950408889634,        // 1 / ln 2
+                                         -0.693147180369123816490,  // -ln2, high part (21 trailing zero bits: exact product)
+                                         -1.90821492927058770002e-10,  // -ln2, low part
+                                         1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
+                                         1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0,
+                                         1.0 / 6.0, 0.5, 0.0};
+__device__ __forceinline__ double fexp_poly(double x) {
+  const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: the low word of x*c + MAGIC is rint(x*c)
+  const double kd = __fma_rn(x, c_fexp2[0], MAGIC);
+  const int k = __double2loint(kd);
+  const double kf = kd - MAGIC;
+  double r = __fma_rn(kf, c_fexp2[1], x);
+  r = __fma_rn(kf, c_fexp2[2], r);
+  // exp(r) - 1 - r = r^2 (c2 + c3 r + ... + c13 r^11), Estrin's scheme: the dependent chain is 6 operations deep
+  // instead of the 13 of Horner's (these kernels run 4 warps per scheduler: the chain length is what they wait on)
+  const double r2 = r * r, r4 = r2 * r2;
+  const double a0 = __fma_rn(r, c_fexp2[13], c_fexp2[14]);  // c2 + c3 r
+  const double a1 = __fma_rn(r, c_fexp2[11], c_fexp2[12]);  // c4 + c5 r
+  const double a2 = __fma_rn(r, c_fexp2[9], c_fexp2[10]);   // c6 + c7 r
+  const double a3 = __fma_rn(r, c_fexp2[7], c_fexp2[8]);    // c8 + c9 r
+  const double a4 = __fma_rn(r, c_fexp2[5], c_fexp2[6]);    // c10 + c11 r
+  const double a5 = __fma_rn(r, c_fexp2[3], c_fexp2[4]);    // c12 + c13 r
+  const double b0 = __fma_rn(r2, a1, a0), b1 = __fma_rn(r2, a3, a2), b2 = __fma_rn(r2, a5, a4);
+  const double q = __fma_rn(r4, __fma_rn(r4, b2, b1), b0);
+  const double t = __fma_rn(r2, q, r);
+  // 2^k by the exponent field (clamped: |x| > 708 saturates instead of wrapping; a NaN argument gives NaN through t)
+  const int m = max(-1022, min(1023, k));
+  const double s = __hiloint2double((m + 1023) << 20, 0);
+  return __fma_rn(s, t, s);
 }
 // visit the set bits of a neighbour mask two at a time; `two` is false for the odd one out (k1 == k0)
 template <int W, class F>

@@ -100,6 +100,7 @@ def lib():
         L.nlps_b200_memcpy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_void_p]
         L.nlps_b200_stream_sync.argtypes = [C.c_void_p]
         L.nlps_b200_migrated_count.restype = C.c_longlong
+        L.nlps_b200_transport.restype = C.c_char_p
         _lib = L
     return _lib
 
@@ -400,6 +401,10 @@ class Engine:
 
     def migrate(self):
         return self.L.nlps_b200_migrate(self.h)
+
+    def transport(self):
+        """The data plane of the per-step halo sums (peer-memory stores, ncclSend/ncclRecv, custom, none)."""
+        return self.L.nlps_b200_transport(self.h).decode()
 
     def migrated_count(self):
         return int(self.L.nlps_b200_migrated_count(self.h))

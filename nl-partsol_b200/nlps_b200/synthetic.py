@@ -97,7 +97,9 @@ def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, mate
         ei, ej, ek = ei[m_], ej[m_], ek[m_]
         P.kept_cells = np.nonzero(m_)[0]
     if d == 2:
-        xi = np.array([[_G, _G], [_G, -_G], [-_G, _G], [-_G, -_G]])          # Q4.c:358-366
+        # Gauss points (xi, eta) of Q4.c:358-366 in order; the element chain is the file order REVERSED
+        # (Read-GID-Mesh.c:406-408), which maps eta to -y: physical offsets (+,-), (+,+), (-,-), (-,+)
+        xi = np.array([[_G, -_G], [_G, _G], [-_G, -_G], [-_G, _G]])
     else:
         xi = np.array([[sx_, sy_, sz_] for sz_ in (_G, -_G) for sy_ in (_G, -_G) for sx_ in (_G, -_G)])
     gp = xi.shape[0]
@@ -148,12 +150,33 @@ def block_2d(cells=16, nsteps=200, material=NH_C1):
                               cel, (0.0, -9.81))
 
 
-def cube_3d(cells=24, nsteps=100, material=NH_C1, gamma_lme=6.0):
-    """BASELINE configs[2] shape: 3D cube on an H8 grid, GPxElement 8, gamma 6."""
+def _top_platen(P, top_layer, nx, ny, nsteps, per_step, layer_offset=0):
+    """Dirichlet set of the cube compression: the node plane on top of the particle block moves down by
+    `per_step` every step (the curve sample k is the nodal displacement INCREMENT of step k, U-Verlet.c:515-521)."""
+    k = top_layer - layer_offset
+    nplane = (nx + 1) * (ny + 1)
+    if k < 0 or (k + 1) * nplane > P.nn:
+        return
+    nodes = (k * nplane + np.arange(nplane)).astype(np.int32)
+    dr = np.zeros((3, nsteps), np.int32)
+    dr[2, :] = 1
+    val = np.zeros((3, nsteps))
+    val[2, :] = -per_step
+    P.bounds.append(dict(nodes=nodes, dir=dr, val=val))
+
+
+def cube_3d(cells=24, nsteps=100, material=NH_C1, gamma_lme=6.0, xy=None, compress=True):
+    """BASELINE configs[2]: 3D Neo-Hookean cube on an H8 grid, GPxElement 8, LME gamma 6, bottom fixed,
+    lateral rollers, the top node plane pushed down by 10 % of the height in 500 steps (compress=True; no gravity), or
+    the cube under gravity (compress=False).  xy: cross-section in cells when it is not a cube (cells = height)."""
     cel = (material[1][1] / material[1][0]) ** 0.5 * 1.3
-    return structured_problem(3, (cells + 4, cells + 4, cells + 4), 1.0 / cells, (cells, cells, cells), (2, 2, 0),
-                              material, nsteps, 0.5, cel, (0.0, 0.0, -9.81), gamma_lme=gamma_lme,
-                              rollers=("left", "right", "front", "back"))
+    cxy = cells if xy is None else xy
+    P = structured_problem(3, (cxy + 4, cxy + 4, cells + 4), 1.0 / cells, (cxy, cxy, cells), (2, 2, 0),
+                           material, nsteps, 0.5, cel, (0.0, 0.0, 0.0 if compress else -9.81), gamma_lme=gamma_lme,
+                           rollers=("left", "right", "front", "back"))
+    if compress:
+        _top_platen(P, cells, cxy + 4, cxy + 4, nsteps, 0.1 / 500.0)
+    return P
 
 
 def column_slab_2d(rank, world, scale=1.0, nsteps=1000, band_cells=6):
@@ -258,14 +281,16 @@ def beam_3d(cells_per_unit=8, nsteps=20, gamma_lme=6.0, E=1e7, cfl=10.0, tractio
     return P
 
 
-def cube_slab_3d(rank, world, cells=126, nsteps=100, gamma_lme=6.0, band_cells=6, material=NH_C1):
+def cube_slab_3d(rank, world, cells=126, nsteps=100, gamma_lme=6.0, band_cells=6, material=NH_C1, xy=None,
+                 compress=True):
     """BASELINE configs[2] split into `world` slabs along z: the global problem is cube_3d(cells)
     (cells^3 particle cells x GPxElement 8; 126 -> 16,003,008 particles); slab r owns the particle-cell layers
     [r*cells//world, (r+1)*cells//world) and builds only the sub-mesh within band_cells + 2 layers of them.
     Strong scaling of a fixed global problem.  Returns (Problem, slab dict)."""
     c = cells
+    cxy = c if xy is None else xy
     h = 1.0 / c
-    nx = ny = c + 4
+    nx = ny = cxy + 4
     nz_glob = c + 4
     lay = [r * c // world for r in range(world + 1)]
     pad = band_cells + 2
@@ -274,13 +299,16 @@ def cube_slab_3d(rank, world, cells=126, nsteps=100, gamma_lme=6.0, band_cells=6
     c0 = max(0, lay[rank] - 1) if rank > 0 else 0
     c1 = min(c, lay[rank + 1] + 1) if rank < world - 1 else c
     cel = (material[1][1] / material[1][0]) ** 0.5 * 1.3
-    P = structured_problem(3, (nx, ny, k1 - k0), h, (c, c, c1 - c0), (2, 2, c0 - k0), material, nsteps, 0.5, cel,
-                           (0.0, 0.0, -9.81), gamma_lme=gamma_lme, fixed=("bottom",) if k0 == 0 else (),
-                           rollers=("left", "right", "front", "back"), cell_offset=(0, 0, k0))
-    e = np.arange(c * c * (c1 - c0), dtype=np.int64)
-    gcell = e + c0 * c * c                               # cells are numbered x fastest, z slowest
+    P = structured_problem(3, (nx, ny, k1 - k0), h, (cxy, cxy, c1 - c0), (2, 2, c0 - k0), material, nsteps, 0.5, cel,
+                           (0.0, 0.0, 0.0 if compress else -9.81), gamma_lme=gamma_lme,
+                           fixed=("bottom",) if k0 == 0 else (), rollers=("left", "right", "front", "back"),
+                           cell_offset=(0, 0, k0))
+    if compress:
+        _top_platen(P, c, nx, ny, nsteps, 0.1 / 500.0, layer_offset=k0)
+    e = np.arange(cxy * cxy * (c1 - c0), dtype=np.int64)
+    gcell = e + c0 * cxy * cxy                           # cells are numbered x fastest, z slowest
     gid = (gcell[:, None] * 8 + np.arange(8)[None, :]).ravel().astype(np.int32)
     cuts = np.array([(lay[r] + 0.5) * h for r in range(1, world)])
-    slab = dict(rank=rank, world=world, axis=2, cuts=cuts, band_cells=band_cells, global_id=gid, n_global=8 * c ** 3,
-                node_offset=k0 * (nx + 1) * (ny + 1))
+    slab = dict(rank=rank, world=world, axis=2, cuts=cuts, band_cells=band_cells, global_id=gid,
+                n_global=8 * cxy * cxy * c, node_offset=k0 * (nx + 1) * (ny + 1))
     return P, slab

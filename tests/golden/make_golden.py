@@ -390,9 +390,80 @@ def gen_kin3d(_case="all"):
     print("3D kinematics:", P.np_, "particles, max |DF - I|", float(np.abs(DF - np.eye(3).ravel()).max()))
 
 
+# ---- BASELINE configs at their stated shape: C1 = 1024 particles x 200 steps, C2 twin = 1/8 linear scale
+# (15,488 particles) x 120 steps with plastic flow.  The problems themselves are NOT stored: the generators of
+# nl-partsol_b200/nlps_b200/synthetic.py rebuild them on the GPU box, and this script asserts that what they build is
+# bit-identical to what the reference's parser, mesh reader and particle seeding produced from the deck.
+from util import CONFIG_CASES, CONFIG_FIELDS_SMALL, config_problem  # noqa: E402
+
+
+def gen_config(case):
+    import hashlib
+    import refexport
+    import refharness
+    c = CONFIG_CASES[case]
+    spec = deckgen.DeckSpec(nx=c["grid"][0], ny=c["grid"][1], h=c["h"], pnx=c["block"][0], pny=c["block"][1], ph=c["h"],
+                            porigin=(c["origin"][0] * c["h"], c["origin"][1] * c["h"]), nsteps=c["nsteps"], cfl=0.5, cel=c["cel"])
+    if c["mat"] == "dp_c2":
+        spec.material = deckgen.Material("Drucker-Prager", {
+            "rho": 2000.0, "E": 1e7, "nu": 0.3, "m": 1.0, "Hardening-modulus": 1.0,
+            "Reference-plastic-strain": 1e-2, "kappa-0": 1e4, "Friction-angle": 30.0, "Dilatancy-angle": 0.0})
+    tmp = tempfile.mkdtemp(prefix="nlps_golden_")
+    h = refharness.RefHarness(deckgen.write_deck(spec, tmp), threads=1)
+    if c["kick"]:
+        v = h.field("vel")
+        v[:, 1] = c["kick"] * c["cel"]
+        h.set_field("vel", v)
+    Pref = refexport.problem_from_ref(h)
+    Psyn = config_problem(case)
+    for nm in ("coords", "r1p", "r1i", "r2p", "r2i", "h_avg", "I0", "MatIdx"):
+        assert np.array_equal(getattr(Pref, nm), getattr(Psyn, nm)), (case, nm)
+    skip = ("tol_radial", "maxiter_radial") if c["mat"] == "nh_c1" else ()   # globals no material of the deck sets (F10-iv)
+    assert Pref.dx == Psyn.dx and all(Pref.solver[k] == Psyn.solver[k] for k in Pref.solver if k not in skip), (Pref.solver, Psyn.solver)
+    # particle fields: the reference interpolates the seeds with the element shape functions and integrates the element
+    # volume, the generator uses closed forms: equal to 1 ulp.  The few fields that differ in the last bit (and the
+    # NaN the reference leaves in Kappa_n of a Neo-Hookean deck) are stored with the fixture and laid over the generated
+    # problem by the test (lambda and Beta are the product of initialize__LME__, which the test runs itself)
+    init = {}
+    for k, v in Pref.fields.items():
+        if k in ("lambda", "Beta") or np.array_equal(v, Psyn.fields[k], equal_nan=True):
+            continue
+        assert v.shape == Psyn.fields[k].shape and (np.isnan(v).any() or np.allclose(v, Psyn.fields[k], rtol=1e-13, atol=1e-300)
+                                                     or k == "b_e_n1"), (case, "field", k)
+        init[k] = v
+    for a, b in zip(Pref.bounds, Psyn.bounds):
+        # (the reference holds the node set in chain order = file order reversed; the order of a Dirichlet set has no effect)
+        assert np.array_equal(np.sort(a["nodes"]), np.sort(b["nodes"])) and all(np.array_equal(a[k], b[k]) for k in ("dir", "val")), (case, "bounds")
+    assert np.array_equal(Pref.gravity, Psyn.gravity)
+    cap = int((Pref.r2p[1:] - Pref.r2p[:-1]).max())
+    small = Pref.np_ > 4096
+    fields = CONFIG_FIELDS_SMALL if small else TRACE_FIELDS
+    out = {"checkpoints": np.array(c["checkpoints"]), "np": Pref.np_, "nn": Pref.nn}
+    for k, v in init.items():
+        out["init_" + k] = v
+    for k in range(c["nsteps"]):
+        assert h.step(k) == 0, (case, k)
+        if k + 1 in c["checkpoints"]:
+            t = f"s{k + 1}_"
+            for f in fields:
+                out[t + f] = h.field(f)
+            out[t + "I0"] = h.ints("I0")
+            out[t + "NumberNodes"] = h.ints("NumberNodes")
+            lp, li = h.table(4)
+            lists = refexport.lists_dense(lp, li, cap)
+            if small:  # the ordered lists as a digest (15 k x 25 ints would be the largest array of the file)
+                out[t + "lists_sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(lists).tobytes()).hexdigest())
+            else:
+                out[t + "lists"] = lists
+            out[t + "active"] = h.active()
+    np.savez_compressed(os.path.join(HERE, f"{case}_config.npz"), **out)
+    print(case, "ok: np", Pref.np_, "nn", Pref.nn, "max EPS", float(h.field("EPS_n").max()),
+          "plastic particles", int((h.field("EPS_n") > 0).sum()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d, "config": gen_config}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
@@ -406,3 +477,5 @@ if __name__ == "__main__":
         subprocess.run([sys.executable, __file__, "nh3d", "all"], check=True)
         subprocess.run([sys.executable, __file__, "lists3d", "all"], check=True)
         subprocess.run([sys.executable, __file__, "kin3d", "all"], check=True)
+        for c in ("c1", "c2twin"):
+            subprocess.run([sys.executable, __file__, "config", c], check=True)

@@ -61,6 +61,53 @@ def test_neumann_traction_on_a_block():
     _run_both(P, nsteps)
 
 
+def test_neumann_traction_3d_uses_area_0():
+    """3D Neumann loads act on Phi.Area_0 (U-Verlet.c:847-849), not on Vol_0 / Thickness_Plain_Stress: a cube pushed
+    down on its top particle layer, against the oracle; without Area_0 the engine refuses the deck."""
+    nsteps = 12
+    P = synthetic.cube_3d(cells=6, nsteps=nsteps, compress=False)
+    x = P.fields["x_GC"]
+    top = np.nonzero(x[:, 2] > x[:, 2].max() - 0.3 * P.dx)[0].astype(np.int32)
+    dr = np.zeros((3, nsteps), np.int32)
+    dr[2, :] = 1
+    val = np.zeros((3, nsteps))
+    val[2, :] = -2e4 * np.linspace(0.2, 1.0, nsteps)
+    P.neumann.append(dict(nodes=top, dir=dr, val=val))
+    with pytest.raises(RuntimeError, match="Area_0"):
+        engine.Engine(P, device=0)
+    P.fields["Area_0"] = np.full(P.np_, 0.25 * P.dx ** 2) * (1.0 + 0.1 * np.sin(np.arange(P.np_)))   # not Vol_0 / h
+    f = _run_both(P, nsteps)
+    assert np.abs(f["acc"][top, 2]).max() > 0.0
+
+
+def test_two_engines_with_different_materials_in_one_process():
+    """The material table belongs to the engine (a kernel parameter), not to the process: a second engine with another
+    deck, and a call of the point-wise stress entry in between, leave the first engine's law untouched."""
+    nsteps = 10
+    Pa = synthetic.column_collapse_2d(scale=0.04, nsteps=nsteps)
+    Pb = synthetic.block_2d(cells=8, nsteps=nsteps)                       # Neo-Hookean, other constants
+    for Q in (Pa, Pb):
+        Q.fields["vel"][:, 1] = -0.05 * Q.solver["cel"]
+    ea = engine.Engine(Pa, device=0)
+    assert ea.initialize_lme() == 0 and ea.run(0, nsteps // 2) == 0
+    eb = engine.Engine(Pb, device=0)                                       # used to overwrite the process-wide table
+    assert eb.initialize_lme() == 0 and eb.run(0, nsteps) == 0
+    ident = np.tile(np.array([1.0, 0.0, 0.0, 1.0, 1.0]), (4, 1))            # 2D tensors: 2x2 block + slot 4 (SURVEY App. B)
+    engine.stress_points(2, "Neo-Hookean-Wriggers", synthetic.NH_C1[1], 1e-14, 10, ident, ident, np.ones(4), ident,
+                         np.zeros(4), np.zeros(4))
+    assert ea.run(nsteps // 2, nsteps - nsteps // 2) == 0, ea.error()
+    fa = ea.download()
+    oa = oracle.Oracle(Pa)
+    assert oa.init_lme() == 0
+    for k in range(nsteps):
+        assert oa.step(k) == 0
+    sc = field_scales(Pa)
+    for name in TRACE_FIELDS:
+        assert_close(fa[name], oa.field(name), "engine A after engine B: " + name, scale=sc.get(name))
+    ea.close()
+    eb.close()
+
+
 def test_particles_on_nodes_and_faces_tie_breaking():
     """x exactly on grid lines: equal distances to several nodes; the first strict minimum in chain order wins."""
     P = synthetic.structured_problem(2, (10, 10), 0.125, (6, 6), (2, 2), synthetic.NH_C1, 12, 0.5,

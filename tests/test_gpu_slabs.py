@@ -253,6 +253,45 @@ def test_excursion_is_latched():
     assert (1, 9) in codes, codes
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_migration_capacity_fails_on_every_slab_without_hanging(world):
+    """A slab without room for the particles that arrive must not leave its neighbours in a half-finished row exchange:
+    with capacity_factor ~ 1 the block flying downstream overflows the last slab, EVERY slab returns EXIT_FAILURE with
+    NLPS_ERR_SLAB_CAPACITY at the same migration, and nobody hangs."""
+    nsteps = 60
+    P = moving_block(nsteps=nsteps)
+    axis, cuts = engine.slab_cuts(P, world)
+    comms = engine.ThreadComm.group(world)
+    out = [None] * world
+
+    def work(r):
+        try:
+            eng = engine.Engine(P, device=0, slab=dict(rank=r, world=world, axis=axis, cuts=cuts, comm=comms[r],
+                                                       migrate_every=4, capacity_factor=1.0 + 1e-9))
+            assert eng.initialize_lme() == 0
+            rc = 0
+            for k0 in range(0, nsteps, 4):   # the slabs stop together, at the migration that fails
+                rc = eng.run(k0, 4)
+                if rc != 0:
+                    break
+            out[r] = (rc, eng.error()[0], k0)
+            eng.close()
+        except BaseException as ex:  # noqa: BLE001
+            out[r] = ("exception", repr(ex))
+            comms[r].sh.barrier.abort()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert not any(t.is_alive() for t in th), "a slab hangs in the exchange"
+    for c in comms:
+        c.close()
+    assert all(o is not None and o[0] == 1 and o[1] == 10 for o in out), out   # NLPS_ERR_SLAB_CAPACITY everywhere
+    assert len({o[2] for o in out}) == 1, out                                    # ... at the same step
+
+
 def test_slabs_nccl_two_gpus():
     import torch
     if torch.cuda.device_count() < 2:

@@ -62,3 +62,37 @@ def field_scales(prob):
     rho = max(m[1][0] for m in prob.materials)
     nat.update(gM=rho * h ** d, gdU=h, gF=E * h ** (d - 1), gA=h / dt ** 2, gR=E * h ** (d - 1))
     return {k: 1e-4 * v for k, v in nat.items()}
+
+
+# ---- BASELINE configs at their stated shape (fixtures tests/golden/{c1,c2twin}_config.npz, tests/golden/make_golden.py)
+CONFIG_CASES = {
+    "c1": dict(grid=(20, 20), h=0.0625, block=(16, 16), origin=(2, 0), mat="nh_c1", nsteps=200, cel=31.622776601683793,
+               checkpoints=(100, 200), kick=0.0),
+    "c2twin": dict(grid=(264, 110), h=0.2 / 44, block=(44, 88), origin=(0, 0), mat="dp_c2", nsteps=120,
+                   cel=(1e7 / 2000.0) ** 0.5 * 1.3, checkpoints=(120,), kick=-0.12),
+}
+CONFIG_FIELDS_SMALL = ("x_GC", "vel", "Stress", "F_n", "J_n", "EPS_n", "Kappa_n", "lambda", "rho")
+
+
+def config_problem(case):
+    """The Problem of a CONFIG_CASES entry from the synthetic generators (what the GPU tests run)."""
+    from nlps_b200 import synthetic
+    c = CONFIG_CASES[case]
+    mat = synthetic.NH_C1 if c["mat"] == "nh_c1" else synthetic.DP_C2
+    P = synthetic.structured_problem(2, c["grid"], c["h"], c["block"], c["origin"], mat, c["nsteps"], 0.5, c["cel"],
+                                     (0.0, -9.81))
+    if c["kick"]:
+        P.fields["vel"][:, 1] = c["kick"] * P.solver["cel"]
+    return P
+
+
+
+
+def load_config(case):
+    """(Problem rebuilt by the generator with the fixture's bit-exact seeds laid over it, golden npz)."""
+    g = np.load(os.path.join(GOLDEN, f"{case}_config.npz"))
+    P = config_problem(case)
+    for k in g.files:
+        if k.startswith("init_"):
+            P.fields[k[5:]] = g[k].copy()
+    return P, g
