@@ -6,7 +6,8 @@
 Default workload: BASELINE.json configs[2] ("c3") -- 3D Neo-Hookean cube compression, 126^3 particle cells x GPxElement 8
 = 16,003,008 particles, LME gamma = 6, explicit NPC-FS; at N > 1 the SAME cube is split into N z-slabs (strong scaling,
 halo sums + migration over NVLink).  --workload c2: configs[1], 2D Drucker-Prager column, 10^6 particles (weak scaling
-over y-slabs); --workload c4: configs[3], 3D Matsuoka-Nakai slope, 8 M particles, slabs + migration (strong scaling).
+over y-slabs); --workload c4: configs[3], 3D Matsuoka-Nakai slope, 8 M particles, slabs + migration (strong scaling);
+--workload c5: configs[4], implicit Newmark-beta 3D beam, 2 M particles, device block-CSR tangent + PCG.
 A "step" is one full time step over all particles.  Prints ONE JSON line.
 
 `--impl reference` times the reference's CPU implementation of the same path on a bounded sample: the reference's own
@@ -621,6 +622,102 @@ def measure_e2e(args, name, rank, world, local, comm, total_particles, K, engine
                     "steps overlapped with the following steps, destroy), host wall clock"}
 
 
+def run_c5(args):
+    """--workload c5: BASELINE configs[4], implicit Newmark-beta finite-strain 3D beam (8 x 1 x 1, Neo-Hookean, LME gamma 6,
+    dt = 10 x the explicit limit), 2,097,152 particles, device block-CSR tangent + Jacobi-PCG.  A step = one converged
+    time step (Newton to TOL 1e-10).  The implicit scheme has no slabs yet: at N > 1 every rank runs its own replica."""
+    import torch
+    import torch.distributed as dist
+
+    from nlps_b200 import engine, synthetic
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "NONE")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    K, Wm = args.steps, max(1, min(args.warmup, 2))
+    c = max(4, int(round(32 * args.scale)))
+    t0 = time.perf_counter()
+    P = synthetic.beam_3d(cells_per_unit=c, nsteps=Wm + K + 1)
+    eng = engine.Engine(P, device=local)
+    assert eng.initialize_lme() == 0
+    assert eng.newmark_setup(tol=1e-10, max_iter=10, pcg_rtol=1e-6) == 0
+    setup_s = time.perf_counter() - t0
+    for k in range(Wm):
+        assert eng.newmark_step(k) == 0, eng.error()
+    s0 = eng.newmark_stats()
+    sampler = NvmlSampler(local)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ta = time.perf_counter()
+    newton = []
+    for k in range(Wm, Wm + K):
+        assert eng.newmark_step(k) == 0, eng.error()     # every step ends with a device synchronisation (Newton's test)
+        newton.append(eng.newmark_stats()["newton_iters"])
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - ta)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    s1 = eng.newmark_stats()
+    pcg = s1["pcg_iters_total"] - s0["pcg_iters_total"]
+    asm = s1["assemblies_total"] - s0["assemblies_total"]
+    ms_pcg_iter = (s1["ms_pcg"] - s0["ms_pcg"]) / max(1, pcg)
+    # block-CSR SpMV: 9 doubles + one 4-byte column index per 3x3 block, plus the vectors of one PCG iteration
+    spmv_bytes = s1["nnz_blocks"] * (72 + 4) + 5 * 3 * s1["n_rows"] * 8
+    peak, peak_src = measured_peak()
+    gbs = spmv_bytes / 1e9 / (ms_pcg_iter * 1e-3)
+    f1 = eng.download()
+    eng.close()
+    # end to end with host buffers: create + H2D of mesh and state, the same steps, D2H of every field at the end
+    P2 = synthetic.beam_3d(cells_per_unit=c, nsteps=Wm + K + 1)
+    state_bytes = sum(v.nbytes for v in P2.fields.values())
+    mesh_bytes = sum(a.nbytes for a in (P2.coords, P2.r1p, P2.r1i, P2.r2p, P2.r2i, P2.h_avg))
+    torch.cuda.synchronize()
+    tb = time.perf_counter()
+    e2 = engine.Engine(P2, device=local)
+    assert e2.initialize_lme() == 0 and e2.newmark_setup(tol=1e-10, max_iter=10, pcg_rtol=1e-6) == 0
+    for k in range(Wm + K):
+        assert e2.newmark_step(k) == 0
+    f2 = e2.download()
+    e2e_s = time.perf_counter() - tb
+    e2.close()
+    assert np.array_equal(f1["x_GC"], f2["x_GC"])     # the two runs are the same computation
+    if rank == 0:
+        value = world * P.np_ * K / (ms_max * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE configs[4]: implicit Newmark-beta finite-strain 3D beam (Neo-Hookean, LME gamma=6, "
+                                       "dt = 10 x explicit limit), device block-CSR tangent + Jacobi-PCG replacing PETSc KSP",
+                           "particles": P.np_, "background_nodes": P.nn, "scale": args.scale,
+                           "multi_gpu": "single GPU" if world == 1 else f"{world} independent replicas (the implicit scheme has no slabs)",
+                           "newton_iters_per_step": newton, "pcg_iters": int(pcg), "block_rows": s1["n_rows"],
+                           "nnz_blocks": s1["nnz_blocks"], "setup_seconds": round(setup_s, 2),
+                           "ms_assemble_per_newton": round((s1["ms_assemble"] - s0["ms_assemble"]) / max(1, asm), 3),
+                           "ms_per_pcg_iter": round(ms_pcg_iter, 4), "l2": "tangent (7 GB) larger than L2"},
+                "clocks": clocks,
+                "e2e": {"value": P.np_ * (Wm + K) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int((mesh_bytes + state_bytes) / (Wm + K)),
+                        "d2h_bytes_per_step": int(state_bytes / (Wm + K)), "steps": Wm + K, "seconds": round(e2e_s, 3),
+                        "call": "create (H2D of mesh and state) + initialize + newmark steps + download of every field, host wall clock"},
+                "gpu_launches": None,
+                "roofline": {"bound": "hbm", "kernel": "k_bsr_spmv (one PCG iteration: SpMV + vector updates)", "achieved": round(gbs, 1),
+                             "peak": peak, "unit": "GB/s", "frac": round(gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                             "bytes_per_iteration": int(spmv_bytes),
+                             "note": "76 bytes per 3x3 block (72 values + one column index) + 5 vectors of 3 x rows doubles"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -631,13 +728,15 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="--impl reference: host threads (0 = all)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer scheme call")
-    ap.add_argument("--workload", default="c3", choices=("c2", "c3", "c4"),
+    ap.add_argument("--workload", default="c3", choices=("c2", "c3", "c4", "c5"),
                     help="c3 (default, the driver's bench line): BASELINE configs[2], 3D cube, 16 M particles, strong scaling; "
                          "c2: configs[1], 2D column, weak scaling; c4: configs[3], 3D Matsuoka-Nakai slope, slabs + migration "
                          "(no e2e leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

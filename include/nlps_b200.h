@@ -43,6 +43,7 @@ extern "C" {
 #define NLPS_ERR_SLAB_EXCURSION 9     /* a particle left the halo band of its slab between two migrations */
 #define NLPS_ERR_SLAB_CAPACITY 10     /* migration would exceed the particle capacity of a slab */
 #define NLPS_ERR_CSR_PATTERN 11       /* implicit: a particle couples two nodes outside the tangent pattern */
+#define NLPS_ERR_HALO_TIMEOUT 12      /* peer-memory halo: the neighbour slab did not deliver within NLPS_HALO_TIMEOUT_S (30 s) */
 #define NLPS_ERR_CUDA 100
 
 /* Background mesh: the parts of `Mesh` (Types.h:631-760) the stepped path reads. */

@@ -146,11 +146,18 @@ extern "C" int nlps_b200_build_locality(int ndim, int n_nodes, int n_elems, int 
   if ((ndim != 2 && ndim != 3) || (nodes_per_elem != 4 && nodes_per_elem != 8)) return 1;
   for (long i = 0; i < (long)n_elems * nodes_per_elem; i++)
     if (connectivity[i] < 0 || connectivity[i] >= n_nodes) return 1;
-  static Locality cache;  // two-call protocol: the second call reuses the result of the first
-  static const int* cache_key = nullptr;
-  if (cache_key != connectivity || (int)cache.r1p.size() != n_nodes + 1) {
+  // two-call protocol: the second call reuses the result of the first.  The cache belongs to the calling THREAD
+  // (several host threads may set up different meshes at once) and is keyed on the sizes, the connectivity pointer
+  // and a digest of the connectivity, not on the pointer alone (a freed and reallocated buffer can have the same address)
+  static thread_local Locality cache;
+  static thread_local const int* cache_key = nullptr;
+  static thread_local unsigned long long cache_digest = 0;
+  unsigned long long digest = 1469598103934665603ull ^ (unsigned long long)n_nodes ^ ((unsigned long long)n_elems << 32);
+  for (long i = 0; i < (long)n_elems * nodes_per_elem; i += 97) digest = (digest ^ (unsigned)connectivity[i]) * 1099511628211ull;
+  if (cache_key != connectivity || cache_digest != digest || (int)cache.r1p.size() != n_nodes + 1) {
     build(ndim, n_nodes, n_elems, nodes_per_elem, connectivity, coords, cache);
     cache_key = connectivity;
+    cache_digest = digest;
   }
   memcpy(ring1_ptr, cache.r1p.data(), sizeof(int) * (n_nodes + 1));
   memcpy(ring2_ptr, cache.r2p.data(), sizeof(int) * (n_nodes + 1));

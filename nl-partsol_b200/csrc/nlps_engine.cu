@@ -1483,7 +1483,8 @@ __global__ void k_halo_add(GridDev G, const int* ids, int n, int which, const do
 // Peer-memory halo exchange (one process per GPU, neighbours' buffers mapped with CUDA IPC): the push kernel packs
 // the band values of BOTH sides and stores them straight into the neighbours' receive buffers over NVLink, the last
 // block to finish publishes the arrival counters; the pull kernel waits for the neighbours' counters and adds.
-// A push never waits, so the pair cannot deadlock; the wait is bounded (about 2 s) and latches NLPS_ERR_CUDA.
+// A push never waits, so the pair cannot deadlock; the wait is bounded (30 s, NLPS_HALO_TIMEOUT_S) and latches
+// NLPS_ERR_HALO_TIMEOUT.  The receive buffers are doubled by the parity of the exchange number.
 struct HaloP2P {
   const int* ids[2];
   int n[2];
@@ -1530,7 +1531,8 @@ __global__ void __launch_bounds__(256) k_halo_push(GridDev G, HaloP2P h, int whi
   }
 }
 template <int D>
-__global__ void __launch_bounds__(256) k_halo_pull(GridDev G, HaloP2P h, int which, unsigned long long seq, int* err) {
+__global__ void __launch_bounds__(256) k_halo_pull(GridDev G, HaloP2P h, int which, unsigned long long seq, int* err,
+                                                   long long timeout_cycles) {
   const int per = (which == 0) ? 1 : ((which == 1) ? 1 + D : D);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int s_ = (i < h.n[0]) ? 0 : 1, j = (s_ == 0) ? i : i - h.n[0];
@@ -1538,7 +1540,7 @@ __global__ void __launch_bounds__(256) k_halo_pull(GridDev G, HaloP2P h, int whi
   const volatile unsigned long long* f = (const volatile unsigned long long*)h.my_flag[s_];
   const long long t0 = clock64();
   while (*f < seq) {
-    if (clock64() - t0 > 4000000000ll) { latch_error(err, NLPS_ERR_CUDA, -1); return; }
+    if (clock64() - t0 > timeout_cycles) { latch_error(err, NLPS_ERR_HALO_TIMEOUT, -1); return; }
     __nanosleep(64);
   }
   __threadfence_system();
@@ -1777,6 +1779,10 @@ struct nlps_engine {
   long long launches = 0;
   int last_code = 0, last_particle = -1;
   int host_fail = 0;  // a host-side failure (migration, halo transport): sticky, reported by every later poll
+  // The n+1 -> n roll is a pointer swap: after a completed step the device *_n1 arrays hold the values of step n - 1,
+  // while the reference COPIES n1 -> n (U-Verlet.c:1040-1081) and leaves both equal.  Downloads taken in that state
+  // write the *_n arrays into both host fields; inside a step (after the kinematics stage) n1 is what it says.
+  int n1_stale = 0;
   // ---- spatial slab (multi-GPU); slab_on == 0: the engine owns every particle
   int slab_on = 0, rank = 0, world = 1, axis = 0, band_cells = 6, migrate_every = 10, n_global = 0;
   int steps_since_migration = 0;
@@ -2329,7 +2335,9 @@ static int halo_exchange(nlps_engine* e, int which) {
       const bool on = sd.peer >= 0 && sd.n > 0;
       h.ids[s_] = sd.ids;
       h.n[s_] = on ? sd.n : 0;
-      const size_t off = (size_t)which * sd.n * (1 + D);
+      // two receive buffers per exchange kind, taken in turn: a neighbour that is one exchange of the same kind ahead
+      // (initialize_lme's search followed by the first step's, a stage called twice) writes into the other one
+      const size_t off = ((size_t)(seq & 1ull) * 3 + which) * sd.n * (1 + D);
       h.peer_rbuf[s_] = on ? sd.peer_rbuf + off : nullptr;
       h.peer_flag[s_] = on ? sd.peer_flag + which : nullptr;
       h.my_rbuf[s_] = on ? sd.p2p_rbuf + off : nullptr;
@@ -2338,7 +2346,9 @@ static int halo_exchange(nlps_engine* e, int which) {
     }
     if (tot > 0) {
       k_halo_push<D><<<nblk(tot, 256), 256, 0, e->stream>>>(e->G, h, which, seq, e->p2p_done);
-      k_halo_pull<D><<<nblk(tot, 256), 256, 0, e->stream>>>(e->G, h, which, seq, e->err);
+      // a neighbour may be busy for a while (set-up, a migration with a host sync): 30 s by default, NLPS_HALO_TIMEOUT_S
+      static const long long tmo = (long long)((getenv("NLPS_HALO_TIMEOUT_S") ? atof(getenv("NLPS_HALO_TIMEOUT_S")) : 30.0) * 1.9e9);
+      k_halo_pull<D><<<nblk(tot, 256), 256, 0, e->stream>>>(e->G, h, which, seq, e->err, tmo);
       e->launches += 2;
     }
     if (e->profile) {
@@ -2576,6 +2586,7 @@ static void stage_kin_stress_t(nlps_engine* e, int step) {
   }
   StepParams sp = make_params(e, step, 1);
   sp.implicit = e->implicit_on;
+  e->n1_stale = 0;
   if (e->kver == 2) {
     const CwLaunch L = cw_launch_record(e, sp);
     if (e->uniform_mat == NLPS_MAT_NEO_HOOKEAN_WRIGGERS && !e->split_nh) {
@@ -2623,6 +2634,7 @@ static void stage_g2p_t(nlps_engine* e, int step) {
     e->inert_synced = 1;
   }
   // roll n+1 -> n (U-Verlet.c:1043-1081) as pointer swaps
+  e->n1_stale = 1;
   std::swap(e->P.F_n, e->P.F_n1);
   std::swap(e->P.J_n, e->P.J_n1);
   std::swap(e->P.be_n, e->P.be_n1);
@@ -3142,7 +3154,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     for (int s_ = 0; s_ < 2 && ok; s_++) {
       auto& h = e->side[s_];
       if (h.peer < 0) continue;
-      const size_t nb = sizeof(double) * 3 * (size_t)std::max(h.n, 1) * (1 + D);
+      const size_t nb = sizeof(double) * 2 * 3 * (size_t)std::max(h.n, 1) * (1 + D);
       P2PCacheEntry* c = ce[s_] = p2p_cache_get(e->device, e->rank, h.peer, s_);
       {
         std::lock_guard<std::mutex> lk(g_p2p_mutex);
@@ -3225,11 +3237,20 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     }
     if (!verdict) {
       if (e->rank == 0) fprintf(stderr, "nlps_b200: peer-memory halo path unavailable, using NCCL send/recv\n");
-      return 0;  // buffers and mappings are released by destroy
+      // (buffers and mappings are released by destroy)
+    } else {
+      if (dev_alloc(e, &e->p2p_done, 4)) return 1;
+      e->p2p_on = 1;
+      mark("peer-memory halo setup");
     }
-    if (dev_alloc(e, &e->p2p_done, 4)) return 1;
-    e->p2p_on = 1;
-    mark("peer-memory halo setup");
+  }
+  // the first collective of a communicator pays NCCL's lazy channel set-up (hundreds of milliseconds): take the
+  // "did every slab succeed" reduction of the migrations once here, not inside the first migration of a run
+  if (e->slab_on && e->world > 1) {
+    int all_ok = 1;
+    if (comm_all_ok(e->comm, e->rank, e->world, 1, e->mig_cnt + 12, e->stream, &all_ok) || !all_ok)
+      return set_err(err, err_len, "slab communicator: the collective of the migration check failed");
+    mark("collective warm-up");
   }
   return 0;
 }
@@ -3320,23 +3341,27 @@ static int download_impl(nlps_engine* e, nlps_particles* out, int rows) {
       get_field(e, out->D_dis, P.ddis, D, D, 0, nullptr, rows) || get_field(e, out->vel, P.vel, D, D, 0, nullptr, rows) ||
       get_field(e, out->acc, P.acc, D, D, 0, nullptr, rows) || get_field(e, out->lambda, P.lam, D, D, 0, nullptr, rows))
     return 1;
+  // after a completed step the *_n1 host fields receive the rolled state, as the reference's copy roll leaves them
+  const bool st_ = e->n1_stale != 0;
+  const double *F1 = st_ ? P.F_n : P.F_n1, *J1 = st_ ? P.J_n : P.J_n1, *be1 = st_ ? P.be_n : P.be_n1;
+  const double *eps1 = st_ ? P.eps_n : P.eps_n1, *kap1 = st_ ? P.kap_n : P.kap_n1;
   if (D == 2) {
-    if (get_field(e, out->F_n, P.F_n, DD, T, 0, P.Fs4, rows) || get_field(e, out->F_n1, P.F_n1, DD, T, 0, P.Fs4, rows) ||
+    if (get_field(e, out->F_n, P.F_n, DD, T, 0, P.Fs4, rows) || get_field(e, out->F_n1, F1, DD, T, 0, P.Fs4, rows) ||
         get_field(e, out->DF, P.DF, DD, T, 0, P.DFs4, rows))
       return 1;
   } else {
-    if (get_field(e, out->F_n, P.F_n, DD, T, 0, nullptr, rows) || get_field(e, out->F_n1, P.F_n1, DD, T, 0, nullptr, rows) ||
+    if (get_field(e, out->F_n, P.F_n, DD, T, 0, nullptr, rows) || get_field(e, out->F_n1, F1, DD, T, 0, nullptr, rows) ||
         get_field(e, out->DF, P.DF, DD, T, 0, nullptr, rows))
       return 1;
   }
-  if (get_field(e, out->b_e_n, P.be_n, T, T, 0, nullptr, rows) || get_field(e, out->b_e_n1, P.be_n1, T, T, 0, nullptr, rows) ||
+  if (get_field(e, out->b_e_n, P.be_n, T, T, 0, nullptr, rows) || get_field(e, out->b_e_n1, be1, T, T, 0, nullptr, rows) ||
       get_field(e, out->Stress, P.stress, T, T, 0, nullptr, rows) || get_field(e, out->C_ep, P.cep, DD, DD, 0, nullptr, rows))
     return 1;
-  if (get_field(e, out->J_n, P.J_n, 1, 1, 0, nullptr, rows) || get_field(e, out->J_n1, P.J_n1, 1, 1, 0, nullptr, rows) ||
+  if (get_field(e, out->J_n, P.J_n, 1, 1, 0, nullptr, rows) || get_field(e, out->J_n1, J1, 1, 1, 0, nullptr, rows) ||
       get_field(e, out->mass, P.mass, 1, 1, 0, nullptr, rows) || get_field(e, out->rho, P.rho, 1, 1, 0, nullptr, rows) ||
       get_field(e, out->Vol_0, P.vol0, 1, 1, 0, nullptr, rows) || get_field(e, out->W, P.W, 1, 1, 0, nullptr, rows) ||
-      get_field(e, out->EPS_n, P.eps_n, 1, 1, 0, nullptr, rows) || get_field(e, out->EPS_n1, P.eps_n1, 1, 1, 0, nullptr, rows) ||
-      get_field(e, out->Kappa_n, P.kap_n, 1, 1, 0, nullptr, rows) || get_field(e, out->Kappa_n1, P.kap_n1, 1, 1, 0, nullptr, rows) ||
+      get_field(e, out->EPS_n, P.eps_n, 1, 1, 0, nullptr, rows) || get_field(e, out->EPS_n1, eps1, 1, 1, 0, nullptr, rows) ||
+      get_field(e, out->Kappa_n, P.kap_n, 1, 1, 0, nullptr, rows) || get_field(e, out->Kappa_n1, kap1, 1, 1, 0, nullptr, rows) ||
       get_field(e, out->Beta, P.beta, 1, 1, 0, nullptr, rows))
     return 1;
   if (get_ints(e, out->I0, P.I0, rows) || get_ints(e, out->NumberNodes, P.nnodes, rows)) return 1;

@@ -167,7 +167,13 @@ static int b200_flatten(b200_inputs *in, Mesh FEM_Mesh, Particle MPM_Mesh, Time_
   /* ---- materials */
   nlps_material *mats = (nlps_material *)calloc(MPM_Mesh.NumberMaterials, sizeof(nlps_material));
   for (int m = 0; m < MPM_Mesh.NumberMaterials; m++)
-    if (material_to_pod(&MPM_Mesh.Mat[m], &mats[m]) == EXIT_FAILURE) return EXIT_FAILURE;
+    if (material_to_pod(&MPM_Mesh.Mat[m], &mats[m]) == EXIT_FAILURE) {
+      free(mats); free(gravity);
+      free_loads(bounds, FEM_Mesh.Bounds.NumBounds);
+      free_loads(neumann, MPM_Mesh.Neumann_Contours.NumBounds);
+      free(r1p); free(r1i); free(r2p); free(r2i);
+      return EXIT_FAILURE;
+    }
 
   /* ---- particle fields: the reference's own buffers */
   nlps_particles st;

@@ -149,3 +149,66 @@ def test_reference_driver_with_b200_static_scheme(tmp_path):
         x = _points(files[0])
         assert np.abs(x - o.field("x_GC")).max() <= 1e-8 * np.abs(o.field("x_GC")).max(), k
     assert np.abs(o.field("dis")).max() > 1e-6
+
+
+@pytest.mark.gpu
+def test_reference_driver_on_two_gpus_from_the_c_host(tmp_path):
+    """NLPS_B200_GPUS=2: the U_Verlet shim (C, no torch) cuts the cloud into two slabs, runs one slab engine per device
+    from two host threads (NCCL id made in C) and merges the rows into the reference's buffers; the VTK files of the
+    run agree with those of the one-GPU run of the same deck to 1e-10."""
+    import torch
+    if not os.path.exists(BIN):
+        pytest.skip("drop-in binary not built (needs /root/reference at build time)")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import deckgen
+    spec = deckgen.DeckSpec(nx=48, ny=14, pnx=40, pny=8, porigin=(4 * 0.0625, 0.0), nsteps=40, out_every=20)
+    runs = {}
+    for tag, env in (("one", {}), ("two", {"NLPS_B200_GPUS": "2"})):
+        d = tmp_path / tag
+        d.mkdir()
+        deckgen.write_deck(spec, str(d))
+        r = subprocess.run([BIN, "--FORMULATION-U", "-f", "deck.nlp"], cwd=str(d), capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "abnormally" not in r.stdout + r.stderr
+        runs[tag] = {k: _points(glob.glob(os.path.join(str(d), "Results", f"*_{k}.vtk"))[0]) for k in (0, 20)}
+    for k in (0, 20):
+        a, b = runs["one"][k], runs["two"][k]
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), k
+    assert np.abs(runs["one"][20] - runs["one"][0]).max() > 1e-9       # the block did move
+
+
+@pytest.mark.gpu
+def test_reference_driver_scalable_setup_at_100k_particles(tmp_path):
+    """102,400 particles through the reference's OWN driver: its quadratic set-up (get_sourrounding_elements,
+    Read_GramsBox.c:293-330, and the element scan of initialize__LME__, LME.c:63-108: 69 s at this size on 8 host threads)
+    is replaced at link time by host/Setup-b200.c (1.4 s), the first lists / beta / lambda come from the engine.  The
+    positions after 21 steps agree with the CPU oracle on the same cloud to 1e-10."""
+    if not os.path.exists(BIN):
+        pytest.skip("drop-in binary not built (needs /root/reference at build time)")
+    import time
+
+    import deckgen
+    import oracle
+    from nlps_b200 import synthetic
+    n, nsteps = 160, 21
+    spec = deckgen.DeckSpec(nx=n + 10, ny=n + 10, h=1.0 / n, pnx=n, pny=n, ph=1.0 / n, porigin=(5.0 / n, 0.0), nsteps=nsteps,
+                            cfl=0.5, out_every=10)
+    deckgen.write_deck(spec, str(tmp_path))
+    t0 = time.perf_counter()
+    r = subprocess.run([BIN, "--FORMULATION-U", "-f", "deck.nlp"], cwd=str(tmp_path), capture_output=True, text=True,
+                       timeout=900)
+    wall = time.perf_counter() - t0
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "abnormally" not in r.stdout + r.stderr
+    assert wall < 60.0, f"the whole driver run took {wall:.1f} s: the quadratic set-up is back"
+    P = synthetic.structured_problem(2, (n + 10, n + 10), 1.0 / n, (n, n), (5, 0), synthetic.NH_C1, nsteps, 0.5, spec.cel,
+                                     (0.0, -9.81))
+    o = oracle.Oracle(P, threads=os.cpu_count() or 1)
+    assert o.init_lme() == 0
+    for k in range(nsteps):
+        assert o.step(k) == 0, o.error()
+    x = _points(glob.glob(os.path.join(str(tmp_path), "Results", "*_20.vtk"))[0])
+    ref = o.field("x_GC")
+    assert x.shape == ref.shape and np.abs(x - ref).max() <= 1e-10 * np.abs(ref).max()
