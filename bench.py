@@ -394,7 +394,8 @@ def run_ours(args):
     name = args.workload
     wl = WORKLOADS[name]
     K, Wm = args.steps, max(args.warmup, 3)
-    nsteps_total = Wm + K + 2
+    trace = int(os.environ.get("NLPS_BENCH_TRACE", "0"))  # diagnostic: per-step wall times of `trace` extra steps on stderr
+    nsteps_total = Wm + K + 2 + trace
     t_setup = time.perf_counter()
     comm = None
     P, slab, total_particles, extra = build_workload(name, rank, world, args.scale, nsteps_total, synthetic)
@@ -441,6 +442,14 @@ def run_ours(args):
     assert eng.run(Wm + K, 2) == 0
     kt = eng.kernel_times()
     eng.profile(False)
+    if trace:
+        per = []
+        for k in range(trace):
+            t0 = time.perf_counter()
+            assert eng.run(Wm + K + 2 + k, 1) == 0
+            torch.cuda.synchronize()
+            per.append(round((time.perf_counter() - t0) * 1e3, 2))
+        print(f"[trace rank {rank}] steps {Wm + K + 2}..: {per}", file=sys.stderr)
     transport = eng.transport() if world > 1 else "none (single GPU)"
     peak, peak_src = measured_peak()
     per_kernel = {}
