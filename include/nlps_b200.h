@@ -30,6 +30,8 @@ extern "C" {
 #define NLPS_MAT_NEO_HOOKEAN_WRIGGERS 0 /* Constitutive/Hyperelastic/Neo-Hookean.c:38 */
 #define NLPS_MAT_DRUCKER_PRAGER 1       /* Constitutive/Plasticity/Drucker-Prager.c:319 */
 #define NLPS_MAT_MATSUOKA_NAKAI 2       /* Constitutive/Plasticity/Matsuoka-Nakai.c:300 */
+#define NLPS_MAT_VON_MISES 3            /* Constitutive/Plasticity/Von-Mises.c:228 (explicit scheme only) */
+#define NLPS_MAT_HENCKY 4               /* Constitutive/Hyperelastic/Hencky.c:30 (explicit scheme only) */
 
 /* error codes latched on the device (first offender wins) */
 #define NLPS_ERR_NONE 0
@@ -44,6 +46,7 @@ extern "C" {
 #define NLPS_ERR_SLAB_CAPACITY 10     /* migration would exceed the particle capacity of a slab */
 #define NLPS_ERR_CSR_PATTERN 11       /* implicit: a particle couples two nodes outside the tangent pattern */
 #define NLPS_ERR_HALO_TIMEOUT 12      /* peer-memory halo: the neighbour slab did not deliver within NLPS_HALO_TIMEOUT_S (30 s) */
+#define NLPS_ERR_RETURN_MAP_VM 13     /* Von-Mises.c:__kappa / __d_kappa (negative equivalent plastic strain) */
 #define NLPS_ERR_CUDA 100
 
 /* Background mesh: the parts of `Mesh` (Types.h:631-760) the stepped path reads. */
@@ -82,6 +85,9 @@ typedef struct nlps_material {
   double cohesion;
   double alpha_hardening_borja;
   double a_hardening_borja[3];
+  /* Von-Mises (InOutFun/Material/Plasticity/Von-Mises.c:69-73 defaults: theta = 1, the others 0); kappa_0 is its
+   * Yield-stress, hardening_modulus its Hardening-Modulus */
+  double theta_hardening_voce, k_0_hardening_voce, k_inf_hardening_voce, delta_hardening_voce;
 } nlps_material;
 
 /* `Time_Int_Params` (Types.h:804-865) + the process globals the scheme reads
@@ -120,6 +126,9 @@ typedef struct nlps_particles {
   double *Area_0; /* n: Particle.Phi.Area_0, the area a 3D Neumann load acts on (U-Verlet.c:847-849,
                    * U-Newmark-beta.c:1442, U-Static.c:930); 2D uses Vol_0 / Thickness_Plain_Stress and ignores it.
                    * nlps_b200_create fails for a 3D deck with Neumann loads and Area_0 == NULL. */
+  double *Back_stress; /* n x 3: Particle.Phi.Back_stress (Types.h:266), the kinematic-hardening back stress of Von-Mises in
+                        * PRINCIPAL components (Von-Mises.c:256-258,729-731), updated in place; NULL = zero and not
+                        * written back. */
 } nlps_particles;
 
 typedef struct nlps_engine nlps_engine;

@@ -574,7 +574,11 @@ __device__ __forceinline__ bool particle_stress(const PartDev& P, const StepPara
   const int mid = P.matidx[p];
   const MatParams& mat = mt.m[mid];
   const int mtype = (MAT >= 0) ? MAT : mat.type;
-  double be[T], eps = 0.0, kap = 0.0;
+  double be[T], eps = 0.0, kap = 0.0, back[3] = {0.0, 0.0, 0.0};
+  if (MAT < 0 && P.back) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) back[i] = P.back[(size_t)i * ld + p];
+  }
   if (mtype != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
 #pragma unroll
     for (int i = 0; i < T; i++) be[i] = P.be_n[(size_t)i * ld + p];
@@ -604,16 +608,23 @@ __device__ __forceinline__ bool particle_stress(const PartDev& P, const StepPara
   } else {
     double cep[D * D];
     int st;
-    if (mtype == NLPS_MAT_DRUCKER_PRAGER) st = stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
-    else st = stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+    if (MAT == NLPS_MAT_DRUCKER_PRAGER) st = stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+    else if (MAT == NLPS_MAT_MATSUOKA_NAKAI) st = stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+    else st = stress_with_history<D>(mtype, mat, sp.rp, DF, Fn1, be, eps, kap, back, tau, Wp, cep);
     if (st != 0) { latch_error(err, st, P.orig[p]); return false; }
+    if (MAT >= 0 || mat_has_history(mtype)) {
 #pragma unroll
-    for (int i = 0; i < T; i++) P.be_n1[(size_t)i * ld + p] = be[i];
-    P.eps_n1[p] = eps;
-    P.kap_n1[p] = kap;
-    if (sp.rp.want_cep)
+      for (int i = 0; i < T; i++) P.be_n1[(size_t)i * ld + p] = be[i];
+      P.eps_n1[p] = eps;
+      if (MAT >= 0 || mtype != NLPS_MAT_VON_MISES) P.kap_n1[p] = kap;  // Von-Mises never touches Kappa
+      if (MAT < 0 && mtype == NLPS_MAT_VON_MISES && P.back) {
 #pragma unroll
-      for (int i = 0; i < D * D; i++) P.cep[(size_t)i * ld + p] = cep[i];
+        for (int i = 0; i < 3; i++) P.back[(size_t)i * ld + p] = back[i];
+      }
+      if (sp.rp.want_cep && mtype != NLPS_MAT_VON_MISES)
+#pragma unroll
+        for (int i = 0; i < D * D; i++) P.cep[(size_t)i * ld + p] = cep[i];
+    }
   }
 #pragma unroll
   for (int i = 0; i < T; i++) P.stress[(size_t)i * ld + p] = tau[i];

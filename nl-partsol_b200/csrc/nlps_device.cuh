@@ -18,6 +18,7 @@ struct MatParams {
   double K, G, lame;                               // bulk, shear and Lame moduli
   double dp_alpha_F, dp_alpha_Q, dp_beta, dp_ads;  // Drucker-Prager cone constants (plane strain or 3D) and sqrt(1 + 3 alpha_Q^2)
   double mn_c;                                     // Matsuoka-Nakai: cohesion / tan(phi)
+  double voce_theta, voce_K0, voce_Kinf, voce_delta;  // Von-Mises: theta / K_0 / K_inf / delta _Hardening_Voce (Types.h Material)
 };
 // Drucker-Prager.c:361-375 (cone constants), Neo-Hookean.c:17-35, Matsuoka-Nakai.c:320-340 (elastic constants)
 static inline void mat_hoist(MatParams& m, int ndim) {
@@ -693,5 +694,121 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
     W = 0.5 * (v[0] * Etr[0] + v[1] * Etr[1] + v[2] * Etr[2]);
   }
   corrector_be<D>(be, evec, Ek1);  // Ek1 == 0 in the elastic branch (:305,:699): b_e := I
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Von-Mises (J2) with linear + Voce isotropic and linear kinematic hardening, radial return in principal Hencky strains
+// (Constitutive/Plasticity/Von-Mises.c:228-391 and helpers :395-757).  Reproduced as compiled: the volumetric part is
+// K tr(E)/3 (:553-559); the elastic branch rotates with eigenvectors in columns (:616-617), the plastic branch with rows
+// (:717-718, SURVEY F10-i, rp.quirk_rows); `back` = Phi.Back_stress, PRINCIPAL components, updated in place.
+template <int D>
+__device__ inline int stress_von_mises(const MatParams& m, const ReturnMapParams& rp, const double* dphi, double* be,
+                                       double& eps, double* back, double* tau, double& W) {
+  double eval[3] = {0, 0, 0}, evec[D * D];
+  double Eh[3], Tvol[3], Tdev[3], Tp[3];
+  trial_be<D>(be, dphi, eval, evec);
+#pragma unroll
+  for (int i = 0; i < 3; i++) Eh[i] = 0.5 * log(eval[i]);
+  const double K = m.K, G = m.G, sigma_y = m.kappa_0, H = m.H, theta = m.voce_theta, dK = m.voce_Kinf - m.voce_K0,
+               delta = m.voce_delta;
+  const double Tb[3] = {back[0], back[1], back[2]};
+  const double eps_n = eps;
+  if (eps_n < 0.0) return NLPS_ERR_RETURN_MAP_VM;  // __kappa :646-647
+  const double trE = Eh[0] + Eh[1] + Eh[2];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double Ev = (1.0 / 3.0) * trE;
+    Tvol[i] = K * Ev;
+    Tdev[i] = 2 * G * (Eh[i] - Ev) - Tb[i];
+  }
+  const double J2 = sqrt(Tdev[0] * Tdev[0] + Tdev[1] * Tdev[1] + Tdev[2] * Tdev[2]);
+  const double s23 = sqrt(2. / 3.);
+  const double kin_n = (1 - theta) * H * eps_n;
+  double iso_k = sigma_y + theta * H * eps_n + dK * (1 - exp(-delta * eps_n)), kin_k = kin_n;
+  const double PHI_0 = J2 - s23 * (iso_k + kin_k - kin_n) - 2.0 * G * 0.0;
+  double dEp[3] = {0, 0, 0};
+  if (PHI_0 <= 0.0) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) Tp[i] = Tvol[i] + Tdev[i];  // :578-586 (the back stress is not added back)
+    spectral_sum<D>(Tp, evec, false, tau);
+  } else {
+    double n[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) n[i] = Tdev[i] / J2;
+    double PHI = PHI_0, dg = 0.0, eps_k = eps_n;
+    int Iter = 0;
+    while (fabs(PHI / PHI_0) >= rp.tol) {
+      Iter++;
+      if (Iter == rp.max_iter) break;
+      if (eps_k < 0.0) return NLPS_ERR_RETURN_MAP_VM;
+      const double d_iso = theta * H + delta * dK * exp(-delta * eps_k), d_kin = (1 - theta) * H;
+      const double d_PHI = -2.0 * G * (1.0 + (d_iso + d_kin) / (3 * G));
+      dg += -PHI / d_PHI;
+      eps_k = eps_n + s23 * dg;
+      if (eps_k < 0.0) return NLPS_ERR_RETURN_MAP_VM;
+      iso_k = sigma_y + theta * H * eps_k + dK * (1 - exp(-delta * eps_k));
+      kin_k = (1 - theta) * H * eps_k;
+      PHI = J2 - s23 * (iso_k + kin_k - kin_n) - 2.0 * G * dg;
+    }
+    const double dKkin = kin_k - kin_n;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Tp[i] = Tvol[i] + Tdev[i] + Tb[i] - dg * 2 * G * n[i];
+      dEp[i] = dg * n[i];
+      back[i] = Tb[i] + s23 * dKkin * n[i];
+    }
+    eps = eps_k;
+    spectral_sum<D>(Tp, evec, rp.quirk_rows != 0, tau);
+  }
+  if (D == 2) tau[4] = Tp[2];
+#pragma unroll
+  for (int i = 0; i < 3; i++) Eh[i] -= dEp[i];
+  corrector_be<D>(be, evec, Eh);
+  W = 0.5 * (Tp[0] * Eh[0] + Tp[1] * Eh[1] + Tp[2] * Eh[2]);
+  return 0;
+}
+
+// Hencky hyperelasticity (Constitutive/Hyperelastic/Hencky.c:30-93): b = F F^T (compute-Strains.c:365-384), principal
+// logarithmic strains (0 out of plane in 2D, :41), T = AA E, eigenvectors in columns (:242-284).
+template <int D>
+__device__ inline void stress_hencky(const MatParams& m, const double* F, double* tau, double& W) {
+  double b[D * D], eval[3] = {0, 0, 1.0}, evec[D * D], Eh[3], Tp[3];
+#pragma unroll
+  for (int i = 0; i < D; i++)
+#pragma unroll
+    for (int j = i; j < D; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; k++) s += F[i * D + k] * F[j * D + k];
+      b[i * D + j] = s;
+      b[j * D + i] = s;
+    }
+  if (D == 2) dsyev2_dev(b[0], b[1], b[3], eval, evec);
+  else jacobi3_dev(b, eval, evec);
+#pragma unroll
+  for (int i = 0; i < 3; i++) Eh[i] = 0.5 * log(eval[i]);
+  const double L = m.lame, L2G = m.lame + 2 * m.G;
+  Tp[0] = L2G * Eh[0] + L * Eh[1] + L * Eh[2];
+  Tp[1] = L * Eh[0] + L2G * Eh[1] + L * Eh[2];
+  Tp[2] = L * Eh[0] + L * Eh[1] + L2G * Eh[2];
+  spectral_sum<D>(Tp, evec, false, tau);
+  if (D == 2) tau[4] = Tp[2];
+  W = 0.5 * (Tp[0] * Eh[0] + Tp[1] * Eh[1] + Tp[2] * Eh[2]);
+}
+
+// Stress_integration__Constitutive__ (Constitutive.c:18-258) for every law except Neo-Hookean: which fields of the
+// history a law reads and writes.  `back` may be nullptr when the cloud holds no Von-Mises particle.
+__host__ __device__ __forceinline__ bool mat_has_history(int mtype) {
+  return mtype == NLPS_MAT_DRUCKER_PRAGER || mtype == NLPS_MAT_MATSUOKA_NAKAI || mtype == NLPS_MAT_VON_MISES;
+}
+template <int D>
+__device__ inline int stress_with_history(int mtype, const MatParams& m, const ReturnMapParams& rp, const double* DF,
+                                          const double* Fn1, double* be, double& eps, double& kap, double* back,
+                                          double* tau, double& W, double* cep) {
+  if (mtype == NLPS_MAT_DRUCKER_PRAGER) return stress_drucker_prager<D>(m, rp, DF, be, eps, kap, tau, W, cep);
+  if (mtype == NLPS_MAT_MATSUOKA_NAKAI) return stress_matsuoka_nakai<D>(m, rp, DF, be, eps, kap, tau, W, cep);
+  if (mtype == NLPS_MAT_VON_MISES) return stress_von_mises<D>(m, rp, DF, be, eps, back, tau, W);
+  stress_hencky<D>(m, Fn1, tau, W);
   return 0;
 }

@@ -1049,7 +1049,11 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
       const double rho_p = P.rho[p], V0 = P.vol0[p];
       const int mid = P.matidx[p];
       const bool plastic = (MAT >= 0) ? (MAT != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) : true;
-      double eps = 0.0, kap = 0.0;
+      double eps = 0.0, kap = 0.0, back[3] = {0.0, 0.0, 0.0};
+      if (MAT < 0 && P.back) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) back[i] = P.back[(size_t)i * np + p];
+      }
       if (plastic) {
 #pragma unroll
         for (int i = 0; i < T; i++) be[i] = P.be_n[(size_t)i * np + p];
@@ -1159,15 +1163,18 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
           double cep[D * D];
           if (MAT == NLPS_MAT_DRUCKER_PRAGER) st = stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
           else if (MAT == NLPS_MAT_MATSUOKA_NAKAI) st = stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
-          else st = (mtype == NLPS_MAT_DRUCKER_PRAGER) ? stress_drucker_prager<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep)
-                                                       : stress_matsuoka_nakai<D>(mat, sp.rp, DF, be, eps, kap, tau, Wp, cep);
+          else st = stress_with_history<D>(mtype, mat, sp.rp, DF, Fn1, be, eps, kap, back, tau, Wp, cep);
           if (st != 0) { latch_error(err, st, P.orig[p]); ok = false; }
-          if (ok) {
+          if (ok && (MAT >= 0 || mat_has_history(mtype))) {
 #pragma unroll
             for (int i = 0; i < T; i++) P.be_n1[(size_t)i * np + p] = be[i];
             P.eps_n1[p] = eps;
-            P.kap_n1[p] = kap;
-            if (sp.rp.want_cep)
+            if (MAT >= 0 || mtype != NLPS_MAT_VON_MISES) P.kap_n1[p] = kap;  // Von-Mises never touches Kappa
+            if (MAT < 0 && mtype == NLPS_MAT_VON_MISES && P.back) {
+#pragma unroll
+              for (int i = 0; i < 3; i++) P.back[(size_t)i * np + p] = back[i];
+            }
+            if (sp.rp.want_cep && (MAT >= 0 || mtype != NLPS_MAT_VON_MISES))
 #pragma unroll
               for (int i = 0; i < D * D; i++) P.cep[(size_t)i * np + p] = cep[i];
           }
@@ -1430,7 +1437,9 @@ template <int D>
 __global__ void k_sync_inert(PartDev P, const __grid_constant__ MatTable mt) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.np) return;
-  if (mt.m[P.matidx[p]].type != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) return;
+  const int mtype = mt.m[P.matidx[p]].type;
+  if (mtype == NLPS_MAT_VON_MISES) P.kap_n[p] = P.kap_n1[p];  // Von-Mises updates b_e and EPS but never Kappa
+  if (mat_has_history(mtype)) return;
   constexpr int TB = (D == 2) ? 5 : 9;
 #pragma unroll
   for (int i = 0; i < TB; i++) P.be_n[(size_t)i * P.ld + p] = P.be_n1[(size_t)i * P.ld + p];
@@ -1709,8 +1718,10 @@ __global__ void k_stress_points(int n, const __grid_constant__ MatTable mt, Retu
   double eps = eps_n[p], kap = kap_n[p];
   int st = 0;
   if (m.type == NLPS_MAT_NEO_HOOKEAN_WRIGGERS) stress_neo_hookean<D>(m, f1, J1[p], tau, Wp);
-  else if (m.type == NLPS_MAT_DRUCKER_PRAGER) st = stress_drucker_prager<D>(m, rp, df, be, eps, kap, tau, Wp, c);
-  else st = stress_matsuoka_nakai<D>(m, rp, df, be, eps, kap, tau, Wp, c);
+  else {
+    double back[3] = {0.0, 0.0, 0.0};  // material points carry no back stress: Von-Mises starts from zero
+    st = stress_with_history<D>(m.type, m, rp, df, f1, be, eps, kap, back, tau, Wp, c);
+  }
   status[p] = st;
 #pragma unroll
   for (int i = 0; i < T; i++) { stress[(size_t)p * T + i] = tau[i]; be_n1[(size_t)p * T + i] = be[i]; }
@@ -2291,7 +2302,7 @@ static void reorder_particles(nlps_engine* e) {
   gd(P.beta, 1); gd(P.mass, 1); gd(P.vol0, 1); gd(P.rho, 1); gd(P.W, 1);
   gd(P.J_n, 1); gd(P.J_n1, 1); gd(P.eps_n, 1); gd(P.eps_n1, 1); gd(P.kap_n, 1); gd(P.kap_n1, 1);
   gd(P.F_n, DD); gd(P.F_n1, DD); gd(P.DF, DD); gd(P.be_n, T); gd(P.be_n1, T); gd(P.stress, T); gd(P.cep, DD);
-  gd(P.Fs4, 1); gd(P.DFs4, 1); gd(P.area0, 1); gd(P.sstar, 1);
+  gd(P.Fs4, 1); gd(P.DFs4, 1); gd(P.area0, 1); gd(P.sstar, 1); gd(P.back, 3);
   gi(P.I0, 1); gi(P.nnodes, 1); gi(P.matidx, 1); gi(P.orig, 1); gi((int*)P.mask, e->W);
   k_after_sort<<<nblk(np, 256), 256, 0, e->stream>>>(P, e->G);
   e->launches++;
@@ -2449,6 +2460,7 @@ static int migrate_t(nlps_engine* e) {
   addd(P.F_n, DD); addd(P.F_n1, DD); addd(P.DF, DD); addd(P.be_n, T); addd(P.be_n1, T); addd(P.stress, T); addd(P.cep, DD);
   addd(P.Fs4, 1); addd(P.DFs4, 1);
   if (P.area0) addd(P.area0, 1);
+  if (P.back) addd(P.back, 3);
   addd(P.sstar, 1);
   addi(P.I0, 1); tab.back().is_int = 2;
   addi(P.nnodes, 1); addi(P.matidx, 1); addi(P.orig, 1); addi((int*)P.mask, e->W);
@@ -3015,11 +3027,13 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     memset(hm, 0, sizeof(hm));
     for (int i = 0; i < n_materials; i++) {
       const nlps_material& s = materials[i];
-      if (s.type < 0 || s.type > 2) return set_err(err, err_len, "unknown material type");
+      if (s.type < 0 || s.type > NLPS_MAT_HENCKY) return set_err(err, err_len, "unknown material type");
       hm[i] = MatParams{s.type, s.rho, s.E, s.nu, s.reference_pressure, s.kappa_0, s.hardening_modulus,
                         s.plastic_strain_0, s.phi_frictional, s.psi_frictional, s.exponent_hardening_ortiz,
                         s.cohesion, s.alpha_hardening_borja, s.a_hardening_borja[0], s.a_hardening_borja[1],
                         s.a_hardening_borja[2]};
+      hm[i].voce_theta = s.theta_hardening_voce; hm[i].voce_K0 = s.k_0_hardening_voce;
+      hm[i].voce_Kinf = s.k_inf_hardening_voce; hm[i].voce_delta = s.delta_hardening_voce;
       mat_hoist(hm[i], D);
       e->mat.m[i] = hm[i];
     }
@@ -3050,6 +3064,12 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
       return set_err(err, err_len, "3D Neumann loads act on Particle.Phi.Area_0 (U-Verlet.c:847-849): state->Area_0 is NULL");
     if (dev_alloc(e, &P.area0, (size_t)ld)) return 1;
   }
+  P.back = nullptr;
+  for (int i = 0; i < n_materials; i++)
+    if (materials[i].type == NLPS_MAT_VON_MISES && !P.back) {
+      if (dev_alloc(e, &P.back, (size_t)ld * 3)) return 1;
+      CUDA_OK(cudaMemsetAsync(P.back, 0, sizeof(double) * (size_t)ld * 3, e->stream));
+    }
   if (dev_alloc(e, &P.I0, ld) || dev_alloc(e, &P.nnodes, ld) || dev_alloc(e, &P.matidx, ld) ||
       dev_alloc(e, &P.orig, ld) || dev_alloc(e, &P.inv, std::max(e->n_global, 1)) || dev_alloc(e, &P.mask, (size_t)ld * e->W))
     return 1;
@@ -3131,7 +3151,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   }
   // ---- migration buffers
   {
-    const size_t row_bytes = 8 * (size_t)(6 * D + 11 + 4 * DD + 3 * T + 2 + 1 + (P.area0 ? 1 : 0)) + 4 * (size_t)(4 + e->W);
+    const size_t row_bytes = 8 * (size_t)(6 * D + 11 + 4 * DD + 3 * T + 2 + 1 + (P.area0 ? 1 : 0) + (P.back ? 3 : 0)) + 4 * (size_t)(4 + e->W);
     e->mig_cap = std::max(4096, ld / 8);
     if (dev_alloc(e, &e->mig_dest, ld) || dev_alloc(e, &e->mig_cnt, 16) || dev_alloc(e, &e->mig_tab, 256)) return 1;
     for (int s_ = 0; s_ < 2; s_++)
@@ -3321,7 +3341,8 @@ static int upload_impl(nlps_engine* e, const nlps_particles* in, int rows) {
       put_field(e, in->Vol_0, P.vol0, 1, 1, 0, rows) || put_field(e, in->W, P.W, 1, 1, 0, rows) ||
       put_field(e, in->EPS_n, P.eps_n, 1, 1, 0, rows) || put_field(e, in->EPS_n1, P.eps_n1, 1, 1, 0, rows) ||
       put_field(e, in->Kappa_n, P.kap_n, 1, 1, 0, rows) || put_field(e, in->Kappa_n1, P.kap_n1, 1, 1, 0, rows) ||
-      put_field(e, in->Beta, P.beta, 1, 1, 0, rows) || put_field(e, in->Area_0, P.area0, 1, 1, 0, rows))
+      put_field(e, in->Beta, P.beta, 1, 1, 0, rows) || put_field(e, in->Area_0, P.area0, 1, 1, 0, rows) ||
+      put_field(e, in->Back_stress, P.back, 3, 3, 0, rows))
     return 1;
   if (e->np) k_sstar_particles<<<nblk(e->np, 256), 256, 0, e->stream>>>(P.beta, e->np, e->neg_log_tol, P.sstar);
   return 0;
@@ -3362,7 +3383,8 @@ static int download_impl(nlps_engine* e, nlps_particles* out, int rows) {
       get_field(e, out->Vol_0, P.vol0, 1, 1, 0, nullptr, rows) || get_field(e, out->W, P.W, 1, 1, 0, nullptr, rows) ||
       get_field(e, out->EPS_n, P.eps_n, 1, 1, 0, nullptr, rows) || get_field(e, out->EPS_n1, eps1, 1, 1, 0, nullptr, rows) ||
       get_field(e, out->Kappa_n, P.kap_n, 1, 1, 0, nullptr, rows) || get_field(e, out->Kappa_n1, kap1, 1, 1, 0, nullptr, rows) ||
-      get_field(e, out->Beta, P.beta, 1, 1, 0, nullptr, rows))
+      get_field(e, out->Beta, P.beta, 1, 1, 0, nullptr, rows) ||
+      (P.back && get_field(e, out->Back_stress, P.back, 3, 3, 0, nullptr, rows)))
     return 1;
   if (get_ints(e, out->I0, P.I0, rows) || get_ints(e, out->NumberNodes, P.nnodes, rows)) return 1;
   return 0;
@@ -3565,7 +3587,7 @@ long long nlps_b200_launch_count(nlps_engine* e) { return e->launches; }
 // flush: the D2H copies run on dl_stream after the snapshot, while the compute stream is already stepping on.
 static int snapshot_prepare(nlps_engine* e) {
   const int D = e->D, T = e->T, DD = D * D;
-  const size_t per = 6 * (size_t)D + 6 * (size_t)T + DD + 11 + 2;
+  const size_t per = 6 * (size_t)D + 6 * (size_t)T + DD + 11 + 2 + 4;
   const size_t need = per * (size_t)std::max(e->np, 1) + 2 * 40;
   if (!e->dl_stream) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->dl_stream, cudaStreamNonBlocking));

@@ -1145,6 +1145,11 @@ extern "C" {
 int nlps_b200_newmark_setup(nlps_engine* e, const nlps_newmark* prm) {
   cudaSetDevice(e->device);
   if (!prm || (!prm->quasi_static && !(prm->beta > 0.0))) return 1;
+  for (int i = 0; i < MAX_MATERIALS; i++)
+    if (e->mat.m[i].type > NLPS_MAT_MATSUOKA_NAKAI) {
+      fprintf(stderr, "nlps_b200_newmark_setup: the implicit scheme has tangents for Neo-Hookean, Drucker-Prager and Matsuoka-Nakai only\n");
+      return 1;
+    }
   return imp_setup(e, prm);
 }
 

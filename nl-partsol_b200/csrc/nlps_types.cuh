@@ -56,6 +56,7 @@ struct PartDev {
   double *Fs4, *DFs4;  // 2D slot 4 of F / DF (never touched by the kinematics, Appendix B)
   double* trac;        // D x np: Neumann traction * A0 of the current step (allocated only with loads)
   double* area0;       // Phi.Area_0 (3D decks with Neumann loads only, else nullptr)
+  double* back;        // Phi.Back_stress, 3 principal components (clouds with a Von-Mises material only, else nullptr)
   // shape-function data of the current step, written by the LME kernel and read by the kinematics / force / G2P
   // kernels (same x_p, lambda, beta within a step): 1 / Z and the inverse Hessian J^-1 (symmetric, D(D+1)/2 entries)
   double *zi, *ji;

@@ -15,8 +15,8 @@
  *      include/nlps_b200.h -- the engine never frees or reallocates them (driver ownership,
  *      driver-nl-partsol.c:575-660);
  *   3. run the steps on the B200, copying fields back into those buffers before each
- *      particle_results_vtk__InOutFun__ call (every ResultsTimeStep steps, U-Verlet.c:1088-1227); the copy and the
- *      writer of output step k overlap the steps after k.
+ *      particle_results_vtk__InOutFun__ / nodal_results_vtk__InOutFun__ call (every ResultsTimeStep steps,
+ *      U-Verlet.c:1088-1227); the copy and the writers of output step k overlap the steps after k.
  *
  * Error convention as the reference: EXIT_SUCCESS / EXIT_FAILURE, RED message on stderr.
  */
@@ -139,6 +139,8 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
    * the B200 computes the steps after k.  The writer reads Phi and I0 / MatIdx only (WriteVtk.c:95-268), not the
    * neighbour chains, which are rebuilt once at the end (b200_finish). */
   int pending_out = -1;
+  b200_nodal nodal;
+  memset(&nodal, 0, sizeof(nodal));
   for (int TimeStep = Parameters_Solver.InitialTimeStep; TimeStep < NumTimeStep && STATUS == EXIT_SUCCESS;) {
     /* run up to (and including) the next output step in one go */
     int next_out = TimeStep;
@@ -154,6 +156,7 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
     if (pending_out >= 0) {
       if (nlps_b200_download_end(eng) != EXIT_SUCCESS) { STATUS = EXIT_FAILURE; break; }
       b200_write_particle_results(MPM_Mesh, pending_out, ResultsTimeStep);
+      b200_nodal_write(&nodal, FEM_Mesh, pending_out, ResultsTimeStep);
       pending_out = -1;
     }
     if (nlps_b200_sync(eng) != EXIT_SUCCESS) {
@@ -164,15 +167,23 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
     TimeStep += count;
     if (ResultsTimeStep > 0 && (TimeStep - 1) % ResultsTimeStep == 0) {
       /* output_selector (U-Verlet.c:1088-1227): vtk results read the host Fields */
-      if (nlps_b200_download_begin(eng, &in.st) != EXIT_SUCCESS) { STATUS = EXIT_FAILURE; break; }
+      if (nlps_b200_download_begin(eng, &in.st) != EXIT_SUCCESS ||
+          b200_nodal_capture(eng, &nodal, FEM_Mesh.NumNodesMesh, NumberDimensions) != EXIT_SUCCESS) {
+        STATUS = EXIT_FAILURE;
+        break;
+      }
       pending_out = TimeStep - 1;
     }
     print_Status("DONE !!!", TimeStep - 1);
   }
   if (STATUS == EXIT_SUCCESS && pending_out >= 0) {
     if (nlps_b200_download_end(eng) != EXIT_SUCCESS) STATUS = EXIT_FAILURE;
-    else b200_write_particle_results(MPM_Mesh, pending_out, ResultsTimeStep);
+    else {
+      b200_write_particle_results(MPM_Mesh, pending_out, ResultsTimeStep);
+      b200_nodal_write(&nodal, FEM_Mesh, pending_out, ResultsTimeStep);
+    }
   }
+  b200_nodal_release(&nodal);
 
   if (STATUS == EXIT_SUCCESS) STATUS = b200_finish(eng, &in, FEM_Mesh, MPM_Mesh);
 

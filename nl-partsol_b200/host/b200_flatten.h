@@ -73,6 +73,8 @@ static int material_to_pod(const Material *M, nlps_material *out) {
   if (strcmp(M->Type, "Neo-Hookean-Wriggers") == 0) out->type = NLPS_MAT_NEO_HOOKEAN_WRIGGERS;
   else if (strcmp(M->Type, "Drucker-Prager") == 0) out->type = NLPS_MAT_DRUCKER_PRAGER;
   else if (strcmp(M->Type, "Matsuoka-Nakai") == 0) out->type = NLPS_MAT_MATSUOKA_NAKAI;
+  else if (strcmp(M->Type, "Von-Mises") == 0) out->type = NLPS_MAT_VON_MISES;
+  else if (strcmp(M->Type, "Hencky") == 0) out->type = NLPS_MAT_HENCKY;
   else {
     /* same wording as Constitutive.c:250-254 */
     fprintf(stderr, "%s : %s %s %s \n", "Error in U_Verlet() [B200]", "The material", M->Type,
@@ -92,6 +94,10 @@ static int material_to_pod(const Material *M, nlps_material *out) {
   out->cohesion = M->Cohesion;
   out->alpha_hardening_borja = M->alpha_Hardening_Borja;
   for (int k = 0; k < 3; k++) out->a_hardening_borja[k] = M->a_Hardening_Borja[k];
+  out->theta_hardening_voce = M->theta_Hardening_Voce;
+  out->k_0_hardening_voce = M->K_0_Hardening_Voce;
+  out->k_inf_hardening_voce = M->K_inf_Hardening_Voce;
+  out->delta_hardening_voce = M->delta_Hardening_Voce;
   return EXIT_SUCCESS;
 }
 
@@ -190,6 +196,7 @@ static int b200_flatten(b200_inputs *in, Mesh FEM_Mesh, Particle MPM_Mesh, Time_
   st.EPS_n = Phi->EPS_n; st.EPS_n1 = Phi->EPS_n1; st.Kappa_n = Phi->Kappa_n; st.Kappa_n1 = Phi->Kappa_n1;
   st.lambda = MPM_Mesh.lambda.nV; st.Beta = MPM_Mesh.Beta.nV;
   st.I0 = MPM_Mesh.I0; st.NumberNodes = MPM_Mesh.NumberNodes; st.MatIdx = MPM_Mesh.MatIdx;
+  st.Back_stress = Phi->Back_stress.nV; /* Von-Mises kinematic hardening (U-Analisys.c:152, Constitutive.c:116) */
   /* 3D Neumann loads act on Phi.Area_0 (U-Verlet.c:847-849); the reference declares the field (Types.h:196) and never
    * allocates it, so a 3D deck with loads fails loudly in nlps_b200_create instead of reading a volume as an area */
 #if NumberDimensions == 3
@@ -202,6 +209,62 @@ static int b200_flatten(b200_inputs *in, Mesh FEM_Mesh, Particle MPM_Mesh, Time_
   in->mats = mats; in->st = st; in->r1p = r1p; in->r1i = r1i; in->r2p = r2p; in->r2i = r2i;
   in->n_bounds = FEM_Mesh.Bounds.NumBounds; in->n_neumann = MPM_Mesh.Neumann_Contours.NumBounds;
   return EXIT_SUCCESS;
+}
+
+/* The nodal results file of a results step (nodal_results_vtk__InOutFun__, InOutFun/Outputs/WriteVtk.c:270-430, called by
+ * output_selector U-Verlet.c:1134): mesh, the ActiveNodes mask and the reactions.  The scheme shims step on while the
+ * files of step k are written, so the two nodal arrays of step k are captured (two small device -> host copies, n_nodes x
+ * (d doubles + 1 byte)) before the next chunk of steps is enqueued and written later, beside the particle file.
+ * NLPS_B200_NO_NODAL_VTK=1 skips the file. */
+typedef struct b200_nodal {
+  int nn, d, valid;
+  double *R;
+  unsigned char *act;
+} b200_nodal;
+
+static int b200_nodal_wanted(void) {
+  const char *s = getenv("NLPS_B200_NO_NODAL_VTK");
+  return !(s && atoi(s) != 0);
+}
+
+static int b200_nodal_capture(nlps_engine *eng, b200_nodal *s, int nn, int d) {
+  s->valid = 0;
+  if (!b200_nodal_wanted()) return EXIT_SUCCESS;
+  if (s->R == NULL) {
+    s->nn = nn; s->d = d;
+    s->R = (double *)malloc(sizeof(double) * (size_t)nn * d);
+    s->act = (unsigned char *)malloc((size_t)nn);
+    if (!s->R || !s->act) return EXIT_FAILURE;
+  }
+  if (nlps_b200_get_nodal(eng, 4, s->R) != EXIT_SUCCESS || nlps_b200_get_active(eng, s->act) != EXIT_SUCCESS)
+    return EXIT_FAILURE;
+  s->valid = 1;
+  return EXIT_SUCCESS;
+}
+
+static void b200_nodal_write(b200_nodal *s, Mesh FEM_Mesh, int TimeStep_i, int ResultsTimeStep_) {
+  if (!s->valid) return;
+  /* generate_NodalMask__MeshTools__ (Nodes-Tools.c:46-84): active nodes numbered in node order, -1 elsewhere */
+  Mask ActiveNodes;
+  ActiveNodes.Nodes2Mask = (int *)malloc(sizeof(int) * (size_t)s->nn);
+  int na = 0;
+  for (int i = 0; i < s->nn; i++) ActiveNodes.Nodes2Mask[i] = s->act[i] ? na++ : -1;
+  ActiveNodes.Nactivenodes = na;
+  Matrix Reactions = allocZ__MatrixLib__(na > 0 ? na : 1, s->d);
+  for (int i = 0; i < s->nn; i++) {
+    const int m = ActiveNodes.Nodes2Mask[i];
+    if (m < 0) continue;
+    for (int k = 0; k < s->d; k++) Reactions.nM[m][k] = s->R[(size_t)i * s->d + k];
+  }
+  nodal_results_vtk__InOutFun__(FEM_Mesh, ActiveNodes, Reactions, TimeStep_i, ResultsTimeStep_);
+  free__MatrixLib__(Reactions);
+  free(ActiveNodes.Nodes2Mask);
+  s->valid = 0;
+}
+
+static void b200_nodal_release(b200_nodal *s) {
+  free(s->R); free(s->act);
+  s->R = NULL; s->act = NULL; s->valid = 0;
 }
 
 static void b200_release(b200_inputs *in) {

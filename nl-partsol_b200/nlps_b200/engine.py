@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 from . import build as _build
-from .problem import MATERIAL_TYPES, Problem
+from .problem import MATERIAL_TYPES, Problem, material_params
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -31,7 +31,9 @@ class Material(C.Structure):
                 ("hardening_modulus", C.c_double), ("plastic_strain_0", C.c_double),
                 ("phi_frictional", C.c_double), ("psi_frictional", C.c_double),
                 ("exponent_hardening_ortiz", C.c_double), ("cohesion", C.c_double),
-                ("alpha_hardening_borja", C.c_double), ("a_hardening_borja", C.c_double * 3)]
+                ("alpha_hardening_borja", C.c_double), ("a_hardening_borja", C.c_double * 3),
+                ("theta_hardening_voce", C.c_double), ("k_0_hardening_voce", C.c_double),
+                ("k_inf_hardening_voce", C.c_double), ("delta_hardening_voce", C.c_double)]
 
 
 class Solver(C.Structure):
@@ -49,7 +51,8 @@ _PFIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "F_n1", "DF", "b_e_n", 
 
 class Particles(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, _dp) for k in _PFIELDS] + [("I0", _ip), ("NumberNodes", _ip),
-                                                                  ("MatIdx", _ip), ("Area_0", _dp)]
+                                                                  ("MatIdx", _ip), ("Area_0", _dp),
+                                                                  ("Back_stress", _dp)]
 
 
 class Msg(C.Structure):
@@ -121,6 +124,8 @@ def _material(t, p):
      m.alpha_hardening_borja) = [float(v) for v in p[:12]]
     for k in range(3):
         m.a_hardening_borja[k] = float(p[12 + k])
+    q = material_params(p)
+    m.theta_hardening_voce, m.k_0_hardening_voce, m.k_inf_hardening_voce, m.delta_hardening_voce = [float(v) for v in q[16:20]]
     return m
 
 
@@ -315,6 +320,9 @@ class _Marshal:
         if "Area_0" in prob.fields:  # 3D Neumann loads (Phi.Area_0); constant, never downloaded
             host["Area_0"] = cp(_d(prob.fields["Area_0"]))
             st.Area_0 = host["Area_0"].ctypes.data_as(_dp)
+        if "Back_stress" in prob.fields:  # Von-Mises kinematic hardening (Phi.Back_stress, n x 3)
+            host["Back_stress"] = cp(_d(prob.fields["Back_stress"]))
+            st.Back_stress = host["Back_stress"].ctypes.data_as(_dp)
         return st, host
 
 
@@ -395,6 +403,8 @@ class Engine:
             setattr(st, k, host[k].ctypes.data_as(_dp) if k in host else None)
         for k in ("I0", "MatIdx", "NumberNodes"):
             setattr(st, k, host[k].ctypes.data_as(_ip))
+        if "Back_stress" in host:
+            st.Back_stress = host["Back_stress"].ctypes.data_as(_dp)
         ids = np.zeros(max(n, 1), np.int32)
         assert self.L.nlps_b200_download_local(self.h, C.byref(st), ids.ctypes.data_as(_ip)) == 0
         return {k: v[:n] for k, v in host.items()}, ids[:n].copy()

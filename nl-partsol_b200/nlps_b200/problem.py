@@ -13,11 +13,21 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-MATERIAL_TYPES = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2}
-# order of the 16-slot material parameter block (oracle/ref_harness.c refh_material_params)
+MATERIAL_TYPES = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2, "Von-Mises": 3, "Hencky": 4}
+# order of the material parameter block (oracle/ref_harness.c refh_material_params; slots 16..19 = the Voce hardening
+# parameters of Von-Mises, refh_material_voce; blocks of 16 are padded with their defaults theta = 1, 0, 0, 0)
 MATERIAL_SLOTS = ("rho", "E", "nu", "ReferencePressure", "kappa_0", "Hardening_modulus",
                   "Plastic_Strain_0", "phi_Frictional", "psi_Frictional", "Exponent_Hardening_Ortiz",
-                  "Cohesion", "alpha_Hardening_Borja", "a1", "a2", "a3", "J2_degradated")
+                  "Cohesion", "alpha_Hardening_Borja", "a1", "a2", "a3", "J2_degradated",
+                  "theta_Hardening_Voce", "K_0_Hardening_Voce", "K_inf_Hardening_Voce", "delta_Hardening_Voce")
+
+
+def material_params(p):
+    """The 20-slot block of a material given 16 or 20 numbers."""
+    p = [float(v) for v in p]
+    if len(p) < 20:
+        p = (p + [0.0] * 16)[:16] + [1.0, 0.0, 0.0, 0.0]
+    return np.array(p[:20])
 
 VECTOR_FIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "lambda")
 TENSOR_FIELDS = ("F_n", "F_n1", "DF", "b_e_n", "b_e_n1", "Stress")
@@ -94,6 +104,8 @@ class Problem:
         is_mn = np.array([m[0] == "Matsuoka-Nakai" for m in self.materials])[self.MatIdx]
         eps0 = np.array([m[1][6] for m in self.materials])[self.MatIdx]
         f["EPS_n"] = np.where(is_mn, eps0, 0.0)
+        if any(m[0] == "Von-Mises" for m in self.materials):
+            f["Back_stress"] = np.zeros((n, 3))  # Phi.Back_stress (U-Analisys.c:152), principal components
         self.fields = f
 
     # ---- npz (golden fixtures)
@@ -105,7 +117,7 @@ class Problem:
                    solver_vals=np.array([float(v) for v in self.solver.values()]),
                    n_bounds=len(self.bounds), n_neumann=len(self.neumann),
                    mat_types=np.array([m[0] for m in self.materials]),
-                   mat_params=np.array([m[1] for m in self.materials]))
+                   mat_params=np.array([material_params(m[1]) for m in self.materials]))
         if self.conn is not None:
             out["conn"] = self.conn
         for i, b in enumerate(self.bounds):

@@ -127,10 +127,13 @@ def structured_problem(ndim, grid_cells, h, block_cells, block_origin_cell, mate
 
 DP_C2 = ("Drucker-Prager", [2000.0, 1e7, 0.3, 0.0, 1e4, 1.0, 1e-2, 30.0, 0.0, 1.0, 0, 0, 0, 0, 0, 0])
 NH_C1 = ("Neo-Hookean-Wriggers", [1000.0, 1e6, 0.3] + [0.0] * 13)
+# SURVEY 8(f)-4 laws.  Von-Mises: slots 4 / 5 = Yield-stress / Hardening-Modulus, 16..19 = theta, K-0, K-inf, delta (Voce)
+VM_SOFT = ("Von-Mises", [2000.0, 1e6, 0.3, 0.0, 400.0, 2e4] + [0.0] * 10 + [0.6, 20.0, 150.0, 40.0])
+HENCKY_C1 = ("Hencky", [1000.0, 1e6, 0.3] + [0.0] * 13)
 MN_C4 = ("Matsuoka-Nakai", [2000.0, 1e7, 0.3, 0.0, 8.0 / 3.0, 0.0, 0.0, 30.0, 0.0, 0.0, 1e3, 0.5, 20000.0, 0.005, 35.0, 0.0])
 
 
-def column_collapse_2d(scale=1.0, nsteps=1000):
+def column_collapse_2d(scale=1.0, nsteps=1000, material=None):
     """BASELINE configs[1]: 2D granular column (aspect 2, 0.2 m x 0.4 m) of Drucker-Prager material
     released in a box 6 column-widths wide with a fixed base and frictionless sides.  scale=1 ->
     354 x 708 particle cells x GPxElement 4 = 1,002,528 particles (the 10^6 of BASELINE.json; SURVEY
@@ -139,7 +142,7 @@ def column_collapse_2d(scale=1.0, nsteps=1000):
     by = 2 * bx
     nx, ny = 6 * bx, by + by // 4
     h = 0.2 / bx
-    return structured_problem(2, (nx, ny), h, (bx, by), (0, 0), DP_C2, nsteps, 0.5, (1e7 / 2000.0) ** 0.5 * 1.3,
+    return structured_problem(2, (nx, ny), h, (bx, by), (0, 0), material or DP_C2, nsteps, 0.5, (1e7 / 2000.0) ** 0.5 * 1.3,
                               (0.0, -9.81))
 
 

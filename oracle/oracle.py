@@ -14,7 +14,7 @@ _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
 _up = ctypes.POINTER(ctypes.c_ubyte)
 
-MAT = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2}
+MAT = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2, "Von-Mises": 3, "Hencky": 4}
 STAGES = dict(search=0, p2g_mass_disp=1, grid_disp=2, kin_stress=3, force=4, grid_acc=5, g2p=6)
 
 
@@ -97,9 +97,12 @@ class Oracle:
                               v.ctypes.data_as(_dp))
         g = _d(prob.gravity)
         L.orc_set_gravity(h, g.ctypes.data_as(_dp))
-        for t, p in prob.materials:
+        for j, (t, p) in enumerate(prob.materials):
             p = _d(p)
             L.orc_add_material(h, MAT[t], p.ctypes.data_as(_dp))
+            if len(p) >= 20:  # Voce hardening of Von-Mises (slots 16..19)
+                v = _d(p[16:20])
+                L.orc_set_material_voce(h, j, v.ctypes.data_as(_dp))
         self.np_ = prob.np_
         L.orc_set_num_particles(h, self.np_)
         for k, v in prob.fields.items():

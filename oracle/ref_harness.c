@@ -213,6 +213,12 @@ void refh_material_params(int m, double *out) {
   out[12] = M.a_Hardening_Borja[0]; out[13] = M.a_Hardening_Borja[1];
   out[14] = M.a_Hardening_Borja[2]; out[15] = M.J2_degradated;
 }
+/* out[4]: the Voce hardening parameters of Von-Mises (theta, K_0, K_inf, delta) */
+void refh_material_voce(int m, double *out) {
+  Material M = MPM_Mesh.Mat[m];
+  out[0] = M.theta_Hardening_Voce; out[1] = M.K_0_Hardening_Voce;
+  out[2] = M.K_inf_Hardening_Voce; out[3] = M.delta_Hardening_Voce;
+}
 
 /* ------------------------------ particle fields ------------------------- */
 static double *field_ptr(const char *name, int *cols) {
@@ -243,6 +249,7 @@ static double *field_ptr(const char *name, int *cols) {
   if (!strcmp(name, "Kappa_n1")) return P->Kappa_n1;
   if (!strcmp(name, "lambda")) { *cols = d; return MPM_Mesh.lambda.nV; }
   if (!strcmp(name, "Beta")) return MPM_Mesh.Beta.nV;
+  if (!strcmp(name, "Back_stress")) { *cols = 3; return P->Back_stress.nV; }
   return NULL;
 }
 int refh_field_cols(const char *name) { int c; return field_ptr(name, &c) ? c : -1; }

@@ -38,6 +38,11 @@ MATERIALS = {
     "mn": ("Matsuoka-Nakai", {"rho": 2000.0, "E": 1e7, "nu": 0.3, "alpha": 0.5, "a1": 20000.0,
                               "a2": 0.005, "a3": 35.0, "Friction-angle": 30.0, "Cohesion": 1e3,
                               "kappa-0": 8.0 / 3.0}, 1.2 * (1e7 / 2000) ** 0.5),
+    # the next laws of the K2 slot.  Von-Mises with mixed isotropic (linear + Voce) / kinematic hardening
+    # (Constitutive/Plasticity/Von-Mises.c), Hencky (Constitutive/Hyperelastic/Hencky.c)
+    "vm": ("Von-Mises", {"rho": 2000.0, "E": 1e6, "nu": 0.3, "Yield-stress": 1500.0, "Hardening-Modulus": 2e4,
+                         "theta": 0.6, "K-0": 100.0, "K-inf": 600.0, "delta": 40.0}, (1e7 / 2000) ** 0.5),
+    "hencky": ("Hencky", dict(rho=1000.0, E=1.0e6, nu=0.3), None),
 }
 POINT_MATERIALS = {
     "dp": ("Drucker-Prager", {"rho": 2000.0, "E": 1e4, "nu": 0.2, "m": 1.0, "Hardening-modulus": 0.1,
@@ -46,7 +51,8 @@ POINT_MATERIALS = {
                               "a2": 0.005, "a3": 35.0, "Friction-angle": 30.0, "Cohesion": 1e3,
                               "kappa-0": 8.0 / 3.0}),
 }
-CHECKPOINTS = {"nh": (1, 2, 5, 20, 60), "dp": (1, 2, 5, 20, 60, 120), "mn": (1, 2, 5, 20, 60)}
+CHECKPOINTS = {"nh": (1, 2, 5, 20, 60), "dp": (1, 2, 5, 20, 60, 120), "mn": (1, 2, 5, 20, 60),
+               "vm": (1, 2, 5, 20, 60, 120), "hencky": (1, 5, 60)}
 TRACE_FIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "DF", "Stress", "rho", "J_n", "W", "b_e_n",
                 "EPS_n", "Kappa_n", "lambda", "Beta", "C_ep")
 
@@ -76,6 +82,8 @@ def gen_sim(case):
             t = f"s{k + 1}_"
             for f in TRACE_FIELDS:
                 trace[t + f] = h.field(f)
+            if case == "vm":
+                trace[t + "Back_stress"] = h.field("Back_stress")
             for w, nm in enumerate(("M", "dU", "F", "A", "R")):
                 trace[t + "g" + nm] = h.nodal(w)
             lp, li = h.table(4)
@@ -465,7 +473,7 @@ if __name__ == "__main__":
     if len(sys.argv) == 3:
         {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d, "config": gen_config}[sys.argv[1]](sys.argv[2])
     else:
-        for c in ("nh", "dp", "mn"):
+        for c in ("nh", "dp", "mn", "vm", "hencky"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
                            if os.environ.get("QUIET") else None)
         for c in ("dp", "mn"):

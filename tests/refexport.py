@@ -33,6 +33,8 @@ def problem_from_ref(h, conn=None) -> Problem:
     p.bounds = h.bounds()
     p.materials = [h.material(m) for m in range(h.lib.refh_num_materials())]
     p.fields = {k: h.field(k) for k in ALL_FIELDS}
+    if any(t == "Von-Mises" for t, _ in p.materials):
+        p.fields["Back_stress"] = h.field("Back_stress")
     p.I0 = h.ints("I0")
     p.MatIdx = h.ints("MatIdx")
     if conn is None:

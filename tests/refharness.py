@@ -90,7 +90,12 @@ class RefHarness:
     def material(self, m=0):
         p = np.zeros(16)
         self.lib.refh_material_params(m, p.ctypes.data_as(_dp))
-        return self.lib.refh_material_type(m).decode(), p
+        t = self.lib.refh_material_type(m).decode()
+        if t == "Von-Mises" and hasattr(self.lib, "refh_material_voce"):
+            v = np.zeros(4)
+            self.lib.refh_material_voce(m, v.ctypes.data_as(_dp))
+            p = np.concatenate([p, v])
+        return t, p
 
     # ---- particles
     def field(self, name: str):

@@ -15,6 +15,12 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "nl-partsol-b200")
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 
 
+def _particle_vtk(d, k):
+    """particle results files of step k (the nodal file Nodes_k.vtk lies beside them)"""
+    return [f for f in glob.glob(os.path.join(str(d), "Results", f"*_{k}.vtk"))
+            if not os.path.basename(f).startswith("Nodes_")]
+
+
 def _points(vtk):
     lines = open(vtk).read().splitlines()
     i = next(k for k, l in enumerate(lines) if l.startswith("POINTS"))
@@ -23,25 +29,46 @@ def _points(vtk):
 
 
 @pytest.mark.gpu
-def test_reference_driver_with_b200_scheme(tmp_path):
+@pytest.mark.parametrize("case", ("nh", "vm"))
+def test_reference_driver_with_b200_scheme(tmp_path, case):
+    """nh: the Neo-Hookean block; vm: a Von-Mises deck (mixed isotropic / kinematic hardening: the back stress lives in
+    the reference's own Phi.Back_stress buffer and is handed to the engine by the shim)."""
     if not os.path.exists(BIN):
         pytest.skip("drop-in binary not built (needs /root/reference at build time)")
     import deckgen
     import make_golden
     from util import load_trace
-    spec = make_golden.spec_for("nh")
+    spec = make_golden.spec_for(case)
     spec.out_every = 1
     deckgen.write_deck(spec, str(tmp_path))
     r = subprocess.run([BIN, "--FORMULATION-U", "-f", "deck.nlp"], cwd=str(tmp_path), capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "abnormally" not in r.stdout + r.stderr
-    tr = load_trace("nh")
+    tr = load_trace(case)
     for cp in (1, 2, 5, 20, 60):
-        files = glob.glob(os.path.join(str(tmp_path), "Results", f"*_{cp - 1}.vtk"))
+        files = _particle_vtk(tmp_path, cp - 1)
         assert files, f"no VTK for step {cp - 1}"
         x = _points(files[0])
         assert np.abs(x - tr[f"s{cp}_x_GC"]).max() <= 1e-10 * np.abs(tr[f"s{cp}_x_GC"]).max()
+        # the nodal file of the same step (nodal_results_vtk__InOutFun__: ActiveNodes mask + reactions, %.20g)
+        nodal = os.path.join(str(tmp_path), "Results", f"Nodes_{cp - 1}.vtk")
+        assert os.path.exists(nodal), "no nodal VTK file"
+        mask, R = _nodal(nodal)
+        assert np.array_equal(mask, tr[f"s{cp}_active"].astype(np.int64))
+        gR = tr[f"s{cp}_gR"]
+        assert np.abs(R[:, :2] - gR).max() <= 1e-10 * max(np.abs(gR).max(), 1e-300)
+
+
+def _nodal(vtk):
+    lines = open(vtk).read().splitlines()
+    i = next(k for k, l in enumerate(lines) if l.startswith("POINT_DATA"))
+    n = int(lines[i].split()[1])
+    j = next(k for k, l in enumerate(lines) if l.startswith("LOOKUP_TABLE"))
+    mask = np.array([int(lines[j + 1 + k]) for k in range(n)])
+    r = next(k for k, l in enumerate(lines) if l.startswith("VECTORS REACTIONS"))
+    R = np.array([[float(v) for v in lines[r + 1 + k].split()[:3]] for k in range(n)])
+    return mask, R
 
 
 @pytest.mark.gpu
@@ -63,7 +90,7 @@ def test_reference_driver_binary_vtk_output(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     tr = load_trace("dp")
     for cp in (1, 5, 60, 120):
-        files = glob.glob(os.path.join(str(tmp_path), "Results", f"*_{cp - 1}.vtk"))
+        files = _particle_vtk(tmp_path, cp - 1)
         assert files, f"no VTK for step {cp - 1}"
         assert b"BINARY" in open(files[0], "rb").read(200)
         v = vtkio.read_binary(files[0])
@@ -107,7 +134,7 @@ def test_reference_driver_with_b200_implicit_scheme(tmp_path):
     o.newmark_setup(tol=tol, max_iter=25)
     for k in range(nsteps):
         assert o.newmark_step(k) == 0, o.error()
-        files = glob.glob(os.path.join(str(tmp_path), "Results", f"*_{k}.vtk"))
+        files = _particle_vtk(tmp_path, k)
         assert files, f"no VTK for step {k}"
         x = _points(files[0])
         assert np.abs(x - o.field("x_GC")).max() <= 1e-8 * np.abs(o.field("x_GC")).max(), k
@@ -144,7 +171,7 @@ def test_reference_driver_with_b200_static_scheme(tmp_path):
     o.static_setup(tol=tol, max_iter=25)
     for k in range(nsteps):
         assert o.newmark_step(k) == 0, o.error()
-        files = glob.glob(os.path.join(str(tmp_path), "Results", f"*_{k}.vtk"))
+        files = _particle_vtk(tmp_path, k)
         assert files, f"no VTK for step {k}"
         x = _points(files[0])
         assert np.abs(x - o.field("x_GC")).max() <= 1e-8 * np.abs(o.field("x_GC")).max(), k
@@ -172,7 +199,7 @@ def test_reference_driver_on_two_gpus_from_the_c_host(tmp_path):
                            timeout=600, env=dict(os.environ, **env))
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "abnormally" not in r.stdout + r.stderr
-        runs[tag] = {k: _points(glob.glob(os.path.join(str(d), "Results", f"*_{k}.vtk"))[0]) for k in (0, 20)}
+        runs[tag] = {k: _points(_particle_vtk(d, k)[0]) for k in (0, 20)}
     for k in (0, 20):
         a, b = runs["one"][k], runs["two"][k]
         assert a.shape == b.shape and np.abs(a - b).max() <= 1e-10 * np.abs(a).max(), k
@@ -209,6 +236,6 @@ def test_reference_driver_scalable_setup_at_100k_particles(tmp_path):
     assert o.init_lme() == 0
     for k in range(nsteps):
         assert o.step(k) == 0, o.error()
-    x = _points(glob.glob(os.path.join(str(tmp_path), "Results", "*_20.vtk"))[0])
+    x = _points(_particle_vtk(tmp_path, 20)[0])
     ref = o.field("x_GC")
     assert x.shape == ref.shape and np.abs(x - ref).max() <= 1e-10 * np.abs(ref).max()

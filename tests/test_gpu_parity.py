@@ -37,7 +37,7 @@ def test_initialize_lme_matches_reference(case):
     eng.close()
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + ("vm", "hencky"))
 def test_steps_match_golden_reference(case):
     """Multi-step run against fixtures produced by the reference's compiled code."""
     P = load_problem(case)
@@ -56,10 +56,12 @@ def test_steps_match_golden_reference(case):
         assert np.array_equal(counts, tr[t + "NumberNodes"]), f"NumberNodes at step {cp}"
         assert np.array_equal(lists[:, :tr[t + "lists"].shape[1]], tr[t + "lists"]), f"lists at step {cp}"
         assert np.array_equal(eng.active(), tr[t + "active"])
-        for name in TRACE_FIELDS:
+        for name in TRACE_FIELDS + (("Back_stress",) if case == "vm" else ()):
             assert_close(f[name], tr[t + name], f"{case} step {cp} {name}", scale=scales.get(name))
         for w, nm in enumerate(NODAL):
             assert_close(eng.nodal(w), tr[t + "g" + nm], f"{case} step {cp} nodal {nm}", scale=scales["g" + nm])
+    if case == "vm":
+        assert (f["EPS_n"] > 0).sum() > 50 and np.abs(f["Back_stress"]).max() > 0
     eng.close()
 
 
@@ -304,7 +306,8 @@ def test_u_verlet_results_callback_sees_its_own_step(sync_io, monkeypatch):
     eng.close()
 
 
-@pytest.mark.parametrize("name", ("column2d_dp", "block2d_nh", "cube3d_nh", "cube3d_dp", "cube3d_mn"))
+@pytest.mark.parametrize("name", ("column2d_dp", "block2d_nh", "cube3d_nh", "cube3d_dp", "cube3d_mn", "cube3d_vm",
+                                  "cube3d_hencky", "column2d_vm"))
 def test_synthetic_clouds_against_oracle(name):
     """Synthetic inputs of the bench shapes (2D and 3D) through engine and oracle.  3D has no
     compilable reference: this is parity with the restatement, physics checks included."""
@@ -313,8 +316,13 @@ def test_synthetic_clouds_against_oracle(name):
                 block2d_nh=lambda: synthetic.block_2d(cells=12, nsteps=12),
                 cube3d_nh=lambda: synthetic.cube_3d(cells=5, nsteps=8),
                 cube3d_dp=lambda: synthetic.cube_3d(cells=5, nsteps=8, material=synthetic.DP_C2),
-                cube3d_mn=lambda: synthetic.cube_3d(cells=5, nsteps=8, material=synthetic.MN_C4))[name]
+                cube3d_mn=lambda: synthetic.cube_3d(cells=5, nsteps=8, material=synthetic.MN_C4),
+                cube3d_vm=lambda: synthetic.cube_3d(cells=5, nsteps=12, material=synthetic.VM_SOFT),
+                cube3d_hencky=lambda: synthetic.cube_3d(cells=5, nsteps=8, material=synthetic.HENCKY_C1),
+                column2d_vm=lambda: synthetic.column_collapse_2d(scale=0.03, nsteps=12, material=synthetic.VM_SOFT))[name]
     P = make()
+    if name.endswith("_vm"):  # a push that takes the cloud past the yield surface within the run
+        P.fields["vel"][:, -1] = -0.1 * P.solver["cel"]
     n = P.nsteps
     eng = engine.Engine(P, compute_c_ep=1)
     o = oracle.Oracle(P)
@@ -330,10 +338,12 @@ def test_synthetic_clouds_against_oracle(name):
     assert np.array_equal(counts, o.ints("NumberNodes")) and np.array_equal(lists, o.lists())
     assert np.array_equal(eng.active(), o.active())
     sc = field_scales(P)
-    for nm in TRACE_FIELDS:
+    for nm in TRACE_FIELDS + (("Back_stress",) if name.endswith("_vm") else ()):
         assert_close(f[nm], o.field(nm), f"{name} {nm}", scale=sc.get(nm))
     for w, nm in enumerate(NODAL):
         assert_close(eng.nodal(w), o.nodal(w), f"{name} nodal {nm}", scale=sc["g" + nm])
+    if name.endswith("_vm"):
+        assert (f["EPS_n"] > 0).sum() > 20 and np.abs(f["Back_stress"]).max() > 0, "the Von-Mises cloud must yield"
     m0 = P.fields["mass"].sum()
     assert abs(eng.nodal(0)[:, 0].sum() - m0) <= 1e-12 * m0       # partition of unity on the device
     eng.close()

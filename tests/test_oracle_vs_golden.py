@@ -36,7 +36,7 @@ def test_initialize_lme(case):
         assert np.abs(dN.sum(0)).max() < 1e-6
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + ("vm", "hencky"))
 def test_steps_match_reference(case):
     P = load_problem(case)
     tr = load_trace(case)
@@ -52,8 +52,12 @@ def test_steps_match_reference(case):
         assert np.array_equal(o.ints("NumberNodes"), tr[t + "NumberNodes"])
         assert np.array_equal(o.lists()[:, :tr[t + "lists"].shape[1]], tr[t + "lists"]), f"lists step {k + 1}"
         assert np.array_equal(o.active(), tr[t + "active"])
-        for f in TRACE_FIELDS + ("C_ep",):
+        # (Von-Mises: the reference's elastic branch builds C_ep from an uninitialised kappa_k, Von-Mises.c:262,377 --
+        # the explicit scheme never reads it; its back stress is compared instead)
+        for f in TRACE_FIELDS + (("Back_stress",) if case == "vm" else ("C_ep",)):
             assert_close(o.field(f), tr[t + f], f"{case} step {k + 1} {f}", scale=scales.get(f))
+            if case in ("vm", "hencky"):
+                assert np.array_equal(o.field(f), tr[t + f]), f"{case} step {k + 1} {f}: not bit-exact"
         for w, nm in enumerate(NODAL):
             assert_close(o.nodal(w), tr[t + "g" + nm], f"{case} step {k + 1} nodal {nm}")
 
