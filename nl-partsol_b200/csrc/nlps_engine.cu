@@ -1933,6 +1933,35 @@ static int comm_all_ok(nlps_comm* c, int rank, int world, int ok, int* d_buf, cu
 }
 
 
+// Element-wise sum of a short device vector over all slabs, result identical (bit for bit) on every slab.  NCCL: one
+// ncclAllReduce on the engine's stream, no host round trip.  Custom transports only know neighbour exchanges: every
+// slab's vector travels along the chain (world - 1 rounds, both directions) into a table tab[(world + 1) x n] (last row =
+// scratch for the messages that have nothing to carry) and the rows are added in rank order.
+__global__ void k_sum_rows(const double* tab, int rows, int n, double* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s_ = 0.0;
+  for (int r = 0; r < rows; r++) s_ += tab[(size_t)r * n + i];
+  out[i] = s_;
+}
+static int comm_allreduce_sum(nlps_comm* c, int rank, int world, double* d_vec, int n, double* tab, cudaStream_t stream) {
+  if (!c || world <= 1) return 0;
+  if (c->is_nccl) return nccl_api()->AllReduce(d_vec, d_vec, (size_t)n, ncclDouble, ncclSum, c->nccl, stream) == ncclSuccess ? 0 : 1;
+  auto row = [&](int r) { return tab + (size_t)((r >= 0 && r < world) ? r : world) * n; };
+  if (cudaMemcpyAsync(row(rank), d_vec, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) return 1;
+  const unsigned long long bytes = sizeof(double) * (unsigned long long)n;
+  for (int r = 1; r < world; r++) {
+    nlps_msg msgs[2];
+    int nm = 0;
+    // to the upper neighbour goes the row that came from below in the previous round (my own in the first), and back
+    if (rank > 0) msgs[nm++] = nlps_msg{rank - 1, row(rank + r - 1), bytes, row(rank - r), bytes};
+    if (rank < world - 1) msgs[nm++] = nlps_msg{rank + 1, row(rank - r + 1), bytes, row(rank + r), bytes};
+    if (comm_exchange(c, nm, msgs, stream)) return 1;
+  }
+  k_sum_rows<<<(n + 255) / 256, 256, 0, stream>>>(tab, world, n, d_vec);
+  return 0;
+}
+
 // Device memory comes from the device's stream-ordered pool with an unlimited release threshold: an engine
 // destroyed and re-created in the same process (a second scheme call, a parameter sweep) gets its blocks back
 // from the pool instead of paying cudaMalloc / cudaFree again (0.8 s + 0.8 s for the 10^6-particle deck).

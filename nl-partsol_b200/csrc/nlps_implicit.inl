@@ -33,6 +33,12 @@ struct ImplicitCtx {
   double *bv = nullptr, *bs = nullptr, *bt = nullptr, *by = nullptr, *brh = nullptr;  // BiCGStab: v, s, t, y, r^
   double* part2 = nullptr;   // BiCGStab partials: rho[2], rr (IMP_NPART each), then rv[2], ts[2], tt[2] (IMP_NSPMV each)
   int plastic = 0;           // some material has an elastoplastic tangent: unsymmetric operator
+  // several slabs (SURVEY 8e "Implicit"): every slab assembles the tangent of ITS particles (K = sum of the slabs' K);
+  // vectors are consistent (identical on the band nodes both slabs hold).  y = K x: local product, then the band sums of
+  // the explicit scheme's force exchange; dot products count every node once (own) and are summed over the slabs.
+  unsigned char* own = nullptr;  // per active rank: this slab owns the node (its coordinate lies between the slab's cuts)
+  double* pair = nullptr;        // [2][2 x IMP_NPART]: r.z | r.r partials by iteration parity (one all-reduce for both)
+  double* ar_tab = nullptr;      // scratch of comm_allreduce_sum for transports without a collective
   unsigned char* fx = nullptr;
   double* part = nullptr;    // [4][IMP_NPART]: 0-1 rz (ping-pong), 2 rr, 3 scratch (|R|^2); then pAp[IMP_NSPMV]
   double* h_part = nullptr;  // pinned
@@ -93,7 +99,8 @@ __global__ void __launch_bounds__(128) k_imp_nodal(GridDev G, BcDev bc, int step
   if (first) { fxr[t] = (unsigned char)fx; G.fixed[A] = (unsigned char)fx; }
   const double M = G.M[A];
 #pragma unroll
-  for (int i = 0; i < D; i++) out[(size_t)t * D + i] = ((fx >> i) & 1u) ? 0.0 : G.MOM[(size_t)A * D + i] / M;
+  for (int i = 0; i < D; i++)  // (M = 0: a node a neighbour slab's particles activated beyond the exchanged band; nothing reads it)
+    out[(size_t)t * D + i] = (((fx >> i) & 1u) || !(M > 0.0)) ? 0.0 : G.MOM[(size_t)A * D + i] / M;
 }
 
 // __form_initial_guess (U-Newmark-beta.c:879-957)
@@ -146,7 +153,8 @@ __device__ __forceinline__ double sum_partials(const double* part, int n = IMP_N
 template <int D>
 __global__ void __launch_bounds__(256) k_imp_residual(GridDev G, const double* grav, int nsteps, int step, double a1, double a2,
                                                       double a3, const double* dU, const double* Vn, const double* An,
-                                                      const unsigned char* fxr, double* R, double* part_out) {
+                                                      const unsigned char* fxr, double* R, double* part_out,
+                                                      const unsigned char* own) {
   __shared__ double sh[8];
   const int n = *G.n_active * D;
   double acc = 0.0;
@@ -159,10 +167,43 @@ __global__ void __launch_bounds__(256) k_imp_residual(GridDev G, const double* g
       r = -G.F[(size_t)A * D + i] + G.M[A] * (a1 * dU[k] - a2 * Vn[k] - a3 * An[k] - b);
     }
     R[k] = r;
-    acc += r * r;
+    if (!own || own[t]) acc += r * r;
   }
   const double s = block_sum(acc, sh);
   if (threadIdx.x == 0) part_out[blockIdx.x] = s;
+}
+
+// ---- several slabs: ownership of the active nodes, band values of a compact vector through the force array
+template <int D>
+__global__ void __launch_bounds__(128) k_imp_own(MeshDev m, GridDev G, SlabDev sl, unsigned char* own) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *G.n_active) return;
+  const double x = m.X[(size_t)G.act_list[t] * NS<D>::X + sl.axis];
+  own[t] = (unsigned char)(x >= sl.own_lo && x < sl.own_hi);
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_band_put(GridDev G, const int* ids0, int n0, const int* ids1, int n1, const double* v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0 + n1) return;
+  const int A = i < n0 ? ids0[i] : ids1[i - n0];
+  const int t = G.active[A] ? G.arank[A] : -1;
+#pragma unroll
+  for (int k = 0; k < D; k++) G.F[(size_t)A * D + k] = t >= 0 ? v[(size_t)t * D + k] : 0.0;
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_band_get(GridDev G, const int* ids0, int n0, const int* ids1, int n1, double* v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0 + n1) return;
+  const int A = i < n0 ? ids0[i] : ids1[i - n0];
+  const int t = G.active[A] ? G.arank[A] : -1;
+  if (t < 0) return;
+#pragma unroll
+  for (int k = 0; k < D; k++) v[(size_t)t * D + k] = G.F[(size_t)A * D + k];
+}
+__global__ void __launch_bounds__(256) k_diag_guard(const int* n_active, int D, double* diag) {
+  const int n = *n_active * D;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    if (diag[k] == 0.0) diag[k] = 1.0;  // a node that carries nothing on this slab and lies outside the exchanged band
 }
 
 // ---------------------------------------------------------------------------
@@ -560,15 +601,16 @@ __global__ void __launch_bounds__(128) k_assemble_cell_nh(MeshDev m, PartDev P, 
 // Jacobi preconditioner: diagonal of (K + alpha_1 M) with unit rows on restricted dofs
 template <int D>
 __global__ void __launch_bounds__(128) k_bsr_diag(GridDev G, const int* row_ptr, const int* cols, const double* vals,
-                                                  const unsigned char* fxr, double a1, double* diag) {
+                                                  const unsigned char* fxr, double a1, double* diag, const unsigned char* own) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= *G.n_active) return;
   const int pos = csr_find(cols, row_ptr[t], row_ptr[t + 1], t);
   const double M = G.M[G.act_list[t]];
+  const double ow = (!own || own[t]) ? 1.0 : 0.0;  // the mass term and the unit rows are the owner's share of the band sum
 #pragma unroll
   for (int i = 0; i < D; i++) {
     const double k = pos >= 0 ? vals[(size_t)pos * D * D + i * D + i] : 0.0;
-    diag[(size_t)t * D + i] = ((fxr[t] >> i) & 1u) ? 1.0 : k + a1 * M;
+    diag[(size_t)t * D + i] = ((fxr[t] >> i) & 1u) ? ow : k + ow * a1 * M;
   }
 }
 
@@ -579,7 +621,8 @@ __global__ void __launch_bounds__(128) k_bsr_diag(GridDev G, const int* row_ptr,
 template <int D>
 __global__ void __launch_bounds__(256) k_bsr_spmv(GridDev G, const int* row_ptr, const int* cols, const double* vals,
                                                   const unsigned char* fxr, double a1, const double* x, double* y,
-                                                  const double* w, double* part_out, double* part_yy) {
+                                                  const double* w, double* part_out, double* part_yy,
+                                                  const unsigned char* own = nullptr) {
   __shared__ double sh[8];
   constexpr int DD = D * D;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -614,7 +657,10 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(GridDev G, const int* row_ptr,
       const int i = lane;
       const double M = G.M[G.act_list[t]];
       const double xi = x[(size_t)t * D + i];
-      const double yi = ((fxr[t] >> i) & 1u) ? xi : acc + a1 * M * xi;
+      // several slabs: y is this slab's share of the band sum -- the mass term and the unit rows belong to the owner; the
+      // partial of w.y then runs over ALL local rows (w^T K w = sum over the slabs of w^T K_slab w)
+      const double ow = (!own || own[t]) ? 1.0 : 0.0;
+      const double yi = ((fxr[t] >> i) & 1u) ? ow * xi : acc + ow * a1 * M * xi;
       y[(size_t)t * D + i] = yi;
       dot += w[(size_t)t * D + i] * yi;
       dyy += yi * yi;
@@ -631,13 +677,15 @@ __global__ void __launch_bounds__(256) k_bsr_spmv(GridDev G, const int* row_ptr,
 // PCG vector kernels; every scalar is re-summed from the partial arrays in a fixed order by every block
 // x = 0, r = b, z = r / diag, p = z; partials of r.z -> part_rz, of r.r -> part_rr
 __global__ void __launch_bounds__(256) k_pcg_init(const int* n_active, int D, const double* b, const double* diag, double* x, double* r,
-                                                  double* z, double* p, double* part_rz, double* part_rr) {
+                                                  double* z, double* p, double* part_rz, double* part_rr,
+                                                  const unsigned char* own = nullptr) {
   __shared__ double sh[8];
   const int n = *n_active * D;
   double a = 0.0, c = 0.0;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const double rv = b[k], zv = rv / diag[k];
     x[k] = 0.0; r[k] = rv; z[k] = zv; p[k] = zv;
+    if (own && !own[k / D]) continue;  // dot products count every node once: on the slab that owns it
     a += rv * zv;
     c += rv * rv;
   }
@@ -646,7 +694,8 @@ __global__ void __launch_bounds__(256) k_pcg_init(const int* n_active, int D, co
 }
 __global__ void __launch_bounds__(256) k_pcg_update1(const int* n_active, int D, const double* part_pAp, const double* part_rz_cur,
                                                      const double* p, const double* Ap, const double* diag, double* x, double* r,
-                                                     double* z, double* part_rz_new, double* part_rr) {
+                                                     double* z, double* part_rz_new, double* part_rr,
+                                                     const unsigned char* own = nullptr) {
   __shared__ double sh[8];
   const int n = *n_active * D;
   const double pAp = sum_partials(part_pAp, IMP_NSPMV), rz = sum_partials(part_rz_cur);
@@ -656,6 +705,7 @@ __global__ void __launch_bounds__(256) k_pcg_update1(const int* n_active, int D,
     x[k] += alpha * p[k];
     const double rv = r[k] - alpha * Ap[k], zv = rv / diag[k];
     r[k] = rv; z[k] = zv;
+    if (own && !own[k / D]) continue;
     a += rv * zv;
     c += rv * rv;
   }
@@ -811,8 +861,9 @@ __global__ void k_csr_cols_to_nodes(GridDev G, const int* cols, int n, int* out)
 // host side
 static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
   implicit_free(e);
-  if (e->slab_on) {
-    fprintf(stderr, "nlps_b200_newmark_setup: the implicit scheme runs on a single slab\n");
+  if (e->slab_on && e->uniform_mat != NLPS_MAT_NEO_HOOKEAN_WRIGGERS) {
+    fprintf(stderr, "nlps_b200_newmark_setup: several slabs run the symmetric (Neo-Hookean) operator only; the elastoplastic "
+                    "tangents (Jacobi-BiCGStab) run on a single slab\n");
     return 1;
   }
   if (!prm->quasi_static && (!(prm->beta > 0.0) || !(prm->gamma > 0.0))) {  // a1 = 1/(beta dt^2): explicit central differences are U_Verlet's job
@@ -897,6 +948,9 @@ static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
       imp_alloc(e, &c->p, nv) || imp_alloc(e, &c->Ap, nv) || imp_alloc(e, &c->diag, nv) || imp_alloc(e, &c->fx, e->max_act) ||
       imp_alloc(e, &c->part, 4 * IMP_NPART + IMP_NSPMV))
     return 1;
+  if (e->slab_on && (imp_alloc(e, &c->own, e->max_act) || imp_alloc(e, &c->pair, 4 * IMP_NPART) ||
+                     imp_alloc(e, &c->ar_tab, (size_t)(e->world + 1) * IMP_NSPMV)))
+    return 1;
   if (c->plastic && (imp_alloc(e, &c->bv, nv) || imp_alloc(e, &c->bs, nv) || imp_alloc(e, &c->bt, nv) || imp_alloc(e, &c->by, nv) ||
                      imp_alloc(e, &c->brh, nv) || imp_alloc(e, &c->part2, 3 * IMP_NPART + 6 * IMP_NSPMV)))
     return 1;
@@ -907,8 +961,46 @@ static int imp_setup(nlps_engine* e, const nlps_newmark* prm) {
   return 0;
 }
 
+// several slabs: element-wise sum of a partial array over the slabs (afterwards identical everywhere), and the band sums
+// of a compact nodal vector (carried through G.F and the force exchange of the explicit scheme)
+static int imp_allreduce(nlps_engine* e, double* d_vec, int n) {
+  if (!e->slab_on) return 0;
+  if (comm_allreduce_sum(e->comm, e->rank, e->world, d_vec, n, e->imp->ar_tab, e->stream)) { e->host_fail = 1; return 1; }
+  e->launches++;
+  return 0;
+}
+template <int D>
+static int imp_band_sum(nlps_engine* e, double* v) {
+  if (!e->slab_on) return 0;
+  const int n0 = e->side[0].peer >= 0 ? e->side[0].n : 0, n1 = e->side[1].peer >= 0 ? e->side[1].n : 0;
+  if (n0 + n1 > 0) k_band_put<D><<<nblk(n0 + n1, 256), 256, 0, e->stream>>>(e->G, e->side[0].ids, n0, e->side[1].ids, n1, v);
+  const int rc = halo_exchange<D>(e, 2);
+  if (n0 + n1 > 0) k_band_get<D><<<nblk(n0 + n1, 256), 256, 0, e->stream>>>(e->G, e->side[0].ids, n0, e->side[1].ids, n1, v);
+  e->launches += 2;
+  return rc;
+}
+// a device error on one slab must stop every slab (the others would wait in the next collective)
+static int imp_poll(nlps_engine* e) {
+  const int bad = poll_error(e);
+  if (!e->slab_on) return bad;
+  int all_ok = 1;
+  if (comm_all_ok(e->comm, e->rank, e->world, !bad, e->mig_cnt + 12, e->stream, &all_ok)) return 1;
+  if (!all_ok && !bad) { e->host_fail = 1; if (!e->last_code) e->last_code = NLPS_ERR_CUDA; }
+  return bad || !all_ok;
+}
+
+static double imp_norm_at(nlps_engine* e, double* d_part) {  // sqrt of the sum of a partial array (over all slabs)
+  ImplicitCtx* c = e->imp;
+  imp_allreduce(e, d_part, IMP_NPART);
+  cudaMemcpyAsync(c->h_part, d_part, sizeof(double) * IMP_NPART, cudaMemcpyDeviceToHost, e->stream);
+  cudaStreamSynchronize(e->stream);
+  double s = 0.0;
+  for (int i = 0; i < IMP_NPART; i++) s += c->h_part[i];
+  return sqrt(s);
+}
 static double imp_norm(nlps_engine* e, int slot) {  // sqrt of the sum of a partial array
   ImplicitCtx* c = e->imp;
+  if (e->slab_on) return imp_norm_at(e, c->part + (size_t)slot * IMP_NPART);
   cudaMemcpyAsync(c->h_part, c->part + (size_t)slot * IMP_NPART, sizeof(double) * IMP_NPART, cudaMemcpyDeviceToHost, e->stream);
   cudaStreamSynchronize(e->stream);
   double s = 0.0;
@@ -924,10 +1016,13 @@ static int imp_begin_t(nlps_engine* e, int step) {
   const int nb128 = nblk(e->max_act, 128);
   stage_search_t<D>(e, step, 1, 0, e->P.vel, 0);
   { auto kf = k_grid_disp<D, 1>; LAUNCH(e, K_GRID_DISP, kf, nb128, 128, e->mesh, G, e->bc, step); }
+  halo_exchange<D>(e, 1);  // (several slabs: band sums of mass and momentum, as in the explicit scheme)
   k_imp_nodal<D><<<nb128, 128, 0, e->stream>>>(G, e->bc, step, 1, c->Vn, c->fx);
   stage_search_t<D>(e, step, 1, 0, e->P.acc, 1);
   { auto kf = k_grid_disp<D, 1>; LAUNCH(e, K_GRID_DISP, kf, nb128, 128, e->mesh, G, e->bc, step); }
+  halo_exchange<D>(e, 1);
   k_imp_nodal<D><<<nb128, 128, 0, e->stream>>>(G, e->bc, step, 0, c->An, c->fx);
+  if (e->slab_on) k_imp_own<D><<<nb128, 128, 0, e->stream>>>(e->mesh, G, slab_dev(e), c->own);
   if (c->prm.quasi_static) {  // the projections above are kept for the lumped mass and the restricted-DOF flags
     cudaMemsetAsync(c->Vn, 0, sizeof(double) * (size_t)e->max_act * D, e->stream);
     cudaMemsetAsync(c->An, 0, sizeof(double) * (size_t)e->max_act * D, e->stream);
@@ -954,8 +1049,9 @@ static void imp_residual_t(nlps_engine* e, int step, const double* dU, double* R
   stage_kin_stress_t<D>(e, step);
   e->implicit_on = 0;
   { auto kf = k_grid_acc<D, 1>; LAUNCH(e, K_GRID_ACC, kf, nb128, 128, e->mesh, e->G, e->grav, e->solver.num_steps, step); }
+  halo_exchange<D>(e, 2);  // (several slabs: band sums of the internal forces)
   k_imp_residual<D><<<IMP_NPART, 256, 0, e->stream>>>(e->G, e->grav, e->solver.num_steps, step, c->a1, c->a2, c->a3, dU, c->Vn, c->An,
-                                                     c->fx, R, c->part + (size_t)part_slot * IMP_NPART);
+                                                     c->fx, R, c->part + (size_t)part_slot * IMP_NPART, c->own);
   e->launches += 2;
   c->residual_evals++;
 }
@@ -991,10 +1087,59 @@ static int imp_assemble_t(nlps_engine* e) {
     if (c->plastic) { if (e->W == 4) launch(k_assemble_nh<3, 4, true>, 4); else launch(k_assemble_nh<3, 8, true>, 8); }
     else { if (e->W == 4) launch(k_assemble_nh<3, 4, false>, 4); else launch(k_assemble_nh<3, 8, false>, 8); }
   }
-  k_bsr_diag<D><<<nblk(e->max_act, 128), 128, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->diag);
+  k_bsr_diag<D><<<nblk(e->max_act, 128), 128, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->diag, c->own);
+  if (e->slab_on) {
+    imp_band_sum<D>(e, c->diag);
+    k_diag_guard<<<IMP_NPART, 256, 0, e->stream>>>(e->G.n_active, D, c->diag);
+  }
   e->launches += 2;
   c->assemblies++;
   return 0;
+}
+
+// The same iteration over several slabs (SURVEY 8e "Implicit").  Per iteration: the local product with this slab's share
+// of the tangent, the band sums of the result (the force exchange of the explicit scheme: peer-memory stores or
+// ncclSend/ncclRecv), one all-reduce of the p.Ap partials and one of the (r.z | r.r) partials -- no host round trip
+// inside an iteration; every slab then re-sums the same reduced partial arrays in the same order, so alpha, beta and
+// the convergence decision are identical everywhere.
+template <int D>
+static int imp_pcg_slabs_t(nlps_engine* e, const double* b, double* x) {
+  ImplicitCtx* c = e->imp;
+  const int* na = e->G.n_active;
+  double* part_pAp = c->part + 4 * IMP_NPART;
+  double* pair[2] = {c->pair, c->pair + 2 * IMP_NPART};  // [r.z | r.r] by parity
+  k_pcg_init<<<IMP_NPART, 256, 0, e->stream>>>(na, D, b, c->diag, x, c->r, c->z, c->p, pair[0], pair[0] + IMP_NPART, c->own);
+  if (imp_allreduce(e, pair[0], 2 * IMP_NPART)) return -1;
+  auto norm_rr = [&](int q) {
+    cudaMemcpyAsync(c->h_part, pair[q] + IMP_NPART, sizeof(double) * IMP_NPART, cudaMemcpyDeviceToHost, e->stream);
+    cudaStreamSynchronize(e->stream);
+    double s_ = 0.0;
+    for (int i = 0; i < IMP_NPART; i++) s_ += c->h_part[i];
+    return sqrt(s_);
+  };
+  const double bnorm = norm_rr(0);
+  if (bnorm == 0.0) return 0;
+  const double target = c->prm.pcg_rtol * bnorm;
+  int it = 0;
+  const int check = 8;
+  while (it < c->prm.pcg_max_iter) {
+    for (int k = 0; k < check; k++, it++) {
+      const int q = it & 1;
+      k_bsr_spmv<D><<<IMP_NSPMV, 256, 0, e->stream>>>(e->G, c->row_ptr, c->cols, c->vals, c->fx, c->a1, c->p, c->Ap, c->p, part_pAp, nullptr,
+                                                      c->own);
+      if (imp_band_sum<D>(e, c->Ap) || imp_allreduce(e, part_pAp, IMP_NSPMV)) return -it - 1;
+      k_pcg_update1<<<IMP_NPART, 256, 0, e->stream>>>(na, D, part_pAp, pair[q], c->p, c->Ap, c->diag, x, c->r, c->z, pair[q ^ 1],
+                                                     pair[q ^ 1] + IMP_NPART, c->own);
+      if (imp_allreduce(e, pair[q ^ 1], 2 * IMP_NPART)) return -it - 1;
+      k_pcg_update2<<<IMP_NPART, 256, 0, e->stream>>>(na, D, pair[q], pair[q ^ 1], c->z, c->p);
+    }
+    e->launches += 3 * check;
+    const double rn = norm_rr(it & 1);
+    if (!(rn == rn)) return -it;  // NaN: breakdown
+    if (rn <= target) { c->pcg_iters += it; return it; }
+  }
+  c->pcg_iters += it;
+  return -it;
 }
 
 // Jacobi-PCG on (K + alpha_1 M) delta = b; returns the iteration count (negative: not converged)
@@ -1005,6 +1150,7 @@ static int imp_pcg_t(nlps_engine* e, const double* b, double* x) {
   double* part_pAp = c->part + 4 * IMP_NPART;
   double* part_rz[2] = {c->part, c->part + IMP_NPART};
   double* part_rr = c->part + 2 * IMP_NPART;
+  if (e->slab_on) return imp_pcg_slabs_t<D>(e, b, x);
   k_pcg_init<<<IMP_NPART, 256, 0, e->stream>>>(na, D, b, c->diag, x, c->r, c->z, c->p, part_rz[0], part_rr);
   const double bnorm = imp_norm(e, 2);
   if (bnorm == 0.0) return 0;
@@ -1079,7 +1225,7 @@ static int imp_step_t(nlps_engine* e, int step) {
   imp_residual_t<D>(e, step, c->dU, c->R, 3);
   double rn = imp_norm(e, 3);
   tock(c->ms_residual);
-  if (poll_error(e)) return 1;
+  if (imp_poll(e)) return 1;
   c->res0 = rn;
   c->newton_iters = 0;
   const double tol = c->prm.tol;
@@ -1092,7 +1238,7 @@ static int imp_step_t(nlps_engine* e, int step) {
     tick();
     const int its = c->plastic ? imp_bicgstab_t<D>(e, c->Rt, c->delta) : imp_pcg_t<D>(e, c->Rt, c->delta);
     tock(c->ms_pcg);
-    if (poll_error(e)) { status = 1; break; }
+    if (imp_poll(e)) { status = 1; break; }
     if (its < 0 && getenv("NLPS_VERBOSE")) fprintf(stderr, "nlps_b200 (implicit): PCG stopped after %d iterations\n", -its);
     // step halving on |R| (the reference: SNES backtracking line search)
     tick();
@@ -1110,7 +1256,7 @@ static int imp_step_t(nlps_engine* e, int step) {
       rt = imp_norm(e, 3);
     }
     tock(c->ms_residual);
-    if (poll_error(e)) { status = 1; break; }
+    if (imp_poll(e)) { status = 1; break; }
     std::swap(c->dU, c->trial);
     std::swap(c->R, c->Rt);
     c->newton_iters++;
@@ -1137,7 +1283,7 @@ static int imp_step_t(nlps_engine* e, int step) {
   std::swap(e->P.be_n, e->P.be_n1);
   std::swap(e->P.eps_n, e->P.eps_n1);
   std::swap(e->P.kap_n, e->P.kap_n1);
-  return poll_error(e);
+  return imp_poll(e);
 }
 
 extern "C" {

@@ -315,3 +315,67 @@ def test_slabs_nccl_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "NCCL slabs OK" in out.stdout
+
+
+@pytest.mark.parametrize("case,world", [("block2d", 2), ("block2d", 3), ("cantilever3d", 2), ("cantilever3d", 3)])
+def test_implicit_newmark_slabs_match_single(case, world):
+    """SURVEY 8(e) "Implicit": every slab assembles the tangent of its own particles, the Krylov vectors are summed over
+    the band nodes each iteration and the dot products over the slabs.  Converged Newmark-beta steps at several times
+    the explicit time step on 2 / 3 slabs (particles migrate in between) against the engine that holds the whole cloud;
+    tolerance = what a Newton loop stopped at |R| <= 1e-12 |R0| supports."""
+    from nlps_b200 import synthetic
+    nsteps = 6
+    if case == "block2d":
+        P = synthetic.structured_problem(2, (64, 16), 1.0 / 16, (48, 8), (8, 0), synthetic.NH_C1, nsteps, 0.5,
+                                         (1e6 / 1000.0) ** 0.5 * 1.3, (0.0, -9.81), fixed=("bottom",), rollers=())
+        P.fields["vel"][:, 0] = 0.05 * P.solver["cel"]
+    elif case == "cantilever3d":  # BASELINE configs[4] shape: clamped beam with a tip traction (Neumann load on Area_0)
+        P = synthetic.beam_3d(cells_per_unit=4 if world == 2 else 5, nsteps=nsteps)
+    if case != "cantilever3d":
+        P.solver["cfl"] = 4.0
+    kw = dict(tol=1e-12, max_iter=25, pcg_rtol=1e-13)
+
+    eng = engine.Engine(P, device=0)
+    assert eng.initialize_lme() == 0 and eng.newmark_setup(**kw) == 0
+    assert eng.newmark_run(0, nsteps) == 0, eng.error()
+    f1 = eng.download()
+    c1, l1 = eng.lists()
+    eng.close()
+
+    axis, cuts = engine.slab_cuts(P, world)
+    comms = engine.ThreadComm.group(world)
+    res, errs = [None] * world, []
+
+    def work(r):
+        try:
+            e = engine.Engine(P, device=0, slab=dict(rank=r, world=world, axis=axis, cuts=cuts, comm=comms[r], migrate_every=2))
+            assert e.initialize_lme() == 0, e.error()
+            assert e.newmark_setup(**kw) == 0
+            assert e.newmark_run(0, nsteps) == 0, e.error()
+            f, ids = e.download_local()
+            counts, lists = e.lists()
+            res[r] = (f, ids, counts, lists, e.newmark_stats(), e.migrated_count())
+            e.close()
+        except BaseException as ex:  # noqa: BLE001
+            errs.append((r, ex))
+            comms[r].sh.barrier.abort()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(900)
+    for c in comms:
+        c.close()
+    assert not errs, errs
+    assert axis == 0
+    m = merge([r[:4] for r in res], P.np_)
+    assert np.array_equal(m["I0"], f1["I0"]) and np.array_equal(m["_counts"], c1) and np.array_equal(m["_lists"], l1)
+    sc = field_scales(P)
+    for k in ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "lambda"):
+        assert_close(m[k], f1[k], f"implicit slabs vs single ({case}, {world} slabs): {k}", rtol=1e-8, scale=sc.get(k))
+    # the slabs agreed on every solver decision: same Newton and Krylov iteration counts on all of them
+    its = {(r[4]["newton_iters"], r[4]["pcg_iters_total"]) for r in res}
+    assert len(its) == 1, its
+    if case == "block2d":
+        assert sum(r[5] for r in res) > 0, "particles must have crossed the cuts"
