@@ -501,13 +501,23 @@ __device__ __forceinline__ void mn_Eh(const MNPar& q, const double* T, double* E
   Eh[1] = c2 * t0 + c1 * t1 + c2 * t2;
   Eh[2] = c2 * t0 + c2 * t1 + c1 * t2;
 }
+// LD = Lade-Duncan (Lade-Duncan.c:966-1032): the same monolithic return mapping with the yield surface
+// cbrt((27 + kappa) I3) - I1 instead of Matsuoka-Nakai's cbrt((9 + kappa) I3) - cbrt(I1 I2)
+template <bool LD>
 __device__ __forceinline__ double mn_F(double kphi, double I1, double I2, double I3) {
-  return cbrt((9.0 + kphi) * I3) - cbrt(I1 * I2);
+  return LD ? cbrt((27.0 + kphi) * I3) - I1 : cbrt((9.0 + kphi) * I3) - cbrt(I1 * I2);
 }
+template <bool LD>
 __device__ __forceinline__ void mn_dGdS(double* g, const double* T, double I1, double I2, double I3, double kpsi) {
-  double K2 = 9.0 + kpsi, cb = cbrt(I1 * I2), ck = cbrt(K2 * I3);
+  const double K2 = (LD ? 27.0 : 9.0) + kpsi, ck = cbrt(K2 * I3);
+  if (LD) {
 #pragma unroll
-  for (int i = 0; i < 3; i++) g[i] = ck / (3.0 * T[i]) - (I1 * (I1 - T[i]) + I2) / (3.0 * (cb * cb));
+    for (int i = 0; i < 3; i++) g[i] = ck / (3.0 * T[i]) - 1.0;
+  } else {
+    const double cb = cbrt(I1 * I2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) g[i] = ck / (3.0 * T[i]) - (I1 * (I1 - T[i]) + I2) / (3.0 * (cb * cb));
+  }
 }
 __device__ __forceinline__ double mn_residual(double* R, const double* Etr, const double* Ek, const double* dG,
                                               double kap0, double kaphat0, double Fk, double dl) {
@@ -521,7 +531,7 @@ __device__ __forceinline__ double mn_residual(double* R, const double* Etr, cons
   return sqrt(s);
 }
 
-template <int D>
+template <int D, bool LD = false>
 __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapParams& rp, const double* dphi,
                                             double* be, double& eps, double& kappa, double* tau, double& W,
                                             double* cep) {
@@ -557,7 +567,7 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
   I1 = Ttr[0] + Ttr[1] + Ttr[2];
   I2 = Ttr[0] * Ttr[1] + Ttr[1] * Ttr[2] + Ttr[0] * Ttr[2];
   I3 = Ttr[0] * Ttr[1] * Ttr[2];
-  F_0 = mn_F(kap_n0, I1, I2, I3);
+  F_0 = mn_F<LD>(kap_n0, I1, I2, I3);
 #pragma unroll
   for (int i = 0; i < 3; i++) Tk1[i] = Ttr[i];
   bool rows = false;
@@ -571,9 +581,11 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
     rows = rp.quirk_rows != 0;
     mn_Eh(q, Tk1, Ek1);
 #pragma unroll
-    for (int i = 0; i < 3; i++) Etr[i] = Ek1[i];
+    for (int i = 0; i < 3; i++) {  // Matsuoka-Nakai.c:431-433 overwrites the trial strain, Lade-Duncan.c:430-432 the iterate
+      if (LD) Ek1[i] = Etr[i]; else Etr[i] = Ek1[i];
+    }
     kaphat = q.a0 * Lambda_n * exp(q.a1 * I1) * exp(-q.a2 * Lambda_n);
-    mn_dGdS(dG, Ttr, I1, I2, I3, q.alpha * kap_n0);
+    mn_dGdS<LD>(dG, Ttr, I1, I2, I3, q.alpha * kap_n0);
     N0 = mn_residual(R1, Etr, Ek1, dG, kap_n0, kaphat, F_0, 0.0);
     kap1 = kap_n0;
     F_k1 = F_0; dl1 = 0.0; Lambda_k1 = Lambda_n; N1 = N0;
@@ -582,15 +594,16 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
       double ek = q.a0 * exp(q.a1 * I1) * exp(-q.a2 * Lambda_k1);
       double dkds = q.a1 * Lambda_k1 * ek;
       double dkdl = (1 - q.a2 * Lambda_k1) * ek;
-      double K1 = 9.0 + kap1, K2 = 9.0 + q.alpha * kap1;
+      const double KOFF = LD ? 27.0 : 9.0;
+      double K1 = KOFF + kap1, K2 = KOFF + q.alpha * kap1;
       double cb = cbrt(I1 * I2), ck1 = cbrt(K1 * I3), ck2 = cbrt(K2 * I3), cI3 = cbrt(I3);
       double dFds[3], dg[3], ddGk[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        dg[i] = (I1 * (I1 - Tk1[i]) + I2) / (3.0 * (cb * cb));
+        dg[i] = LD ? 1.0 : (I1 * (I1 - Tk1[i]) + I2) / (3.0 * (cb * cb));
         dFds[i] = ck1 / (3.0 * Tk1[i]) - dg[i];
         double c2 = cbrt(K2);
-        ddGk[i] = (cI3 / (3.0 * Tk1[i])) / (3.0 * (c2 * c2));
+        ddGk[i] = LD ? cI3 / (3.0 * Tk1[i]) : (cI3 / (3.0 * Tk1[i])) / (3.0 * (c2 * c2));  // (Lade-Duncan.c:1030-1032 as compiled)
       }
       double c1k = cbrt(K1);
       double dFdk = (1.0 / 3.0) * (1.0 / (c1k * c1k)) * cI3;
@@ -598,8 +611,8 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
       for (int A = 0; A < 3; A++)
 #pragma unroll
         for (int B = 0; B < 3; B++) {
-          double ddg = (1.0 / (cb * cb)) / 3.0 * (3.0 * I1 - Tk1[A] - Tk1[B] - I1 * (A == B)) -
-                       (2.0 / cb) * dg[A] * dg[B];
+          double ddg = LD ? 0.0 : (1.0 / (cb * cb)) / 3.0 * (3.0 * I1 - Tk1[A] - Tk1[B] - I1 * (A == B)) -
+                                      (2.0 / cb) * dg[A] * dg[B];
           ddG[A * 3 + B] = (1.0 / 3.0) * ck2 * (1.0 / (3.0 * Tk1[A] * Tk1[B]) - 1.0 * (A == B) / (Tk1[A] * Tk1[A])) - ddg;
         }
 #pragma unroll
@@ -634,8 +647,8 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
   I3 = Tk2[0] * Tk2[1] * Tk2[2];                                              \
   mn_Eh(q, Tk2, Ek2);                                                         \
   kaphat = q.a0 * Lambda_k2 * exp(q.a1 * I1) * exp(-q.a2 * Lambda_k2);        \
-  mn_dGdS(dG, Tk2, I1, I2, I3, q.alpha * kap2);                               \
-  F_k2 = mn_F(kap2, I1, I2, I3);                                              \
+  mn_dGdS<LD>(dG, Tk2, I1, I2, I3, q.alpha * kap2);                           \
+  F_k2 = mn_F<LD>(kap2, I1, I2, I3);                                          \
   N2 = mn_residual(R2, Etr, Ek2, dG, kap2, kaphat, F_k2, dl2);
       NLPS_MN_EVAL2();
       while ((fabs(N2 - N1) > TOL) && (fabs(F_k2 / F_0) >= TOL)) {
@@ -800,7 +813,8 @@ __device__ inline void stress_hencky(const MatParams& m, const double* F, double
 // Stress_integration__Constitutive__ (Constitutive.c:18-258) for every law except Neo-Hookean: which fields of the
 // history a law reads and writes.  `back` may be nullptr when the cloud holds no Von-Mises particle.
 __host__ __device__ __forceinline__ bool mat_has_history(int mtype) {
-  return mtype == NLPS_MAT_DRUCKER_PRAGER || mtype == NLPS_MAT_MATSUOKA_NAKAI || mtype == NLPS_MAT_VON_MISES;
+  return mtype == NLPS_MAT_DRUCKER_PRAGER || mtype == NLPS_MAT_MATSUOKA_NAKAI || mtype == NLPS_MAT_VON_MISES ||
+         mtype == NLPS_MAT_LADE_DUNCAN;
 }
 template <int D>
 __device__ inline int stress_with_history(int mtype, const MatParams& m, const ReturnMapParams& rp, const double* DF,
@@ -809,6 +823,7 @@ __device__ inline int stress_with_history(int mtype, const MatParams& m, const R
   if (mtype == NLPS_MAT_DRUCKER_PRAGER) return stress_drucker_prager<D>(m, rp, DF, be, eps, kap, tau, W, cep);
   if (mtype == NLPS_MAT_MATSUOKA_NAKAI) return stress_matsuoka_nakai<D>(m, rp, DF, be, eps, kap, tau, W, cep);
   if (mtype == NLPS_MAT_VON_MISES) return stress_von_mises<D>(m, rp, DF, be, eps, back, tau, W);
+  if (mtype == NLPS_MAT_LADE_DUNCAN) return stress_matsuoka_nakai<D, true>(m, rp, DF, be, eps, kap, tau, W, cep);
   stress_hencky<D>(m, Fn1, tau, W);
   return 0;
 }

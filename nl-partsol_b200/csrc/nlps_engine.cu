@@ -3056,7 +3056,7 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
     memset(hm, 0, sizeof(hm));
     for (int i = 0; i < n_materials; i++) {
       const nlps_material& s = materials[i];
-      if (s.type < 0 || s.type > NLPS_MAT_HENCKY) return set_err(err, err_len, "unknown material type");
+      if (s.type < 0 || s.type > NLPS_MAT_LADE_DUNCAN) return set_err(err, err_len, "unknown material type");
       hm[i] = MatParams{s.type, s.rho, s.E, s.nu, s.reference_pressure, s.kappa_0, s.hardening_modulus,
                         s.plastic_strain_0, s.phi_frictional, s.psi_frictional, s.exponent_hardening_ortiz,
                         s.cohesion, s.alpha_hardening_borja, s.a_hardening_borja[0], s.a_hardening_borja[1],

@@ -75,6 +75,7 @@ static int material_to_pod(const Material *M, nlps_material *out) {
   else if (strcmp(M->Type, "Matsuoka-Nakai") == 0) out->type = NLPS_MAT_MATSUOKA_NAKAI;
   else if (strcmp(M->Type, "Von-Mises") == 0) out->type = NLPS_MAT_VON_MISES;
   else if (strcmp(M->Type, "Hencky") == 0) out->type = NLPS_MAT_HENCKY;
+  else if (strcmp(M->Type, "Lade-Duncan") == 0) out->type = NLPS_MAT_LADE_DUNCAN;
   else {
     /* same wording as Constitutive.c:250-254 */
     fprintf(stderr, "%s : %s %s %s \n", "Error in U_Verlet() [B200]", "The material", M->Type,

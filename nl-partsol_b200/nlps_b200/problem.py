@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-MATERIAL_TYPES = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2, "Von-Mises": 3, "Hencky": 4}
+MATERIAL_TYPES = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2, "Von-Mises": 3, "Hencky": 4, "Lade-Duncan": 5}
 # order of the material parameter block (oracle/ref_harness.c refh_material_params; slots 16..19 = the Voce hardening
 # parameters of Von-Mises, refh_material_voce; blocks of 16 are padded with their defaults theta = 1, 0, 0, 0)
 MATERIAL_SLOTS = ("rho", "E", "nu", "ReferencePressure", "kappa_0", "Hardening_modulus",

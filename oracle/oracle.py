@@ -14,7 +14,7 @@ _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
 _up = ctypes.POINTER(ctypes.c_ubyte)
 
-MAT = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2, "Von-Mises": 3, "Hencky": 4}
+MAT = {"Neo-Hookean-Wriggers": 0, "Drucker-Prager": 1, "Matsuoka-Nakai": 2, "Von-Mises": 3, "Hencky": 4, "Lade-Duncan": 5}
 STAGES = dict(search=0, p2g_mass_disp=1, grid_disp=2, kin_stress=3, force=4, grid_acc=5, g2p=6)
 
 

@@ -50,6 +50,10 @@ POINT_MATERIALS = {
     "mn": ("Matsuoka-Nakai", {"rho": 2000.0, "E": 1e7, "nu": 0.3, "alpha": 0.5, "a1": 20000.0,
                               "a2": 0.005, "a3": 35.0, "Friction-angle": 30.0, "Cohesion": 1e3,
                               "kappa-0": 8.0 / 3.0}),
+    # Lade-Duncan has no cohesion in the reference's reader (the key aborts): the law only makes sense from a compressed
+    # state, so its paths start from an isotropically pre-compressed elastic left Cauchy-Green tensor
+    "ld": ("Lade-Duncan", {"rho": 2000.0, "E": 1e7, "nu": 0.3, "alpha": 0.5, "a1": 20000.0, "a2": 0.005, "a3": 35.0,
+                           "Friction-angle": 30.0, "Atmospheric-pressure": 100.0}),
 }
 CHECKPOINTS = {"nh": (1, 2, 5, 20, 60), "dp": (1, 2, 5, 20, 60, 120), "mn": (1, 2, 5, 20, 60),
                "vm": (1, 2, 5, 20, 60, 120), "hencky": (1, 5, 60)}
@@ -116,6 +120,8 @@ def gen_points(case):
     rows_in, rows_out = [], []
     for path in range(24):
         be = np.array([1, 0, 0, 1, 1.0])
+        if case == "ld":
+            be = be * (1.0 - 0.002 * (1 + path % 5)) ** 2
         eps, kap = float(P.fields["EPS_n"][0]), float(P.fields["Kappa_n"][0])
         F = np.array([1, 0, 0, 1, 1.0])
         amp = 10.0 ** rng.uniform(-4, -2)
@@ -126,6 +132,8 @@ def gen_points(case):
                 D = np.diag([1.0, 0.999])  # the reference's own stand-alone test path
             elif path % 4 == 0:
                 D = np.diag([1.0, 1 - amp])
+            if case == "ld" and path % 4 != 0:  # shear-dominated increments keep the state inside the compression octant
+                D = np.eye(2) + 0.2 * (D - np.eye(2)) + np.diag([0.0, -0.5 * amp])
             DF = np.array([D[0, 0], D[0, 1], D[1, 0], D[1, 1], 1.0])
             Fm = D @ F[:4].reshape(2, 2)
             F = np.array([Fm[0, 0], Fm[0, 1], Fm[1, 0], Fm[1, 1], 1.0])
@@ -476,7 +484,7 @@ if __name__ == "__main__":
         for c in ("nh", "dp", "mn", "vm", "hencky"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
                            if os.environ.get("QUIET") else None)
-        for c in ("dp", "mn"):
+        for c in ("dp", "mn", "ld"):
             subprocess.run([sys.executable, __file__, "points", c], check=True)
         subprocess.run([sys.executable, __file__, "tangent", "all"], check=True)
         for c in ("dp", "mn"):

@@ -62,10 +62,13 @@ def test_steps_match_reference(case):
             assert_close(o.nodal(w), tr[t + "g" + nm], f"{case} step {k + 1} nodal {nm}")
 
 
-@pytest.mark.parametrize("case", ("dp", "mn"))
+@pytest.mark.parametrize("case", ("dp", "mn", "ld"))
 def test_material_points(case):
+    """ld: Lade-Duncan.  The reference's reader refuses a cohesion for it and its cloud runs diverge from the unstressed
+    state (NaN hardening variable within a few steps), so the law is pinned on material points that start from a
+    pre-compressed state (1200 updates, 1056 plastic) and not on a golden trace."""
     z = load_points(case)
-    P = load_problem(case)
+    P = load_problem("mn" if case == "ld" else case)
     P.materials = [(str(z["mat_type"]), z["mat_params"])]
     P.solver["tol_radial"] = float(z["tol_radial"])
     P.solver["maxiter_radial"] = int(z["maxiter_radial"])
