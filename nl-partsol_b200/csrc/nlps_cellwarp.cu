@@ -708,6 +708,7 @@ __global__ void __launch_bounds__(128, MODE == CW_KIN_FUSED ? 3 : 4) cw_kin(cons
       }
       if (MODE == CW_FORCE) cw_prefetch_rows(P.gop, ld, D * D, tn, P.np, lane);
       if (lane < PPW && tn + lane < P.np) prefetch_l2(P.clist + (size_t)(tn + lane) * CL);
+      if (lane >= 16 && lane < 16 + cfg.W) prefetch_l2(&P.mask[(size_t)(lane - 16) * ld + tn]);  // the union of the masks opens the next cell
     }
     cw_union(P, G, c, cfg.W, T, lane);
     cw_stage<SCATTER, GATHER ? 1 : 0, false, true>(m, G, SL, c, T, lane);
@@ -908,6 +909,7 @@ __global__ void __launch_bounds__(128, 4) cw_g2p(const MeshDev m, const PartDev 
       cw_prefetch_rows(P.beta, ld, 1, tn, P.np, lane);
       cw_prefetch_rows(P.zi, ld, 1, tn, P.np, lane);
       if (lane < PPW && tn + lane < P.np) prefetch_l2(P.clist + (size_t)(tn + lane) * CL);
+      if (lane >= 16 && lane < 16 + cfg.W) prefetch_l2(&P.mask[(size_t)(lane - 16) * ld + tn]);  // the union of the masks opens the next cell
     }
     cw_union(P, G, c, cfg.W, T, lane);
     cw_stage<false, 2, false, true>(m, G, SL, c, T, lane);

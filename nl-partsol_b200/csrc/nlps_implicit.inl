@@ -1278,6 +1278,7 @@ static int imp_step_t(nlps_engine* e, int step) {
     if (e->np) k_sync_inert<D><<<nblk(e->np, 256), 256, 0, e->stream>>>(e->P, e->mat);
     e->inert_synced = 1;
   }
+  e->n1_stale = 1;  // downloads hand the rolled state to the *_n1 host fields, as the reference's copy roll leaves them
   std::swap(e->P.F_n, e->P.F_n1);
   std::swap(e->P.J_n, e->P.J_n1);
   std::swap(e->P.be_n, e->P.be_n1);
