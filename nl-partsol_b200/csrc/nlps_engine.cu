@@ -937,13 +937,28 @@ struct BcDev {
   int maxdim, nsteps, nb;
 };
 
+__global__ void k_set_flags(const int* ids, int n, unsigned char* flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[ids[i]] = 1;
+}
 // MODE 0: everything (single slab).  MODE 1: sums only, M and MOM stored (the slab halo exchange adds the
-// neighbour slabs' sums on the shared nodes).  MODE 2: division + Dirichlet from the stored sums.
+// neighbour slabs' sums on the shared nodes).  MODE 2: division + Dirichlet from the stored sums -- over all active
+// nodes, or (band lists given) over the nodes of the halo bands only.  MODE 3 (slabs): MODE 0 for the nodes outside
+// the halo bands, MODE 1 for the band nodes, which MODE 2 finishes after the exchange: the second pass touches a few
+// thousand nodes instead of all of them.
 template <int D, int MODE>
-__global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev bc, int step) {
+__global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev bc, int step, const int* ids0 = nullptr,
+                                                   int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= *G.n_active) return;
-  const int A = G.act_list[t];
+  int A;
+  if (MODE == 2 && (ids0 || ids1)) {
+    if (t >= n0 + n1) return;
+    A = t < n0 ? ids0[t] : ids1[t - n0];
+    if (!G.active[A]) return;
+  } else {
+    if (t >= *G.n_active) return;
+    A = G.act_list[t];
+  }
   double mom[D], M = 0.0;
 #pragma unroll
   for (int i = 0; i < D; i++) mom[i] = 0.0;
@@ -963,7 +978,7 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
       for (int i = 0; i < D; i++) mom[i] += src[1 + i];
     }
   }
-  if (MODE == 1) {
+  if (MODE == 1 || (MODE == 3 && G.band[A])) {
     G.M[A] = M;
 #pragma unroll
     for (int i = 0; i < D; i++) G.MOM[(size_t)A * D + i] = mom[i];
@@ -1305,11 +1320,19 @@ __global__ void k_traction(PartDev P, NeuDev nu, double thickness, int step) {
 
 // K3 stage 2 + G2 (node kernel): f_A = sum of cell partials; a_A = g + f_A / M_A on free DOFs, 0 on
 // restricted ones (U-Verlet.c:947-958; gravity as U-Newmark-beta.c:1539-1543).
-template <int D, int MODE>
-__global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const double* grav, int nsteps, int step) {
+template <int D, int MODE>  // MODE as in k_grid_disp
+__global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const double* grav, int nsteps, int step,
+                                                  const int* ids0 = nullptr, int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= *G.n_active) return;
-  const int A = G.act_list[t];
+  int A;
+  if (MODE == 2 && (ids0 || ids1)) {
+    if (t >= n0 + n1) return;
+    A = t < n0 ? ids0[t] : ids1[t - n0];
+    if (!G.active[A]) return;
+  } else {
+    if (t >= *G.n_active) return;
+    A = G.act_list[t];
+  }
   double f[D];
 #pragma unroll
   for (int i = 0; i < D; i++) f[i] = (MODE == 2) ? G.F[(size_t)A * D + i] : 0.0;
@@ -1323,7 +1346,7 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
       for (int i = 0; i < D; i++) f[i] += src[i];
     }
   }
-  if (MODE == 1) {
+  if (MODE == 1 || (MODE == 3 && G.band[A])) {
 #pragma unroll
     for (int i = 0; i < D; i++) G.F[(size_t)A * D + i] = f[i];
     return;
@@ -2612,11 +2635,13 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
 template <int D>
 static void stage_p2g_mass_disp_t(nlps_engine* e, int step) {
   if (!e->slab_on) {
-    { auto kf = k_grid_disp<D, 0>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step); }
+    { auto kf = k_grid_disp<D, 0>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step, nullptr, 0, nullptr, 0); }
   } else {
-    { auto kf = k_grid_disp<D, 1>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step); }
+    // everything outside the halo bands is finished in the first pass; the band nodes after the exchange
+    const int n0 = e->side[0].peer >= 0 ? e->side[0].n : 0, n1 = e->side[1].peer >= 0 ? e->side[1].n : 0;
+    { auto kf = k_grid_disp<D, 3>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step, nullptr, 0, nullptr, 0); }
     halo_exchange<D>(e, 1);
-    { auto kf = k_grid_disp<D, 2>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step); }
+    if (n0 + n1 > 0) { auto kf = k_grid_disp<D, 2>; LAUNCH(e, K_GRID_DISP, kf, nblk(n0 + n1, 128), 128, e->mesh, e->G, e->bc, step, e->side[0].ids, n0, e->side[1].ids, n1); }
   }
 }
 template <int D>
@@ -2651,11 +2676,12 @@ static void stage_kin_stress_t(nlps_engine* e, int step) {
 template <int D>
 static void stage_force_t(nlps_engine* e, int step) {
   if (!e->slab_on) {
-    { auto kf = k_grid_acc<D, 0>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step); }
+    { auto kf = k_grid_acc<D, 0>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, nullptr, 0, nullptr, 0); }
   } else {
-    { auto kf = k_grid_acc<D, 1>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step); }
+    const int n0 = e->side[0].peer >= 0 ? e->side[0].n : 0, n1 = e->side[1].peer >= 0 ? e->side[1].n : 0;
+    { auto kf = k_grid_acc<D, 3>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, nullptr, 0, nullptr, 0); }
     halo_exchange<D>(e, 2);
-    { auto kf = k_grid_acc<D, 2>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step); }
+    if (n0 + n1 > 0) { auto kf = k_grid_acc<D, 2>; LAUNCH(e, K_GRID_ACC, kf, nblk(n0 + n1, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, e->side[0].ids, n0, e->side[1].ids, n1); }
   }
 }
 template <int D>
@@ -3177,6 +3203,16 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
         dev_alloc(e, &h.rbuf, (size_t)n * (1 + D)))
       return 1;
     CUDA_OK(cudaStreamSynchronize(e->stream));
+    // band flags: the node kernels leave these nodes to the pass after the exchange
+    if (!e->G.band) {
+      if (dev_alloc(e, &e->G.band, (size_t)e->nn)) return 1;
+      CUDA_OK(cudaMemsetAsync(e->G.band, 0, (size_t)e->nn, e->stream));
+    }
+    if (n > 0) k_set_flags<<<nblk(n, 256), 256, 0, e->stream>>>(h.ids, n, e->G.band);
+  }
+  if (e->slab_on && !e->G.band) {  // a slab without neighbours (world = 1)
+    if (dev_alloc(e, &e->G.band, (size_t)e->nn)) return 1;
+    CUDA_OK(cudaMemsetAsync(e->G.band, 0, (size_t)e->nn, e->stream));
   }
   // ---- migration buffers
   {

@@ -71,6 +71,7 @@ struct GridDev {
   double *M, *F;  // M: nn ; F: nn x D (row-major)
   double* MOM;    // nn x D: sum m N DU_p before the division by M (kept for the slab halo sums)
   unsigned char* rocc;  // cell occupied by particles of a NEIGHBOUR slab (multi-GPU), zero otherwise
+  unsigned char* band;  // node lies in the halo band of one of the slab's cuts (its sums wait for the exchange), or nullptr
   double* UA;     // per node [dU (NS) | A (NS)]: the two nodal fields the G2P gathers read, one record
   unsigned char *active, *fixed;
   int *cnt, *cursor, *cell_start, *plist, *act_list, *n_active;
