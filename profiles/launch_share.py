@@ -26,7 +26,9 @@ def main():
     searches = [i for i, (n, _) in enumerate(launches) if n.startswith("k_search")]
     # the last 2 searches open the two per-kernel profile steps; the K before them are the timed steps
     lo, hi = searches[-(K + 2)], searches[-2]
-    win = launches[lo:hi]
+    # the download between the timed steps and the profile steps (neighbour count for the roofline) is not part of a step
+    NOT_STEP = ("k_soa_to_aos", "k_unpermute", "k_expand_lists", "k_export")
+    win = [(n, t) for n, t in launches[lo:hi] if not n.startswith(NOT_STEP)]
     tot = sum(t for _, t in win)
     agg = {}
     for n, t in win:
