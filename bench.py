@@ -719,7 +719,7 @@ def run_c5(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te.item())
         # parity of the slab data plane: a reduced beam on the slabs against one engine holding all of it
-        Ps = synthetic.beam_3d(cells_per_unit=6, nsteps=5)
+        Ps = synthetic.beam_3d(cells_per_unit=max(6, (13 * world + 7) // 8), nsteps=5)  # a slab must span two halo bands
         ax, cu = engine.slab_cuts(Ps, world)
         es = engine.Engine(Ps, device=local, slab=dict(rank=rank, world=world, axis=ax, cuts=cu, comm=comm, migrate_every=2))
         assert es.initialize_lme() == 0 and es.newmark_setup(tol=1e-12, max_iter=25, pcg_rtol=1e-13) == 0
