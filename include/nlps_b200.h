@@ -333,7 +333,11 @@ int nlps_b200_u_verlet_slab(const nlps_mesh *mesh, const nlps_solver *solver,
  * Time_Int_Params) (Formulations/Displacements/U-Newmark-beta.c:130-425).  The PETSc objects of
  * the reference (Vec/Mat/IS/SNES/KSP/PC, :220-425) are replaced by device vectors over the active
  * nodes, a block-CSR tangent and a hand-written Jacobi-PCG; the nonlinear driver is Newton with
- * step halving.  Tangent: Neo-Hookean-Wriggers (Neo-Hookean.c:89-141).  Single slab. */
+ * step halving.  Tangents: Neo-Hookean-Wriggers (Neo-Hookean.c:89-141; symmetric, Jacobi-PCG) and the spectral
+ * elastoplastic tangent of Drucker-Prager / Matsuoka-Nakai (Elastoplastic-Tangent-Matrix.c:42-160; unsymmetric,
+ * Jacobi-BiCGStab).  Slab engines (nlps_b200_create_slab) run the Neo-Hookean operator over several GPUs: every slab
+ * assembles the tangent of its own particles, the Krylov vectors are summed over the halo-band nodes each iteration
+ * and the dot products over the slabs; the elastoplastic tangents are single-slab. */
 typedef struct nlps_newmark {
   double beta, gamma;      /* Time_Int_Params.beta_Newmark_beta / gamma_Newmark_beta */
   double tol;              /* TOL_Newmark_beta: rtol; atol = 100 * tol (U-Newmark-beta.c:171-172) */
