@@ -56,7 +56,7 @@ struct CwLayout {
     Carve k;
     const size_t SL = c.SL;
     const bool lme = kernel == CW_LME_P2G, fused = kernel == CW_KIN_FUSED, force = kernel == CW_FORCE;
-    const bool wantQ = lme || fused || force;
+    const bool wantQ = false;  // ranks and transposed-ring positions were the addresses of the slot-major cell sums
     const bool wantU = fused || kernel == CW_KIN_GATHER || kernel == CW_G2P;
     mrec = k.take(16 * 4);                    // ring of 4 cell records (int4)
     um = k.take(4 * MAX_MASK_WORDS);          // union of the neighbour masks of the cell's particles
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const Part
       cw_prefetch_rows(P.mass, ld, 1, tn, P.np, lane);
       cw_prefetch_rows(P.sstar, ld, 1, tn, P.np, lane);
     }
-    cw_stage<true, 0, true, false>(m, G, SL, c, T, lane);
+    cw_stage<false, 0, true, false>(m, G, SL, c, T, lane);  // (no ranks / ring positions: the cell sums are stored cell-major)
     __syncwarp();
     cw_pipe_next(m, G, T, ic, u, nwarps, nocc, lane);
     for (int tb = c.t0; tb < c.t1; tb += PPW) {
@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const Part
       // ---- cell sums: lane k sums column k of the weight table over the particles of the chunk
       const int cnt = min(PPW, c.t1 - tb);
       const bool first = tb == c.t0;
-      for (int k = lane; k < SL; k += 32) {
-        const int rank = T.rank[k];
+      // (cell-major partial sums: the records of a cell are one contiguous run, lane k writes record k)
+      for (int k = lane; k < c.len; k += 32) {
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         for (int jq = 0; jq < cnt; jq++) {
           const double w = T.wd[(size_t)jq * WS + k];
@@ -534,8 +534,8 @@ __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const Part
           const double2 q23 = *reinterpret_cast<const double2*>(T.pv + jq * 4 + 2);
           a0 += w * q01.x; a1 += w * q01.y; a2 += w * q23.x; a3 += w * q23.y;
         }
-        if (rank >= 0) {
-          double* dst = G.part + ((size_t)T.q[k] * G.max_act + rank) * NV;
+        {
+          double* dst = G.part + ((size_t)u * G.cm_sl + k) * NV;
           if (!first) {  // cells with more than 8 particles: add to what the earlier chunks wrote
             const double2 o01 = *reinterpret_cast<const double2*>(dst), o23 = *reinterpret_cast<const double2*>(dst + 2);
             a0 += o01.x; a1 += o01.y; a2 += o23.x; a3 += o23.y;
@@ -543,6 +543,10 @@ __global__ void __launch_bounds__(128, 4) cw_lme_p2g(const MeshDev m, const Part
           *reinterpret_cast<double2*>(dst) = make_double2(a0, a1);
           *reinterpret_cast<double2*>(dst + 2) = make_double2(a2, a3);
         }
+        // which records of the cell are non-zero (a slot is some particle's neighbour <=> its mass sum is positive): the
+        // node kernels skip the others
+        const uint32_t nz = __ballot_sync(__activemask(), a0 != 0.0);
+        if ((k & 31) == 0) G.cum[(size_t)u * G.cm_w + (k >> 5)] = nz;
       }
       __syncwarp();
       // the table returns to zero: every lane clears the entries it wrote
@@ -711,7 +715,7 @@ __global__ void __launch_bounds__(128, MODE == CW_KIN_FUSED ? 3 : 4) cw_kin(cons
       if (lane >= 16 && lane < 16 + cfg.W) prefetch_l2(&P.mask[(size_t)(lane - 16) * ld + tn]);  // the union of the masks opens the next cell
     }
     cw_union(P, G, c, cfg.W, T, lane);
-    cw_stage<SCATTER, GATHER ? 1 : 0, false, true>(m, G, SL, c, T, lane);
+    cw_stage<false, GATHER ? 1 : 0, false, true>(m, G, SL, c, T, lane);
     if (SCATTER)
       for (int e = lane; e < SL * D; e += 32) T.acc[e] = 0.0;
     __syncwarp();
@@ -870,12 +874,11 @@ __global__ void __launch_bounds__(128, MODE == CW_KIN_FUSED ? 3 : 4) cw_kin(cons
       }
     }
     if (SCATTER) {
-      for (int k = lane; k < SL; k += 32) {
-        const int rank = T.rank[k];
-        if (rank < 0) continue;
-        double* dst = G.part + ((size_t)T.q[k] * G.max_act + rank) * D;
-#pragma unroll
-        for (int v = 0; v < D; v++) dst[v] = T.acc[v * SL + k];
+      // cell-major partial sums: 32-byte records, the cell's run is contiguous (see GridDev::part)
+      for (int k = lane; k < c.len; k += 32) {
+        double* dst = G.part + ((size_t)u * G.cm_sl + k) * 4;
+        *reinterpret_cast<double2*>(dst) = make_double2(T.acc[k], T.acc[SL + k]);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(T.acc[2 * SL + k], 0.0);
       }
     }
     cw_pipe_wait();

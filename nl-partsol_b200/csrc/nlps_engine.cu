@@ -937,6 +937,11 @@ struct BcDev {
   int maxdim, nsteps, nb;
 };
 
+__global__ void k_build_r2ts(int nn, const int* r2p, const int* r2i, const unsigned char* r2q, const int* r2tp, unsigned char* r2ts) {
+  const int B = blockIdx.x * blockDim.x + threadIdx.x;
+  if (B >= nn) return;
+  for (int q = r2p[B]; q < r2p[B + 1]; q++) r2ts[r2tp[r2i[q]] + r2q[q]] = (unsigned char)(q - r2p[B]);
+}
 __global__ void k_set_flags(const int* ids, int n, unsigned char* flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[ids[i]] = 1;
@@ -946,10 +951,35 @@ __global__ void k_set_flags(const int* ids, int n, unsigned char* flags) {
 // nodes, or (band lists given) over the nodes of the halo bands only.  MODE 3 (slabs): MODE 0 for the nodes outside
 // the halo bands, MODE 1 for the band nodes, which MODE 2 finishes after the exchange: the second pass touches a few
 // thousand nodes instead of all of them.
-template <int D, int MODE>
+// Cell-major partial sums (G.cm_sl > 0, 3D): NV doubles of every non-zero record (cell, slot of node A) over the occupied
+// cells of A's transposed 2-ring, a WARP per node: the lanes take the ring positions q, q + 32, ..., every lane has its
+// (scattered, 32-byte) record loads in flight at once, and the lane sums meet in a fixed butterfly (deterministic).
+template <int NV>
+__device__ __forceinline__ void node_sums_cm(const MeshDev& m, const GridDev& G, int A, int t, int lane, double* out) {
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
+  for (int q = lane; q < nq; q += 32) {
+    const uint32_t occ = G.occm[(size_t)(q >> 5) * G.max_act + t];
+    if (!((occ >> (q & 31)) & 1u)) continue;
+    const int u = G.occ_pos[m.r2ti[q0 + q]], s_ = m.r2ts[q0 + q];
+    if (!((G.cum[(size_t)u * G.cm_w + (s_ >> 5)] >> (s_ & 31)) & 1u)) continue;  // the record is zero: not a neighbour of any particle
+    const double* src = G.part + ((size_t)u * G.cm_sl + s_) * 4;
+    const double2 v01 = *reinterpret_cast<const double2*>(src), v23 = *reinterpret_cast<const double2*>(src + 2);
+    a[0] += v01.x; a[1] += v01.y; a[2] += v23.x; a[3] += v23.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int i = 0; i < NV; i++) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+#pragma unroll
+  for (int i = 0; i < NV; i++) out[i] = a[i];
+}
+
+template <int D, int MODE, int LPN = 1>  // LPN: lanes per node (32 with the cell-major partial sums)
 __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev bc, int step, const int* ids0 = nullptr,
                                                    int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) / LPN;
+  const int lane = threadIdx.x % LPN;
   int A;
   if (MODE == 2 && (ids0 || ids1)) {
     if (t >= n0 + n1) return;
@@ -967,7 +997,17 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
 #pragma unroll
     for (int i = 0; i < D; i++) mom[i] = G.MOM[(size_t)A * D + i];
   }
-  for (int w = 0; MODE != 2 && w < G.w2t; w++) {
+  if (LPN == 32) {
+    if (MODE != 2) {
+      double sums[4];
+      node_sums_cm<1 + D>(m, G, A, t, lane, sums);
+      M = sums[0];
+#pragma unroll
+      for (int i = 0; i < D; i++) mom[i] = sums[1 + i];
+    }
+    if (lane != 0) return;
+  }
+  for (int w = 0; LPN == 1 && MODE != 2 && w < G.w2t; w++) {
     uint32_t mm = G.occm[(size_t)w * G.max_act + t];
     while (mm) {
       const int q = w * 32 + __ffs(mm) - 1;
@@ -1320,10 +1360,11 @@ __global__ void k_traction(PartDev P, NeuDev nu, double thickness, int step) {
 
 // K3 stage 2 + G2 (node kernel): f_A = sum of cell partials; a_A = g + f_A / M_A on free DOFs, 0 on
 // restricted ones (U-Verlet.c:947-958; gravity as U-Newmark-beta.c:1539-1543).
-template <int D, int MODE>  // MODE as in k_grid_disp
+template <int D, int MODE, int LPN = 1>  // MODE, LPN as in k_grid_disp
 __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const double* grav, int nsteps, int step,
                                                   const int* ids0 = nullptr, int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int t = (blockIdx.x * blockDim.x + threadIdx.x) / LPN;
+  const int lane = threadIdx.x % LPN;
   int A;
   if (MODE == 2 && (ids0 || ids1)) {
     if (t >= n0 + n1) return;
@@ -1336,7 +1377,16 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
   double f[D];
 #pragma unroll
   for (int i = 0; i < D; i++) f[i] = (MODE == 2) ? G.F[(size_t)A * D + i] : 0.0;
-  for (int w = 0; MODE != 2 && w < G.w2t; w++) {
+  if (LPN == 32) {
+    if (MODE != 2) {
+      double sums[4];
+      node_sums_cm<D>(m, G, A, t, lane, sums);
+#pragma unroll
+      for (int i = 0; i < D; i++) f[i] = sums[i];
+    }
+    if (lane != 0) return;
+  }
+  for (int w = 0; LPN == 1 && MODE != 2 && w < G.w2t; w++) {
     uint32_t mm = G.occm[(size_t)w * G.max_act + t];
     while (mm) {
       const int q = w * 32 + __ffs(mm) - 1;
@@ -2632,16 +2682,40 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
 #undef CASE_W
 #undef CASE_WC
 }
+// node kernels: a thread per node with the slot-major partial sums, a warp per node with the cell-major ones (3D)
+template <int D, int MODE>
+static void launch_grid_disp(nlps_engine* e, int step, const int* ids0 = nullptr, int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
+  const bool band = MODE == 2 && (ids0 || ids1);
+  if (e->G.cm_sl && MODE != 2) {
+    auto kf = k_grid_disp<D, MODE, 32>;
+    LAUNCH(e, K_GRID_DISP, kf, nblk((size_t)e->max_act * 32, 128), 128, e->mesh, e->G, e->bc, step, ids0, n0, ids1, n1);
+  } else {
+    auto kf = k_grid_disp<D, MODE, 1>;
+    LAUNCH(e, K_GRID_DISP, kf, nblk(band ? n0 + n1 : e->max_act, 128), 128, e->mesh, e->G, e->bc, step, ids0, n0, ids1, n1);
+  }
+}
+template <int D, int MODE>
+static void launch_grid_acc(nlps_engine* e, int step, const int* ids0 = nullptr, int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
+  const bool band = MODE == 2 && (ids0 || ids1);
+  if (e->G.cm_sl && MODE != 2) {
+    auto kf = k_grid_acc<D, MODE, 32>;
+    LAUNCH(e, K_GRID_ACC, kf, nblk((size_t)e->max_act * 32, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, ids0, n0, ids1, n1);
+  } else {
+    auto kf = k_grid_acc<D, MODE, 1>;
+    LAUNCH(e, K_GRID_ACC, kf, nblk(band ? n0 + n1 : e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, ids0, n0, ids1, n1);
+  }
+}
+
 template <int D>
 static void stage_p2g_mass_disp_t(nlps_engine* e, int step) {
   if (!e->slab_on) {
-    { auto kf = k_grid_disp<D, 0>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step, nullptr, 0, nullptr, 0); }
+    launch_grid_disp<D, 0>(e, step);
   } else {
     // everything outside the halo bands is finished in the first pass; the band nodes after the exchange
     const int n0 = e->side[0].peer >= 0 ? e->side[0].n : 0, n1 = e->side[1].peer >= 0 ? e->side[1].n : 0;
-    { auto kf = k_grid_disp<D, 3>; LAUNCH(e, K_GRID_DISP, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->bc, step, nullptr, 0, nullptr, 0); }
+    launch_grid_disp<D, 3>(e, step);
     halo_exchange<D>(e, 1);
-    if (n0 + n1 > 0) { auto kf = k_grid_disp<D, 2>; LAUNCH(e, K_GRID_DISP, kf, nblk(n0 + n1, 128), 128, e->mesh, e->G, e->bc, step, e->side[0].ids, n0, e->side[1].ids, n1); }
+    if (n0 + n1 > 0) launch_grid_disp<D, 2>(e, step, e->side[0].ids, n0, e->side[1].ids, n1);
   }
 }
 template <int D>
@@ -2676,12 +2750,12 @@ static void stage_kin_stress_t(nlps_engine* e, int step) {
 template <int D>
 static void stage_force_t(nlps_engine* e, int step) {
   if (!e->slab_on) {
-    { auto kf = k_grid_acc<D, 0>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, nullptr, 0, nullptr, 0); }
+    launch_grid_acc<D, 0>(e, step);
   } else {
     const int n0 = e->side[0].peer >= 0 ? e->side[0].n : 0, n1 = e->side[1].peer >= 0 ? e->side[1].n : 0;
-    { auto kf = k_grid_acc<D, 3>; LAUNCH(e, K_GRID_ACC, kf, nblk(e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, nullptr, 0, nullptr, 0); }
+    launch_grid_acc<D, 3>(e, step);
     halo_exchange<D>(e, 2);
-    if (n0 + n1 > 0) { auto kf = k_grid_acc<D, 2>; LAUNCH(e, K_GRID_ACC, kf, nblk(n0 + n1, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, e->side[0].ids, n0, e->side[1].ids, n1); }
+    if (n0 + n1 > 0) launch_grid_acc<D, 2>(e, step, e->side[0].ids, n0, e->side[1].ids, n1);
   }
 }
 template <int D>
@@ -2909,6 +2983,12 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   if (dev_alloc(e, &dsst, (size_t)nn)) return 1;
   if (nn) k_sstar_nodes<<<nblk(nn, 256), 256, 0, e->stream>>>(dh, nn, solver->gamma_lme, e->neg_log_tol, dsst);
   e->mesh = MeshDev{nn, dX, r1p, r1i, r2p, r2i, t1p, t1i, t2p, t2i, dq, dh, dsst};
+  {  // inverse of r2q: the slot a node holds in the 2-ring of each cell that lists it (cell-major partial sums)
+    unsigned char* r2ts = nullptr;
+    if (dev_alloc(e, &r2ts, (size_t)std::max(mesh->ring2_ptr[nn], 1))) return 1;
+    k_build_r2ts<<<nblk(nn, 256), 256, 0, e->stream>>>(nn, r2p, r2i, dq, t2p, r2ts);
+    e->mesh.r2ts = r2ts;
+  }
   mark("transposed adjacency upload");
   e->max_occ = (int)std::min<long long>(nn, std::max(ld, 1));
   e->max_act = (int)std::min<long long>(nn, (long long)std::max(ld, 1) * maxr1);
@@ -2929,7 +3009,8 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   G.cap = maxr2t;
   G.max_act = e->max_act;
   G.w2t = (maxr2t + 31) / 32;
-  if (dev_alloc(e, &G.part, (size_t)e->max_act * G.cap * (1 + D))) return 1;
+  // (sized for both layouts of the partial sums: slot-major max_act x cap x (1 + D), cell-major max_occ x maxr2 x 4)
+  if (dev_alloc(e, &G.part, std::max((size_t)e->max_act * G.cap * (1 + D), (size_t)e->max_occ * maxr2 * 4))) return 1;
   if (dev_alloc(e, &G.occm, (size_t)e->max_act * G.w2t)) return 1;
   // ---- cell-block kernel configuration: cells per block, shared-memory budget
   {
@@ -3000,6 +3081,9 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
       if (const char* s_ = getenv("NLPS_KERNELS")) e->kver = (atoi(s_) == 1 || D != 3) ? 1 : 2;
       if (const char* s_ = getenv("NLPS_SPLIT_NH")) e->split_nh = atoi(s_) != 0;
       if (maxr2 > 256) e->kver = 1;  // slot ids of the compact lists are bytes
+      e->G.cm_sl = (e->kver == 2) ? w.SL : 0;
+      e->G.cm_w = w.W;
+      if (e->G.cm_sl && dev_alloc(e, &e->G.cum, (size_t)(e->max_occ + 1) * w.W)) return 1;
     }
     if (const char* s_ = getenv("NLPS_REORDER_EVERY")) e->reorder_every = atoi(s_);
     CUDA_OK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));

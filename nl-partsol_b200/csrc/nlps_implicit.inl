@@ -1015,11 +1015,11 @@ static int imp_begin_t(nlps_engine* e, int step) {
   GridDev& G = e->G;
   const int nb128 = nblk(e->max_act, 128);
   stage_search_t<D>(e, step, 1, 0, e->P.vel, 0);
-  { auto kf = k_grid_disp<D, 1>; LAUNCH(e, K_GRID_DISP, kf, nb128, 128, e->mesh, G, e->bc, step, nullptr, 0, nullptr, 0); }
+  launch_grid_disp<D, 1>(e, step);
   halo_exchange<D>(e, 1);  // (several slabs: band sums of mass and momentum, as in the explicit scheme)
   k_imp_nodal<D><<<nb128, 128, 0, e->stream>>>(G, e->bc, step, 1, c->Vn, c->fx);
   stage_search_t<D>(e, step, 1, 0, e->P.acc, 1);
-  { auto kf = k_grid_disp<D, 1>; LAUNCH(e, K_GRID_DISP, kf, nb128, 128, e->mesh, G, e->bc, step, nullptr, 0, nullptr, 0); }
+  launch_grid_disp<D, 1>(e, step);
   halo_exchange<D>(e, 1);
   k_imp_nodal<D><<<nb128, 128, 0, e->stream>>>(G, e->bc, step, 0, c->An, c->fx);
   if (e->slab_on) k_imp_own<D><<<nb128, 128, 0, e->stream>>>(e->mesh, G, slab_dev(e), c->own);
@@ -1048,7 +1048,7 @@ static void imp_residual_t(nlps_engine* e, int step, const double* dU, double* R
   e->implicit_on = 1;
   stage_kin_stress_t<D>(e, step);
   e->implicit_on = 0;
-  { auto kf = k_grid_acc<D, 1>; LAUNCH(e, K_GRID_ACC, kf, nb128, 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, nullptr, 0, nullptr, 0); }
+  launch_grid_acc<D, 1>(e, step);
   halo_exchange<D>(e, 2);  // (several slabs: band sums of the internal forces)
   k_imp_residual<D><<<IMP_NPART, 256, 0, e->stream>>>(e->G, e->grav, e->solver.num_steps, step, c->a1, c->a2, c->a3, dU, c->Vn, c->An,
                                                      c->fx, R, c->part + (size_t)part_slot * IMP_NPART, c->own);

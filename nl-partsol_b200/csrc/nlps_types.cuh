@@ -42,6 +42,7 @@ struct MeshDev {
   const unsigned char* r2q;              // r2q[r2p[B]+s] = position of B inside the r2t row of node r2i[r2p[B]+s]
   const double* h_avg;
   const double* sst;  // per node: s* of beta = gamma / h_avg^2 (what a particle of that cell tests its neighbours with next step)
+  const unsigned char* r2ts;  // r2ts[r2tp[A]+q] = slot of node A inside the 2-ring of the cell r2ti[r2tp[A]+q] (inverse of r2q)
 };
 
 struct PartDev {
@@ -84,8 +85,14 @@ struct GridDev {
   // previous step) / must be processed by the node kernels this step (= dirty now or last step: leaving blocks are
   // visited once more so that their flags return to zero)
   unsigned char *occ_blk, *dirty_cur, *dirty_prev, *live;
-  double* part;     // slot-major cell partial sums: part[(q * max_act + rank) * NV + v]
+  double* part;     // cell partial sums.  Slot-major (2D kernels): part[(q * max_act + rank) * NV + v], coalesced for the node
+                    // kernels that read it.  Cell-major (3D warp-per-cell kernels, cm_sl > 0): part[(cell rank * cm_sl + slot) * 4 + v]:
+                    // a cell's sums leave the SM as ONE contiguous run -- the scattered 8-byte stores of the slot-major layout
+                    // were a third of cw_kin (profiles/ab/r02_probe_phases.txt); the node kernels gather 32-byte records instead
   int cap, max_act, w2t;
+  int cm_sl;        // 0: slot-major part[]; > 0: cell-major with this many slots per cell
+  uint32_t* cum;    // cell-major: per occupied cell, the slots that carry a non-zero record (cm_w words per cell)
+  int cm_w;
 };
 
 struct StepParams {

@@ -1,7 +1,10 @@
 #!/bin/bash
-# round 2, GPU session 17 (1 GPU): timing probe -- the 3D kernels without the exponential / without the X loads
-# (profiles/ab/libprobe.so is built from a patched copy of nlps_cellwarp.cu: `fexp_poly` and the T.X loads of cw_kin / cw_g2p
-# switchable at run time; the product library is untouched)
+# round 2, GPU session 17 (1 GPU): timing probes of the 3D kernels (profiles/ab/libprobe.so, built from a patched copy of
+# nlps_cellwarp.cu -- profiles/ab/r02_probe*.patch; the product library is untouched)
 cd "$(dirname "$0")/../.."
 O=gpurun_out/r02_s17; mkdir -p $O
-NLPS_LIB=$PWD/profiles/ab/libprobe.so timeout 600 python profiles/ab/probe_exp.py 64 > $O/probe.json 2> $O/probe.err; echo "rc=$?"; cat $O/probe.json; tail -3 $O/probe.err
+: > $O/probe_phases.txt
+for pr in 0 4 8 16 32 96 128 12 28 60 224; do
+  NLPS_LIB=$PWD/profiles/ab/libprobe.so timeout 120 python profiles/ab/probe_phases.py 64 $pr >> $O/probe_phases.txt 2>> $O/probe_phases.err
+done
+cat $O/probe_phases.txt
