@@ -212,6 +212,12 @@ __device__ __forceinline__ void cw_stage(const MeshDev& m, const GridDev& G, int
     }
   }
 }
+// The same union, as the LME kernel of this step left it: the slots of the cell that carry a non-zero mass sum
+// (G.cum, one coalesced load instead of the particle-id and mask round trips of cw_union).
+__device__ __forceinline__ void cw_union_cum(const GridDev& G, int u, int W, const WarpTile& T, int lane) {
+  if (lane < MAX_MASK_WORDS) T.um[lane] = lane < W ? G.cum[(size_t)u * G.cm_w + lane] : 0u;
+  __syncwarp();
+}
 // union of the neighbour masks of the cell's particles -> T.um
 __device__ __forceinline__ void cw_union(const PartDev& P, const GridDev& G, const Cell& c, int W, const WarpTile& T, int lane) {
   if (lane < MAX_MASK_WORDS) T.um[lane] = 0u;
@@ -714,7 +720,7 @@ __global__ void __launch_bounds__(128, MODE == CW_KIN_FUSED ? 3 : 4) cw_kin(cons
       if (lane < PPW && tn + lane < P.np) prefetch_l2(P.clist + (size_t)(tn + lane) * CL);
       if (lane >= 16 && lane < 16 + cfg.W) prefetch_l2(&P.mask[(size_t)(lane - 16) * ld + tn]);  // the union of the masks opens the next cell
     }
-    cw_union(P, G, c, cfg.W, T, lane);
+    cw_union_cum(G, u, cfg.W, T, lane);
     cw_stage<false, GATHER ? 1 : 0, false, true>(m, G, SL, c, T, lane);
     if (SCATTER)
       for (int e = lane; e < SL * D; e += 32) T.acc[e] = 0.0;
@@ -914,7 +920,7 @@ __global__ void __launch_bounds__(128, 4) cw_g2p(const MeshDev m, const PartDev 
       if (lane < PPW && tn + lane < P.np) prefetch_l2(P.clist + (size_t)(tn + lane) * CL);
       if (lane >= 16 && lane < 16 + cfg.W) prefetch_l2(&P.mask[(size_t)(lane - 16) * ld + tn]);  // the union of the masks opens the next cell
     }
-    cw_union(P, G, c, cfg.W, T, lane);
+    cw_union_cum(G, u, cfg.W, T, lane);
     cw_stage<false, 2, false, true>(m, G, SL, c, T, lane);
     __syncwarp();
     cw_pipe_next(m, G, T, ic, u, nwarps, nocc, lane);

@@ -958,14 +958,33 @@ template <int NV>
 __device__ __forceinline__ void node_sums_cm(const MeshDev& m, const GridDev& G, int A, int t, int lane, double* out) {
   double a[4] = {0.0, 0.0, 0.0, 0.0};
   const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
-  for (int q = lane; q < nq; q += 32) {
-    const uint32_t occ = G.occm[(size_t)(q >> 5) * G.max_act + t];
-    if (!((occ >> (q & 31)) & 1u)) continue;
-    const int u = G.occ_pos[m.r2ti[q0 + q]], s_ = m.r2ts[q0 + q];
-    if (!((G.cum[(size_t)u * G.cm_w + (s_ >> 5)] >> (s_ & 31)) & 1u)) continue;  // the record is zero: not a neighbour of any particle
-    const double* src = G.part + ((size_t)u * G.cm_sl + s_) * 4;
-    const double2 v01 = *reinterpret_cast<const double2*>(src), v23 = *reinterpret_cast<const double2*>(src + 2);
-    a[0] += v01.x; a[1] += v01.y; a[2] += v23.x; a[3] += v23.y;
+  // the dependent chain ring position -> cell -> (rank of the cell, non-zero mask) -> record is walked level by level
+  // for four ring positions of the lane at once: the loads of a level are independent and in flight together
+  constexpr int R = 4;
+  for (int qb = 0; qb < nq; qb += 32 * R) {
+    int B[R], sl[R], u[R];
+    bool on[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int q = qb + 32 * r + lane;
+      on[r] = q < nq && ((G.occm[(size_t)(q >> 5) * G.max_act + t] >> (q & 31)) & 1u);
+      B[r] = on[r] ? m.r2ti[q0 + q] : 0;
+      sl[r] = on[r] ? (int)m.r2ts[q0 + q] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) u[r] = on[r] ? G.occ_pos[B[r]] : 0;
+#pragma unroll
+    for (int r = 0; r < R; r++)  // a zero record (the slot is no particle's neighbour) is skipped
+      on[r] = on[r] && ((G.cum[(size_t)u[r] * G.cm_w + (sl[r] >> 5)] >> (sl[r] & 31)) & 1u);
+    double2 v01[R], v23[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const double* src = G.part + ((size_t)u[r] * G.cm_sl + sl[r]) * 4;
+      v01[r] = on[r] ? *reinterpret_cast<const double2*>(src) : make_double2(0.0, 0.0);
+      v23[r] = on[r] ? *reinterpret_cast<const double2*>(src + 2) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) { a[0] += v01[r].x; a[1] += v01[r].y; a[2] += v23[r].x; a[3] += v23[r].y; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
