@@ -431,7 +431,7 @@ __device__ __forceinline__ void stage_nodes(const MeshDev& m, const GridDev& G, 
       rank[u] = G.arank[nd];
       x0[u] = *reinterpret_cast<const double2*>(px);
       if (D == 3) x1[u] = *reinterpret_cast<const double2*>(px + 2);
-      if (WANT_Q) qv[u] = m.r2q[idx[u]];
+      if (WANT_Q) qv[u] = G.cm_sl ? m.r2pos[idx[u]] : m.r2q[idx[u]];  // cell-major sums: position in the cell's run
       if (NF >= 1) {
         u0[u] = *reinterpret_cast<const double2*>(pu);
         if (D == 3) u1[u] = *reinterpret_cast<const double2*>(pu + 2);
@@ -528,7 +528,7 @@ __device__ __forceinline__ void stage_nodes_ids(const MeshDev& m, const GridDev&
         qv[u] = 0;
         if (ids[b0 + u] >= 0) {
           const int c = (int)(((unsigned)e * cfg.magic) >> 21), k = e - c * SL;
-          qv[u] = m.r2q[s.base[c] + k];
+          qv[u] = G.cm_sl ? m.r2pos[s.base[c] + k] : m.r2q[s.base[c] + k];
         }
       }
       if (NF >= 1) {
@@ -910,7 +910,9 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
           for (int i = 0; i < D; i++) a[i] += mN * s_ddis[j * D + i];
         }
       }
-      double* dst = G.part + ((size_t)s_q[e] * G.max_act + rank) * (1 + D);
+      // (cell-major: slot-fastest pairs write consecutive 32-byte records of the cell's run; GridDev::part)
+      double* dst = G.cm_sl ? G.part + ((size_t)(grp * cfg.C + c) * G.cm_sl + s_q[e]) * 4
+                            : G.part + ((size_t)s_q[e] * G.max_act + rank) * (1 + D);
       if (first) {
         dst[0] = a0;
 #pragma unroll
@@ -937,10 +939,21 @@ struct BcDev {
   int maxdim, nsteps, nb;
 };
 
-__global__ void k_build_r2ts(int nn, const int* r2p, const int* r2i, const unsigned char* r2q, const int* r2tp, unsigned char* r2ts) {
+__global__ void k_build_r2ts(int nn, const int* r2p, const int* r2i, const unsigned char* r2q, const int* r2tp, unsigned char* r2ts,
+                             unsigned char* r2pos, int sorted) {
   const int B = blockIdx.x * blockDim.x + threadIdx.x;
   if (B >= nn) return;
-  for (int q = r2p[B]; q < r2p[B + 1]; q++) r2ts[r2tp[r2i[q]] + r2q[q]] = (unsigned char)(q - r2p[B]);
+  const int b0 = r2p[B], len = r2p[B + 1] - b0;
+  for (int s_ = 0; s_ < len; s_++) {
+    const int A = r2i[b0 + s_];
+    int pos = s_;
+    if (sorted) {  // rank of A among the node ids of the ring (ids are distinct)
+      pos = 0;
+      for (int k = 0; k < len; k++) pos += r2i[b0 + k] < A;
+    }
+    r2ts[r2tp[A] + r2q[b0 + s_]] = (unsigned char)pos;
+    r2pos[b0 + s_] = (unsigned char)pos;
+  }
 }
 __global__ void k_set_flags(const int* ids, int n, unsigned char* flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -954,19 +967,19 @@ __global__ void k_set_flags(const int* ids, int n, unsigned char* flags) {
 // Cell-major partial sums (G.cm_sl > 0, 3D): NV doubles of every non-zero record (cell, slot of node A) over the occupied
 // cells of A's transposed 2-ring, a WARP per node: the lanes take the ring positions q, q + 32, ..., every lane has its
 // (scattered, 32-byte) record loads in flight at once, and the lane sums meet in a fixed butterfly (deterministic).
-template <int NV>
+template <int NV, int LPN>
 __device__ __forceinline__ void node_sums_cm(const MeshDev& m, const GridDev& G, int A, int t, int lane, double* out) {
   double a[4] = {0.0, 0.0, 0.0, 0.0};
   const int q0 = m.r2tp[A], nq = m.r2tp[A + 1] - q0;
   // the dependent chain ring position -> cell -> (rank of the cell, non-zero mask) -> record is walked level by level
   // for four ring positions of the lane at once: the loads of a level are independent and in flight together
   constexpr int R = 4;
-  for (int qb = 0; qb < nq; qb += 32 * R) {
+  for (int qb = 0; qb < nq; qb += LPN * R) {
     int B[R], sl[R], u[R];
     bool on[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      const int q = qb + 32 * r + lane;
+      const int q = qb + LPN * r + lane;
       on[r] = q < nq && ((G.occm[(size_t)(q >> 5) * G.max_act + t] >> (q & 31)) & 1u);
       B[r] = on[r] ? m.r2ti[q0 + q] : 0;
       sl[r] = on[r] ? (int)m.r2ts[q0 + q] : 0;
@@ -975,7 +988,7 @@ __device__ __forceinline__ void node_sums_cm(const MeshDev& m, const GridDev& G,
     for (int r = 0; r < R; r++) u[r] = on[r] ? G.occ_pos[B[r]] : 0;
 #pragma unroll
     for (int r = 0; r < R; r++)  // a zero record (the slot is no particle's neighbour) is skipped
-      on[r] = on[r] && ((G.cum[(size_t)u[r] * G.cm_w + (sl[r] >> 5)] >> (sl[r] & 31)) & 1u);
+      on[r] = on[r] && (!G.cum || ((G.cum[(size_t)u[r] * G.cm_w + (sl[r] >> 5)] >> (sl[r] & 31)) & 1u));
     double2 v01[R], v23[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -987,25 +1000,31 @@ __device__ __forceinline__ void node_sums_cm(const MeshDev& m, const GridDev& G,
     for (int r = 0; r < R; r++) { a[0] += v01[r].x; a[1] += v01[r].y; a[2] += v23[r].x; a[3] += v23[r].y; }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
+  for (int o = LPN / 2; o > 0; o >>= 1)  // (the lanes of a node are LPN consecutive lanes of the warp)
 #pragma unroll
     for (int i = 0; i < NV; i++) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
 #pragma unroll
   for (int i = 0; i < NV; i++) out[i] = a[i];
 }
 
-template <int D, int MODE, int LPN = 1>  // LPN: lanes per node (32 with the cell-major partial sums)
+template <int D, int MODE, int LPN = 1>  // LPN: lanes per node (cell-major partial sums: 32 in 3D, 8 in 2D; 1 = slot-major)
 __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev bc, int step, const int* ids0 = nullptr,
                                                    int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
   int t = (blockIdx.x * blockDim.x + threadIdx.x) / LPN;
   const int lane = threadIdx.x % LPN;
   int A;
+  bool live = true;
   if (MODE == 2 && (ids0 || ids1)) {
     if (t >= n0 + n1) return;
     A = t < n0 ? ids0[t] : ids1[t - n0];
     if (!G.active[A]) return;
   } else {
-    if (t >= *G.n_active) return;
+    const int na = *G.n_active;
+    if (LPN == 1 ? t >= na : na == 0) return;
+    // several nodes per warp (LPN < 32): the lanes of a node past the end keep running on node 0 (the shuffles below
+    // are warp-wide) and drop out after the sums
+    live = t < na;
+    if (!live) t = 0;
     A = G.act_list[t];
   }
   double mom[D], M = 0.0;
@@ -1016,15 +1035,15 @@ __global__ void __launch_bounds__(128) k_grid_disp(MeshDev m, GridDev G, BcDev b
 #pragma unroll
     for (int i = 0; i < D; i++) mom[i] = G.MOM[(size_t)A * D + i];
   }
-  if (LPN == 32) {
+  if (LPN > 1) {
     if (MODE != 2) {
       double sums[4];
-      node_sums_cm<1 + D>(m, G, A, t, lane, sums);
+      node_sums_cm<1 + D, LPN>(m, G, A, t, lane, sums);
       M = sums[0];
 #pragma unroll
       for (int i = 0; i < D; i++) mom[i] = sums[1 + i];
     }
-    if (lane != 0) return;
+    if (lane != 0 || !live) return;
   }
   for (int w = 0; LPN == 1 && MODE != 2 && w < G.w2t; w++) {
     uint32_t mm = G.occm[(size_t)w * G.max_act + t];
@@ -1337,7 +1356,8 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
           f[i] += N * gl;
         }
       }
-      double* dst = G.part + ((size_t)s_q[e] * G.max_act + rank) * D;
+      double* dst = G.cm_sl ? G.part + ((size_t)(grp * cfg.C + c) * G.cm_sl + s_q[e]) * 4
+                            : G.part + ((size_t)s_q[e] * G.max_act + rank) * D;
       if (first) {
 #pragma unroll
         for (int i = 0; i < D; i++) dst[i] = f[i];
@@ -1385,25 +1405,31 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
   int t = (blockIdx.x * blockDim.x + threadIdx.x) / LPN;
   const int lane = threadIdx.x % LPN;
   int A;
+  bool live = true;
   if (MODE == 2 && (ids0 || ids1)) {
     if (t >= n0 + n1) return;
     A = t < n0 ? ids0[t] : ids1[t - n0];
     if (!G.active[A]) return;
   } else {
-    if (t >= *G.n_active) return;
+    const int na = *G.n_active;
+    if (LPN == 1 ? t >= na : na == 0) return;
+    // several nodes per warp (LPN < 32): the lanes of a node past the end keep running on node 0 (the shuffles below
+    // are warp-wide) and drop out after the sums
+    live = t < na;
+    if (!live) t = 0;
     A = G.act_list[t];
   }
   double f[D];
 #pragma unroll
   for (int i = 0; i < D; i++) f[i] = (MODE == 2) ? G.F[(size_t)A * D + i] : 0.0;
-  if (LPN == 32) {
+  if (LPN > 1) {
     if (MODE != 2) {
       double sums[4];
-      node_sums_cm<D>(m, G, A, t, lane, sums);
+      node_sums_cm<D, LPN>(m, G, A, t, lane, sums);
 #pragma unroll
       for (int i = 0; i < D; i++) f[i] = sums[i];
     }
-    if (lane != 0) return;
+    if (lane != 0 || !live) return;
   }
   for (int w = 0; LPN == 1 && MODE != 2 && w < G.w2t; w++) {
     uint32_t mm = G.occm[(size_t)w * G.max_act + t];
@@ -2706,8 +2732,9 @@ template <int D, int MODE>
 static void launch_grid_disp(nlps_engine* e, int step, const int* ids0 = nullptr, int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
   const bool band = MODE == 2 && (ids0 || ids1);
   if (e->G.cm_sl && MODE != 2) {
-    auto kf = k_grid_disp<D, MODE, 32>;
-    LAUNCH(e, K_GRID_DISP, kf, nblk((size_t)e->max_act * 32, 128), 128, e->mesh, e->G, e->bc, step, ids0, n0, ids1, n1);
+    constexpr int LPN = (D == 3) ? 32 : 8;
+    auto kf = k_grid_disp<D, MODE, LPN>;
+    LAUNCH(e, K_GRID_DISP, kf, nblk((size_t)e->max_act * LPN, 128), 128, e->mesh, e->G, e->bc, step, ids0, n0, ids1, n1);
   } else {
     auto kf = k_grid_disp<D, MODE, 1>;
     LAUNCH(e, K_GRID_DISP, kf, nblk(band ? n0 + n1 : e->max_act, 128), 128, e->mesh, e->G, e->bc, step, ids0, n0, ids1, n1);
@@ -2717,8 +2744,9 @@ template <int D, int MODE>
 static void launch_grid_acc(nlps_engine* e, int step, const int* ids0 = nullptr, int n0 = 0, const int* ids1 = nullptr, int n1 = 0) {
   const bool band = MODE == 2 && (ids0 || ids1);
   if (e->G.cm_sl && MODE != 2) {
-    auto kf = k_grid_acc<D, MODE, 32>;
-    LAUNCH(e, K_GRID_ACC, kf, nblk((size_t)e->max_act * 32, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, ids0, n0, ids1, n1);
+    constexpr int LPN = (D == 3) ? 32 : 8;
+    auto kf = k_grid_acc<D, MODE, LPN>;
+    LAUNCH(e, K_GRID_ACC, kf, nblk((size_t)e->max_act * LPN, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, ids0, n0, ids1, n1);
   } else {
     auto kf = k_grid_acc<D, MODE, 1>;
     LAUNCH(e, K_GRID_ACC, kf, nblk(band ? n0 + n1 : e->max_act, 128), 128, e->mesh, e->G, e->grav, e->solver.num_steps, step, ids0, n0, ids1, n1);
@@ -3003,10 +3031,12 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
   if (nn) k_sstar_nodes<<<nblk(nn, 256), 256, 0, e->stream>>>(dh, nn, solver->gamma_lme, e->neg_log_tol, dsst);
   e->mesh = MeshDev{nn, dX, r1p, r1i, r2p, r2i, t1p, t1i, t2p, t2i, dq, dh, dsst};
   {  // inverse of r2q: the slot a node holds in the 2-ring of each cell that lists it (cell-major partial sums)
-    unsigned char* r2ts = nullptr;
-    if (dev_alloc(e, &r2ts, (size_t)std::max(mesh->ring2_ptr[nn], 1))) return 1;
-    k_build_r2ts<<<nblk(nn, 256), 256, 0, e->stream>>>(nn, r2p, r2i, dq, t2p, r2ts);
+    unsigned char *r2ts = nullptr, *r2pos = nullptr;
+    if (dev_alloc(e, &r2ts, (size_t)std::max(mesh->ring2_ptr[nn], 1)) || dev_alloc(e, &r2pos, (size_t)std::max(mesh->ring2_ptr[nn], 1)))
+      return 1;
+    k_build_r2ts<<<nblk(nn, 256), 256, 0, e->stream>>>(nn, r2p, r2i, dq, t2p, r2ts, r2pos, D == 2 ? 1 : 0);
     e->mesh.r2ts = r2ts;
+    e->mesh.r2pos = r2pos;
   }
   mark("transposed adjacency upload");
   e->max_occ = (int)std::min<long long>(nn, std::max(ld, 1));
@@ -3100,9 +3130,14 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
       if (const char* s_ = getenv("NLPS_KERNELS")) e->kver = (atoi(s_) == 1 || D != 3) ? 1 : 2;
       if (const char* s_ = getenv("NLPS_SPLIT_NH")) e->split_nh = atoi(s_) != 0;
       if (maxr2 > 256) e->kver = 1;  // slot ids of the compact lists are bytes
+      // cell sums: cell-major with the warp-per-cell kernels (3D).  The block-per-cell-group kernels (2D) keep the slot-major
+      // layout: their writers gain as much (lme -31 %, kin -19 % on BASELINE configs[1]) but a node there reads only 25
+      // records and the gathering node kernels lose more (0.04 -> 0.18 ms each): 1.07 vs 1.18 ms per step,
+      // profiles/ab/r02_ab_cellmajor_2d.txt.  NLPS_PART_CELLMAJOR=1 switches them over for A/B runs.
       e->G.cm_sl = (e->kver == 2) ? w.SL : 0;
+      if (e->kver == 1 && getenv("NLPS_PART_CELLMAJOR") && atoi(getenv("NLPS_PART_CELLMAJOR")) != 0) e->G.cm_sl = w.SL;
       e->G.cm_w = w.W;
-      if (e->G.cm_sl && dev_alloc(e, &e->G.cum, (size_t)(e->max_occ + 1) * w.W)) return 1;
+      if (e->kver == 2 && dev_alloc(e, &e->G.cum, (size_t)(e->max_occ + 1) * w.W)) return 1;
     }
     if (const char* s_ = getenv("NLPS_REORDER_EVERY")) e->reorder_every = atoi(s_);
     CUDA_OK(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));

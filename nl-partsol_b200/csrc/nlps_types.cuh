@@ -42,7 +42,12 @@ struct MeshDev {
   const unsigned char* r2q;              // r2q[r2p[B]+s] = position of B inside the r2t row of node r2i[r2p[B]+s]
   const double* h_avg;
   const double* sst;  // per node: s* of beta = gamma / h_avg^2 (what a particle of that cell tests its neighbours with next step)
-  const unsigned char* r2ts;  // r2ts[r2tp[A]+q] = slot of node A inside the 2-ring of the cell r2ti[r2tp[A]+q] (inverse of r2q)
+  // cell-major cell sums: the record of ring slot s of cell B sits at position r2pos[r2p[B]+s] of the cell's run, and
+  // r2ts[r2tp[A]+q] is the position of node A's record in the run of the cell r2ti[r2tp[A]+q].  3D: position = slot.  2D
+  // (a thread per (cell, slot) pair writes, any order is free): position = rank of the slot's node id in the ring, so that
+  // the records x-consecutive nodes read from a cell are adjacent -- one 128-byte line serves four nodes of a warp.
+  const unsigned char* r2ts;
+  const unsigned char* r2pos;
 };
 
 struct PartDev {
