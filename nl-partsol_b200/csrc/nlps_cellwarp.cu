@@ -18,10 +18,14 @@
 //
 // Particle-to-grid without atomics.  Mass / momentum: the weights of the converged LME evaluation sit in a dense
 // [particle][slot] table in shared memory (zero for non-neighbours); lane k sums column k over the particles of the
-// chunk and writes part[(slot of the cell in the node's transposed ring, node rank)] straight from registers.  Forces:
-// the particles of a chunk are taken one after the other, the lanes run over THAT particle's neighbours (distinct
-// slots: no conflict) and add into the cell's accumulators in shared memory.  Either way the cell's sums are added per
-// node in a fixed order by k_grid_disp / k_grid_acc (nlps_engine.cu): deterministic.
+// chunk and writes record k of the cell's run part[(cell rank, slot)] straight from registers.  Forces: the particles
+// of a chunk are taken one after the other, the lanes run over THAT particle's neighbours (distinct slots: no conflict)
+// and add into the cell's accumulators in shared memory, which are flushed as the same kind of run.  The runs are
+// CELL-major: 32-byte records, 4 KB contiguous per cell -- with the slot-major layout of the 2D kernels (coalesced for
+// the reader) the 125 scattered stores of a cell were a third of the kinematics kernel (GridDev::part, DESIGN.md
+// section 4).  The LME kernel also leaves the mask of the cell's non-zero records (G.cum = union of its particles'
+// lists).  The node kernels k_grid_disp / k_grid_acc (nlps_engine.cu) gather the non-zero records of a node with a warp
+// and add them in a fixed order: deterministic.
 //
 // The LME kernel leaves 1/Z and the inverse Hessian J^-1 of the converged evaluation per particle (P.zi, P.ji): the
 // kinematics, force and G2P kernels evaluate the weights exp(-beta |l|^2 + lambda.l) once and need no second pass
@@ -212,25 +216,10 @@ __device__ __forceinline__ void cw_stage(const MeshDev& m, const GridDev& G, int
     }
   }
 }
-// The same union, as the LME kernel of this step left it: the slots of the cell that carry a non-zero mass sum
-// (G.cum, one coalesced load instead of the particle-id and mask round trips of cw_union).
+// Union of the neighbour masks of the cell's particles -> T.um, as the LME kernel of this step left it: the slots of the
+// cell that carry a non-zero mass sum (G.cum, one coalesced load instead of a particle-id and a mask round trip).
 __device__ __forceinline__ void cw_union_cum(const GridDev& G, int u, int W, const WarpTile& T, int lane) {
   if (lane < MAX_MASK_WORDS) T.um[lane] = lane < W ? G.cum[(size_t)u * G.cm_w + lane] : 0u;
-  __syncwarp();
-}
-// union of the neighbour masks of the cell's particles -> T.um
-__device__ __forceinline__ void cw_union(const PartDev& P, const GridDev& G, const Cell& c, int W, const WarpTile& T, int lane) {
-  if (lane < MAX_MASK_WORDS) T.um[lane] = 0u;
-  __syncwarp();
-  for (int tt = c.t0; tt < c.t1; tt += 32) {
-    const int t = tt + lane;
-    const int p = t < c.t1 ? G.plist[t] : -1;
-    for (int w = 0; w < W; w++) {
-      uint32_t v = p >= 0 ? P.mask[(size_t)w * P.ld + p] : 0u;
-      v = __reduce_or_sync(FULL, v);
-      if (lane == 0) T.um[w] |= v;
-    }
-  }
   __syncwarp();
 }
 // shape of a pass (fused kinematics kernel): the 8 particles of a chunk share 8 * NC compact-cache entries; lists
