@@ -241,6 +241,20 @@ def test_slope_slabs_match_global_engine(law):
         compact.append((f, rows, cc, ll, *rest))
     compare(G, single, compact, check_active=False)
     assert np.abs(single[0]["Stress"]).max() > 0.0
+    # ... and against the ORACLE (the CPU restatement pinned to the reference's compiled laws), not only against a second
+    # engine: the whole slope, same steps, the 1e-10 bar.
+    import oracle
+    o = oracle.Oracle(G)
+    assert o.init_lme() == 0
+    for k in range(nsteps):
+        assert o.step(k) == 0, o.error()
+    m = merge([c[:4] for c in compact], G.np_)
+    assert np.array_equal(m["I0"], o.ints("I0")) and np.array_equal(m["_counts"], o.ints("NumberNodes"))
+    assert np.array_equal(m["_lists"], o.lists())
+    sc = field_scales(G)
+    rtol = 1e-10  # (the Matsuoka-Nakai slope stays elastic over these steps: no ill-conditioned return mapping is involved)
+    for kf in COMPARE:
+        assert_close(m[kf], o.field(kf), f"slope slabs vs oracle ({law}): {kf}", rtol=rtol, scale=sc.get(kf))
 
 
 def test_excursion_is_latched():
