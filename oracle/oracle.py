@@ -189,6 +189,21 @@ class Oracle:
     def newmark_begin(self, step):
         return self.L.orc_newmark_begin(self.h, int(step))
 
+    def newmark_begin_after_search(self, step):
+        return self.L.orc_newmark_begin_after_search(self.h, int(step))
+
+    def newmark_set(self, which, arr):
+        a = _d(arr)
+        self.L.orc_newmark_set(self.h, dict(Vn=0, An=1, dU=2)[which], a.ctypes.data_as(_dp))
+
+    def newmark_coeffs(self):
+        out = np.zeros(6)
+        self.L.orc_newmark_coeffs(out.ctypes.data_as(_dp))
+        return out
+
+    def newmark_finish(self):
+        return self.L.orc_newmark_finish(self.h)
+
     def newmark_residual(self, step, dU):
         dU = _d(dU)
         R = np.zeros_like(dU)

@@ -58,11 +58,13 @@ def test_more_slabs_than_layers_is_refused():
         engine.slab_cuts(P, 64)
 
 
-@pytest.mark.parametrize("case,port", [("column2d", "29731"), ("slope3d", "29733")])
+@pytest.mark.parametrize("case,port", [("column2d", "29731"), ("slope3d", "29733"), ("implicit2d", "29735")])
 def test_slab_protocol_world2_gloo(case, port):
     """Two gloo ranks, each stepping its slab with the oracle and exchanging exactly what the engine
     exchanges; particle fields match the single-domain oracle to 1e-10, lists bit-exact.  column2d: the
-    Drucker-Prager column of the bench line; slope3d: the Matsuoka-Nakai slope of bench.py --workload c4."""
+    Drucker-Prager column of the bench line; slope3d: the Matsuoka-Nakai slope of bench.py --workload c4; implicit2d:
+    the Newmark-beta scheme over two slabs (per-slab tangents, band sums of the Krylov vector, owner's share of the mass
+    term, dot products over owned rows) against the single-domain oracle's dense-LU Newton, 1e-8."""
     env = dict(os.environ, OMP_NUM_THREADS="2", SLAB_CASE=case)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", port, os.path.join(ROOT, "tests", "workers", "slab_gloo_worker.py")]
