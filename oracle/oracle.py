@@ -168,7 +168,7 @@ class Oracle:
     def search_lists(self):
         return self.L.orc_search_lists(self.h, None)
 
-    # ---- implicit Newmark-beta restatement (parity unpinned: no PETSc here)
+    # ---- implicit Newmark-beta restatement (pinned in 2D to the reference's compiled scheme run against oracle/minipetsc)
     def newmark_setup(self, beta=0.25, gamma=0.5, tol=1e-10, max_iter=10, explicit_trial=False):
         self.L.orc_newmark_setup(self.h, ctypes.c_double(beta), ctypes.c_double(gamma), ctypes.c_double(tol),
                                  int(max_iter), int(explicit_trial))

@@ -477,9 +477,89 @@ def gen_config(case):
           "plastic particles", int((h.field("EPS_n") > 0).sum()))
 
 
+# ---- the reference's OWN implicit schemes (U-Newmark-beta.c, U-Static.c) run against oracle/minipetsc
+NEWMARK_SO = os.path.join(HERE, "..", "..", "oracle", "_ref", "libnlps2d_newmark_ref.so")
+NEWMARK_CASES = {
+    # key: (deck material, scheme, CFL, TOL-Newmark-beta, Max-Iter, Explicit-trial, checkpoints (steps run))
+    "nh": ("nh", "Newmark-beta-Finite-Strains", 4.0, 1e-12, 25, 0, (1, 3, 6)),
+    "nh_trial": ("nh", "Newmark-beta-Finite-Strains", 4.0, 1e-12, 25, 1, (6,)),
+    "dp": ("dp", "Newmark-beta-Finite-Strains", 2.0, 1e-11, 25, 0, (1, 4, 8)),
+    "mn": ("mn", "Newmark-beta-Finite-Strains", 1.0, 1e-11, 25, 0, (1, 4)),
+    "static_nh": ("nh", "Static", 0.5, 1e-11, 30, 0, (1, 3)),
+}
+NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda",
+                  "Beta")
+
+
+def newmark_spec(key, nsteps):
+    case, scheme, cfl, tol, max_iter, trial, _ = NEWMARK_CASES[key]
+    spec = spec_for(case)
+    spec.scheme = scheme
+    spec.nsteps, spec.cfl, spec.out_every = nsteps, cfl, 100000
+    spec.solver_extra = {"Beta-Newmark-beta": 0.25, "Gamma-Newmark-beta": 0.5, "TOL-Newmark-beta": tol,
+                         "Max-Iter": max_iter, "Epsilon": 0.0}
+    if trial:
+        spec.solver_extra["Explicit-trial"] = 1
+    return spec
+
+
+def gen_newmark_run(key_steps):
+    """One run of the reference's compiled U_Newmark_Beta / U_Static over `steps` time steps (fresh process: the reference
+    keeps its simulation in process globals); prints nothing, writes a temporary npz that gen_newmark collects."""
+    import ctypes
+    import refexport
+    import refharness
+    key, steps, out = key_steps.split(":")
+    steps = int(steps)
+    tmp = tempfile.mkdtemp(prefix="nlps_golden_")
+    h = refharness.RefHarness(deckgen.write_deck(newmark_spec(key, steps), tmp), so=NEWMARK_SO, threads=1)
+    P = refexport.problem_from_ref(h)
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        rc = h.lib.refh_static_run() if NEWMARK_CASES[key][1] == "Static" else h.lib.refh_newmark_run()
+    finally:
+        os.chdir(cwd)
+    assert rc == 0, (key, steps, rc)
+    st = np.zeros(5)
+    h.lib.refh_newmark_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    res = {f: h.field(f) for f in NEWMARK_FIELDS}
+    res["I0"] = h.ints("I0")
+    res["NumberNodes"] = h.ints("NumberNodes")
+    res["stats"] = st
+    res["x0"] = P.fields["x_GC"]
+    res["dt"] = np.array(P.dt())
+    np.savez(out, **res)
+
+
+def gen_newmark(key):
+    """Golden states of the implicit schemes from the reference's own compiled scheme code: every stage function is the
+    reference's; the Newton loop / linear solve are oracle/mini_petsc.c (Newton + step halving, dense LU).  `stats` =
+    SNES solves, Newton iterations, residual evaluations, solves stopped by Max-Iter, last |F|."""
+    case, scheme, cfl, tol, max_iter, trial, cps = NEWMARK_CASES[key]
+    out = dict(case=np.array(case), scheme=np.array(scheme), cfl=np.array(cfl), tol=np.array(tol),
+               max_iter=np.array(max_iter), explicit_trial=np.array(trial), checkpoints=np.array(cps))
+    ref_problem = np.load(os.path.join(HERE, f"{case}_problem.npz"))
+    for k in cps:
+        tmpf = os.path.join(tempfile.mkdtemp(prefix="nlps_golden_"), "run.npz")
+        subprocess.run([sys.executable, __file__, "newmark_run", f"{key}:{k}:{tmpf}"], check=True,
+                       stdout=subprocess.DEVNULL)
+        r = np.load(tmpf)
+        # the fixture {case}_problem.npz (written by gen_sim from the same deck generator) is the same initial state
+        assert np.array_equal(r["x0"], ref_problem["f_x_GC"])
+        for f in r.files:
+            if f not in ("x0", "dt"):
+                out[f"s{k}_{f}"] = r[f]
+        out["dt"] = r["dt"]
+    np.savez_compressed(os.path.join(HERE, f"newmark_{key}.npz"), **out)
+    last = max(cps)
+    print("newmark", key, "ok: stats", out[f"s{last}_stats"], "max |dis|", float(np.abs(out[f"s{last}_dis"]).max()),
+          "max EPS", float(out[f"s{last}_EPS_n"].max()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3:
-        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d, "config": gen_config}[sys.argv[1]](sys.argv[2])
+        {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d, "config": gen_config, "newmark": gen_newmark, "newmark_run": gen_newmark_run}[sys.argv[1]](sys.argv[2])
     else:
         for c in ("nh", "dp", "mn", "vm", "hencky"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
@@ -495,3 +575,5 @@ if __name__ == "__main__":
         subprocess.run([sys.executable, __file__, "kin3d", "all"], check=True)
         for c in ("c1", "c2twin"):
             subprocess.run([sys.executable, __file__, "config", c], check=True)
+        for c in NEWMARK_CASES:     # needs `make -C oracle ref-newmark`
+            subprocess.run([sys.executable, __file__, "newmark", c], check=True)

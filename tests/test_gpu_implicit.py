@@ -189,3 +189,34 @@ def test_implicit_refuses_invalid_parameters():
     assert eng.newmark_step(0) != 0                  # no scheme was set up
     assert eng.newmark_setup() == 0 and eng.newmark_step(0) == 0
     eng.close()
+
+
+@pytest.mark.parametrize("key,rtol", [("nh", 1e-8), ("nh_trial", 1e-8), ("dp", 2e-6), ("mn", 2e-6), ("static_nh", 1e-8)])
+def test_converged_steps_match_the_reference_compiled_scheme(key, rtol):
+    """The device scheme against the reference's OWN U_Newmark_Beta / U_Static: tests/golden/newmark_*.npz hold the states
+    the reference's compiled scheme code reached on 2D decks (run against oracle/minipetsc -- PETSc is absent --, see
+    tests/golden/make_golden.py::gen_newmark; the CPU suite checks the oracle against the same files to 1e-12).
+    Tolerances as in the oracle comparisons above: what a Newton loop stopped at the scheme's tolerance supports."""
+    from util import newmark_golden, newmark_problem
+    g = newmark_golden(key)
+    k = int(max(g["checkpoints"]))
+    P = newmark_problem(g, k)
+    static = str(g["scheme"]) == "Static"
+    eng = engine.Engine(P, device=0)
+    assert eng.initialize_lme() == 0
+    assert eng.newmark_setup(tol=float(g["tol"]), max_iter=int(g["max_iter"]), explicit_trial=bool(g["explicit_trial"]),
+                             pcg_rtol=1e-13, quasi_static=static) == 0
+    for s in range(k):
+        assert eng.newmark_step(s) == 0, eng.error()
+    f = eng.download()
+    sc = field_scales(P)
+    names = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "lambda") if rtol <= 1e-8 else \
+            ("x_GC", "dis", "vel", "F_n", "Stress", "J_n", "EPS_n", "b_e_n")
+    for name in names:
+        assert_close(f[name], g[f"s{k}_{name}"], f"reference scheme {key} {name}", rtol=rtol, scale=sc.get(name))
+    assert np.array_equal(f["I0"], g[f"s{k}_I0"])
+    counts, _ = eng.lists()
+    assert np.array_equal(counts, g[f"s{k}_NumberNodes"])
+    if key == "dp":
+        assert (f["EPS_n"] > 0).sum() > 20
+    eng.close()

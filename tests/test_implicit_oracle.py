@@ -1,6 +1,7 @@
-"""CPU checks of the implicit Newmark-beta restatement in oracle/.  The scheme as a whole is parity-unpinned
-(PETSc is absent, the reference's U_Newmark_Beta cannot run here), but its per-particle tangent blocks are pinned to
-the reference's own compiled functions (tests/golden/tangent_blocks.npz).  Beyond that: the tangent is the derivative
+"""CPU checks of the implicit Newmark-beta restatement in oracle/.  The scheme is pinned in 2D to the reference's own
+compiled U-Newmark-beta.c / U-Static.c (run against oracle/minipetsc because PETSc is absent; fixtures
+tests/golden/newmark_*.npz), its per-particle tangent blocks to the reference's own compiled functions
+(tests/golden/tangent_blocks.npz).  Beyond that: the tangent is the derivative
 of the residual, the trapezoidal scheme converges to the explicit oracle as dt -> 0, Newton converges quadratically."""
 import os
 
@@ -144,3 +145,44 @@ def test_static_scheme_balances_gravity():
     weight = 9.81 * float(P.fields["mass"].sum())
     assert st == 0 and np.abs(R[free]).max() <= 1e-6 * weight    # one more step is already (nearly) in equilibrium
     assert np.abs(o.field("dis")[:, 1]).max() > 1e-4               # the block did settle
+
+
+# ---- the scheme itself, pinned: the reference's OWN compiled U-Newmark-beta.c / U-Static.c (run against oracle/minipetsc,
+# tests/golden/make_golden.py::gen_newmark) froze converged states of 2D decks; the restatement reproduces them
+NEWMARK_KEYS = ["nh", "nh_trial", "dp", "mn", "static_nh"]
+NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda")
+
+
+@pytest.mark.parametrize("key", NEWMARK_KEYS)
+def test_scheme_matches_the_reference_compiled_scheme(key):
+    """orc_newmark_* against the reference's own U_Newmark_Beta / U_Static (every stage function compiled from the
+    reference; Newton + step halving and dense LU from oracle/mini_petsc.c, the same algorithm as the restatement's):
+    all particle fields after 1 .. 8 implicit steps at 2 .. 8 times the explicit time step, plastic flow included (dp),
+    and the same number of Newton iterations and residual evaluations."""
+    from util import assert_close, field_scales, newmark_golden, newmark_problem
+    g = newmark_golden(key)
+    for k in g["checkpoints"]:
+        k = int(k)
+        P = newmark_problem(g, k)
+        o = oracle.Oracle(P)
+        assert o.init_lme() == 0
+        if str(g["scheme"]) == "Static":
+            o.static_setup(tol=float(g["tol"]), max_iter=int(g["max_iter"]))
+        else:
+            o.newmark_setup(tol=float(g["tol"]), max_iter=int(g["max_iter"]), explicit_trial=bool(g["explicit_trial"]))
+        iters = 0
+        for s in range(k):
+            assert o.newmark_step(s) == 0, o.error()
+            iters += o.newmark_iters()
+        stats = g[f"s{k}_stats"]
+        assert stats[0] == k and stats[3] == 0            # every solve of the reference run converged
+        assert iters == int(stats[1]), (iters, stats)
+        sc = field_scales(P)
+        for name in NEWMARK_FIELDS:
+            assert_close(o.field(name), g[f"s{k}_{name}"], f"newmark {key} step {k} {name}", rtol=1e-12, scale=sc.get(name))
+        assert np.array_equal(o.ints("I0"), g[f"s{k}_I0"])
+        assert np.array_equal(o.ints("NumberNodes"), g[f"s{k}_NumberNodes"])
+    last = int(max(g["checkpoints"]))
+    assert np.abs(g[f"s{last}_dis"]).max() > 1e-5
+    if key == "dp":
+        assert (g[f"s{last}_EPS_n"] > 0).sum() > 20   # plastic flow reached

@@ -96,3 +96,19 @@ def load_config(case):
         if k.startswith("init_"):
             P.fields[k[5:]] = g[k].copy()
     return P, g
+
+
+def newmark_golden(key):
+    return np.load(os.path.join(GOLDEN, f"newmark_{key}.npz"))
+
+
+def newmark_problem(g, nsteps):
+    """The deck of the golden run as a Problem: the 2D fixture exported from the reference's own parser with the run's
+    CFL and step count (its load curves are constant, so the tables are cut to the run's length)."""
+    P = load_problem(str(g["case"]))
+    P.solver["cfl"], P.solver["nsteps"] = float(g["cfl"]), nsteps
+    for b in P.bounds:
+        b["dir"], b["val"] = b["dir"][:, :nsteps], b["val"][:, :nsteps]
+    P.gravity = P.gravity[:, :nsteps]
+    assert abs(P.dt() - float(g["dt"])) <= 1e-15 * float(g["dt"])
+    return P
