@@ -30,8 +30,8 @@ extern "C" {
 #define NLPS_MAT_NEO_HOOKEAN_WRIGGERS 0 /* Constitutive/Hyperelastic/Neo-Hookean.c:38 */
 #define NLPS_MAT_DRUCKER_PRAGER 1       /* Constitutive/Plasticity/Drucker-Prager.c:319 */
 #define NLPS_MAT_MATSUOKA_NAKAI 2       /* Constitutive/Plasticity/Matsuoka-Nakai.c:300 */
-#define NLPS_MAT_VON_MISES 3            /* Constitutive/Plasticity/Von-Mises.c:228 (explicit scheme only) */
-#define NLPS_MAT_HENCKY 4               /* Constitutive/Hyperelastic/Hencky.c:30 (explicit scheme only) */
+#define NLPS_MAT_VON_MISES 3            /* Constitutive/Plasticity/Von-Mises.c:228 */
+#define NLPS_MAT_HENCKY 4               /* Constitutive/Hyperelastic/Hencky.c:30 */
 #define NLPS_MAT_LADE_DUNCAN 5          /* Constitutive/Plasticity/Lade-Duncan.c:290 (explicit scheme only) */
 
 /* error codes latched on the device (first offender wins) */

@@ -620,7 +620,7 @@ __device__ __forceinline__ bool particle_stress(const PartDev& P, const StepPara
 #pragma unroll
         for (int i = 0; i < 3; i++) P.back[(size_t)i * ld + p] = back[i];
       }
-      if (sp.rp.want_cep && mtype != NLPS_MAT_VON_MISES)
+      if (sp.rp.want_cep)
 #pragma unroll
         for (int i = 0; i < D * D; i++) P.cep[(size_t)i * ld + p] = cep[i];
     }

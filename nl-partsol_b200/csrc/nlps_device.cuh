@@ -715,9 +715,12 @@ __device__ inline int stress_matsuoka_nakai(const MatParams& m, const ReturnMapP
 // (Constitutive/Plasticity/Von-Mises.c:228-391 and helpers :395-757).  Reproduced as compiled: the volumetric part is
 // K tr(E)/3 (:553-559); the elastic branch rotates with eigenvectors in columns (:616-617), the plastic branch with rows
 // (:717-718, SURVEY F10-i, rp.quirk_rows); `back` = Phi.Back_stress, PRINCIPAL components, updated in place.
+// rp.want_cep: the tangent moduli of __tangent_moduli (:207-226, 730-757) in principal space, as compiled -- "K_iso_k",
+// "K_kin_k" are the hardening VALUES kappa_k (not their derivatives), theta = 0 while J2 <= TOL_NR (an unstressed point has
+// no shear stiffness); in the elastic branch the reference hands an uninitialised kappa_k that only multiplies n (x) n = 0.
 template <int D>
 __device__ inline int stress_von_mises(const MatParams& m, const ReturnMapParams& rp, const double* dphi, double* be,
-                                       double& eps, double* back, double* tau, double& W) {
+                                       double& eps, double* back, double* tau, double& W, double* cep) {
   double eval[3] = {0, 0, 0}, evec[D * D];
   double Eh[3], Tvol[3], Tdev[3], Tp[3];
   trial_be<D>(be, dphi, eval, evec);
@@ -740,16 +743,15 @@ __device__ inline int stress_von_mises(const MatParams& m, const ReturnMapParams
   const double kin_n = (1 - theta) * H * eps_n;
   double iso_k = sigma_y + theta * H * eps_n + dK * (1 - exp(-delta * eps_n)), kin_k = kin_n;
   const double PHI_0 = J2 - s23 * (iso_k + kin_k - kin_n) - 2.0 * G * 0.0;
-  double dEp[3] = {0, 0, 0};
+  double dEp[3] = {0, 0, 0}, n[3] = {0, 0, 0}, dg = 0.0;
   if (PHI_0 <= 0.0) {
 #pragma unroll
     for (int i = 0; i < 3; i++) Tp[i] = Tvol[i] + Tdev[i];  // :578-586 (the back stress is not added back)
     spectral_sum<D>(Tp, evec, false, tau);
   } else {
-    double n[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) n[i] = Tdev[i] / J2;
-    double PHI = PHI_0, dg = 0.0, eps_k = eps_n;
+    double PHI = PHI_0, eps_k = eps_n;
     int Iter = 0;
     while (fabs(PHI / PHI_0) >= rp.tol) {
       Iter++;
@@ -778,6 +780,15 @@ __device__ inline int stress_von_mises(const MatParams& m, const ReturnMapParams
 #pragma unroll
   for (int i = 0; i < 3; i++) Eh[i] -= dEp[i];
   corrector_be<D>(be, evec, Eh);
+  if (rp.want_cep) {
+    const double th = J2 > 10E-6 /* TOL_NR, Macros.h:40 */ ? 1.0 - 2.0 * G * dg / J2 : 0.0;
+    const double thb = 1.0 / (1.0 + (iso_k + kin_k) / (3.0 * G)) - (1.0 - th);
+#pragma unroll
+    for (int i = 0; i < D; i++)
+#pragma unroll
+      for (int j = 0; j < D; j++)
+        cep[i * D + j] = K + 2.0 * G * th * ((i == j ? 1.0 : 0.0) - (1.0 / 3.0)) - 2.0 * G * thb * n[i] * n[j];
+  }
   W = 0.5 * (Tp[0] * Eh[0] + Tp[1] * Eh[1] + Tp[2] * Eh[2]);
   return 0;
 }
@@ -822,7 +833,7 @@ __device__ inline int stress_with_history(int mtype, const MatParams& m, const R
                                           double* tau, double& W, double* cep) {
   if (mtype == NLPS_MAT_DRUCKER_PRAGER) return stress_drucker_prager<D>(m, rp, DF, be, eps, kap, tau, W, cep);
   if (mtype == NLPS_MAT_MATSUOKA_NAKAI) return stress_matsuoka_nakai<D>(m, rp, DF, be, eps, kap, tau, W, cep);
-  if (mtype == NLPS_MAT_VON_MISES) return stress_von_mises<D>(m, rp, DF, be, eps, back, tau, W);
+  if (mtype == NLPS_MAT_VON_MISES) return stress_von_mises<D>(m, rp, DF, be, eps, back, tau, W, cep);
   if (mtype == NLPS_MAT_LADE_DUNCAN) return stress_matsuoka_nakai<D, true>(m, rp, DF, be, eps, kap, tau, W, cep);
   stress_hencky<D>(m, Fn1, tau, W);
   return 0;

@@ -1267,7 +1267,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
 #pragma unroll
               for (int i = 0; i < 3; i++) P.back[(size_t)i * np + p] = back[i];
             }
-            if (sp.rp.want_cep && (MAT >= 0 || mtype != NLPS_MAT_VON_MISES))
+            if (sp.rp.want_cep)
 #pragma unroll
               for (int i = 0; i < D * D; i++) P.cep[(size_t)i * np + p] = cep[i];
           }

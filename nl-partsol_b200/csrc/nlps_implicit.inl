@@ -242,7 +242,7 @@ __device__ __forceinline__ int csr_find(const int* cols, int lo, int hi, int key
 // Tangent values, one warp per particle (U-Newmark-beta.c:1646-1830 with compute_stiffness_density_Neo_Hookean,
 // Neo-Hookean.c:89-141):  K_AB += V0 [ c0 g1_A (x) g1_B + G (g_B . b_n g_A) I + c1 g1_B (x) g1_A ],
 // g = grad N at t_n, g1 = DF^-T g, b_n = F_n F_n^T, c0 = lambda J^2, c1 = G - lambda (J^2 - 1)/2, J = J_n1.
-// EP: elastoplastic laws (Drucker-Prager, Matsuoka-Nakai) use compute_stiffness_elastoplastic__Constitutive__
+// EP: elastoplastic laws (Drucker-Prager, Matsuoka-Nakai, Von-Mises) and Hencky use compute_stiffness_elastoplastic__Constitutive__
 // (Constitutive/Plasticity/Elastoplastic-Tangent-Matrix.c:42-160): spectral form with C_ep of the return mapping, the
 // eigen-pairs of b_e_n1 and the eigenvalues of tau, plus the geometric term -tau (g1_B (x) g1_A); unsymmetric when the
 // flow rule is not associated, hence BiCGStab below.  The law is read per particle (mixed clouds work).
@@ -358,6 +358,23 @@ __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridD
         be[i] = P.be_n1[(size_t)i * np + p];
         ta[i] = P.stress[(size_t)i * np + p];
         cep[i] = P.cep[(size_t)i * np + p];
+      }
+      if (mat.type == NLPS_MAT_HENCKY) {
+        // compute_stiffness_density_Hencky__Constitutive__ (Constitutive/Hyperelastic/Hencky.c:98-232): the same spectral
+        // block with b = F_n1 F_n1^T and the constant elastic moduli AA in place of b_e_n1 and C_ep
+        double F1[DD];
+#pragma unroll
+        for (int i = 0; i < DD; i++) F1[i] = P.F_n1[(size_t)i * np + p];
+#pragma unroll
+        for (int i = 0; i < D; i++)
+#pragma unroll
+          for (int j = 0; j < D; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; k++) s += F1[i * D + k] * F1[j * D + k];
+            be[i * D + j] = s;
+            cep[i * D + j] = (i == j) ? mat.lame + 2 * mat.G : mat.lame;
+          }
       }
       if (D == 2) { dsyev2_dev(be[0], be[1], be[3], lb, ev); dsyev2_dev(ta[0], ta[1], ta[3], lT, evT); }
       else { jacobi3_dev(be, lb, ev); jacobi3_dev(ta, lT, evT); }
@@ -1293,8 +1310,8 @@ int nlps_b200_newmark_setup(nlps_engine* e, const nlps_newmark* prm) {
   cudaSetDevice(e->device);
   if (!prm || (!prm->quasi_static && !(prm->beta > 0.0))) return 1;
   for (int i = 0; i < MAX_MATERIALS; i++)
-    if (e->mat.m[i].type > NLPS_MAT_MATSUOKA_NAKAI) {
-      fprintf(stderr, "nlps_b200_newmark_setup: the implicit scheme has tangents for Neo-Hookean, Drucker-Prager and Matsuoka-Nakai only\n");
+    if (e->mat.m[i].type == NLPS_MAT_LADE_DUNCAN) {  // (no reference trace of a Lade-Duncan cloud exists to pin it to)
+      fprintf(stderr, "nlps_b200_newmark_setup: the implicit scheme has tangents for Neo-Hookean, Hencky, Drucker-Prager, Matsuoka-Nakai and Von-Mises only\n");
       return 1;
     }
   return imp_setup(e, prm);

@@ -486,9 +486,17 @@ NEWMARK_CASES = {
     "dp": ("dp", "Newmark-beta-Finite-Strains", 2.0, 1e-11, 25, 0, (1, 4, 8)),
     "mn": ("mn", "Newmark-beta-Finite-Strains", 1.0, 1e-11, 25, 0, (1, 4)),
     "static_nh": ("nh", "Static", 0.5, 1e-11, 30, 0, (1, 3)),
+    # Von-Mises / Hencky tangents (Constitutive.c:284-297,316-329).  "vm" stays elastic and converges; "vm_plastic" yields:
+    # the reference updates the back stress IN PLACE at every residual evaluation (Constitutive.c:110-143 restarts b_e and
+    # EPS from step n, Phi.Back_stress has no n / n1 pair), so its residual is not a function of dU any more, the line
+    # search stalls on some steps (stats[3] > 0) and the result depends on the sequence of evaluations -- reproduced by
+    # the oracle (same sequence), not asked of the device
+    "vm": ("vm", "Newmark-beta-Finite-Strains", 1.0, 1e-11, 50, 0, (1, 5)),
+    "vm_plastic": ("vm", "Newmark-beta-Finite-Strains", 2.0, 1e-12, 25, 0, (8,)),
+    "hencky": ("hencky", "Newmark-beta-Finite-Strains", 1.0, 1e-10, 100, 0, (1, 3)),
 }
 NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda",
-                  "Beta")
+                  "Beta", "Back_stress")
 
 
 def newmark_spec(key, nsteps):

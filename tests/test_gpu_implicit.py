@@ -24,6 +24,8 @@ CASES = {
     "cube3d": lambda n: synthetic.cube_3d(cells=3, nsteps=n),
     "dp2d": _golden("dp"),
     "mn2d": _golden("mn"),
+    "vm2d": _golden("vm"),
+    "hencky2d": _golden("hencky"),
     "dp3d": lambda n: synthetic.cube_3d(cells=3, nsteps=n, material=synthetic.DP_C2),
 }
 
@@ -107,10 +109,12 @@ def test_converged_steps_match_the_oracle(case, cfl):
     eng.close()
 
 
-@pytest.mark.parametrize("case,cfl,pre", [("dp2d", -4.0, 5), ("mn2d", -2.0, 2), ("dp3d", 2.0, 2)])
+@pytest.mark.parametrize("case,cfl,pre", [("dp2d", -4.0, 5), ("mn2d", -2.0, 2), ("dp3d", 2.0, 2), ("vm2d", -2.0, 3),
+                                          ("hencky2d", -2.0, 2)])
 def test_elastoplastic_stages_match_the_oracle(case, cfl, pre):
-    """Drucker-Prager / Matsuoka-Nakai tangent (compute_stiffness_elastoplastic__Constitutive__,
-    Elastoplastic-Tangent-Matrix.c:42-160): every block of the device CSR against the oracle's dense matrix, on a state
+    """Drucker-Prager / Matsuoka-Nakai / Von-Mises tangent (compute_stiffness_elastoplastic__Constitutive__,
+    Elastoplastic-Tangent-Matrix.c:42-160; Von-Mises with the moduli of its own __tangent_moduli, Von-Mises.c:730-757) and
+    the Hencky block (Hencky.c:98-232): every block of the device CSR against the oracle's dense matrix, on a state
     reached by `pre` converged implicit steps (plastic for dp2d)."""
     P, o, eng = _pair(case, pre + 2, cfl, tol=1e-10)
     for k in range(pre):
@@ -128,7 +132,7 @@ def test_elastoplastic_stages_match_the_oracle(case, cfl, pre):
     Kg, rows, rp = dense_from_csr(eng, P, o, 1.0 / (0.25 * P.dt() ** 2))
     assert st == 0
     assert np.abs(Kg - Ko).max() <= 1e-6 * np.abs(Ko).max()
-    if case != "mn2d":       # non-associated flow: the operator is not symmetric, hence BiCGStab
+    if case in ("dp2d", "dp3d"):       # non-associated flow: the operator is not symmetric, hence BiCGStab
         assert np.abs(Ko - Ko.T).max() > 1e-9 * np.abs(Ko).max()
     eng.close()
 
@@ -191,7 +195,8 @@ def test_implicit_refuses_invalid_parameters():
     eng.close()
 
 
-@pytest.mark.parametrize("key,rtol", [("nh", 1e-8), ("nh_trial", 1e-8), ("dp", 2e-6), ("mn", 2e-6), ("static_nh", 1e-8)])
+@pytest.mark.parametrize("key,rtol", [("nh", 1e-8), ("nh_trial", 1e-8), ("dp", 2e-6), ("mn", 2e-6), ("static_nh", 1e-8),
+                                      ("vm", 2e-6), ("hencky", 2e-6)])
 def test_converged_steps_match_the_reference_compiled_scheme(key, rtol):
     """The device scheme against the reference's OWN U_Newmark_Beta / U_Static: tests/golden/newmark_*.npz hold the states
     the reference's compiled scheme code reached on 2D decks (run against oracle/minipetsc -- PETSc is absent --, see
@@ -211,7 +216,7 @@ def test_converged_steps_match_the_reference_compiled_scheme(key, rtol):
     f = eng.download()
     sc = field_scales(P)
     names = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "lambda") if rtol <= 1e-8 else \
-            ("x_GC", "dis", "vel", "F_n", "Stress", "J_n", "EPS_n", "b_e_n")
+            ("x_GC", "dis", "vel", "F_n", "Stress", "J_n") + (("EPS_n", "b_e_n") if key != "hencky" else ())
     for name in names:
         assert_close(f[name], g[f"s{k}_{name}"], f"reference scheme {key} {name}", rtol=rtol, scale=sc.get(name))
     assert np.array_equal(f["I0"], g[f"s{k}_I0"])
