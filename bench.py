@@ -86,12 +86,22 @@ def library_hash():
 
 def ncu_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this
-    workload -- or None when no capture exists for exactly this build (profiles/ncu_traffic.json: {workload: {hash,
-    particles, kernels: {name: bytes}}})."""
+    workload -- or None when no capture exists for exactly this build (profiles/ncu_traffic.json: {workload: {hash, sass,
+    particles, kernels: {name: bytes}}}).  "Exactly this build" = the MACHINE CODE of the captured kernels: `sass` holds the
+    sha256 of the SASS of every kernel the capture covers, the build leaves the same hashes of the library it linked in
+    nl-partsol_b200/libnlps_b200.sass.json (nlps_b200/build.py:sass_stamp); a record without `sass` is keyed by the hash of
+    the source files instead."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             rec = json.load(f).get(workload)
-        if rec and rec.get("hash") == library_hash() and kernel in rec.get("kernels", {}):
+        if not rec or kernel not in rec.get("kernels", {}):
+            return None
+        if rec.get("sass"):
+            with open(os.path.join(ROOT, "nl-partsol_b200", "libnlps_b200.sass.json")) as f:
+                stamp = json.load(f)
+            if all(stamp.get(k) == v for k, v in rec["sass"].items()):
+                return rec
+        elif rec.get("hash") == library_hash():
             return rec
     except Exception:
         pass

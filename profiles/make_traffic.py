@@ -2,8 +2,9 @@
 
     python profiles/make_traffic.py raw.csv c3 16003008 "profiles/r02_ncu_full_c3.txt"
 
-The entry is keyed by the hash of the kernel sources (bench.py:library_hash): bench.py quotes `roofline.traffic` only when
-the library it runs was built from exactly these sources, else it prints null."""
+The entry is keyed by the machine code of the captured kernels: `sass` = sha256 of the SASS of every kernel whose name
+matches a captured one, taken from the stamp the build left next to the library (nl-partsol_b200/libnlps_b200.sass.json).
+bench.py quotes `roofline.traffic` only when the library it runs holds exactly these kernels, else it prints null."""
 import csv
 import json
 import os
@@ -33,7 +34,10 @@ def main():
     kernels = {k: sum(v) / len(v) for k, v in acc.items()}
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     data = json.load(open(path)) if os.path.exists(path) else {}
-    data[workload] = {"hash": bench.library_hash(), "particles": particles, "source": source,
+    stamp = json.load(open(os.path.join(ROOT, "nl-partsol_b200", "libnlps_b200.sass.json")))
+    keys = {key for key, name in NAMES if name in kernels and any(key in r[ki] for r in rows[2:])}
+    sass = {k: v for k, v in stamp.items() if any(k == key or k.startswith(key + "<") for key in keys)}
+    data[workload] = {"hash": bench.library_hash(), "sass": sass, "particles": particles, "source": source,
                       "kernels": {k: int(v) for k, v in kernels.items()},
                       "launches_captured": {k: len(v) for k, v in acc.items()}}
     json.dump(data, open(path, "w"), indent=1, sort_keys=True)
