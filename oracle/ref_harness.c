@@ -198,6 +198,22 @@ void refh_gravity_table(double *g) {
       g[k * N + s] = (gravity_field.STATUS == true) ? gravity_field.Value[k].Fx[s] : 0.0;
 }
 int refh_num_neumann(void) { return MPM_Mesh.Neumann_Contours.NumBounds; }
+/* Neumann sets (Particle.Neumann_Contours, NLPS-Read-u-Neumann-Boundary-Conditions.c:46-210): loaded particles and the
+ * Dim x NumTimeStep direction / value tables, as refh_bound_* give them for the Dirichlet sets */
+int refh_neumann_num_nodes(int b) { return MPM_Mesh.Neumann_Contours.BCC_i[b].NumNodes; }
+int refh_neumann_dim(int b) { return MPM_Mesh.Neumann_Contours.BCC_i[b].Dim; }
+void refh_neumann_nodes(int b, int *out) {
+  memcpy(out, MPM_Mesh.Neumann_Contours.BCC_i[b].Nodes, sizeof(int) * MPM_Mesh.Neumann_Contours.BCC_i[b].NumNodes);
+}
+void refh_neumann_table(int b, int *dir, double *val) {
+  Load L = MPM_Mesh.Neumann_Contours.BCC_i[b];
+  int N = Params.NumTimeStep;
+  for (int k = 0; k < L.Dim; k++)
+    for (int s = 0; s < N; s++) {
+      dir[k * N + s] = L.Dir[k * N + s];
+      val[k * N + s] = (L.Dir[k * N + s] == 1) ? L.Value[k].Fx[s] : 0.0;
+    }
+}
 
 /* -------------------------------- materials ----------------------------- */
 int refh_num_materials(void) { return MPM_Mesh.NumberMaterials; }

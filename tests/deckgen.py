@@ -57,6 +57,9 @@ class DeckSpec:
         ("Left", "left", {"V.x": 0.0, "V.y": None}, "CONSTANT_CURVE"),
         ("Right", "right", {"V.x": 0.0, "V.y": None}, "CONSTANT_CURVE"),
     ])
+    # Neumann sets (NLPS-Read-u-Neumann-Boundary-Conditions.c:46-210): list of (name, particle-mesh element ids,
+    # {"T.x": scale or None, "T.y": ...}, curve kind); the loaded particles are element * GPxElement + 0 .. GPxElement-1
+    neumann: list = field(default_factory=list)
     out_every: int = 1000000
     solver_extra: dict = field(default_factory=dict)   # e.g. Beta-Newmark-beta, TOL-Newmark-beta, Max-Iter
 
@@ -153,6 +156,20 @@ def write_deck(spec: DeckSpec, outdir: str) -> str:
     lines.append("}")
     lines.append(f"One-Phase-Analysis (File=Particles.msh,GPxElement={spec.gpx}) {{")
     lines.append("}")
+    for name, elems, comps, kind in spec.neumann:
+        with open(os.path.join(outdir, f"{name}.txt"), "w") as f:
+            for e in elems:
+                f.write(f"{int(e)}\n")
+        lines.append(f"Define-Neumann-Boundary(File={name}.txt)")
+        lines.append("{")
+        for comp, scale in comps.items():
+            if scale is None:
+                lines.append(f"  {comp} NULL")
+            else:
+                cname = f"{name}_{comp.replace('.', '')}.curve"
+                _write_curve(os.path.join(outdir, cname), kind, scale, spec.nsteps)
+                lines.append(f"  {comp} {cname}")
+        lines.append("}")
     lines.append("GramsShapeFun (Type=LME) {")
     lines.append(f"  gamma={spec.gamma!r}")
     lines.append(f"  TOL-Zero={spec.tol_zero!r}")

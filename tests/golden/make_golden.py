@@ -56,7 +56,8 @@ POINT_MATERIALS = {
                            "Friction-angle": 30.0, "Atmospheric-pressure": 100.0}),
 }
 CHECKPOINTS = {"nh": (1, 2, 5, 20, 60), "dp": (1, 2, 5, 20, 60, 120), "mn": (1, 2, 5, 20, 60),
-               "vm": (1, 2, 5, 20, 60, 120), "hencky": (1, 5, 60)}
+               "vm": (1, 2, 5, 20, 60, 120), "hencky": (1, 5, 60), "nhload": (1, 5, 40)}
+MATERIALS["nhload"] = MATERIALS["nh"]
 TRACE_FIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "DF", "Stress", "rho", "J_n", "W", "b_e_n",
                 "EPS_n", "Kappa_n", "lambda", "Beta", "C_ep")
 
@@ -68,6 +69,14 @@ def spec_for(case):
     if cel:
         spec.cel = cel
     spec.nsteps = max(CHECKPOINTS[case])
+    if case == "nhload":
+        # the loads the other decks do not have: a Neumann traction (K3: U-Verlet.c:805-902, __nodal_traction_forces of
+        # U-Newmark-beta.c:1388-1500) on the right column of particle cells, and a platen -- Dirichlet set with non-zero
+        # displacement increments (U-Newmark-beta.c:909-946) -- on the top boundary of the grid, which the block reaches
+        spec.pny = 12
+        spec.dirichlet = spec.dirichlet + [("Top", "top", {"V.x": None, "V.y": -2.0e-5}, "CONSTANT_CURVE")]
+        right = [j * spec.pnx + (spec.pnx - 1) for j in range(spec.pny)]
+        spec.neumann = [("RightFace", right, {"T.x": 4.0e3, "T.y": -1.0e3}, "CONSTANT_CURVE")]
     return spec
 
 
@@ -494,6 +503,9 @@ NEWMARK_CASES = {
     "vm": ("vm", "Newmark-beta-Finite-Strains", 1.0, 1e-11, 50, 0, (1, 5)),
     "vm_plastic": ("vm", "Newmark-beta-Finite-Strains", 2.0, 1e-12, 25, 0, (8,)),
     "hencky": ("hencky", "Newmark-beta-Finite-Strains", 1.0, 1e-10, 100, 0, (1, 3)),
+    # Neumann traction + moving platen (spec_for("nhload")), dynamic and quasi-static
+    "nhload": ("nhload", "Newmark-beta-Finite-Strains", 4.0, 1e-12, 25, 0, (1, 6)),
+    "static_nhload": ("nhload", "Static", 0.5, 1e-11, 30, 0, (1, 3)),
 }
 NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda",
                   "Beta", "Back_stress")
@@ -569,7 +581,7 @@ if __name__ == "__main__":
     if len(sys.argv) == 3:
         {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d, "config": gen_config, "newmark": gen_newmark, "newmark_run": gen_newmark_run}[sys.argv[1]](sys.argv[2])
     else:
-        for c in ("nh", "dp", "mn", "vm", "hencky"):
+        for c in ("nh", "dp", "mn", "vm", "hencky", "nhload"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
                            if os.environ.get("QUIET") else None)
         for c in ("dp", "mn", "ld"):

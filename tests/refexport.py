@@ -31,6 +31,7 @@ def problem_from_ref(h, conn=None) -> Problem:
     p = Problem(ndim=h.ndim, coords=h.coords(), r1p=r1p, r1i=r1i, r2p=r2p, r2i=r2i, h_avg=h.h_avg(),
                 dx=s["delta_x"], solver=solver, gravity=h.gravity())
     p.bounds = h.bounds()
+    p.neumann = h.neumann() if hasattr(h.lib, "refh_neumann_nodes") else []
     p.materials = [h.material(m) for m in range(h.lib.refh_num_materials())]
     p.fields = {k: h.field(k) for k in ALL_FIELDS}
     if any(t == "Von-Mises" for t, _ in p.materials):

@@ -82,6 +82,19 @@ class RefHarness:
             res.append(dict(nodes=nodes, dir=dirs, val=vals))
         return res
 
+    def neumann(self):
+        res = []
+        for b in range(self.lib.refh_num_neumann()):
+            nb = self.lib.refh_neumann_num_nodes(b)
+            dim = self.lib.refh_neumann_dim(b)
+            nodes = np.zeros(nb, dtype=np.int32)
+            self.lib.refh_neumann_nodes(b, nodes.ctypes.data_as(_ip))
+            dirs = np.zeros((dim, self.nsteps), dtype=np.int32)
+            vals = np.zeros((dim, self.nsteps))
+            self.lib.refh_neumann_table(b, dirs.ctypes.data_as(_ip), vals.ctypes.data_as(_dp))
+            res.append(dict(nodes=nodes, dir=dirs, val=vals))
+        return res
+
     def gravity(self):
         g = np.zeros((self.ndim, self.nsteps))
         self.lib.refh_gravity_table(g.ctypes.data_as(_dp))

@@ -37,9 +37,10 @@ def test_initialize_lme_matches_reference(case):
     eng.close()
 
 
-@pytest.mark.parametrize("case", CASES + ("vm", "hencky"))
+@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload"))
 def test_steps_match_golden_reference(case):
-    """Multi-step run against fixtures produced by the reference's compiled code."""
+    """Multi-step run against fixtures produced by the reference's compiled code.  nhload: Neumann traction on a column of
+    particles + a platen (Dirichlet set with non-zero displacement increments)."""
     P = load_problem(case)
     tr = load_trace(case)
     eng = engine.Engine(P, compute_c_ep=1)

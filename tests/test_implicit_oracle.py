@@ -149,7 +149,7 @@ def test_static_scheme_balances_gravity():
 
 # ---- the scheme itself, pinned: the reference's OWN compiled U-Newmark-beta.c / U-Static.c (run against oracle/minipetsc,
 # tests/golden/make_golden.py::gen_newmark) froze converged states of 2D decks; the restatement reproduces them
-NEWMARK_KEYS = ["nh", "nh_trial", "dp", "mn", "static_nh", "vm", "vm_plastic", "hencky"]
+NEWMARK_KEYS = ["nh", "nh_trial", "dp", "mn", "static_nh", "vm", "vm_plastic", "hencky", "nhload", "static_nhload"]
 NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda")
 
 

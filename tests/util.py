@@ -107,7 +107,7 @@ def newmark_problem(g, nsteps):
     CFL and step count (its load curves are constant, so the tables are cut to the run's length)."""
     P = load_problem(str(g["case"]))
     P.solver["cfl"], P.solver["nsteps"] = float(g["cfl"]), nsteps
-    for b in P.bounds:
+    for b in list(P.bounds) + list(P.neumann):
         b["dir"], b["val"] = b["dir"][:, :nsteps], b["val"][:, :nsteps]
     P.gravity = P.gravity[:, :nsteps]
     assert abs(P.dt() - float(g["dt"])) <= 1e-15 * float(g["dt"])
