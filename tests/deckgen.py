@@ -60,6 +60,9 @@ class DeckSpec:
     # Neumann sets (NLPS-Read-u-Neumann-Boundary-Conditions.c:46-210): list of (name, particle-mesh element ids,
     # {"T.x": scale or None, "T.y": ...}, curve kind); the loaded particles are element * GPxElement + 0 .. GPxElement-1
     neumann: list = field(default_factory=list)
+    # further materials: list of (Material, particle-mesh element ids); idx = 1, 2, ... in this order
+    # (Generate-One-Phase-Analysis.c:497-560: each assignment sets MatIdx of element * GPxElement + 0 .. GPxElement-1)
+    more_materials: list = field(default_factory=list)
     out_every: int = 1000000
     solver_extra: dict = field(default_factory=dict)   # e.g. Beta-Newmark-beta, TOL-Newmark-beta, Max-Iter
 
@@ -183,6 +186,16 @@ def write_deck(spec: DeckSpec, outdir: str) -> str:
         lines.append(f"  {k}={v!r}")
     lines.append("}")
     lines.append("Assign-material-to-particles (MatIdx=0,Particles=AllElems.txt)")
+    for idx, (mat, elems) in enumerate(spec.more_materials, start=1):
+        lines.append(f"Define-Material(idx={idx},Model={mat.model})")
+        lines.append("{")
+        for k, v in mat.params.items():
+            lines.append(f"  {k}={v!r}")
+        lines.append("}")
+        with open(os.path.join(outdir, f"Mat{idx}Elems.txt"), "w") as f:
+            for e in elems:
+                f.write(f"{int(e)}\n")
+        lines.append(f"Assign-material-to-particles (MatIdx={idx},Particles=Mat{idx}Elems.txt)")
     lines.append(f"GramsOutputs (i={spec.out_every}) {{")
     lines.append("  DIR=Results")
     lines.append("  Out-velocity=true")

@@ -58,6 +58,9 @@ POINT_MATERIALS = {
 CHECKPOINTS = {"nh": (1, 2, 5, 20, 60), "dp": (1, 2, 5, 20, 60, 120), "mn": (1, 2, 5, 20, 60),
                "vm": (1, 2, 5, 20, 60, 120), "hencky": (1, 5, 60), "nhload": (1, 5, 40)}
 MATERIALS["nhload"] = MATERIALS["nh"]
+# two materials in one cloud (MatIdx per particle): the lower half Drucker-Prager, the upper half Neo-Hookean
+MATERIALS["mixed"] = MATERIALS["dp"]
+CHECKPOINTS["mixed"] = (1, 5, 60)
 TRACE_FIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "DF", "Stress", "rho", "J_n", "W", "b_e_n",
                 "EPS_n", "Kappa_n", "lambda", "Beta", "C_ep")
 
@@ -69,6 +72,10 @@ def spec_for(case):
     if cel:
         spec.cel = cel
     spec.nsteps = max(CHECKPOINTS[case])
+    if case == "mixed":
+        nh_model, nh_params, _ = MATERIALS["nh"]
+        upper = [j * spec.pnx + i for j in range(spec.pny // 2, spec.pny) for i in range(spec.pnx)]
+        spec.more_materials = [(deckgen.Material(nh_model, dict(nh_params, rho=2000.0)), upper)]
     if case == "nhload":
         # the loads the other decks do not have: a Neumann traction (K3: U-Verlet.c:805-902, __nodal_traction_forces of
         # U-Newmark-beta.c:1388-1500) on the right column of particle cells, and a platen -- Dirichlet set with non-zero
@@ -506,6 +513,7 @@ NEWMARK_CASES = {
     # Neumann traction + moving platen (spec_for("nhload")), dynamic and quasi-static
     "nhload": ("nhload", "Newmark-beta-Finite-Strains", 4.0, 1e-12, 25, 0, (1, 6)),
     "static_nhload": ("nhload", "Static", 0.5, 1e-11, 30, 0, (1, 3)),
+    "mixed": ("mixed", "Newmark-beta-Finite-Strains", 2.0, 1e-11, 25, 0, (1, 6)),
 }
 NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda",
                   "Beta", "Back_stress")
@@ -581,7 +589,7 @@ if __name__ == "__main__":
     if len(sys.argv) == 3:
         {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d, "config": gen_config, "newmark": gen_newmark, "newmark_run": gen_newmark_run}[sys.argv[1]](sys.argv[2])
     else:
-        for c in ("nh", "dp", "mn", "vm", "hencky", "nhload"):
+        for c in ("nh", "dp", "mn", "vm", "hencky", "nhload", "mixed"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
                            if os.environ.get("QUIET") else None)
         for c in ("dp", "mn", "ld"):

@@ -37,10 +37,11 @@ def test_initialize_lme_matches_reference(case):
     eng.close()
 
 
-@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload"))
+@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload", "mixed"))
 def test_steps_match_golden_reference(case):
     """Multi-step run against fixtures produced by the reference's compiled code.  nhload: Neumann traction on a column of
-    particles + a platen (Dirichlet set with non-zero displacement increments)."""
+    particles + a platen (Dirichlet set with non-zero displacement increments); mixed: two materials in one cloud
+    (Drucker-Prager below, Neo-Hookean above: the kernels that read the law per particle)."""
     P = load_problem(case)
     tr = load_trace(case)
     eng = engine.Engine(P, compute_c_ep=1)

@@ -36,7 +36,7 @@ def test_initialize_lme(case):
         assert np.abs(dN.sum(0)).max() < 1e-6
 
 
-@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload"))
+@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload", "mixed"))
 def test_steps_match_reference(case):
     P = load_problem(case)
     tr = load_trace(case)
