@@ -104,6 +104,10 @@ class Oracle:
                 v = _d(p[16:20])
                 L.orc_set_material_voce(h, j, v.ctypes.data_as(_dp))
         self.np_ = prob.np_
+        # GramsShapeFun (Type=aLME): the field "Beta" is the d x d metric, "Cut_off_Ellipsoid" the neighbour test
+        self.alme = bool(s.get("alme", 0))
+        if self.alme:
+            L.orc_set_shape_alme(h, 1)
         L.orc_set_num_particles(h, self.np_)
         for k, v in prob.fields.items():
             self.set_field(k, v)
@@ -114,11 +118,16 @@ class Oracle:
     def set_flags(self, quirk_transposed, compute_cep):
         self.L.orc_set_flags(self.h, int(quirk_transposed), int(compute_cep))
 
+    def _fname(self, name):
+        return "Beta_tensor" if (self.alme and name == "Beta") else name
+
     def set_field(self, name, arr):
         a = _d(arr)
+        name = self._fname(name)
         assert self.L.orc_set_field(self.h, name.encode(), a.ctypes.data_as(_dp)) == 0, name
 
     def field(self, name):
+        name = self._fname(name)
         c = self.L.orc_field_cols(self.h, name.encode())
         out = np.zeros((self.np_, c))
         self.L.orc_get_field(self.h, name.encode(), out.ctypes.data_as(_dp))

@@ -264,7 +264,15 @@ static double *field_ptr(const char *name, int *cols) {
   if (!strcmp(name, "Kappa_n")) return P->Kappa_n;
   if (!strcmp(name, "Kappa_n1")) return P->Kappa_n1;
   if (!strcmp(name, "lambda")) { *cols = d; return MPM_Mesh.lambda.nV; }
-  if (!strcmp(name, "Beta")) return MPM_Mesh.Beta.nV;
+  if (!strcmp(name, "Beta")) { /* LME: one thermalisation parameter; aLME: the d x d metric (Generate-One-Phase-Analysis.c:192-202) */
+    if (!strcmp(ShapeFunctionGP, "aLME")) *cols = d * d;
+    return MPM_Mesh.Beta.nV;
+  }
+  if (!strcmp(name, "Cut_off_Ellipsoid")) {
+    if (strcmp(ShapeFunctionGP, "aLME")) return NULL;
+    *cols = d * d;
+    return MPM_Mesh.Cut_off_Ellipsoid.nV;
+  }
   if (!strcmp(name, "Back_stress")) { *cols = 3; return P->Back_stress.nV; }
   return NULL;
 }

@@ -46,6 +46,7 @@ class DeckSpec:
     nsteps: int = 20
     gravity: tuple = (0.0, -9.81)
     gamma: float = 3.0
+    shape: str = "LME"      # GramsShapeFun type: "LME" | "aLME" (Read_GramsShapeFun.c:84-176)
     tol_zero: float = 1e-6
     tol_wrapper: float = 1e-10
     max_iter: int = 10
@@ -173,7 +174,7 @@ def write_deck(spec: DeckSpec, outdir: str) -> str:
                 _write_curve(os.path.join(outdir, cname), kind, scale, spec.nsteps)
                 lines.append(f"  {comp} {cname}")
         lines.append("}")
-    lines.append("GramsShapeFun (Type=LME) {")
+    lines.append(f"GramsShapeFun (Type={spec.shape}) {{")
     lines.append(f"  gamma={spec.gamma!r}")
     lines.append(f"  TOL-Zero={spec.tol_zero!r}")
     lines.append(f"  TOL-Wrapper={spec.tol_wrapper!r}")

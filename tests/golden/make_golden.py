@@ -61,8 +61,11 @@ MATERIALS["nhload"] = MATERIALS["nh"]
 # two materials in one cloud (MatIdx per particle): the lower half Drucker-Prager, the upper half Neo-Hookean
 MATERIALS["mixed"] = MATERIALS["dp"]
 CHECKPOINTS["mixed"] = (1, 5, 60)
+# GramsShapeFun (Type=aLME) (Nodes/aLME.c): the anisotropic shape functions, elastic and in plastic flow
+MATERIALS["almenh"], MATERIALS["almedp"] = MATERIALS["nh"], MATERIALS["dp"]
+CHECKPOINTS["almenh"], CHECKPOINTS["almedp"] = (1, 5, 40), (1, 20, 120)
 TRACE_FIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "DF", "Stress", "rho", "J_n", "W", "b_e_n",
-                "EPS_n", "Kappa_n", "lambda", "Beta", "C_ep")
+                "EPS_n", "Kappa_n", "lambda", "Beta", "C_ep")   # (aLME: Beta is the d x d metric; + Cut_off_Ellipsoid)
 
 
 def spec_for(case):
@@ -72,6 +75,8 @@ def spec_for(case):
     if cel:
         spec.cel = cel
     spec.nsteps = max(CHECKPOINTS[case])
+    if case.startswith("alme"):
+        spec.shape = "aLME"
     if case == "mixed":
         nh_model, nh_params, _ = MATERIALS["nh"]
         upper = [j * spec.pnx + i for j in range(spec.pny // 2, spec.pny) for i in range(spec.pnx)]
@@ -104,6 +109,8 @@ def gen_sim(case):
                 trace[t + f] = h.field(f)
             if case == "vm":
                 trace[t + "Back_stress"] = h.field("Back_stress")
+            if case.startswith("alme"):
+                trace[t + "Cut_off_Ellipsoid"] = h.field("Cut_off_Ellipsoid")
             for w, nm in enumerate(("M", "dU", "F", "A", "R")):
                 trace[t + "g" + nm] = h.nodal(w)
             lp, li = h.table(4)
@@ -514,6 +521,8 @@ NEWMARK_CASES = {
     "nhload": ("nhload", "Newmark-beta-Finite-Strains", 4.0, 1e-12, 25, 0, (1, 6)),
     "static_nhload": ("nhload", "Static", 0.5, 1e-11, 30, 0, (1, 3)),
     "mixed": ("mixed", "Newmark-beta-Finite-Strains", 2.0, 1e-11, 25, 0, (1, 6)),
+    "almenh": ("almenh", "Newmark-beta-Finite-Strains", 4.0, 1e-12, 25, 0, (1, 6)),
+    "almedp": ("almedp", "Newmark-beta-Finite-Strains", 2.0, 1e-11, 25, 0, (1, 8)),
 }
 NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda",
                   "Beta", "Back_stress")
@@ -552,6 +561,8 @@ def gen_newmark_run(key_steps):
     st = np.zeros(5)
     h.lib.refh_newmark_stats(st.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
     res = {f: h.field(f) for f in NEWMARK_FIELDS}
+    if key.startswith("alme"):
+        res["Cut_off_Ellipsoid"] = h.field("Cut_off_Ellipsoid")
     res["I0"] = h.ints("I0")
     res["NumberNodes"] = h.ints("NumberNodes")
     res["stats"] = st
@@ -589,7 +600,7 @@ if __name__ == "__main__":
     if len(sys.argv) == 3:
         {"sim": gen_sim, "points": gen_points, "tangent": gen_tangent_blocks, "points3d": gen_points3d, "lme3d": gen_lme3d, "nh3d": gen_nh3d, "lists3d": gen_lists3d, "kin3d": gen_kin3d, "config": gen_config, "newmark": gen_newmark, "newmark_run": gen_newmark_run}[sys.argv[1]](sys.argv[2])
     else:
-        for c in ("nh", "dp", "mn", "vm", "hencky", "nhload", "mixed"):
+        for c in ("nh", "dp", "mn", "vm", "hencky", "nhload", "mixed", "almenh", "almedp"):
             subprocess.run([sys.executable, __file__, "sim", c], check=True, stdout=subprocess.DEVNULL
                            if os.environ.get("QUIET") else None)
         for c in ("dp", "mn", "ld"):

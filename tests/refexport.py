@@ -34,6 +34,11 @@ def problem_from_ref(h, conn=None) -> Problem:
     p.neumann = h.neumann() if hasattr(h.lib, "refh_neumann_nodes") else []
     p.materials = [h.material(m) for m in range(h.lib.refh_num_materials())]
     p.fields = {k: h.field(k) for k in ALL_FIELDS}
+    try:  # GramsShapeFun (Type=aLME): Beta is the d x d metric (exported above), plus the cut-off ellipsoid
+        p.fields["Cut_off_Ellipsoid"] = h.field("Cut_off_Ellipsoid")
+        solver["alme"] = 1
+    except KeyError:
+        pass
     if any(t == "Von-Mises" for t, _ in p.materials):
         p.fields["Back_stress"] = h.field("Back_stress")
     p.I0 = h.ints("I0")

@@ -149,7 +149,7 @@ def test_static_scheme_balances_gravity():
 
 # ---- the scheme itself, pinned: the reference's OWN compiled U-Newmark-beta.c / U-Static.c (run against oracle/minipetsc,
 # tests/golden/make_golden.py::gen_newmark) froze converged states of 2D decks; the restatement reproduces them
-NEWMARK_KEYS = ["nh", "nh_trial", "dp", "mn", "static_nh", "vm", "vm_plastic", "hencky", "nhload", "static_nhload", "mixed"]
+NEWMARK_KEYS = ["nh", "nh_trial", "dp", "mn", "static_nh", "vm", "vm_plastic", "hencky", "nhload", "static_nhload", "mixed", "almenh", "almedp"]
 NEWMARK_FIELDS = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "W", "b_e_n", "EPS_n", "Kappa_n", "lambda")
 
 
@@ -180,11 +180,12 @@ def test_scheme_matches_the_reference_compiled_scheme(key):
             assert stats[3] == 0     # every solve of the reference run converged
         assert iters == int(stats[1]), (iters, stats)
         sc = field_scales(P)
-        for name in NEWMARK_FIELDS + (("Back_stress",) if key.startswith("vm") else ()):
+        for name in NEWMARK_FIELDS + (("Back_stress",) if key.startswith("vm") else ()) + \
+                (("Beta", "Cut_off_Ellipsoid") if key.startswith("alme") else ()):
             assert_close(o.field(name), g[f"s{k}_{name}"], f"newmark {key} step {k} {name}", rtol=1e-12, scale=sc.get(name))
         assert np.array_equal(o.ints("I0"), g[f"s{k}_I0"])
         assert np.array_equal(o.ints("NumberNodes"), g[f"s{k}_NumberNodes"])
     last = int(max(g["checkpoints"]))
     assert np.abs(g[f"s{last}_dis"]).max() > 1e-5
-    if key in ("dp", "vm_plastic", "mixed"):
+    if key in ("dp", "vm_plastic", "mixed", "almedp"):
         assert (g[f"s{last}_EPS_n"] > 0).sum() > 20   # plastic flow reached

@@ -19,15 +19,20 @@ def test_locality_bit_exact(case):
     assert dx == P.dx
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + ("almenh",))
 def test_initialize_lme(case):
+    """almenh: initialize__aLME__ (Nodes/aLME.c:32-166) -- isotropic metric and cut-off ellipsoid, lists, lambda."""
     P = load_problem(case)
     P0 = P.copy()
     P0.fields["Beta"][:] = 0.0
     P0.fields["lambda"][:] = 0.0
+    if case.startswith("alme"):
+        P0.fields["Cut_off_Ellipsoid"][:] = 0.0
     o = oracle.Oracle(P0)
     assert o.init_lme() == 0
     assert np.array_equal(o.field("Beta"), P.fields["Beta"])
+    if case.startswith("alme"):
+        assert np.array_equal(o.field("Cut_off_Ellipsoid"), P.fields["Cut_off_Ellipsoid"])
     assert_close(o.field("lambda"), P.fields["lambda"], "lambda after initialize__LME__")
     # partition of unity / first-order consistency of the converged weights
     for p in (0, P.np_ // 2, P.np_ - 1):
@@ -36,7 +41,7 @@ def test_initialize_lme(case):
         assert np.abs(dN.sum(0)).max() < 1e-6
 
 
-@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload", "mixed"))
+@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload", "mixed", "almenh", "almedp"))
 def test_steps_match_reference(case):
     P = load_problem(case)
     tr = load_trace(case)
@@ -54,10 +59,11 @@ def test_steps_match_reference(case):
         assert np.array_equal(o.active(), tr[t + "active"])
         # (Von-Mises: the reference's elastic branch hands an uninitialised kappa_k to __tangent_moduli, Von-Mises.c:262,379,
         # where it only multiplies n (x) n = 0: C_ep is defined and compared, like the back stress)
-        for f in TRACE_FIELDS + (("Back_stress", "C_ep") if case == "vm" else ("C_ep",)):
+        for f in TRACE_FIELDS + (("Back_stress", "C_ep") if case == "vm" else ("C_ep",)) + \
+                (("Cut_off_Ellipsoid",) if case.startswith("alme") else ()):
             assert_close(o.field(f), tr[t + f], f"{case} step {k + 1} {f}", scale=scales.get(f))
-            if case in ("vm", "hencky"):
-                assert np.array_equal(o.field(f), tr[t + f]), f"{case} step {k + 1} {f}: not bit-exact"
+            if case in ("vm", "hencky", "almenh", "almedp"):  # (nan == nan: the apex tangent of Drucker-Prager with psi = 0)
+                assert np.array_equal(o.field(f), tr[t + f], equal_nan=True), f"{case} step {k + 1} {f}: not bit-exact"
         for w, nm in enumerate(NODAL):
             assert_close(o.nodal(w), tr[t + "g" + nm], f"{case} step {k + 1} nodal {nm}")
 
