@@ -108,7 +108,13 @@ typedef struct nlps_solver {
                                 * reproduces them, but its result depends on the arbitrary eigenvectors of degenerate
                                 * trial states -- DESIGN.md section 6, deviation 3) */
   int compute_c_ep;            /* write Phi.C_ep (needed by the implicit tangent only) */
+  int shape_function;          /* the global ShapeFunctionGP (GramsShapeFun, Read_GramsShapeFun.c:84-176): NLPS_SHAPE_LME
+                                * (Nodes/LME.c) or NLPS_SHAPE_ALME (Nodes/aLME.c: a d x d thermalisation metric and a
+                                * cut-off ellipsoid per particle, both convected with DF^-1 at every search; 2D only, as
+                                * in the reference, whose aLME.c:693-809 exits in 3D; single engine, no slabs) */
 } nlps_solver;
+#define NLPS_SHAPE_LME 0
+#define NLPS_SHAPE_ALME 1
 
 /* Host views of `Particle` / `Fields` (Types.h:548-623,184-283).  Any pointer may
  * be NULL in download()/upload() calls (then that field is skipped); create()
@@ -122,7 +128,7 @@ typedef struct nlps_particles {
   double *J_n, *J_n1, *mass, *rho, *Vol_0, *W;            /* n */
   double *EPS_n, *EPS_n1, *Kappa_n, *Kappa_n1;            /* n */
   double *lambda; /* n x d  (Particle.lambda) */
-  double *Beta;   /* n      (Particle.Beta)   */
+  double *Beta;   /* n      (Particle.Beta); n x d*d with NLPS_SHAPE_ALME (Generate-One-Phase-Analysis.c:192-202) */
   int *I0, *NumberNodes, *MatIdx;                         /* n */
   double *Area_0; /* n: Particle.Phi.Area_0, the area a 3D Neumann load acts on (U-Verlet.c:847-849,
                    * U-Newmark-beta.c:1442, U-Static.c:930); 2D uses Vol_0 / Thickness_Plain_Stress and ignores it.
@@ -130,6 +136,8 @@ typedef struct nlps_particles {
   double *Back_stress; /* n x 3: Particle.Phi.Back_stress (Types.h:266), the kinematic-hardening back stress of Von-Mises in
                         * PRINCIPAL components (Von-Mises.c:256-258,729-731), updated in place; NULL = zero and not
                         * written back. */
+  double *Cut_off_Ellipsoid; /* n x d*d: Particle.Cut_off_Ellipsoid, the metric of the neighbour test of aLME
+                              * (aLME.c:811-872); read and written with NLPS_SHAPE_ALME only, else ignored */
 } nlps_particles;
 
 typedef struct nlps_engine nlps_engine;

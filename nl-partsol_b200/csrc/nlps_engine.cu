@@ -631,7 +631,7 @@ __device__ __forceinline__ double pair_sum(double v, unsigned pm) {
 }
 template <int D, int W, bool CACHE>
 __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg, int* err,
-                                                 int do_predictor) {
+                                                 int do_predictor, const AlmeDev al) {
   extern __shared__ __align__(16) unsigned char smem[];
   const LayoutA<D, W, CACHE> L(cfg);
   int* s_rank = (int*)(smem + L.rank); unsigned char* s_q = smem + L.q; double* s_X = (double*)(smem + L.X);
@@ -671,6 +671,34 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
       for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
       const double beta_old = P.beta[p];
       const double mp = P.mass[p];
+      // aLME (Nodes/aLME.c): the particle's metric B and cut-off ellipsoid C of this search -- set from h_avg of the closest
+      // node by the initialisation (:32-166), convected with the last DF^-1 by every later search (:645-652)
+      double Bm[4] = {0.0, 0.0, 0.0, 0.0}, Cm[4] = {0.0, 0.0, 0.0, 0.0};
+      const bool alme = (D == 2) && al.bten != nullptr;
+      if (D == 2 && alme) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) { Bm[c] = al.bten[(size_t)c * np + p]; Cm[c] = al.cten[(size_t)c * np + p]; }
+        if (!sp.reuse_lists) {
+          if (!sp.update_I0) {
+            const double hA = m.h_avg[s_B[ci]];
+            Bm[0] = Bm[3] = __ddiv_rn(sp.gamma_lme, __dmul_rn(hA, hA));
+            Cm[0] = Cm[3] = __ddiv_rn(sp.gamma_lme, __dmul_rn(__dmul_rn(sp.neg_log_tol, hA), hA));
+            Bm[1] = Bm[2] = Cm[1] = Cm[2] = 0.0;
+          } else {
+            double DFm[4], Fi[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) DFm[c] = P.DF[(size_t)c * np + p];
+            if (inverse<2>(DFm, Fi) == 0.0) { if (sub == 0) latch_error(err, NLPS_ERR_SINGULAR_DF, P.orig[p]); }
+            alme_push_forward(Fi, Bm);
+            alme_push_forward(Fi, Cm);
+          }
+          if (sub == 0) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) { al.bten[(size_t)c * np + p] = Bm[c]; al.cten[(size_t)c * np + p] = Cm[c]; }
+          }
+        }
+      }
+      const MetricB MB = {Bm[0], Bm[1] + Bm[2], Bm[3], alme ? 1 : 0};
       double pv[D], pa_[D];  // requested now, consumed by the predictor after the Newton loop
 #pragma unroll
       for (int i = 0; i < D; i++) {
@@ -696,7 +724,8 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
             if (rk[k] < 0) continue;  // inactive node
             double l[D];
             const double s = dist2_exact<D>(xp, Xc + k * D, l);
-            if (s <= sstar) { mk[k >> 5] |= 1u << (k & 31); n++; }
+            const bool in = (D == 2 && alme) ? alme_distance(Cm, l) <= 1.0 : s <= sstar;  // tributary__aLME__ (aLME.c:811-872)
+            if (in) { mk[k >> 5] |= 1u << (k & 31); n++; }
           }
         } else {
 #pragma unroll
@@ -707,7 +736,8 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
               if (rk[k] < 0) continue;
               double l[D];
               const double s = dist2_exact<D>(xp, Xc + k * D, l);
-              if (s <= sstar) { mk[w] |= 1u << (k & 31); n++; }
+              const bool in = (D == 2 && alme) ? alme_distance(Cm, l) <= 1.0 : s <= sstar;
+              if (in) { mk[w] |= 1u << (k & 31); n++; }
             }
           }
 #pragma unroll
@@ -756,8 +786,8 @@ __global__ void __launch_bounds__(128) k_lme_p2g(MeshDev m, PartDev P, GridDev G
             lx0 += l0[i] * lam[i];
             lx1 += l1[i] * lam[i];
           }
-          const double e0 = fexp(-beta * ll0 + lx0, s_tab) * w0;
-          const double e1 = fexp(-beta * ll1 + lx1, s_tab) * w1;
+          const double e0 = fexp(-metric_q<D>(MB, beta, ll0, l0) + lx0, s_tab) * w0;
+          const double e1 = fexp(-metric_q<D>(MB, beta, ll1, l1) + lx1, s_tab) * w1;
           if (CACHE) {
             s_pa[(size_t)j * SL + k0] = e0;
             if (k1 != k0) s_pa[(size_t)j * SL + k1] = e1;
@@ -1097,7 +1127,8 @@ template <int D, int W, int MAT, bool CACHE>
 __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_force(MeshDev m, PartDev P, GridDev G,
                                                                                 StepParams sp, BlockCfg cfg, int* err,
                                                                                 int has_traction,
-                                                                                const __grid_constant__ MatTable mt) {
+                                                                                const __grid_constant__ MatTable mt,
+                                                                                const AlmeDev al) {
   extern __shared__ __align__(16) unsigned char smem[];
   const LayoutB<D, W, CACHE> L(cfg);
   int* s_rank = (int*)(smem + L.rank); unsigned char* s_q = smem + L.q; double* s_X = (double*)(smem + L.X);
@@ -1123,6 +1154,7 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
 #pragma unroll
       for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
       const double beta = P.beta[p];
+      const MetricB MB = metric_load<D>(al, P.ld, p);  // aLME: the particle's metric instead of beta
       uint32_t mk[W];
 #pragma unroll
       for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
@@ -1173,8 +1205,8 @@ __global__ void __launch_bounds__(128, (MAT == 0 || MAT == 1) ? 3 : 2) k_kin_for
           lx0 += l0[i] * lam[i];
           lx1 += l1[i] * lam[i];
         }
-        const double e0 = fexp(-beta * ll0 + lx0, s_tab) * w0;
-        const double e1 = fexp(-beta * ll1 + lx1, s_tab) * w1;
+        const double e0 = fexp(-metric_q<D>(MB, beta, ll0, l0) + lx0, s_tab) * w0;
+        const double e1 = fexp(-metric_q<D>(MB, beta, ll1, l1) + lx1, s_tab) * w1;
         if (CACHE) {
           s_pa[(size_t)j * SL + k0] = e0;
           if (k1 != k0) s_pa[(size_t)j * SL + k1] = e1;
@@ -1459,7 +1491,7 @@ __global__ void __launch_bounds__(128) k_grid_acc(MeshDev m, GridDev G, const do
 // K4: G2P + corrector (U-Verlet.c:963-1084).  The n+1 -> n roll of F, J, b_e, kappa, EPS is a
 // pointer swap on the host side of the engine.
 template <int D, int W>
-__global__ void __launch_bounds__(128, D == 2 ? 5 : 3) k_g2p(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg) {
+__global__ void __launch_bounds__(128, D == 2 ? 5 : 3) k_g2p(MeshDev m, PartDev P, GridDev G, StepParams sp, BlockCfg cfg, const AlmeDev al) {
   extern __shared__ __align__(16) unsigned char smem[];
   const LayoutC<D> L(cfg);
   int* s_rank = (int*)(smem + L.rank); double* s_X = (double*)(smem + L.X);
@@ -1490,6 +1522,7 @@ __global__ void __launch_bounds__(128, D == 2 ? 5 : 3) k_g2p(MeshDev m, PartDev 
       pvl[i] = P.vel[i * np + p]; pds[i] = P.dis[i * np + p];  // consumed by the corrector after the loop
     }
     const double beta = P.beta[p];
+    const MetricB MB = metric_load<D>(al, P.ld, p);  // aLME: the particle's metric instead of beta
     double Z = 0.0;
     uint32_t mk[W];
 #pragma unroll
@@ -1502,16 +1535,18 @@ __global__ void __launch_bounds__(128, D == 2 ? 5 : 3) k_g2p(MeshDev m, PartDev 
       ldsvec<D>(Uc + k1 * D, U1);
       ldsvec<D>(Ac + k0 * D, A0);
       ldsvec<D>(Ac + k1 * D, A1);
+      double l0[D], l1[D];
 #pragma unroll
       for (int i = 0; i < D; i++) {
-        const double l0 = xp[i] - X0[i], l1 = xp[i] - X1[i];
-        ll0 += l0 * l0;
-        ll1 += l1 * l1;
-        lx0 += l0 * lam[i];
-        lx1 += l1 * lam[i];
+        l0[i] = xp[i] - X0[i];
+        l1[i] = xp[i] - X1[i];
+        ll0 += l0[i] * l0[i];
+        ll1 += l1[i] * l1[i];
+        lx0 += l0[i] * lam[i];
+        lx1 += l1[i] * lam[i];
       }
-      const double e0 = fexp(-beta * ll0 + lx0, s_tab) * w0;
-      const double e1 = fexp(-beta * ll1 + lx1, s_tab) * w1;
+      const double e0 = fexp(-metric_q<D>(MB, beta, ll0, l0) + lx0, s_tab) * w0;
+      const double e1 = fexp(-metric_q<D>(MB, beta, ll1, l1) + lx1, s_tab) * w1;
       Z += e0;
 #pragma unroll
       for (int i = 0; i < D; i++) {
@@ -1858,6 +1893,7 @@ struct nlps_engine {
   cudaStream_t stream = nullptr;
   MeshDev mesh{};
   PartDev P{};
+  AlmeDev alme{};  // aLME shape functions (2D): metric and cut-off ellipsoid per particle, else nullptr
   GridDev G{};
   BcDev bc{};
   NeuDev neu{};
@@ -2449,7 +2485,7 @@ static void reorder_particles(nlps_engine* e) {
   gd(P.beta, 1); gd(P.mass, 1); gd(P.vol0, 1); gd(P.rho, 1); gd(P.W, 1);
   gd(P.J_n, 1); gd(P.J_n1, 1); gd(P.eps_n, 1); gd(P.eps_n1, 1); gd(P.kap_n, 1); gd(P.kap_n1, 1);
   gd(P.F_n, DD); gd(P.F_n1, DD); gd(P.DF, DD); gd(P.be_n, T); gd(P.be_n1, T); gd(P.stress, T); gd(P.cep, DD);
-  gd(P.Fs4, 1); gd(P.DFs4, 1); gd(P.area0, 1); gd(P.sstar, 1); gd(P.back, 3);
+  gd(P.Fs4, 1); gd(P.DFs4, 1); gd(P.area0, 1); gd(P.sstar, 1); gd(P.back, 3); gd(e->alme.bten, 4); gd(e->alme.cten, 4);
   gi(P.I0, 1); gi(P.nnodes, 1); gi(P.matidx, 1); gi(P.orig, 1); gi((int*)P.mask, e->W);
   k_after_sort<<<nblk(np, 256), 256, 0, e->stream>>>(P, e->G);
   e->launches++;
@@ -2681,7 +2717,7 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
       return;
     }
     const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
-#define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, 0); }
+#define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, 0, e->alme); }
 #define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
 #define CASE_WF(w) case w: CASE_WC(w, false) break;
     if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_WF(4) CASE_WF(8) } }
@@ -2718,7 +2754,7 @@ static void stage_search_t(nlps_engine* e, int step, int update_I0, int do_predi
     return;
   }
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
-#define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, do_predictor); }
+#define CASE_WC(w, c) { auto kfn = k_lme_p2g<D, w, c>; LAUNCH_SMEM(e, K_LME_P2G, kfn, grid, e->cfg.threads, e->smemA, e->mesh, e->P, e->G, sp, e->cfg, e->err, do_predictor, e->alme); }
 #define CASE_W(w) case w: if (e->cache_pa) CASE_WC(w, true) else CASE_WC(w, false) break;
 #define CASE_WF(w) case w: CASE_WC(w, false) break;
   // instantiated: 2D with 1-2 mask words (weights cached or not), 3D with 4-8 words (no weight cache)
@@ -2786,7 +2822,7 @@ static void stage_kin_stress_t(nlps_engine* e, int step) {
     return;
   }
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
-#define CASE_WMC(w, mt, c) { auto kfn = k_kin_force<D, w, mt, c>; LAUNCH_SMEM(e, K_KIN_FORCE, kfn, grid, e->cfg.threads, e->smemB, e->mesh, e->P, e->G, sp, e->cfg, e->err, e->has_traction, e->mat); }
+#define CASE_WMC(w, mt, c) { auto kfn = k_kin_force<D, w, mt, c>; LAUNCH_SMEM(e, K_KIN_FORCE, kfn, grid, e->cfg.threads, e->smemB, e->mesh, e->P, e->G, sp, e->cfg, e->err, e->has_traction, e->mat, e->alme); }
 #define CASE_WM(w, mt) if (D == 2 && e->cache_pa) CASE_WMC(w, mt, (D == 2)) else CASE_WMC(w, mt, false)
 #define CASE_W(w) case w: switch (e->uniform_mat) { case 0: CASE_WM(w, 0) break; case 1: CASE_WM(w, 1) break; case 2: CASE_WM(w, 2) break; default: CASE_WM(w, -1) break; } break;
   if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_W(4) CASE_W(8) } }
@@ -2813,7 +2849,7 @@ static void stage_g2p_t(nlps_engine* e, int step) {
     CW_TIMED(e, K_G2P, cw_launch_g2p(D, L, e->cws, e->sm_count, e->max_smem_optin));
   } else {
   const int grid = std::max(1, nblk((size_t)e->max_occ, e->cfg.C));
-#define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH_SMEM(e, K_G2P, kfn, grid, e->cfg.threads, e->smemC, e->mesh, e->P, e->G, sp, e->cfg); } break;
+#define CASE_W(w) case w: { auto kfn = k_g2p<D, w>; LAUNCH_SMEM(e, K_G2P, kfn, grid, e->cfg.threads, e->smemC, e->mesh, e->P, e->G, sp, e->cfg, e->alme); } break;
   if constexpr (D == 2) { switch (e->W) { CASE_W(1) CASE_W(2) } } else { switch (e->W) { CASE_W(4) CASE_W(8) } }
 #undef CASE_W
   }
@@ -3257,6 +3293,20 @@ static int create_impl(nlps_engine* e, const nlps_mesh* mesh, const nlps_solver*
       return set_err(err, err_len, "3D Neumann loads act on Particle.Phi.Area_0 (U-Verlet.c:847-849): state->Area_0 is NULL");
     if (dev_alloc(e, &P.area0, (size_t)ld)) return 1;
   }
+  // GramsShapeFun (Type=aLME): metric and cut-off ellipsoid per particle (Nodes/aLME.c).  2D only, as the reference
+  // (aLME.c:693-809 exits in 3D); the weights of the 2D kernels must stay cached in shared memory (the uncached cell
+  // phases re-evaluate them with the scalar beta); single engine (the columns do not migrate between slabs)
+  e->alme.bten = e->alme.cten = nullptr;
+  if (e->solver.shape_function == NLPS_SHAPE_ALME) {
+    if (D != 2) return set_err(err, err_len, "aLME shape functions are 2D only (Nodes/aLME.c:693-809 exits in 3D)");
+    if (e->slab_on) return set_err(err, err_len, "aLME shape functions: single engine only (no slabs)");
+    if (!e->cache_pa) return set_err(err, err_len, "aLME shape functions need NLPS_CACHE_PA=1 (the default in 2D)");
+    if (dev_alloc(e, &e->alme.bten, (size_t)ld * 4) || dev_alloc(e, &e->alme.cten, (size_t)ld * 4)) return 1;
+    CUDA_OK(cudaMemsetAsync(e->alme.bten, 0, sizeof(double) * (size_t)ld * 4, e->stream));
+    CUDA_OK(cudaMemsetAsync(e->alme.cten, 0, sizeof(double) * (size_t)ld * 4, e->stream));
+  } else if (e->solver.shape_function != NLPS_SHAPE_LME) {
+    return set_err(err, err_len, "solver.shape_function must be NLPS_SHAPE_LME or NLPS_SHAPE_ALME");
+  }
   P.back = nullptr;
   for (int i = 0; i < n_materials; i++)
     if (materials[i].type == NLPS_MAT_VON_MISES && !P.back) {
@@ -3544,8 +3594,9 @@ static int upload_impl(nlps_engine* e, const nlps_particles* in, int rows) {
       put_field(e, in->Vol_0, P.vol0, 1, 1, 0, rows) || put_field(e, in->W, P.W, 1, 1, 0, rows) ||
       put_field(e, in->EPS_n, P.eps_n, 1, 1, 0, rows) || put_field(e, in->EPS_n1, P.eps_n1, 1, 1, 0, rows) ||
       put_field(e, in->Kappa_n, P.kap_n, 1, 1, 0, rows) || put_field(e, in->Kappa_n1, P.kap_n1, 1, 1, 0, rows) ||
-      put_field(e, in->Beta, P.beta, 1, 1, 0, rows) || put_field(e, in->Area_0, P.area0, 1, 1, 0, rows) ||
-      put_field(e, in->Back_stress, P.back, 3, 3, 0, rows))
+      (e->alme.bten ? put_field(e, in->Beta, e->alme.bten, 4, 4, 0, rows) : put_field(e, in->Beta, P.beta, 1, 1, 0, rows)) ||
+      (e->alme.cten && put_field(e, in->Cut_off_Ellipsoid, e->alme.cten, 4, 4, 0, rows)) ||
+      put_field(e, in->Area_0, P.area0, 1, 1, 0, rows) || put_field(e, in->Back_stress, P.back, 3, 3, 0, rows))
     return 1;
   if (e->np) k_sstar_particles<<<nblk(e->np, 256), 256, 0, e->stream>>>(P.beta, e->np, e->neg_log_tol, P.sstar);
   return 0;
@@ -3586,7 +3637,8 @@ static int download_impl(nlps_engine* e, nlps_particles* out, int rows) {
       get_field(e, out->Vol_0, P.vol0, 1, 1, 0, nullptr, rows) || get_field(e, out->W, P.W, 1, 1, 0, nullptr, rows) ||
       get_field(e, out->EPS_n, P.eps_n, 1, 1, 0, nullptr, rows) || get_field(e, out->EPS_n1, eps1, 1, 1, 0, nullptr, rows) ||
       get_field(e, out->Kappa_n, P.kap_n, 1, 1, 0, nullptr, rows) || get_field(e, out->Kappa_n1, kap1, 1, 1, 0, nullptr, rows) ||
-      get_field(e, out->Beta, P.beta, 1, 1, 0, nullptr, rows) ||
+      (e->alme.bten ? get_field(e, out->Beta, e->alme.bten, 4, 4, 0, nullptr, rows) : get_field(e, out->Beta, P.beta, 1, 1, 0, nullptr, rows)) ||
+      (e->alme.cten && get_field(e, out->Cut_off_Ellipsoid, e->alme.cten, 4, 4, 0, nullptr, rows)) ||
       (P.back && get_field(e, out->Back_stress, P.back, 3, 3, 0, nullptr, rows)))
     return 1;
   if (get_ints(e, out->I0, P.I0, rows) || get_ints(e, out->NumberNodes, P.nnodes, rows)) return 1;
@@ -3790,7 +3842,7 @@ long long nlps_b200_launch_count(nlps_engine* e) { return e->launches; }
 // flush: the D2H copies run on dl_stream after the snapshot, while the compute stream is already stepping on.
 static int snapshot_prepare(nlps_engine* e) {
   const int D = e->D, T = e->T, DD = D * D;
-  const size_t per = 6 * (size_t)D + 6 * (size_t)T + DD + 11 + 2 + 4;
+  const size_t per = 6 * (size_t)D + 6 * (size_t)T + DD + 11 + 2 + 4 + (e->alme.bten ? 8 : 0);  // aLME: metric + ellipsoid
   const size_t need = per * (size_t)std::max(e->np, 1) + 2 * 40;
   if (!e->dl_stream) {
     CUDA_OK(cudaStreamCreateWithFlags(&e->dl_stream, cudaStreamNonBlocking));

@@ -248,7 +248,7 @@ __device__ __forceinline__ int csr_find(const int* cols, int lo, int hi, int key
 // flow rule is not associated, hence BiCGStab below.  The law is read per particle (mixed clouds work).
 template <int D, int W, bool EP>
 __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridDev G, const int* row_ptr, const int* cols, double* vals,
-                                                     int* err, const __grid_constant__ MatTable mt) {
+                                                     int* err, const __grid_constant__ MatTable mt, const AlmeDev al) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int NMAX = 32 * W, DD = D * D;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridD
 #pragma unroll
     for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
     const double beta = P.beta[p];
+    const MetricB MB = metric_load<D>(al, P.ld, p);  // aLME: the particle's metric instead of beta
     uint32_t mk[W];
     int n = 0, off[W];
 #pragma unroll
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridD
         ldvec<D>(&m.X[(size_t)node * NS<D>::X], XA);
 #pragma unroll
         for (int i = 0; i < D; i++) { l_[w][i] = xp[i] - XA[i]; ll += l_[w][i] * l_[w][i]; lx += l_[w][i] * lam[i]; }
-        e_[w] = exp(-beta * ll + lx);
+        e_[w] = exp(-metric_q<D>(MB, beta, ll, l_[w]) + lx);
         red[0] += e_[w];
 #pragma unroll
         for (int i = 0; i < D; i++) {
@@ -453,7 +454,8 @@ __global__ void __launch_bounds__(128) k_assemble_nh(MeshDev m, PartDev P, GridD
 // particle (3D, 8 particles per cell: 2.8x fewer RED.E.ADD.F64, the unit that bounds the assembly).
 template <int D, int W>
 __global__ void __launch_bounds__(128) k_assemble_cell_nh(MeshDev m, PartDev P, GridDev G, const int* row_ptr, const int* cols,
-                                                          double* vals, int* err, const __grid_constant__ MatTable mats) {
+                                                          double* vals, int* err, const __grid_constant__ MatTable mats,
+                                                          const AlmeDev al) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int SL = 32 * W, DD = D * D, MP = 8, V = 3 * D;
   double* s_g = (double*)smem;                        // [MP][SL][V]: g | g1 | b_n g
@@ -480,6 +482,7 @@ __global__ void __launch_bounds__(128) k_assemble_cell_nh(MeshDev m, PartDev P, 
 #pragma unroll
         for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; }
         const double beta = P.beta[p];
+        const MetricB MB = metric_load<D>(al, P.ld, p);  // aLME: the particle's metric instead of beta
         uint32_t mk[W];
 #pragma unroll
         for (int w = 0; w < W; w++) mk[w] = P.mask[(size_t)w * np + p];
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(128) k_assemble_cell_nh(MeshDev m, PartDev P, 
             ldvec<D>(&m.X[(size_t)node * NS<D>::X], XA);
 #pragma unroll
             for (int i = 0; i < D; i++) { l_[w][i] = xp[i] - XA[i]; ll += l_[w][i] * l_[w][i]; lx += l_[w][i] * lam[i]; }
-            e_[w] = exp(-beta * ll + lx);
+            e_[w] = exp(-metric_q<D>(MB, beta, ll, l_[w]) + lx);
             red[0] += e_[w];
 #pragma unroll
             for (int i = 0; i < D; i++) {
@@ -812,7 +815,8 @@ __global__ void __launch_bounds__(256) k_vec_neg(const int* n_active, int D, con
 // alpha_blend = 1) and rho = m / (V0 J) (:1929-1932); thread per particle
 template <int D, int W>
 __global__ void __launch_bounds__(128) k_g2p_implicit(MeshDev m, PartDev P, GridDev G, double a1, double a2, double a3, double a4,
-                                                      double a5, double a6, const double* dU, const double* Vn, const double* An) {
+                                                      double a5, double a6, const double* dU, const double* Vn, const double* An,
+                                                      const AlmeDev al) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P.np) return;
   const int np = P.ld, base = m.r2p[P.I0[p]];
@@ -820,6 +824,7 @@ __global__ void __launch_bounds__(128) k_g2p_implicit(MeshDev m, PartDev P, Grid
 #pragma unroll
   for (int i = 0; i < D; i++) { xp[i] = P.x[i * np + p]; lam[i] = P.lam[i * np + p]; sU[i] = sV[i] = sA[i] = 0.0; }
   const double beta = P.beta[p];
+  const MetricB MB = metric_load<D>(al, P.ld, p);  // aLME: the particle's metric instead of beta
 #pragma unroll
   for (int w = 0; w < W; w++) {
     uint32_t mm = P.mask[(size_t)w * np + p];
@@ -829,9 +834,10 @@ __global__ void __launch_bounds__(128) k_g2p_implicit(MeshDev m, PartDev P, Grid
       const int node = m.r2i[base + k];
       double XA[D], ll = 0.0, lx = 0.0;
       ldvec<D>(&m.X[(size_t)node * NS<D>::X], XA);
+      double lv[D];
 #pragma unroll
-      for (int i = 0; i < D; i++) { const double l = xp[i] - XA[i]; ll += l * l; lx += l * lam[i]; }
-      const double e = exp(-beta * ll + lx);
+      for (int i = 0; i < D; i++) { lv[i] = xp[i] - XA[i]; ll += lv[i] * lv[i]; lx += lv[i] * lam[i]; }
+      const double e = exp(-metric_q<D>(MB, beta, ll, lv) + lx);
       const size_t t = (size_t)G.arank[node];
       Z += e;
 #pragma unroll
@@ -1082,7 +1088,7 @@ static int imp_assemble_t(nlps_engine* e) {
     const size_t smem = (size_t)wpb * 32 * W * (3 * D * sizeof(double) + sizeof(int));
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = std::max(1, std::min(nblk(e->np, wpb), e->sm_count * 8));
-    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err, e->mat);
+    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err, e->mat, e->alme);
   };
   auto launch_cell = [&](auto kfn, int W) {
     const int SL = 32 * W, MP = 8;
@@ -1090,7 +1096,7 @@ static int imp_assemble_t(nlps_engine* e) {
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int per_sm = std::max(1, std::min(8, (int)((size_t)e->max_smem_optin / (smem + 1024))));
     const int grid = std::max(1, std::min(std::max(e->max_occ, 1), e->sm_count * per_sm));
-    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err, e->mat);
+    kfn<<<grid, threads, smem, e->stream>>>(e->mesh, e->P, e->G, c->row_ptr, c->cols, c->vals, e->err, e->mat, e->alme);
   };
   static const bool cell_asm = !(getenv("NLPS_ASM_CELL") && atoi(getenv("NLPS_ASM_CELL")) == 0);
   if (!c->plastic && cell_asm) {
@@ -1286,7 +1292,7 @@ static int imp_step_t(nlps_engine* e, int step) {
   if (status) return status;
   // G3 + K4
   auto g2p = [&](auto kfn) {
-    kfn<<<nblk(std::max(e->np, 1), 128), 128, 0, e->stream>>>(e->mesh, e->P, e->G, c->a1, c->a2, c->a3, c->a4, c->a5, c->a6, c->dU, c->Vn, c->An);
+    kfn<<<nblk(std::max(e->np, 1), 128), 128, 0, e->stream>>>(e->mesh, e->P, e->G, c->a1, c->a2, c->a3, c->a4, c->a5, c->a6, c->dU, c->Vn, c->An, e->alme);
   };
   if constexpr (D == 2) { if (e->W == 1) g2p(k_g2p_implicit<2, 1>); else g2p(k_g2p_implicit<2, 2>); }
   else { if (e->W == 4) g2p(k_g2p_implicit<3, 4>); else g2p(k_g2p_implicit<3, 8>); }

@@ -139,6 +139,62 @@ __device__ __forceinline__ double dist2_exact(const double* xp, const double* XA
   return s;
 }
 
+// aLME (Nodes/aLME.c:382-434): the weight exponent is -l^T B l + lambda.l with the particle's metric B instead of
+// -beta |l|^2 + lambda.l.  The 2D metric is kept as (B00, B01 + B10, B11); `on` is uniform over a launch.
+struct MetricB { double b00, bs, b11; int on; };
+// the per-particle aLME arrays (2D: 4 columns each, component-major with the leading dimension of PartDev): the
+// thermalisation metric (Particle.Beta) and the cut-off ellipsoid of the neighbour test; both nullptr with LME.  Kept out
+// of PartDev and handed to the 2D kernels as an argument of its own, so that the 3D warp-per-cell kernels keep their
+// parameter layout (and their machine code: the ncu captures under profiles/ are keyed by it)
+struct AlmeDev { double *bten, *cten; };
+template <int D>
+__device__ __forceinline__ MetricB metric_load(const AlmeDev& al, int ld, int p) {
+  MetricB M;
+  M.on = 0; M.b00 = M.bs = M.b11 = 0.0;
+  if (D == 2 && al.bten) {
+    M.on = 1;
+    M.b00 = al.bten[p];
+    M.bs = al.bten[(size_t)ld + p] + al.bten[(size_t)2 * ld + p];
+    M.b11 = al.bten[(size_t)3 * ld + p];
+  }
+  return M;
+}
+// beta |l|^2 (LME.c:700-737) or l^T B l (aLME.c:382-405)
+template <int D>
+__device__ __forceinline__ double metric_q(const MetricB& M, double beta, double ll, const double* l) {
+  if (D == 2 && M.on) return M.b00 * (l[0] * l[0]) + M.bs * (l[0] * l[1]) + M.b11 * (l[1] * l[1]);
+  return beta * ll;
+}
+// M <- DF^-T M DF^-1 (update_beta__aLME__ / update_cut_off_ellipsoid__aLME__, aLME.c:693-809), 2 x 2 row-major, the four
+// terms of every entry in the reference's order
+__device__ __forceinline__ void alme_push_forward(const double* Fi, double* M) {
+  double U[4];
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int l = 0; l < 2; l++) s += Fi[k * 2 + i] * M[k * 2 + l] * Fi[l * 2 + j];
+      U[i * 2 + j] = s;
+    }
+#pragma unroll
+  for (int i = 0; i < 4; i++) M[i] = U[i];
+}
+// generalised_Euclidean_distance__MatrixLib__ (MatrixOp.c:895-920) with the reference's rounding sequence (products and
+// sums rounded separately): sqrt(l^T C l), compared with 1 by tributary__aLME__ (aLME.c:811-872)
+__device__ __forceinline__ double alme_distance(const double* C, const double* l) {
+  double q = 0.0;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const double Cl = __dadd_rn(__dmul_rn(C[i * 2 + 0], l[0]), __dmul_rn(C[i * 2 + 1], l[1]));
+    q = __dadd_rn(q, __dmul_rn(l[i], Cl));
+  }
+  return __dsqrt_rn(q);
+}
+
 // largest s with sqrt_rn(s) <= Ra, so that "s <= sstar" is EXACTLY the reference's
 // "sqrt(s) <= Ra" (LME.c:1074) without a square root per candidate.
 __device__ inline double sstar_from_Ra(double Ra) {

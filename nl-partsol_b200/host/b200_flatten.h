@@ -160,6 +160,9 @@ static int b200_flatten(b200_inputs *in, Mesh FEM_Mesh, Particle MPM_Mesh, Time_
   solver.thickness = Thickness_Plain_Stress;
   solver.quirk_transposed_eigvec = -1;
   solver.compute_c_ep = 0;
+  /* GramsShapeFun (Type=aLME): Particle.Beta is Np x Ndim^2 and Particle.Cut_off_Ellipsoid exists
+   * (Generate-One-Phase-Analysis.c:192-202) */
+  solver.shape_function = strcmp(ShapeFunctionGP, "aLME") == 0 ? NLPS_SHAPE_ALME : NLPS_SHAPE_LME;
 
   /* ---- loads */
   nlps_load *bounds = loads_to_pod(&FEM_Mesh.Bounds, NumTimeStep);
@@ -196,6 +199,7 @@ static int b200_flatten(b200_inputs *in, Mesh FEM_Mesh, Particle MPM_Mesh, Time_
   st.Vol_0 = Phi->Vol_0.nV; st.W = Phi->W;
   st.EPS_n = Phi->EPS_n; st.EPS_n1 = Phi->EPS_n1; st.Kappa_n = Phi->Kappa_n; st.Kappa_n1 = Phi->Kappa_n1;
   st.lambda = MPM_Mesh.lambda.nV; st.Beta = MPM_Mesh.Beta.nV;
+  st.Cut_off_Ellipsoid = solver.shape_function == NLPS_SHAPE_ALME ? MPM_Mesh.Cut_off_Ellipsoid.nV : NULL;
   st.I0 = MPM_Mesh.I0; st.NumberNodes = MPM_Mesh.NumberNodes; st.MatIdx = MPM_Mesh.MatIdx;
   st.Back_stress = Phi->Back_stress.nV; /* Von-Mises kinematic hardening (U-Analisys.c:152, Constitutive.c:116) */
   /* 3D Neumann loads act on Phi.Area_0 (U-Verlet.c:847-849); the reference declares the field (Types.h:196) and never

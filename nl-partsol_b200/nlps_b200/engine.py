@@ -41,7 +41,8 @@ class Solver(C.Structure):
                 ("num_steps", C.c_int), ("gamma_lme", C.c_double), ("tol_zero_lme", C.c_double),
                 ("tol_wrapper_lme", C.c_double), ("max_iter_lme", C.c_int),
                 ("tol_radial_returning", C.c_double), ("max_iter_radial_returning", C.c_int),
-                ("thickness", C.c_double), ("quirk_transposed_eigvec", C.c_int), ("compute_c_ep", C.c_int)]
+                ("thickness", C.c_double), ("quirk_transposed_eigvec", C.c_int), ("compute_c_ep", C.c_int),
+                ("shape_function", C.c_int)]
 
 
 _PFIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "F_n1", "DF", "b_e_n", "b_e_n1", "Stress", "C_ep",
@@ -52,7 +53,7 @@ _PFIELDS = ("x_GC", "dis", "D_dis", "vel", "acc", "F_n", "F_n1", "DF", "b_e_n", 
 class Particles(C.Structure):
     _fields_ = [("n", C.c_int)] + [(k, _dp) for k in _PFIELDS] + [("I0", _ip), ("NumberNodes", _ip),
                                                                   ("MatIdx", _ip), ("Area_0", _dp),
-                                                                  ("Back_stress", _dp)]
+                                                                  ("Back_stress", _dp), ("Cut_off_Ellipsoid", _dp)]
 
 
 class Msg(C.Structure):
@@ -286,7 +287,8 @@ class _Marshal:
         self.solver = Solver(float(s["cfl"]), float(s["cel"]), int(initial_step), int(s["nsteps"]),
                              float(s["gamma_lme"]), float(s["tol_zero"]), float(s["tol_wrapper"]),
                              int(s["max_iter_lme"]), float(s["tol_radial"]), int(s["maxiter_radial"]),
-                             float(s.get("thickness", 1.0)), int(quirk), int(compute_c_ep))
+                             float(s.get("thickness", 1.0)), int(quirk), int(compute_c_ep),
+                             1 if s.get("alme", 0) else 0)   # GramsShapeFun (Type=aLME)
         self.bounds = self._loads(prob.bounds)
         self.neumann = self._loads(prob.neumann)
         self.gravity = _d(prob.gravity) if prob.gravity is not None else None
@@ -323,6 +325,9 @@ class _Marshal:
         if "Back_stress" in prob.fields:  # Von-Mises kinematic hardening (Phi.Back_stress, n x 3)
             host["Back_stress"] = cp(_d(prob.fields["Back_stress"]))
             st.Back_stress = host["Back_stress"].ctypes.data_as(_dp)
+        if "Cut_off_Ellipsoid" in prob.fields:  # aLME: the metric of the neighbour test (n x d*d); Beta is n x d*d too
+            host["Cut_off_Ellipsoid"] = cp(_d(prob.fields["Cut_off_Ellipsoid"]))
+            st.Cut_off_Ellipsoid = host["Cut_off_Ellipsoid"].ctypes.data_as(_dp)
         return st, host
 
 
@@ -405,6 +410,8 @@ class Engine:
             setattr(st, k, host[k].ctypes.data_as(_ip))
         if "Back_stress" in host:
             st.Back_stress = host["Back_stress"].ctypes.data_as(_dp)
+        if "Cut_off_Ellipsoid" in host:
+            st.Cut_off_Ellipsoid = host["Cut_off_Ellipsoid"].ctypes.data_as(_dp)
         ids = np.zeros(max(n, 1), np.int32)
         assert self.L.nlps_b200_download_local(self.h, C.byref(st), ids.ctypes.data_as(_ip)) == 0
         return {k: v[:n] for k, v in host.items()}, ids[:n].copy()

@@ -196,7 +196,7 @@ def test_implicit_refuses_invalid_parameters():
 
 
 @pytest.mark.parametrize("key,rtol", [("nh", 1e-8), ("nh_trial", 1e-8), ("dp", 2e-6), ("mn", 2e-6), ("static_nh", 1e-8),
-                                      ("vm", 2e-6), ("hencky", 2e-6), ("nhload", 1e-8), ("static_nhload", 1e-8), ("mixed", 2e-6)])
+                                      ("vm", 2e-6), ("hencky", 2e-6), ("nhload", 1e-8), ("static_nhload", 1e-8), ("mixed", 2e-6), ("almenh", 1e-8), ("almedp", 2e-6)])
 def test_converged_steps_match_the_reference_compiled_scheme(key, rtol):
     """The device scheme against the reference's OWN U_Newmark_Beta / U_Static: tests/golden/newmark_*.npz hold the states
     the reference's compiled scheme code reached on 2D decks (run against oracle/minipetsc -- PETSc is absent --, see
@@ -217,11 +217,13 @@ def test_converged_steps_match_the_reference_compiled_scheme(key, rtol):
     sc = field_scales(P)
     names = ("x_GC", "dis", "vel", "acc", "F_n", "Stress", "rho", "J_n", "lambda") if rtol <= 1e-8 else \
             ("x_GC", "dis", "vel", "F_n", "Stress", "J_n") + (("EPS_n", "b_e_n") if key != "hencky" else ())
+    if key.startswith("alme"):      # GramsShapeFun (Type=aLME): the convected metric and cut-off ellipsoid
+        names = names + ("Beta", "Cut_off_Ellipsoid")
     for name in names:
         assert_close(f[name], g[f"s{k}_{name}"], f"reference scheme {key} {name}", rtol=rtol, scale=sc.get(name))
     assert np.array_equal(f["I0"], g[f"s{k}_I0"])
     counts, _ = eng.lists()
     assert np.array_equal(counts, g[f"s{k}_NumberNodes"])
-    if key in ("dp", "mixed"):
+    if key in ("dp", "mixed", "almedp"):
         assert (f["EPS_n"] > 0).sum() > 20
     eng.close()

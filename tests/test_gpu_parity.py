@@ -17,16 +17,21 @@ def _close_nodal(eng, o, P, what):
         assert_close(eng.nodal(w), o.nodal(w), f"{what} nodal {nm}")
 
 
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", CASES + ("almenh",))
 def test_initialize_lme_matches_reference(case):
+    """almenh: initialize__aLME__ (Nodes/aLME.c:32-166) -- the isotropic metric and cut-off ellipsoid, lists, lambda."""
     P = load_problem(case)
     P0 = P.copy()
     P0.fields["Beta"][:] = 0.0
     P0.fields["lambda"][:] = 0.0
+    if case.startswith("alme"):
+        P0.fields["Cut_off_Ellipsoid"][:] = 0.0
     eng = engine.Engine(P0)
     assert eng.initialize_lme() == 0, eng.error()
     f = eng.download()
     assert np.array_equal(f["Beta"], P.fields["Beta"])          # bit-exact (one division)
+    if case.startswith("alme"):
+        assert np.array_equal(f["Cut_off_Ellipsoid"], P.fields["Cut_off_Ellipsoid"])
     assert_close(f["lambda"], P.fields["lambda"], "lambda", scale=1e-3 / P.dx)
     o = oracle.Oracle(P0)
     assert o.init_lme() == 0
@@ -37,11 +42,13 @@ def test_initialize_lme_matches_reference(case):
     eng.close()
 
 
-@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload", "mixed"))
+@pytest.mark.parametrize("case", CASES + ("vm", "hencky", "nhload", "mixed", "almenh", "almedp"))
 def test_steps_match_golden_reference(case):
     """Multi-step run against fixtures produced by the reference's compiled code.  nhload: Neumann traction on a column of
     particles + a platen (Dirichlet set with non-zero displacement increments); mixed: two materials in one cloud
-    (Drucker-Prager below, Neo-Hookean above: the kernels that read the law per particle)."""
+    (Drucker-Prager below, Neo-Hookean above: the kernels that read the law per particle); almenh / almedp:
+    GramsShapeFun (Type=aLME), Nodes/aLME.c -- metric tensor and cut-off ellipsoid convected with DF^-1 at every search,
+    elastic and with 7 % equivalent plastic strain (TRACE_FIELDS holds Beta: here the 2 x 2 metric)."""
     P = load_problem(case)
     tr = load_trace(case)
     eng = engine.Engine(P, compute_c_ep=1)
@@ -59,7 +66,8 @@ def test_steps_match_golden_reference(case):
         assert np.array_equal(lists[:, :tr[t + "lists"].shape[1]], tr[t + "lists"]), f"lists at step {cp}"
         assert np.array_equal(eng.active(), tr[t + "active"])
         # (Von-Mises: also the tangent moduli of its return mapping, Von-Mises.c:730-757, which the implicit tangent reads)
-        for name in TRACE_FIELDS + (("Back_stress", "C_ep") if case == "vm" else ()):
+        for name in TRACE_FIELDS + (("Back_stress", "C_ep") if case == "vm" else ()) + \
+                (("Cut_off_Ellipsoid",) if case.startswith("alme") else ()):
             assert_close(f[name], tr[t + name], f"{case} step {cp} {name}", scale=scales.get(name))
         for w, nm in enumerate(NODAL):
             assert_close(eng.nodal(w), tr[t + "g" + nm], f"{case} step {cp} nodal {nm}", scale=scales["g" + nm])
