@@ -29,10 +29,12 @@ def _points(vtk):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ("nh", "vm"))
+@pytest.mark.parametrize("case", ("nh", "vm", "almenh"))
 def test_reference_driver_with_b200_scheme(tmp_path, case):
     """nh: the Neo-Hookean block; vm: a Von-Mises deck (mixed isotropic / kinematic hardening: the back stress lives in
-    the reference's own Phi.Back_stress buffer and is handed to the engine by the shim)."""
+    the reference's own Phi.Back_stress buffer and is handed to the engine by the shim); almenh: GramsShapeFun (Type=aLME)
+    -- the reference's driver initialises metric and ellipsoid (initialize__aLME__), the shim hands Particle.Beta (n x 4)
+    and Particle.Cut_off_Ellipsoid to the engine."""
     if not os.path.exists(BIN):
         pytest.skip("drop-in binary not built (needs /root/reference at build time)")
     import deckgen
@@ -46,7 +48,7 @@ def test_reference_driver_with_b200_scheme(tmp_path, case):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "abnormally" not in r.stdout + r.stderr
     tr = load_trace(case)
-    for cp in (1, 2, 5, 20, 60):
+    for cp in [int(c) for c in tr["checkpoints"] if c <= 60]:
         files = _particle_vtk(tmp_path, cp - 1)
         assert files, f"no VTK for step {cp - 1}"
         x = _points(files[0])
