@@ -19,8 +19,8 @@ static int b200_implicit_scheme(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Param
   const int NumTimeStep = Parameters_Solver.NumTimeStep;
   int STATUS = EXIT_SUCCESS;
 
-  if (strcmp(ShapeFunctionGP, "LME") != 0) {
-    fprintf(stderr, "" RED "Error in %s() [B200]: only GramsShapeFun (Type=LME) is supported" RESET " \n",
+  if (strcmp(ShapeFunctionGP, "LME") != 0 && (strcmp(ShapeFunctionGP, "aLME") != 0 || NumberDimensions != 2)) {
+    fprintf(stderr, "" RED "Error in %s() [B200]: only GramsShapeFun (Type=LME) and, in 2D, (Type=aLME) are supported" RESET " \n",
             quasi_static ? "U_Static" : "U_Newmark_Beta");
     return EXIT_FAILURE;
   }

@@ -107,8 +107,8 @@ int U_Verlet(Mesh FEM_Mesh, Particle MPM_Mesh, Time_Int_Params Parameters_Solver
   const int Np = MPM_Mesh.NumGP;
   int STATUS = EXIT_SUCCESS;
 
-  if (strcmp(ShapeFunctionGP, "LME") != 0) {
-    fprintf(stderr, "" RED "Error in U_Verlet() [B200]: only GramsShapeFun (Type=LME) is supported" RESET " \n");
+  if (strcmp(ShapeFunctionGP, "LME") != 0 && (strcmp(ShapeFunctionGP, "aLME") != 0 || NumberDimensions != 2)) {
+    fprintf(stderr, "" RED "Error in U_Verlet() [B200]: only GramsShapeFun (Type=LME) and, in 2D, (Type=aLME) are supported" RESET " \n");
     return EXIT_FAILURE;
   }
   b200_inputs in;
