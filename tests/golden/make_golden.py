@@ -1,9 +1,16 @@
 """Generate the golden fixtures that pin the oracle (and through it the CUDA engine) to the
 reference's OWN compiled 2D code.
 
-Run here (the container that has /root/reference), after `make -C oracle ref`:
+Run here (the container that has /root/reference), after `make -C oracle ref ref3d ref-newmark`:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py                 # everything
+    python tests/golden/make_golden.py sim almedp      # one explicit case: <case>_problem.npz + <case>_trace.npz
+    python tests/golden/make_golden.py newmark dp      # one implicit case: newmark_<key>.npz
+
+Explicit cases (`sim`): nh, dp, mn, vm, hencky (one law each), nhload (Neumann traction + moving platen), mixed (two
+materials in one cloud), almenh / almedp (GramsShapeFun Type=aLME).  Implicit cases (`newmark`, NEWMARK_CASES): the
+reference's OWN U_Newmark_Beta / U_Static, compiled unmodified against oracle/minipetsc (oracle/_ref/
+libnlps2d_newmark_ref.so), run over the same decks.
 
 Each case is produced in a fresh subprocess (the reference keeps its state in process globals):
 a deck is written with tests/deckgen.py, parsed by the reference's parser, initialised by the
